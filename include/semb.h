@@ -1,0 +1,219 @@
+/*
+ * semb.h -- C ABI of libsemb.so: the B200-native (sm_100a) implementation of the matrix-free
+ * spectral-element operator hot path of vpuri3/SpectralElements.jl.
+ *
+ * The reference is pure Julia and has NO FFI layer for this path: its "operator
+ * API" is the set of exported Julia functions below.  Each entry point here names the reference
+ * function (file:line under /root/reference/src) it replaces; INTEGRATION.md shows the Julia
+ * `ccall` method a maintainer adds per function so examples (p2d, d2d, cd2d) run unmodified.
+ *
+ * Conventions
+ *   - Every function returns int: 0 = SEMB_OK, <0 = error (message via semb_last_error()),
+ *     +1 = SEMB_NOT_CONVERGED (pcg hit maxiter; mirrors pcg.jl:39 "warn and return the iterate").
+ *   - No C++ exception crosses the ABI.  Only plain pointers / ints / doubles in signatures.
+ *   - Host arrays are column-major (Julia / Fortran order) FP64, shape (nr*Ex) x (ns*Ey_local):
+ *     first index = x (contiguous).  The library never retains a host pointer after returning.
+ *   - The library owns all device memory.  Internally a field is stored with a padded row pitch
+ *     (multiple of 16 doubles); upload/download convert.
+ *   - Multi-GPU: one process per GPU (rank).  Element rows are split into contiguous y-slabs;
+ *     `Ey` arguments below are GLOBAL element-row counts, host arrays hold the LOCAL slab
+ *     (rows [ey0*ns, (ey0+ney)*ns) of the global matrix, see semb_partition).
+ *   - There is NO CPU fallback: every compute entry point fails with SEMB_ECUDA without a GPU.
+ */
+#ifndef SEMB_H
+#define SEMB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEMB_OK 0
+#define SEMB_NOT_CONVERGED 1
+#define SEMB_EINVAL (-1)  /* bad argument / size mismatch (Julia: DimensionMismatch / InexactError, ABu.jl:16,26) */
+#define SEMB_ECUDA (-2)   /* CUDA runtime error, or no CUDA device */
+#define SEMB_ENCCL (-3)   /* NCCL error */
+#define SEMB_ENOMEM (-4)
+#define SEMB_ESTATE (-5)  /* call sequence error (e.g. comm not initialised) */
+
+typedef struct semb_ctx semb_ctx;     /* one GPU + stream (+ NCCL communicator) */
+typedef struct semb_mesh semb_mesh;   /* device copy of Mesh{T} operator data, mesh.jl:25-64 */
+typedef struct semb_field semb_field; /* one device-resident (nr*Ex) x (ns*Ey_local) FP64 array */
+
+/* built-in deformation maps for semb_mesh_create_deform (mesh.jl:108 `deform(x,y)`) */
+#define SEMB_DEFORM_IDENTITY 0 /* fixU, mesh.jl:6-8 */
+#define SEMB_DEFORM_ANNULUS 1  /* geom.jl:40-49, params = {r0, r1, span} */
+#define SEMB_DEFORM_WAVY 2     /* bench map: (x+d, y+d), d = a sin(pi x) sin(pi y); params = {a} */
+
+/* selectors for semb_mesh_get (field names of Mesh{T}, mesh.jl:41-62) */
+enum semb_mesh_array {
+  SEMB_X = 0, SEMB_Y, SEMB_JAC, SEMB_JACI, SEMB_RX, SEMB_RY, SEMB_SX, SEMB_SY,
+  SEMB_B, SEMB_BI, SEMB_G11, SEMB_G12, SEMB_G22, SEMB_MULT, SEMB_MESH_ARRAY_COUNT
+};
+
+/* ---- library / context ------------------------------------------------------------------ */
+int semb_version(void);
+const char* semb_last_error(void); /* thread-local message of the last failing call */
+/* Create a context on CUDA device `device` (owns a non-default stream + scratch). */
+int semb_init(int device, semb_ctx** ctx);
+int semb_finalize(semb_ctx* ctx);
+int semb_sync(semb_ctx* ctx);                         /* cudaStreamSynchronize of the ctx stream */
+int semb_stream(semb_ctx* ctx, void** cuda_stream);   /* the cudaStream_t every kernel is launched on */
+/* Device timing helpers (CUDA events on the ctx stream), used by bench.py. */
+int semb_timer_start(semb_ctx* ctx);
+int semb_timer_stop(semb_ctx* ctx, double* elapsed_ms); /* synchronises, returns ms since start */
+/* Number of library kernels launched on this ctx since creation (bench.py's gpu_launches). */
+int semb_launch_count(semb_ctx* ctx, long long* n);
+/* Writes >L2-size scratch to evict L2 between timed repetitions. */
+int semb_flush_l2(semb_ctx* ctx);
+
+/* ---- multi-GPU plumbing (new; the reference is single-process) ------------------ */
+/* Contiguous y-slab owned by `rank`: element rows [ey0, ey0+ney). No GPU needed. */
+int semb_partition(int Ey, int nranks, int rank, int* ey0, int* ney);
+/* rank 0: fill a 128-byte ncclUniqueId; the host language broadcasts it (torch.distributed / MPI). */
+int semb_comm_unique_id(char id[128]);
+/* every rank: join the communicator (ncclCommInitRank on the ctx device). */
+int semb_comm_init(semb_ctx* ctx, int nranks, int rank, const char id[128]);
+int semb_comm_info(semb_ctx* ctx, int* nranks, int* rank);
+int semb_comm_barrier(semb_ctx* ctx);                 /* allreduce + stream sync */
+int semb_comm_allreduce_max(semb_ctx* ctx, double* v, int n); /* host doubles, in place */
+
+/* ---- 1-D setup helpers (host C++, no GPU) ---------------------------------------------------- */
+/* FastGaussQuadrature.gausslobatto(n) as used at mesh.jl:70-71, semmesh.jl:11 */
+int semb_gausslobatto(int n, double* z, double* w);
+/* derivMat(x), derivMat.jl:9-35; D is n x n column-major */
+int semb_deriv_mat(int n, const double* x, double* D);
+/* interpMat(xo, xi), interp.jl:10-35; J is no x ni column-major */
+int semb_interp_mat(int no, const double* xo, int ni, const double* xi, double* J);
+/* semmesh(E, n), semmesh.jl:9-27; z, w have E*n entries */
+int semb_semmesh(int E, int n, double* z, double* w);
+/* bdfExtK(t; k), time.jl:31-53; t has nt entries, a has k, b has k+1 */
+int semb_bdf_ext_k(int nt, const double* t, int k, double* a, double* b);
+
+/* ---- mesh --------------------------------------------------------------------------------------- */
+/* Mesh(nr,ns,Ex,Ey,ifperiodic,deform) from deformed coordinates, mesh.jl:66-133: runs jac
+ * (jac.jl:24-40) and the B/G11/G12/G22 factors (mesh.jl:114-123) and mult (mesh.jl:94-96) ON DEVICE.
+ * x, y: host, local slab, already deformed.  Dr (nr x nr), Ds (ns x ns) column-major; wr, ws weights. */
+int semb_mesh_create_xy(semb_ctx* ctx, int nr, int ns, int Ex, int Ey, int perx, int pery,
+                        const double* Dr, const double* Ds, const double* wr, const double* ws,
+                        const double* x, const double* y, semb_mesh** mesh);
+/* Same, but the grid (semmesh.jl + ndgrid.jl) and a built-in deformation are generated on device:
+ * nothing of size O(n) touches the host (needed for the 1e8-DOF meshes). */
+int semb_mesh_create_deform(semb_ctx* ctx, int nr, int ns, int Ex, int Ey, int perx, int pery,
+                            int deform_kind, const double* params, int nparams, semb_mesh** mesh);
+/* Mesh from ready-made operator arrays (what a Julia `Mesh` already holds); B may be NULL. */
+int semb_mesh_create_arrays(semb_ctx* ctx, int nr, int ns, int Ex, int Ey, int perx, int pery,
+                            const double* Dr, const double* Ds, const double* G11, const double* G12,
+                            const double* G22, const double* B, semb_mesh** mesh);
+int semb_mesh_destroy(semb_mesh* mesh);
+/* nxl = nr*Ex, nyl = ns*ney (local), ey0/ney = this rank's slab. Any out pointer may be NULL. */
+int semb_mesh_dims(semb_mesh* mesh, int* nr, int* ns, int* Ex, int* Ey, int* nxl, int* nyl, int* ey0, int* ney);
+/* Copy one Mesh array (enum semb_mesh_array) to a host nxl x nyl buffer. */
+int semb_mesh_get(semb_mesh* mesh, int which, double* host_out);
+/* Dr / Ds as held on the device side (column-major). */
+int semb_mesh_get_D(semb_mesh* mesh, double* Dr, double* Ds);
+/* generateMask(bc, msh), mesh.jl:149-175: bc = "DDNN" = [xmin,xmax,ymin,ymax]; writes 0/1 doubles. */
+int semb_generate_mask(semb_mesh* mesh, const char bc[4], double* host_out);
+
+/* ---- fields ---------------------------------------------------------------------------------------- */
+int semb_field_create(semb_mesh* mesh, semb_field** f); /* zero-initialised */
+int semb_field_destroy(semb_field* f);
+int semb_field_upload(semb_field* f, const double* host);   /* nxl x nyl column-major */
+int semb_field_download(semb_field* f, double* host);
+int semb_field_fill(semb_field* f, double value);
+int semb_field_copy(semb_field* dst, const semb_field* src);
+/* Fill with the portable splitmix64 uniform(-1,1) stream, global column-major index. */
+int semb_field_fill_random(semb_field* f, uint64_t seed);
+/* y = a*x + b*y (pointwise; host-language broadcasts like `u .+= ub`, diffusion.jl:75) */
+int semb_field_axpby(double a, const semb_field* x, double b, semb_field* y);
+/* Raw device pointer + pitch (in doubles), for zero-copy interop (e.g. torch.from_blob / CuPtr). */
+int semb_field_devptr(semb_field* f, void** dptr, long long* pitch);
+
+/* ---- operators on device-resident fields --------------------------------------------------------- */
+/* Optional array coefficients: pass NULL to use the scalar.  `out` must not alias `u`. */
+/* laplace(u,Dr,Ds,G11,G12,G22), lapl.jl:70-81 == lapl(u,msh), lapl.jl:26-36 (no gs, no mask) */
+int semb_lapl(semb_mesh* m, const semb_field* u, semb_field* out);
+/* hlmz(u,nu,k,msh), hlmz.jl:12-19: out = nu .* lapl(u) + k .* (B .* u); nu/k scalar or array */
+int semb_hlmz(semb_mesh* m, const semb_field* u, const semb_field* nu_arr, double nu,
+              const semb_field* k_arr, double k, semb_field* out);
+/* mass(u,msh), mass.jl:12-22: out = B .* u */
+int semb_mass(semb_mesh* m, const semb_field* u, semb_field* out);
+/* gatherScatter(u,msh), gatherScatter.jl:8-21: out = QQ^T u (x pairs first, then y pairs;
+ * bitwise equal to the reference's dense product).  Multi-GPU: halo exchange inside. */
+int semb_gather_scatter(semb_mesh* m, const semb_field* u, semb_field* out);
+/* mask(u,M), mask.jl:10-18: out = M .* u; M = NULL copies (length(M)==0 branch). */
+int semb_mask(semb_mesh* m, const semb_field* u, const semb_field* M, semb_field* out);
+/* The fused unit opLHS(u,dfn), diffusion.jl:36-45 / convectionDiffusion.jl:76-85:
+ * out = mask(gatherScatter(hlmz(u,nu,k,msh)), M).  Mask: bc = "DDNN"-style flags (NULL = no mask)
+ * or an explicit 0/1 array M_arr (overrides bc).  One fused strip kernel + two seam kernels. */
+int semb_oplhs(semb_mesh* m, const semb_field* u, const semb_field* nu_arr, double nu,
+               const semb_field* k_arr, double k, const char* bc, const semb_field* M_arr,
+               semb_field* out);
+/* jac(x,y,Dr,Ds), jac.jl:24-40, as a standalone op on fields (Mesh creation uses the same kernel). */
+int semb_jac(semb_mesh* m, const semb_field* x, const semb_field* y, semb_field* J, semb_field* Ji,
+             semb_field* rx, semb_field* ry, semb_field* sx, semb_field* sy);
+/* sum(a .* b .* mult), pcg.jl:45,52 (deterministic fixed-order reduction; all-reduced over ranks) */
+int semb_dot_mult(semb_mesh* m, const semb_field* a, const semb_field* b, double* result);
+/* norm(a, Inf), pcg.jl:36 */
+int semb_norm_inf(semb_mesh* m, const semb_field* a, double* result);
+
+/* ---- PCG --------------------------------------------------------------------------------------------- */
+/* pcg(b, opA; opM, mult, tol, maxiter), pcg.jl:16-60, with opA = the fused opLHS above and
+ * opM = identity (diffusion.jl:47-49) or u ./ B ./ b0 (convectionDiffusion.jl:87-91).
+ * The whole loop is device-resident (alpha/beta/convergence live in device memory; the host polls a
+ * done flag).  x is overwritten (pcg! semantics, pcg.jl:64-79: zero initial guess always).
+ * maxiter < 0 => length(b) (global).  iters / resinf (final norm(r,Inf)) may be NULL. */
+typedef struct semb_pcg_opts {
+  double nu;                /* scalar viscosity (used when nu_arr == NULL) */
+  const semb_field* nu_arr; /* array viscosity, diffusion.jl:11,40 */
+  double k;                 /* scalar Helmholtz coefficient = bdfB[1] */
+  const semb_field* k_arr;  /* array coefficient, examples/poissonNonlin.jl:84,87 */
+  const char* bc;           /* "DDDD"-style flags or NULL */
+  const semb_field* M_arr;  /* explicit mask array or NULL */
+  int precond;              /* 0 = identity, 1 = u ./ B ./ prec_b0 */
+  double prec_b0;
+  double tol;               /* absolute, on norm(r,Inf); pcg.jl:20 default 1e-8 */
+  long long maxiter;        /* <0 => length(b) */
+  int check_every;          /* host polls the device done flag every this many iterations (<=0: auto) */
+} semb_pcg_opts;
+int semb_pcg(semb_mesh* m, const semb_pcg_opts* opts, const semb_field* b, semb_field* x,
+             long long* iters, double* resinf);
+/* One PCG iteration's worth of kernels `n` times without convergence polling (bench: iterations/s).
+ * State must have been initialised by semb_pcg_begin. */
+int semb_pcg_begin(semb_mesh* m, const semb_pcg_opts* opts, const semb_field* b, semb_field* x);
+int semb_pcg_iterate(semb_mesh* m, int n);
+int semb_pcg_status(semb_mesh* m, long long* iters, double* resinf, int* done);
+
+/* ---- host-pointer convenience twins (value semantics of the Julia functions) ------------------- */
+/* Each uploads its inputs, runs the device op, downloads `out` (fresh array in Julia). */
+int semb_lapl_host(semb_mesh* m, const double* u, double* out);
+int semb_hlmz_host(semb_mesh* m, const double* u, const double* nu_arr, double nu,
+                   const double* k_arr, double k, double* out);
+int semb_mass_host(semb_mesh* m, const double* u, double* out);
+int semb_gather_scatter_host(semb_mesh* m, const double* u, double* out);
+int semb_mask_host(semb_mesh* m, const double* u, const double* M, double* out);
+int semb_oplhs_host(semb_mesh* m, const double* u, const double* nu_arr, double nu,
+                    const double* k_arr, double k, const char* bc, const double* M_arr, double* out);
+int semb_pcg_host(semb_mesh* m, const semb_pcg_opts* opts_scalars, const double* nu_arr,
+                  const double* k_arr, const double* M_arr, const double* b, double* x,
+                  long long* iters, double* resinf);
+/* ABu(As,Br,u), ABu.jl:9-37, general rectangular blocks.  As is ma x na, Br is mb x nb (column-major);
+ * a NULL pointer / zero size is Julia's `[]` (identity).  u is m x n; out is (m*mb/nb) x (n*ma/na).
+ * Needs no mesh. */
+int semb_abu_host(semb_ctx* ctx, const double* As, int ma, int na, const double* Br, int mb, int nb,
+                  const double* u, int m, int n, double* out);
+
+/* ---- diagnostics / tuning hooks (no reference counterpart) ------------------------------------- */
+/* registers / shared memory / resident CTAs per SM of the fused strip kernel for polynomial size N */
+int semb_strip_kernel_info(int N, int pcg, int massterm, int* regs, int* smem, int* occ);
+/* launch plan of the fused operator: strips x chunks, seam counts, fast = templated strip kernel used */
+int semb_mesh_plan(semb_mesh* mesh, int* nstrips, int* nchunks, int* nxseam, int* nyseam, int* fast);
+/* override the number of y chunks (tests exercise every seam configuration with it) */
+int semb_mesh_set_chunks(semb_mesh* mesh, int nchunks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEMB_H */

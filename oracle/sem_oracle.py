@@ -1,0 +1,645 @@
+"""CPU ORACLE (test infrastructure, NOT product code) -- NumPy restatement of the
+matrix-free hot path of vpuri3/SpectralElements.jl.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  The product (spectralelements.jl_b200/) never does.
+
+PARITY UNPINNED: the reference is pure Julia; Julia is not installed in this image
+(nor on the GPU box), the reference ships no golden vectors / known-answer tests
+for this path (its test/ directory only covers the unused `Spectral` sub-module),
+and its third-party arithmetic (FastGaussQuadrature.gausslobatto, OpenBLAS `*`,
+Base.sum) is unpinned (no Manifest.toml, no [compat]).  What pins this restatement
+instead (tests/test_oracle_*.py):
+  * the explicit Kronecker-assembled operators of examples/p2d_explicit.jl:142-180,
+  * closed-form GLL nodes/weights and polynomial exactness of derivMat/interpMat,
+  * analytic solutions (examples/d2d.jl:13-16; annulus -lap u = 1 closed form),
+  * algebraic identities (symmetry, constants in the null space, sum(B*mult)=area).
+tools/ref_dump.jl regenerates true-reference goldens on a machine that has Julia.
+
+Conventions: every 2-D field is an (nxl, nyl) = (nr*Ex, ns*Ey) array, first index = x/r
+(the contiguous one in the reference's column-major storage, mesh.jl:94).  Arrays are
+kept Fortran-ordered so `reshape(u, nb, :)` of ABu.jl:17 is a view exactly as in Julia.
+Every function cites the reference file:line it follows (paths relative to
+/root/reference/src unless stated).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+EMPTY = np.zeros((0,))  # Julia's `[]` (length-0 => identity in ABu, ABu.jl:14,23)
+
+
+def _F(a):
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+# ----------------------------------------------------------------------------
+# third-party arithmetic restated: FastGaussQuadrature.gausslobatto (unpinned)
+# call sites mesh.jl:70-71, semmesh.jl:11
+# ----------------------------------------------------------------------------
+def _legendre(n: int, x):
+    """P_n(x) and P_{n-1}(x) by the three-term recurrence."""
+    x = np.asarray(x, dtype=np.float64)
+    p0 = np.ones_like(x)
+    if n == 0:
+        return p0, np.zeros_like(x)
+    p1 = x.copy()
+    for k in range(2, n + 1):
+        p0, p1 = p1, ((2 * k - 1) * x * p1 - (k - 1) * p0) / k
+    return p1, p0
+
+
+def gausslobatto(n: int):
+    """GLL nodes/weights on [-1,1]: roots of (1-x^2) P'_{n-1}(x), w = 2/(n(n-1) P_{n-1}(x)^2).
+
+    Published algorithm of FastGaussQuadrature.gausslobatto(n) restated (Newton on the
+    Chebyshev-Gauss-Lobatto initial guess).  Pinned by closed forms for n=2..5 in tests.
+    """
+    if n < 2:
+        raise ValueError("gausslobatto needs n >= 2")
+    N = n - 1
+    x = -np.cos(np.pi * np.arange(n) / N)
+    for _ in range(100):
+        PN, PNm1 = _legendre(N, x)
+        # q(x) = (1-x^2) P'_N = N (P_{N-1} - x P_N);  q'(x) = -N (N+1) P_N
+        q = N * (PNm1 - x * PN)
+        dq = -N * (N + 1) * PN
+        dx = q / dq
+        dx[0] = 0.0
+        dx[-1] = 0.0
+        x = x - dx
+        if np.max(np.abs(dx)) < 1e-16:
+            break
+    x[0], x[-1] = -1.0, 1.0
+    x = 0.5 * (x - x[::-1])  # enforce antisymmetry (exact 0 at the centre for odd n)
+    PN, _ = _legendre(N, x)
+    w = 2.0 / (N * (N + 1) * PN * PN)
+    return x, w
+
+
+# ----------------------------------------------------------------------------
+# derivMat.jl:9-35
+# ----------------------------------------------------------------------------
+def derivMat(x):
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    n = x.size
+    a = np.ones(n)
+    for i in range(n):  # derivMat.jl:14-17
+        for j in range(i):
+            a[i] = a[i] * (x[i] - x[j])
+        for j in range(i + 1, n):
+            a[i] = a[i] * (x[i] - x[j])
+    a = 1.0 / a  # barycentric weights, derivMat.jl:18
+    D = x[:, None] - x[None, :]  # derivMat.jl:21
+    for i in range(n):
+        D[i, i] = 1.0
+    D = 1.0 / D
+    for i in range(n):  # derivMat.jl:24-27
+        D[i, i] = 0.0
+        D[i, i] = np.sum(D[i, :])
+    for j in range(n):  # derivMat.jl:30-32
+        for i in range(n):
+            if i != j:
+                D[i, j] = a[j] / (a[i] * (x[i] - x[j]))
+    return D
+
+
+# ----------------------------------------------------------------------------
+# interp.jl:10-35
+# ----------------------------------------------------------------------------
+def interpMat(xo, xi):
+    xo = np.atleast_1d(np.asarray(xo, dtype=np.float64)).reshape(-1)
+    xi = np.atleast_1d(np.asarray(xi, dtype=np.float64)).reshape(-1)
+    no, ni = xo.size, xi.size
+    a = np.ones(ni)
+    for i in range(ni):
+        for j in range(i):
+            a[i] = a[i] * (xi[i] - xi[j])
+        for j in range(i + 1, ni):
+            a[i] = a[i] * (xi[i] - xi[j])
+    a = 1.0 / a
+    J = np.zeros((no, ni))
+    s = np.ones(ni)
+    t = np.ones(ni)
+    for i in range(no):
+        x = xo[i]
+        for j in range(1, ni):  # interp.jl:27-30 (1-based j=2:ni)
+            s[j] = s[j - 1] * (x - xi[j - 1])
+            t[ni - 1 - j] = t[ni - j] * (x - xi[ni - j])
+        J[i, :] = a * s * t
+    return J
+
+
+# ----------------------------------------------------------------------------
+# semq.jl:6-25   (dense here; the reference densifies it anyway, mesh.jl:44-45)
+# ----------------------------------------------------------------------------
+def semq(E: int, n: int, periodic: bool):
+    Q = np.zeros((E * n, E * (n - 1) + 1))
+    i = j = 0
+    for _ in range(E):
+        Q[i:i + n, j:j + n] = np.eye(n)
+        i += n
+        j += n - 1
+    if periodic:
+        Q[-1, 0] = 1.0
+        Q = Q[:, :-1]
+    return Q
+
+
+# ----------------------------------------------------------------------------
+# semmesh.jl:9-27
+# ----------------------------------------------------------------------------
+def semmesh(E: int, n: int):
+    z0, w0 = gausslobatto(n)
+    z0 = 0.5 * (z0 + 1.0)
+    w0 = 0.5 * w0
+    ze = np.linspace(-1.0, 1.0, E + 1)
+    dz = np.diff(ze)
+    z = np.kron(dz, z0) + np.kron(ze[:-1], np.ones(n))
+    w = np.kron(dz, w0)
+    return z, w
+
+
+# ndgrid.jl:8-13
+def ndgrid(xe, ye):
+    xe = np.asarray(xe, dtype=np.float64)
+    ye = np.asarray(ye, dtype=np.float64)
+    x = _F(np.repeat(xe[:, None], ye.size, axis=1))
+    y = _F(np.repeat(ye[None, :], xe.size, axis=0))
+    return x, y
+
+
+# ----------------------------------------------------------------------------
+# ABu.jl:9-37  -- (As (x) Br) u, line-faithful: one big GEMM for Br, an Ey-long loop
+# of small GEMMs for As.  `[]` (length 0) is the identity.
+# ----------------------------------------------------------------------------
+def ABu(As, Br, u):
+    As = np.asarray(As)
+    Br = np.asarray(Br)
+    u = np.asarray(u)
+    m, n = u.shape
+    Bu = u
+    if Br.size != 0:  # ABu.jl:14-20
+        mb, nb = Br.shape
+        if (m * mb) % nb != 0 or m % nb != 0:
+            raise ValueError("ABu: InexactError (rows not a multiple of Br columns)")
+        m = (m * mb) // nb
+        Bu = np.reshape(Bu, (nb, -1), order="F")
+        Bu = Br @ Bu
+        Bu = np.reshape(Bu, (m, n), order="F")
+    out = Bu
+    if As.size != 0:  # ABu.jl:23-34
+        ma, na = As.shape
+        if n % na != 0:
+            raise ValueError("ABu: InexactError (cols not a multiple of As columns)")
+        Ey = n // na
+        n2 = Ey * ma
+        tmp = np.zeros((m, n2), order="F")
+        AsT = As.T
+        for i in range(Ey):
+            tmp[:, i * ma:(i + 1) * ma] = out[:, i * na:(i + 1) * na] @ AsT
+        out = tmp
+    return out
+
+
+# jac.jl:24-40
+def jac(x, y, Dr, Ds):
+    xr = ABu(EMPTY, Dr, x)
+    xs = ABu(Ds, EMPTY, x)
+    yr = ABu(EMPTY, Dr, y)
+    ys = ABu(Ds, EMPTY, y)
+    J = xr * ys - xs * yr
+    Ji = 1.0 / J
+    rx = Ji * ys
+    ry = -Ji * xs
+    sx = -Ji * yr
+    sy = Ji * xr
+    return J, Ji, rx, ry, sx, sy
+
+
+# geom.jl:40-49
+def annulus(r, s, r0=0.5, r1=1.0, span=2 * math.pi):
+    R = (r1 - r0) / 2 * (r + 1) + r0
+    th = span / 2 * (s + 1) + 0.0
+    return R * np.cos(th), R * np.sin(th)
+
+
+def wavy(x, y, amp=0.1):
+    """Synthetic deformation used by the bench: (x+d, y+d), d = amp sin(pi x) sin(pi y)."""
+    d = amp * np.sin(np.pi * x) * np.sin(np.pi * y)
+    return x + d, y + d
+
+
+def fixU(x, y):  # mesh.jl:6-8
+    return x, y
+
+
+# gatherScatter.jl:8-21 ; the dense-matmul form the reference uses
+def gatherScatter(u, QQtx, QQty=None):
+    if QQty is None:  # gatherScatter(u, msh)
+        msh = QQtx
+        if msh.QQtx is None:
+            return gatherScatter_index(u, msh.nr, msh.ns, msh.Ex, msh.Ey, msh.ifperiodic)
+        return ABu(msh.QQty, msh.QQtx, u)
+    return ABu(QQty, QQtx, u)
+
+
+def gatherScatter_index(u, nr, ns, Ex, Ey, ifperiodic=(False, False)):
+    """Index form of QQ^T u: sum adjacent duplicated interface rows, then columns.
+
+    Bitwise equal to the dense product of gatherScatter.jl:13 (every dot product there
+    has exactly two non-zero terms; QQtx is applied before QQty, ABu.jl:14-33), which
+    tests/test_oracle_ops.py proves on small meshes.  Needed where dense QQt is too big.
+    """
+    v = np.array(u, dtype=np.float64, order="F", copy=True)
+    nxl, nyl = v.shape
+    if Ex > 1:
+        a = np.arange(1, Ex) * nr - 1
+        s = v[a, :] + v[a + 1, :]
+        v[a, :] = s
+        v[a + 1, :] = s
+    if ifperiodic[0]:
+        s = v[nxl - 1, :] + v[0, :]
+        v[0, :] = s
+        v[nxl - 1, :] = s
+    if Ey > 1:
+        a = np.arange(1, Ey) * ns - 1
+        s = v[:, a] + v[:, a + 1]
+        v[:, a] = s
+        v[:, a + 1] = s
+    if ifperiodic[1]:
+        s = v[:, nyl - 1] + v[:, 0]
+        v[:, 0] = s
+        v[:, nyl - 1] = s
+    return v
+
+
+# ----------------------------------------------------------------------------
+# mesh.jl:25-133
+# ----------------------------------------------------------------------------
+@dataclass
+class Mesh:
+    nr: int
+    ns: int
+    Ex: int
+    Ey: int
+    deform: Callable
+    ifperiodic: Sequence[bool]
+    zr: np.ndarray
+    zs: np.ndarray
+    wr: np.ndarray
+    ws: np.ndarray
+    Dr: np.ndarray
+    Ds: np.ndarray
+    x: np.ndarray
+    y: np.ndarray
+    QQtx: Optional[np.ndarray]
+    QQty: Optional[np.ndarray]
+    mult: np.ndarray
+    Jac: np.ndarray
+    Jaci: np.ndarray
+    rx: np.ndarray
+    ry: np.ndarray
+    sx: np.ndarray
+    sy: np.ndarray
+    B: np.ndarray
+    Bi: np.ndarray
+    G11: np.ndarray
+    G12: np.ndarray
+    G22: np.ndarray
+
+
+def make_mesh(nr, ns, Ex, Ey, ifperiodic=(False, False), deform=fixU, dense_qqt=None) -> Mesh:
+    """mesh.jl:66-133.  Deviation, flagged: mesh.jl:80 builds Qy with `Ex`; we use `Ey`
+    (identical for the square meshes every example and BASELINE config uses).
+    dense_qqt=None -> dense QQt (as the reference) iff nr*Ex <= 4608, else index form."""
+    ifperiodic = [bool(ifperiodic[0]), bool(ifperiodic[1])]
+    zr, wr = gausslobatto(nr)
+    zs, ws = gausslobatto(ns)
+    Dr = derivMat(zr)
+    Ds = derivMat(zs)
+    if dense_qqt is None:
+        dense_qqt = max(nr * Ex, ns * Ey) <= 4608
+    if dense_qqt:
+        Qx = semq(Ex, nr, ifperiodic[0])
+        Qy = semq(Ey, ns, ifperiodic[1])
+        QQtx = Qx @ Qx.T
+        QQty = Qy @ Qy.T
+    else:
+        QQtx = QQty = None
+    mult = _F(np.ones((nr * Ex, ns * Ey)))  # mesh.jl:94-96
+    if dense_qqt:
+        mult = gatherScatter(mult, QQtx, QQty)
+    else:
+        mult = gatherScatter_index(mult, nr, ns, Ex, Ey, ifperiodic)
+    mult = 1.0 / mult
+    xe, _ = semmesh(Ex, nr)  # mesh.jl:98-100
+    ye, _ = semmesh(Ey, ns)
+    x, y = ndgrid(xe, ye)
+    x, y = deform(x, y)  # mesh.jl:108
+    x, y = _F(x), _F(y)
+    Jac, Jaci, rx, ry, sx, sy = jac(x, y, Dr, Ds)  # mesh.jl:111
+    wx = np.kron(np.ones(Ex), wr)  # mesh.jl:114-118
+    wy = np.kron(np.ones(Ey), ws)
+    B = Jac * _F(np.outer(wx, wy))
+    Bi = 1.0 / B
+    G11 = B * (rx * rx + ry * ry)  # mesh.jl:121-123
+    G12 = B * (rx * sx + ry * sy)
+    G22 = B * (sx * sx + sy * sy)
+    return Mesh(nr, ns, Ex, Ey, deform, ifperiodic, zr, zs, wr, ws, Dr, Ds, x, y,
+                QQtx, QQty, _F(mult), _F(Jac), _F(Jaci), _F(rx), _F(ry), _F(sx), _F(sy),
+                _F(B), _F(Bi), _F(G11), _F(G12), _F(G22))
+
+
+# mesh.jl:149-175 ; bc = [xmin, xmax, ymin, ymax], 'D' zeros the line, periodic overrides
+def generateMask(bc, msh: Mesh):
+    nxl, nyl = msh.nr * msh.Ex, msh.ns * msh.Ey
+    mx = np.ones(nxl)
+    my = np.ones(nyl)
+    if bc[0] == "D":
+        mx[0] = 0.0
+    if bc[1] == "D":
+        mx[-1] = 0.0
+    if bc[2] == "D":
+        my[0] = 0.0
+    if bc[3] == "D":
+        my[-1] = 0.0
+    if msh.ifperiodic[0]:
+        mx[:] = 1.0
+    if msh.ifperiodic[1]:
+        my[:] = 1.0
+    M = np.outer(mx, my)
+    return np.asfortranarray(M == 1.0)  # BitMatrix, mesh.jl:171
+
+
+# mask.jl:10-18
+def mask(u, M):
+    M = np.asarray(M)
+    if M.size == 0:
+        return np.array(u, copy=True, order="F")
+    return M * u
+
+
+# lapl.jl:70-81
+def laplace(u, Dr, Ds, G11, G12, G22):
+    ur = ABu(EMPTY, Dr, u)
+    us = ABu(Ds, EMPTY, u)
+    wr = G11 * ur + G12 * us
+    ws = G12 * ur + G22 * us
+    Au = ABu(EMPTY, Dr.T, wr) + ABu(Ds.T, EMPTY, ws)
+    return Au
+
+
+# lapl.jl:83-103 (dealiased)
+def laplace_dealias(u, Jr, Js, Dr, Ds, G11, G12, G22):
+    ur = ABu(EMPTY, Dr, u)
+    us = ABu(Ds, EMPTY, u)
+    Jur = ABu(Js, Jr, ur)
+    Jus = ABu(Js, Jr, us)
+    vr = G11 * Jur + G12 * Jus
+    vs = G12 * Jur + G22 * Jus
+    wr = ABu(Js.T, Jr.T, vr)
+    ws = ABu(Js.T, Jr.T, vs)
+    return ABu(EMPTY, Dr.T, wr) + ABu(Ds.T, EMPTY, ws)
+
+
+# lapl.jl:26-45
+def lapl(u, msh: Mesh, nu=None):
+    Au = laplace(u, msh.Dr, msh.Ds, msh.G11, msh.G12, msh.G22)
+    if nu is not None:
+        Au = nu * Au  # lapl.jl:44 -- nu multiplies the OUTPUT
+    return Au
+
+
+# mass.jl:12-22
+def mass(u, msh: Mesh):
+    return msh.B * u
+
+
+# hlmz.jl:12-19
+def hlmz(u, nu, k, msh: Mesh):
+    Hu = nu * lapl(u, msh)
+    Hu = Hu + k * mass(u, msh)
+    return Hu
+
+
+# diffusion.jl:36-45 / convectionDiffusion.jl:76-85 : hlmz -> gs -> mask
+def opLHS(u, nu, b0, M, msh: Mesh):
+    lhs = hlmz(u, nu, b0, msh)
+    lhs = gatherScatter(lhs, msh)
+    lhs = mask(lhs, M)
+    return lhs
+
+
+# ----------------------------------------------------------------------------
+# pcg.jl:16-60
+# ----------------------------------------------------------------------------
+def _apply(op, x):
+    """`op * x` (SpectralElements.jl:21 pirates * for functions; matrices use matmul)."""
+    if callable(op):
+        return op(x)
+    return (np.asarray(op) @ x.reshape(-1, order="F")).reshape(x.shape, order="F")
+
+
+def pcg(b, opA, opM=lambda x: x, mult=None, ifv=False, tol=1e-8, maxiter=None, info=None):
+    """Returns x (as the reference).  `info`, if a dict, receives iters / resinf / hist."""
+    b = np.asarray(b, dtype=np.float64)
+    if mult is None:
+        mult = np.ones(b.shape)
+    if maxiter is None:
+        maxiter = b.size
+    x = np.zeros_like(b)
+    ra = b - np.zeros_like(b)
+    hp = np.zeros_like(b)
+    rp = np.zeros_like(b)
+    u = np.zeros_like(b)
+    k = 0
+    hist = []
+    warned = False
+    while True:
+        rinf = float(np.max(np.abs(ra))) if ra.size else 0.0
+        hist.append(rinf)
+        if not (rinf > tol):  # pcg.jl:36
+            break
+        ha = _apply(opM, ra)  # pcg.jl:37
+        if k == maxiter:  # pcg.jl:39
+            warned = True
+            break
+        k += 1
+        hpp, rpp = hp, rp
+        hp, rp = ha, ra
+        t = np.sum(rp * hp * mult)  # pcg.jl:45
+        if k == 1:
+            u = hp.copy()
+        else:
+            u = hp + (t / np.sum(rpp * hpp * mult)) * u  # pcg.jl:49
+        Au = _apply(opA, u)  # pcg.jl:51
+        a = t / np.sum(u * Au * mult)  # pcg.jl:52
+        x = x + a * u
+        ra = rp - a * Au
+    if info is not None:
+        info["iters"] = k
+        info["resinf"] = hist[-1]
+        info["hist"] = hist
+        info["warned"] = warned
+    return x
+
+
+# ----------------------------------------------------------------------------
+# time.jl:31-53  (bdfExtK) -- host scalar work, needed for bdfB[1] in opLHS
+# ----------------------------------------------------------------------------
+def bdfExtK(t, k=3):
+    t = np.asarray(t, dtype=np.float64)
+    _, idx = np.unique(t, return_index=True)
+    t = t[np.sort(idx)]  # Julia unique keeps first-occurrence order
+    kk = t.size - 1
+    t1 = t[0]
+    t0 = t[1:]
+    a = interpMat(t1, t0).reshape(-1) if t0.size else np.zeros(0)
+    b = derivMat(t)[0, :]
+    if kk < k:
+        a = np.concatenate([a, np.zeros(k - kk)])
+        b = np.concatenate([b, np.zeros(k - kk)])
+    else:
+        a = a[:k]
+        b = b[:k + 1]
+    if kk == 0:
+        a[0] = 1.0
+    return a, b
+
+
+# ----------------------------------------------------------------------------
+# diffusion.jl:20-137 -- the caller that defines the fused unit (steady + BDF stepping)
+# ----------------------------------------------------------------------------
+@dataclass
+class Diffusion:
+    bc: Sequence[str]
+    msh: Mesh
+    Ti: float = 0.0
+    Tf: float = 0.0
+    dt: float = 0.0
+    k: int = 3
+    u: np.ndarray = field(default=None)
+    uh: list = field(default=None)
+    ub: np.ndarray = field(default=None)
+    M: np.ndarray = field(default=None)
+    nu: np.ndarray = field(default=None)
+    f: np.ndarray = field(default=None)
+    rhs: np.ndarray = field(default=None)
+    time: np.ndarray = field(default=None)
+    bdfA: np.ndarray = field(default=None)
+    bdfB: np.ndarray = field(default=None)
+    istep: int = 0
+    pcg_iters: list = field(default_factory=list)
+
+    def __post_init__(self):
+        z = lambda: _F(np.zeros_like(self.msh.x))
+        self.u, self.ub, self.nu, self.f, self.rhs = z(), z(), z(), z(), z()
+        self.uh = [z() for _ in range(self.k)]
+        self.M = generateMask(self.bc, self.msh).astype(np.float64)  # Field.M is Array{T}, mesh.jl:183
+        self.time = self.Ti * np.ones(self.k + 1)  # time.jl:87
+        self.bdfA, self.bdfB = bdfExtK(self.time, self.k)
+
+
+def diffusion_opLHS(u, dfn: Diffusion):  # diffusion.jl:36-45
+    return opLHS(u, dfn.nu, dfn.bdfB[0], dfn.M, dfn.msh)
+
+
+def diffusion_makeRHS(dfn: Diffusion):  # diffusion.jl:51-65  (mask THEN gs)
+    msh = dfn.msh
+    rhs = mass(dfn.f, msh)
+    rhs = rhs - dfn.nu * lapl(dfn.ub, msh)
+    for i in range(len(dfn.uh)):
+        rhs = rhs - dfn.bdfB[1 + i] * mass(dfn.uh[i], msh)
+    rhs = mask(rhs, dfn.M)
+    rhs = gatherScatter(rhs, msh)
+    dfn.rhs = rhs
+
+
+def diffusion_solve(dfn: Diffusion, tol=1e-8):  # diffusion.jl:67-77
+    info = {}
+    x = pcg(dfn.rhs, lambda v: diffusion_opLHS(v, dfn), mult=dfn.msh.mult, tol=tol, info=info)
+    dfn.pcg_iters.append(info["iters"])
+    dfn.u = x + dfn.ub
+
+
+def diffusion_evolve(dfn: Diffusion, setBC=None, setForcing=None, setVisc=None):  # diffusion.jl:81-106
+    for i in range(len(dfn.uh) - 1, 0, -1):  # updateHist!, mesh.jl:207-215
+        dfn.uh[i] = dfn.uh[i - 1].copy()
+    dfn.uh[0] = dfn.u.copy()
+    for i in range(dfn.time.size - 1, 0, -1):  # updateHist!(time), mesh.jl:217-224
+        dfn.time[i] = dfn.time[i - 1]
+    dfn.time[0] = dfn.time[1]
+    dfn.istep += 1
+    dfn.time[0] += dfn.dt
+    dfn.bdfA, dfn.bdfB = bdfExtK(dfn.time, dfn.time.size - 1)
+    x, y, t = dfn.msh.x, dfn.msh.y, dfn.time[0]
+    if setBC is not None:
+        dfn.ub = _F(setBC(x, y, t))
+    if setForcing is not None:
+        dfn.f = _F(setForcing(x, y, t))
+    if setVisc is not None:
+        dfn.nu = _F(setVisc(x, y, t))
+    diffusion_makeRHS(dfn)
+    diffusion_solve(dfn)
+
+
+def diffusion_simulate(dfn: Diffusion, setIC=None, setBC=None, setForcing=None, setVisc=None,
+                       callback=None, max_steps=None):  # diffusion.jl:110-137
+    if setIC is not None:
+        dfn.u = _F(setIC(dfn.msh.x, dfn.msh.y, dfn.time[0]))
+    if callback:
+        callback(dfn)
+    steps = 0
+    while dfn.time[0] <= dfn.Tf:
+        diffusion_evolve(dfn, setBC, setForcing, setVisc)
+        steps += 1
+        if callback:
+            callback(dfn)
+        if dfn.time[0] < 1e-12:
+            break
+        if max_steps is not None and steps >= max_steps:
+            break
+
+
+# ----------------------------------------------------------------------------
+# explicit Kronecker-assembled cross-check, examples/p2d_explicit.jl:142-180
+# (an independent construction used to PIN this oracle at small sizes)
+# ----------------------------------------------------------------------------
+def kron_operators(msh: Mesh):
+    nxl, nyl = msh.nr * msh.Ex, msh.ns * msh.Ey
+    Ixl = np.eye(nxl)
+    Iyl = np.eye(nyl)
+    Dx1 = np.kron(np.eye(msh.Ex), msh.Dr)  # p2d_explicit.jl: Dx1 = kron(Iex, Dr1)
+    Dy1 = np.kron(np.eye(msh.Ey), msh.Ds)
+    Dr = np.kron(Iyl, Dx1)  # p2d_explicit.jl:155
+    Ds = np.kron(Dy1, Ixl)  # :156
+    Drs = np.vstack([Dr, Ds])
+    vec = lambda a: np.asarray(a).reshape(-1, order="F")
+    g11, g12, g22 = np.diag(vec(msh.G11)), np.diag(vec(msh.G12)), np.diag(vec(msh.G22))
+    G = np.block([[g11, g12], [g12, g22]])
+    A = Drs.T @ G @ Drs  # :162
+    Bm = np.diag(vec(msh.B))
+    Qx = semq(msh.Ex, msh.nr, msh.ifperiodic[0])
+    Qy = semq(msh.Ey, msh.ns, msh.ifperiodic[1])
+    Q = np.kron(Qy, Qx)  # :153
+    return A, Bm, Q
+
+
+# ----------------------------------------------------------------------------
+# portable pseudo-random input: splitmix64 seeded 0x5EED, column-major index
+# ----------------------------------------------------------------------------
+def splitmix_uniform(shape, seed=0x5EED):
+    n = int(np.prod(shape))
+    with np.errstate(over="ignore"):
+        idx = np.arange(1, n + 1, dtype=np.uint64)
+        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)  # [0,1)
+    return _F((2.0 * u - 1.0).reshape(shape, order="F"))

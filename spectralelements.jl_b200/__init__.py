@@ -1,0 +1,701 @@
+"""spectralelements.jl_b200 -- host-side mirror (Python, over ctypes) of the SpectralElements.jl
+operator API for the matrix-free hot path, backed by libsemb.so (hand-written sm_100a CUDA).
+
+The names, argument order and value semantics follow the reference's exported Julia functions
+(file:line under /root/reference/src) so parity tests read like the reference's own call sites:
+
+    Mesh(nr,ns,Ex,Ey,ifperiodic,deform)      mesh.jl:66-133      generateMask(bc,msh)   mesh.jl:149-175
+    ABu(As,Br,u)                              ABu.jl:9-37         jac(x,y,Dr,Ds)          jac.jl:24-40
+    lapl(u,msh) / lapl(u,nu,msh)              lapl.jl:26-45       hlmz(u,nu,k,msh)        hlmz.jl:12-19
+    mass(u,msh)                               mass.jl:12-22       gatherScatter(u,msh)    gatherScatter.jl:8-21
+    mask(u,M)                                 mask.jl:10-18       pcg / pcg_b (pcg!)      pcg.jl:16-79
+    opLHS / makeRHS_b / solve_b (Diffusion)   diffusion.jl:36-77
+
+Arrays in, fresh NumPy arrays out (column-major (nr*Ex) x (ns*Ey)); every computation runs on the
+GPU through the C ABI -- there is no CPU or PyTorch fallback (importing works without a GPU, any
+compute call raises SembError).  Device-resident handles (DeviceField, Mesh.oplhs_device, PCG on
+device) avoid the host round trip; `pcg` runs the whole Krylov loop on the device.
+
+The directory name contains a dot, so import it through the repo-root shim:
+    import spectralelements_jl_b200 as sem
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import PcgOpts, SembError, as_f64, check, dptr
+
+__all__ = [
+    "init", "finalize", "default_context", "Context", "Mesh", "DeviceField", "generateMask", "ABu", "jac", "lapl",
+    "hlmz", "mass", "gatherScatter", "mask", "pcg", "pcg_b", "OpLHS", "opLHS", "Diffusion", "makeRHS_b",
+    "solve_b", "evolve_b", "simulate_b", "annulus", "wavy", "fixU", "gausslobatto", "derivMat", "interpMat",
+    "semmesh", "ndgrid", "bdfExtK", "partition", "SembError",
+]
+
+SEMB_ARR = {"x": 0, "y": 1, "Jac": 2, "Jaci": 3, "rx": 4, "ry": 5, "sx": 6, "sy": 7, "B": 8, "Bi": 9, "G11": 10,
+            "G12": 11, "G22": 12, "mult": 13}
+DEFORM_KIND = {"identity": 0, "annulus": 1, "wavy": 2}
+
+
+# ---------------------------------------------------------------------------------------------
+# context
+# ---------------------------------------------------------------------------------------------
+class Context:
+    """semb_ctx: one GPU + stream (+ NCCL communicator)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        check(self.lib.semb_init(int(device), C.byref(h)))
+        self.h = h
+        self.device = device
+        self.nranks, self.rank = 1, 0
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        check(self.lib.semb_comm_init(self.h, nranks, rank, unique_id))
+        self.nranks, self.rank = nranks, rank
+
+    def comm_init_torch(self):
+        """Join an NCCL communicator using torch.distributed (already initialised) for the id broadcast."""
+        import torch.distributed as dist
+        nranks, rank = dist.get_world_size(), dist.get_rank()
+        if nranks == 1:
+            return
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            check(self.lib.semb_comm_unique_id(buf))
+        obj = [bytes(buf.raw)]
+        dist.broadcast_object_list(obj, src=0)
+        self.comm_init(nranks, rank, obj[0])
+
+    def sync(self):
+        check(self.lib.semb_sync(self.h))
+
+    def barrier(self):
+        check(self.lib.semb_comm_barrier(self.h))
+
+    def timer_start(self):
+        check(self.lib.semb_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        check(self.lib.semb_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        n = C.c_longlong()
+        check(self.lib.semb_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def flush_l2(self):
+        check(self.lib.semb_flush_l2(self.h))
+
+    def allreduce_max(self, vals):
+        a = np.ascontiguousarray(vals, dtype=np.float64)
+        check(self.lib.semb_comm_allreduce_max(self.h, dptr(a), a.size))
+        return a
+
+    def close(self):
+        if self.h:
+            self.lib.semb_finalize(self.h)
+            self.h = None
+
+
+_default_ctx: Optional[Context] = None
+
+
+def init(device: int = 0) -> Context:
+    global _default_ctx
+    _default_ctx = Context(device)
+    return _default_ctx
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def finalize():
+    global _default_ctx
+    if _default_ctx is not None:
+        _default_ctx.close()
+        _default_ctx = None
+
+
+# ---------------------------------------------------------------------------------------------
+# 1-D set-up helpers (host C++ inside libsemb; no GPU needed)
+# ---------------------------------------------------------------------------------------------
+def gausslobatto(n: int):
+    """FastGaussQuadrature.gausslobatto(n) (mesh.jl:70-71)."""
+    z, w = np.zeros(n), np.zeros(n)
+    check(_lib.load().semb_gausslobatto(n, dptr(z), dptr(w)))
+    return z, w
+
+
+def derivMat(x):
+    """derivMat.jl:9-35"""
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+    D = np.zeros((x.size, x.size), order="F")
+    check(_lib.load().semb_deriv_mat(x.size, dptr(x), dptr(D)))
+    return D
+
+
+def interpMat(xo, xi):
+    """interp.jl:10-35"""
+    xo = np.ascontiguousarray(np.atleast_1d(xo), dtype=np.float64).reshape(-1)
+    xi = np.ascontiguousarray(np.atleast_1d(xi), dtype=np.float64).reshape(-1)
+    J = np.zeros((xo.size, xi.size), order="F")
+    check(_lib.load().semb_interp_mat(xo.size, dptr(xo), xi.size, dptr(xi), dptr(J)))
+    return J
+
+
+def semmesh(E: int, n: int):
+    """semmesh.jl:9-27"""
+    z, w = np.zeros(E * n), np.zeros(E * n)
+    check(_lib.load().semb_semmesh(E, n, dptr(z), dptr(w)))
+    return z, w
+
+
+def ndgrid(xe, ye):
+    """ndgrid.jl:8-13 (data movement only)"""
+    xe, ye = np.asarray(xe, dtype=np.float64), np.asarray(ye, dtype=np.float64)
+    return (np.asfortranarray(np.repeat(xe[:, None], ye.size, axis=1)),
+            np.asfortranarray(np.repeat(ye[None, :], xe.size, axis=0)))
+
+
+def bdfExtK(t, k: int = 3):
+    """time.jl:31-53"""
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    a, b = np.zeros(k), np.zeros(k + 1)
+    check(_lib.load().semb_bdf_ext_k(t.size, dptr(t), k, dptr(a), dptr(b)))
+    return a, b
+
+
+def partition(Ey: int, nranks: int, rank: int):
+    e0, ne = C.c_int(), C.c_int()
+    check(_lib.load().semb_partition(Ey, nranks, rank, C.byref(e0), C.byref(ne)))
+    return e0.value, ne.value
+
+
+# deformation maps (user-side closures in the reference: evaluated on the host, as there)
+def fixU(x, y):  # mesh.jl:6-8
+    return x, y
+
+
+def annulus(r, s, r0=0.5, r1=1.0, span=2 * math.pi):  # geom.jl:40-49
+    R = (r1 - r0) / 2 * (r + 1) + r0
+    th = span / 2 * (s + 1) + 0.0
+    return R * np.cos(th), R * np.sin(th)
+
+
+def wavy(x, y, amp=0.1):
+    d = amp * np.sin(np.pi * x) * np.sin(np.pi * y)
+    return x + d, y + d
+
+
+# ---------------------------------------------------------------------------------------------
+# device field
+# ---------------------------------------------------------------------------------------------
+class DeviceField:
+    """semb_field: a device-resident (nr*Ex) x (ns*Ey_local) array owned by the library."""
+
+    def __init__(self, msh: "Mesh", host=None):
+        self.msh = msh
+        self.lib = msh.lib
+        h = C.c_void_p()
+        check(self.lib.semb_field_create(msh.h, C.byref(h)))
+        self.h = h
+        if host is not None:
+            self.upload(host)
+
+    def upload(self, host):
+        a = as_f64(host, self.msh.shape)
+        check(self.lib.semb_field_upload(self.h, dptr(a)))
+        return self
+
+    def download(self):
+        out = np.zeros(self.msh.shape, order="F")
+        check(self.lib.semb_field_download(self.h, dptr(out)))
+        return out
+
+    def fill(self, v: float):
+        check(self.lib.semb_field_fill(self.h, float(v)))
+        return self
+
+    def fill_random(self, seed: int = 0x5EED):
+        check(self.lib.semb_field_fill_random(self.h, seed))
+        return self
+
+    def copy_from(self, other: "DeviceField"):
+        check(self.lib.semb_field_copy(self.h, other.h))
+        return self
+
+    def axpby(self, a: float, x: "DeviceField", b: float):
+        """self = a*x + b*self"""
+        check(self.lib.semb_field_axpby(float(a), x.h, float(b), self.h))
+        return self
+
+    def free(self):
+        if self.h:
+            self.lib.semb_field_destroy(self.h)
+            self.h = None
+
+
+def _fh(f: Optional[DeviceField]):
+    return f.h if f is not None else None
+
+
+# ---------------------------------------------------------------------------------------------
+# Mesh  (mesh.jl:25-133)
+# ---------------------------------------------------------------------------------------------
+class Mesh:
+    """Mesh(nr,ns,Ex,Ey,ifperiodic=[false,false],deform=fixU), mesh.jl:66-68.
+
+    Host work mirrors the reference constructor up to `deform(x,y)` (GLL rule, D matrices, grid);
+    jac (jac.jl), B/G factors (mesh.jl:114-123) and mult (mesh.jl:94-96) are computed on the device.
+    deform may also be the name of a built-in map ("identity" | "annulus" | "wavy"), in which case
+    the grid itself is generated on the device (no O(n) host arrays; needed at 1e8 DOF).
+    Multi-GPU: each rank holds the y-slab of element rows [ey0, ey0+ney); arrays are local.
+    """
+
+    def __init__(self, nr: int, ns: int, Ex: int, Ey: int, ifperiodic: Sequence[bool] = (False, False),
+                 deform=fixU, deform_params: Sequence[float] = (), ctx: Optional[Context] = None, _arrays=None):
+        self.ctx = ctx or default_context()
+        self.lib = self.ctx.lib
+        self.nr, self.ns, self.Ex, self.Ey = int(nr), int(ns), int(Ex), int(Ey)
+        self.ifperiodic = [bool(ifperiodic[0]), bool(ifperiodic[1])]
+        self.deform = deform
+        self.zr, self.wr = gausslobatto(nr)  # mesh.jl:70-71
+        self.zs, self.ws = gausslobatto(ns)
+        self.Dr = derivMat(self.zr)  # mesh.jl:73-74
+        self.Ds = derivMat(self.zs)
+        self.ey0, self.ney = partition(Ey, self.ctx.nranks, self.ctx.rank)
+        self._cache = {}
+        h = C.c_void_p()
+        px, py = int(self.ifperiodic[0]), int(self.ifperiodic[1])
+        if _arrays is not None:
+            G11, G12, G22, B = (None if a is None else as_f64(a) for a in _arrays)
+            Dr, Ds = as_f64(self.Dr), as_f64(self.Ds)
+            check(self.lib.semb_mesh_create_arrays(self.ctx.h, nr, ns, Ex, Ey, px, py, dptr(Dr), dptr(Ds), dptr(G11),
+                                                   dptr(G12), dptr(G22), dptr(B), C.byref(h)))
+        elif isinstance(deform, str):
+            p = np.ascontiguousarray(deform_params, dtype=np.float64)
+            check(self.lib.semb_mesh_create_deform(self.ctx.h, nr, ns, Ex, Ey, px, py, DEFORM_KIND[deform],
+                                                   dptr(p) if p.size else None, p.size, C.byref(h)))
+        else:
+            xe, _ = semmesh(Ex, nr)  # mesh.jl:98-100
+            ye, _ = semmesh(Ey, ns)
+            ye = ye[self.ey0 * ns:(self.ey0 + self.ney) * ns]
+            x, y = ndgrid(xe, ye)
+            x, y = deform(x, y)  # mesh.jl:108
+            x, y = as_f64(x), as_f64(y)
+            Dr, Ds = as_f64(self.Dr), as_f64(self.Ds)
+            check(self.lib.semb_mesh_create_xy(self.ctx.h, nr, ns, Ex, Ey, px, py, dptr(Dr), dptr(Ds),
+                                               dptr(self.wr), dptr(self.ws), dptr(x), dptr(y), C.byref(h)))
+        self.h = h
+        self.shape = (nr * Ex, ns * self.ney)
+
+    @classmethod
+    def from_arrays(cls, nr, ns, Ex, Ey, ifperiodic, Dr, Ds, G11, G12, G22, B=None, ctx=None):
+        """Mesh from ready-made operator arrays (what a Julia Mesh already holds)."""
+        m = cls.__new__(cls)
+        m.ctx = ctx or default_context()
+        m.lib = m.ctx.lib
+        m.nr, m.ns, m.Ex, m.Ey = int(nr), int(ns), int(Ex), int(Ey)
+        m.ifperiodic = [bool(ifperiodic[0]), bool(ifperiodic[1])]
+        m.deform = None
+        m.zr, m.wr = gausslobatto(nr)
+        m.zs, m.ws = gausslobatto(ns)
+        m.Dr, m.Ds = as_f64(Dr), as_f64(Ds)
+        m.ey0, m.ney = partition(Ey, m.ctx.nranks, m.ctx.rank)
+        m._cache = {}
+        h = C.c_void_p()
+        G11, G12, G22 = as_f64(G11), as_f64(G12), as_f64(G22)
+        Bf = None if B is None else as_f64(B)
+        check(m.lib.semb_mesh_create_arrays(m.ctx.h, nr, ns, Ex, Ey, int(m.ifperiodic[0]), int(m.ifperiodic[1]),
+                                            dptr(m.Dr), dptr(m.Ds), dptr(G11), dptr(G12), dptr(G22), dptr(Bf),
+                                            C.byref(h)))
+        m.h = h
+        m.shape = (nr * Ex, ns * m.ney)
+        return m
+
+    def __getattr__(self, name):  # x, y, Jac, Jaci, rx, ry, sx, sy, B, Bi, G11, G12, G22, mult
+        if name in SEMB_ARR:
+            c = self.__dict__["_cache"]
+            if name not in c:
+                out = np.zeros(self.shape, order="F")
+                check(self.lib.semb_mesh_get(self.h, SEMB_ARR[name], dptr(out)))
+                c[name] = out
+            return c[name]
+        raise AttributeError(name)
+
+    def field(self, host=None) -> DeviceField:
+        return DeviceField(self, host)
+
+    def plan(self):
+        v = [C.c_int() for _ in range(5)]
+        check(self.lib.semb_mesh_plan(self.h, *[C.byref(a) for a in v]))
+        return dict(zip(("nstrips", "nchunks", "nxseam", "nyseam", "fast"), [a.value for a in v]))
+
+    def set_chunks(self, n: int):
+        check(self.lib.semb_mesh_set_chunks(self.h, int(n)))
+
+    # device-resident operators ------------------------------------------------------------------
+    def lapl_device(self, u: DeviceField, out: DeviceField):
+        check(self.lib.semb_lapl(self.h, u.h, out.h))
+
+    def hlmz_device(self, u, nu, k, out):
+        nua, nus = (nu, 1.0) if isinstance(nu, DeviceField) else (None, float(nu))
+        ka, ks = (k, 0.0) if isinstance(k, DeviceField) else (None, float(k))
+        check(self.lib.semb_hlmz(self.h, u.h, _fh(nua), nus, _fh(ka), ks, out.h))
+
+    def mass_device(self, u, out):
+        check(self.lib.semb_mass(self.h, u.h, out.h))
+
+    def gs_device(self, u, out):
+        check(self.lib.semb_gather_scatter(self.h, u.h, out.h))
+
+    def mask_device(self, u, M, out):
+        check(self.lib.semb_mask(self.h, u.h, _fh(M), out.h))
+
+    def oplhs_device(self, u, out, nu=1.0, k=0.0, bc=None, M=None):
+        nua, nus = (nu, 1.0) if isinstance(nu, DeviceField) else (None, float(nu))
+        ka, ks = (k, 0.0) if isinstance(k, DeviceField) else (None, float(k))
+        check(self.lib.semb_oplhs(self.h, u.h, _fh(nua), nus, _fh(ka), ks, _bc_bytes(bc), _fh(M), out.h))
+
+    def dot_mult(self, a: DeviceField, b: DeviceField) -> float:
+        r = C.c_double()
+        check(self.lib.semb_dot_mult(self.h, a.h, b.h, C.byref(r)))
+        return r.value
+
+    def norm_inf(self, a: DeviceField) -> float:
+        r = C.c_double()
+        check(self.lib.semb_norm_inf(self.h, a.h, C.byref(r)))
+        return r.value
+
+    def pcg_device(self, b: DeviceField, x: DeviceField, nu=1.0, k=0.0, bc=None, M=None, precond=False,
+                   prec_b0=1.0, tol=1e-8, maxiter=-1, check_every=0):
+        """Device-resident pcg! (pcg.jl:64-79).  Returns (iters, resinf, converged)."""
+        o, keep = _pcg_opts(nu, k, bc, M, precond, prec_b0, tol, maxiter, check_every)
+        it, res = C.c_longlong(), C.c_double()
+        rc = check(self.lib.semb_pcg(self.h, C.byref(o), b.h, x.h, C.byref(it), C.byref(res)))
+        return it.value, res.value, rc == 0
+
+    def pcg_begin(self, b, x, **kw):
+        o, keep = _pcg_opts(kw.get("nu", 1.0), kw.get("k", 0.0), kw.get("bc"), kw.get("M"), kw.get("precond", False),
+                            kw.get("prec_b0", 1.0), kw.get("tol", 1e-8), kw.get("maxiter", -1), 0)
+        self._pcg_keep = (o, keep)
+        check(self.lib.semb_pcg_begin(self.h, C.byref(o), b.h, x.h))
+
+    def pcg_iterate(self, n: int):
+        check(self.lib.semb_pcg_iterate(self.h, int(n)))
+
+    def pcg_status(self):
+        it, res, done = C.c_longlong(), C.c_double(), C.c_int()
+        check(self.lib.semb_pcg_status(self.h, C.byref(it), C.byref(res), C.byref(done)))
+        return it.value, res.value, bool(done.value)
+
+    def free(self):
+        if getattr(self, "h", None):
+            self.lib.semb_mesh_destroy(self.h)
+            self.h = None
+
+
+def _bc_bytes(bc):
+    if bc is None:
+        return None
+    s = "".join(bc) if not isinstance(bc, (str, bytes)) else bc
+    if isinstance(s, str):
+        s = s.encode()
+    if len(s) != 4:
+        raise ValueError("bc must have 4 entries [xmin,xmax,ymin,ymax] (mesh.jl:138)")
+    return s
+
+
+def _pcg_opts(nu, k, bc, M, precond, prec_b0, tol, maxiter, check_every):
+    o = PcgOpts()
+    keep = []
+    o.nu, o.nu_arr = (1.0, nu.h) if isinstance(nu, DeviceField) else (float(nu), None)
+    o.k, o.k_arr = (0.0, k.h) if isinstance(k, DeviceField) else (float(k), None)
+    b = _bc_bytes(bc)
+    keep.append(b)
+    o.bc = b
+    o.M_arr = M.h if isinstance(M, DeviceField) else None
+    o.precond = 1 if precond else 0
+    o.prec_b0 = float(prec_b0)
+    o.tol = float(tol)
+    o.maxiter = int(maxiter)
+    o.check_every = int(check_every)
+    return o, keep
+
+
+# ---------------------------------------------------------------------------------------------
+# value-semantics operators (NumPy in, fresh NumPy out) -- the reference's function signatures
+# ---------------------------------------------------------------------------------------------
+def generateMask(bc, msh: Mesh):
+    """generateMask(bc,msh), mesh.jl:149-175 -> Bool matrix"""
+    out = np.zeros(msh.shape, order="F")
+    check(msh.lib.semb_generate_mask(msh.h, _bc_bytes(bc), dptr(out)))
+    return np.asfortranarray(out == 1.0)
+
+
+def _split_coef(c, shape):
+    """scalar-or-array coefficient (hlmz.jl:13: nu, k untyped)"""
+    if np.isscalar(c) or np.ndim(c) == 0:
+        return None, float(c)
+    return as_f64(c, shape), 0.0
+
+
+def ABu(As, Br, u, ctx: Optional[Context] = None):
+    """ABu(As,Br,u) = (As (x) Br) u, ABu.jl:9-37; [] / empty = identity"""
+    ctx = ctx or default_context()
+    u = as_f64(u)
+    As = None if As is None or np.size(As) == 0 else as_f64(As)
+    Br = None if Br is None or np.size(Br) == 0 else as_f64(Br)
+    m, n = u.shape
+    ma, na = As.shape if As is not None else (0, 0)
+    mb, nb = Br.shape if Br is not None else (0, 0)
+    if Br is not None and m % nb:
+        raise ValueError("InexactError: Int(m*mb/nb) (ABu.jl:16)")
+    if As is not None and n % na:
+        raise ValueError("InexactError: Int(Ey*ma) (ABu.jl:26)")
+    mo = m // nb * mb if Br is not None else m
+    no = n // na * ma if As is not None else n
+    out = np.zeros((mo, no), order="F")
+    check(ctx.lib.semb_abu_host(ctx.h, dptr(As), ma, na, dptr(Br), mb, nb, dptr(u), m, n, dptr(out)))
+    return out
+
+
+def jac(x, y, Dr, Ds, msh: Optional[Mesh] = None):
+    """jac(x,y,Dr,Ds), jac.jl:24-40 -> J,Ji,rx,ry,sx,sy.  Runs on `msh`'s device kernel."""
+    if msh is None:
+        raise ValueError("jac needs the mesh whose element layout x,y follow (pass msh=...)")
+    fx, fy = msh.field(x), msh.field(y)
+    outs = [msh.field() for _ in range(6)]
+    try:
+        check(msh.lib.semb_jac(msh.h, fx.h, fy.h, *[o.h for o in outs]))
+        return tuple(o.download() for o in outs)
+    finally:
+        for f in [fx, fy] + outs:
+            f.free()
+
+
+def lapl(u, *args):
+    """lapl(u,msh) lapl.jl:26-36 ; lapl(u,nu,msh) lapl.jl:38-45 ; lapl(u,msh1,msh2) lapl.jl:47-52"""
+    if len(args) == 1:
+        msh, nu = args[0], None
+    elif isinstance(args[0], Mesh):
+        msh, nu = args[0], None  # dealias pass-through ignores msh2
+    else:
+        nu, msh = args
+    u = as_f64(u, msh.shape)
+    out = np.zeros(msh.shape, order="F")
+    if nu is None:
+        check(msh.lib.semb_lapl_host(msh.h, dptr(u), dptr(out)))
+    else:
+        nua, nus = _split_coef(nu, msh.shape)
+        check(msh.lib.semb_hlmz_host(msh.h, dptr(u), dptr(nua), nus, None, 0.0, dptr(out)))
+    return out
+
+
+def hlmz(u, nu, k, msh: Mesh, msh2: Optional[Mesh] = None):
+    """hlmz(u,nu,k,msh), hlmz.jl:12-19 (5-arg dealias form ignores msh2, hlmz.jl:22-30)"""
+    u = as_f64(u, msh.shape)
+    nua, nus = _split_coef(nu, msh.shape)
+    ka, ks = _split_coef(k, msh.shape)
+    out = np.zeros(msh.shape, order="F")
+    check(msh.lib.semb_hlmz_host(msh.h, dptr(u), dptr(nua), nus, dptr(ka), ks, dptr(out)))
+    return out
+
+
+def mass(u, msh: Mesh, msh2: Optional[Mesh] = None):
+    """mass(u,msh), mass.jl:12-22"""
+    u = as_f64(u, msh.shape)
+    out = np.zeros(msh.shape, order="F")
+    check(msh.lib.semb_mass_host(msh.h, dptr(u), dptr(out)))
+    return out
+
+
+def gatherScatter(u, *args):
+    """gatherScatter(u,msh) gatherScatter.jl:18-21 ; gatherScatter(u,QQtx,QQty) :8-16 (dense, via ABu)"""
+    if len(args) == 2:
+        return ABu(args[1], args[0], u)
+    msh = args[0]
+    u = as_f64(u, msh.shape)
+    out = np.zeros(msh.shape, order="F")
+    check(msh.lib.semb_gather_scatter_host(msh.h, dptr(u), dptr(out)))
+    return out
+
+
+def mask(u, M, msh: Optional[Mesh] = None):
+    """mask(u,M), mask.jl:10-18.  Needs a mesh for the device layout: pass msh= or a masked-field owner."""
+    if msh is None:
+        raise ValueError("mask needs msh= (the device layout of u)")
+    u = as_f64(u, msh.shape)
+    Mf = None if M is None or np.size(M) == 0 else as_f64(M, msh.shape)
+    out = np.zeros(msh.shape, order="F")
+    check(msh.lib.semb_mask_host(msh.h, dptr(u), dptr(Mf), dptr(out)))
+    return out
+
+
+class OpLHS:
+    """The fused unit opLHS(u,dfn) = mask(gatherScatter(hlmz(u,nu,b0,msh)),M), diffusion.jl:36-45.
+
+    Calling it on a NumPy array applies the fused kernel; handing it to `pcg` runs the Krylov loop on
+    the device (an arbitrary host closure cannot execute there; there is no CPU fallback)."""
+
+    def __init__(self, msh: Mesh, nu=1.0, k=0.0, M=None, bc=None):
+        self.msh, self.nu, self.k, self.M, self.bc = msh, nu, k, M, bc
+
+    def __call__(self, u):
+        msh = self.msh
+        u = as_f64(u, msh.shape)
+        nua, nus = _split_coef(self.nu, msh.shape)
+        ka, ks = _split_coef(self.k, msh.shape)
+        Mf = None if self.M is None or np.size(self.M) == 0 else as_f64(self.M, msh.shape)
+        out = np.zeros(msh.shape, order="F")
+        check(msh.lib.semb_oplhs_host(msh.h, dptr(u), dptr(nua), nus, dptr(ka), ks, _bc_bytes(self.bc), dptr(Mf),
+                                      dptr(out)))
+        return out
+
+    def __mul__(self, u):  # `opA * u`, SpectralElements.jl:21
+        return self(u)
+
+
+def opLHS(u, dfn: "Diffusion"):
+    """opLHS(u,dfn), diffusion.jl:36-45"""
+    return OpLHS(dfn.msh, dfn.nu, dfn.bdfB[0], dfn.M)(u)
+
+
+class DiagPrecond:
+    """opPrecond(u,cdn) = u ./ B ./ bdfB[1], convectionDiffusion.jl:87-91"""
+
+    def __init__(self, msh: Mesh, b0: float):
+        self.msh, self.b0 = msh, float(b0)
+
+
+def pcg(b, opA, opM=None, mult=None, ifv=False, tol=1e-8, maxiter=None, info: Optional[dict] = None):
+    """pcg(b,opA;opM,mult,ifv,tol,maxiter), pcg.jl:16-60 -- whole loop on the device.
+
+    opA must be an OpLHS (see its docstring); opM None/identity or DiagPrecond; mult must be the
+    mesh's own (msh.mult) or None.  Returns x; `info` receives iters/resinf/converged."""
+    if not isinstance(opA, OpLHS):
+        raise TypeError("pcg: opA must be an OpLHS (device operator); host closures cannot run on the GPU and "
+                        "this package has no CPU fallback")
+    msh = opA.msh
+    b = as_f64(b, msh.shape)
+    nua, nus = _split_coef(opA.nu, msh.shape)
+    ka, ks = _split_coef(opA.k, msh.shape)
+    Mf = None if opA.M is None or np.size(opA.M) == 0 else as_f64(opA.M, msh.shape)
+    o = PcgOpts()
+    o.nu, o.k = nus, ks
+    bcb = _bc_bytes(opA.bc)
+    o.bc = bcb
+    if isinstance(opM, DiagPrecond):
+        o.precond, o.prec_b0 = 1, opM.b0
+    elif opM is not None and not getattr(opM, "_semb_identity", False):
+        raise TypeError("pcg: opM must be None (identity, diffusion.jl:47-49) or DiagPrecond")
+    o.tol = float(tol)
+    o.maxiter = -1 if maxiter is None else int(maxiter)
+    o.check_every = 0
+    x = np.zeros(msh.shape, order="F")
+    it, res = C.c_longlong(), C.c_double()
+    rc = check(msh.lib.semb_pcg_host(msh.h, C.byref(o), dptr(nua), dptr(ka), dptr(Mf), dptr(b), dptr(x),
+                                     C.byref(it), C.byref(res)))
+    if rc == 1:
+        print("warning: res:", res.value)  # pcg.jl:39
+    if ifv:
+        print("PCG iter: %d, res: %g" % (it.value, res.value))
+    if info is not None:
+        info.update(iters=it.value, resinf=res.value, converged=(rc == 0))
+    return x
+
+
+def pcg_b(x, b, opA, **kw):
+    """pcg!(x,b,opA;...), pcg.jl:64-79"""
+    x[...] = pcg(b, opA, **kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# Diffusion driver (diffusion.jl) -- "next" row 8f-1, thin host mirror over the device ops
+# ---------------------------------------------------------------------------------------------
+class Diffusion:
+    """Diffusion(bc,msh;Ti,Tf,dt,k), diffusion.jl:20-34 (+ Field, mesh.jl:188-195; TimeStepper, time.jl:84-99)"""
+
+    def __init__(self, bc, msh: Mesh, Ti=0.0, Tf=0.0, dt=0.0, k=3):
+        self.bc, self.msh = list(bc), msh
+        z = lambda: np.zeros(msh.shape, order="F")
+        self.u, self.ub, self.nu, self.f, self.rhs = z(), z(), z(), z(), z()
+        self.uh = [z() for _ in range(k)]
+        self.M = generateMask(bc, msh).astype(np.float64)
+        self.time = Ti * np.ones(k + 1)
+        self.bdfA, self.bdfB = bdfExtK(self.time, k)
+        self.istep, self.dt, self.Ti, self.Tf = 0, dt, Ti, Tf
+        self.pcg_iters = []
+
+
+def makeRHS_b(dfn: Diffusion):
+    """makeRHS!(dfn), diffusion.jl:51-65 (mask THEN gatherScatter)"""
+    msh = dfn.msh
+    rhs = mass(dfn.f, msh)
+    rhs = rhs - dfn.nu * lapl(dfn.ub, msh)
+    for i in range(len(dfn.uh)):
+        if dfn.bdfB[1 + i] != 0.0:
+            rhs = rhs - dfn.bdfB[1 + i] * mass(dfn.uh[i], msh)
+    rhs = mask(rhs, dfn.M, msh)
+    dfn.rhs = gatherScatter(rhs, msh)
+
+
+def solve_b(dfn: Diffusion, tol=1e-8):
+    """solve!(dfn), diffusion.jl:67-77"""
+    info = {}
+    x = pcg(dfn.rhs, OpLHS(dfn.msh, dfn.nu, dfn.bdfB[0], dfn.M), mult=dfn.msh.mult, tol=tol, info=info)
+    dfn.pcg_iters.append(info["iters"])
+    dfn.u = x + dfn.ub
+
+
+def evolve_b(dfn: Diffusion, setBC=None, setForcing=None, setVisc=None):
+    """evolve!(dfn,...), diffusion.jl:81-106"""
+    for i in range(len(dfn.uh) - 1, 0, -1):
+        dfn.uh[i] = dfn.uh[i - 1].copy()
+    dfn.uh[0] = dfn.u.copy()
+    for i in range(dfn.time.size - 1, 0, -1):
+        dfn.time[i] = dfn.time[i - 1]
+    dfn.time[0] = dfn.time[1]
+    dfn.istep += 1
+    dfn.time[0] += dfn.dt
+    dfn.bdfA, dfn.bdfB = bdfExtK(dfn.time, dfn.time.size - 1)
+    x, y, t = dfn.msh.x, dfn.msh.y, dfn.time[0]
+    if setBC is not None:
+        dfn.ub = as_f64(setBC(x, y, t))
+    if setForcing is not None:
+        dfn.f = as_f64(setForcing(x, y, t))
+    if setVisc is not None:
+        dfn.nu = as_f64(setVisc(x, y, t))
+    makeRHS_b(dfn)
+    solve_b(dfn)
+
+
+def simulate_b(dfn: Diffusion, callback=None, setIC=None, setBC=None, setForcing=None, setVisc=None, max_steps=None):
+    """simulate!(dfn,callback!,setIC!,setBC!,setForcing!,setVisc!), diffusion.jl:110-137"""
+    if setIC is not None:
+        dfn.u = as_f64(setIC(dfn.msh.x, dfn.msh.y, dfn.time[0]))
+    if callback:
+        callback(dfn)
+    steps = 0
+    while dfn.time[0] <= dfn.Tf:
+        evolve_b(dfn, setBC, setForcing, setVisc)
+        steps += 1
+        if callback:
+            callback(dfn)
+        if dfn.time[0] < 1e-12:
+            break
+        if max_steps is not None and steps >= max_steps:
+            break

@@ -1,0 +1,1254 @@
+// C-ABI entry points of libsemb.so (see include/semb.h).  Host-side orchestration only: contexts,
+// meshes, fields, the launch plan of the fused operator, the device-resident PCG loop, NCCL plumbing.
+#include <stdarg.h>
+
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+
+#include <stddef.h>
+
+#include "semb_internal.cuh"
+#include "semb_vec.cuh"
+
+#define SEMB_SCAL_PTR(m, member) ((double*)((char*)(m)->d_scal + offsetof(SembScal, member)))
+
+// ---- error handling ---------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void semb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* semb_last_error(void) { return g_err; }
+extern "C" int semb_version(void) { return 100; }
+
+#define SEMB_NPARTIALS 4096
+
+// ---- strip-kernel dispatch -----------------------------------------------------------------------------
+#define SEMB_DECL_STRIP(n)                                                                                 \
+  int semb_launch_strip_n##n(semb_ctx*, const OpArgs&, const double*, const double*, int, int, bool, bool); \
+  int semb_strip_attr_n##n(bool, bool, int*, int*, int*);
+SEMB_DECL_STRIP(2) SEMB_DECL_STRIP(3) SEMB_DECL_STRIP(4) SEMB_DECL_STRIP(5) SEMB_DECL_STRIP(6) SEMB_DECL_STRIP(7)
+SEMB_DECL_STRIP(8) SEMB_DECL_STRIP(9) SEMB_DECL_STRIP(10) SEMB_DECL_STRIP(11) SEMB_DECL_STRIP(12)
+SEMB_DECL_STRIP(13) SEMB_DECL_STRIP(14) SEMB_DECL_STRIP(15) SEMB_DECL_STRIP(16) SEMB_DECL_STRIP(17)
+
+int semb_launch_strip(semb_ctx* ctx, const OpArgs& a, const double* hDr, const double* hDs, int nstrips,
+                      int nchunks, bool pcg, bool massterm) {
+  switch (a.N) {
+#define SEMB_CASE(n) \
+  case n:            \
+    return semb_launch_strip_n##n(ctx, a, hDr, hDs, nstrips, nchunks, pcg, massterm);
+    SEMB_CASE(2) SEMB_CASE(3) SEMB_CASE(4) SEMB_CASE(5) SEMB_CASE(6) SEMB_CASE(7) SEMB_CASE(8) SEMB_CASE(9)
+    SEMB_CASE(10) SEMB_CASE(11) SEMB_CASE(12) SEMB_CASE(13) SEMB_CASE(14) SEMB_CASE(15) SEMB_CASE(16)
+    SEMB_CASE(17)
+#undef SEMB_CASE
+  }
+  semb_set_error("no strip kernel for N=%d", a.N);
+  return SEMB_EINVAL;
+}
+
+int semb_strip_regs(int N, bool pcg, bool massterm, int* regs, int* smem, int* occ) {
+  switch (N) {
+#define SEMB_CASE(n) \
+  case n:            \
+    return semb_strip_attr_n##n(pcg, massterm, regs, smem, occ);
+    SEMB_CASE(2) SEMB_CASE(3) SEMB_CASE(4) SEMB_CASE(5) SEMB_CASE(6) SEMB_CASE(7) SEMB_CASE(8) SEMB_CASE(9)
+    SEMB_CASE(10) SEMB_CASE(11) SEMB_CASE(12) SEMB_CASE(13) SEMB_CASE(14) SEMB_CASE(15) SEMB_CASE(16)
+    SEMB_CASE(17)
+#undef SEMB_CASE
+  }
+  return SEMB_EINVAL;
+}
+
+extern "C" int semb_strip_kernel_info(int N, int pcg, int massterm, int* regs, int* smem, int* occ) {
+  return semb_strip_regs(N, pcg != 0, massterm != 0, regs, smem, occ);
+}
+
+// ---- context ---------------------------------------------------------------------------------------------
+extern "C" int semb_init(int device, semb_ctx** out) {
+  SEMB_REQUIRE(out, "semb_init: null output");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    semb_set_error("semb_init: no CUDA device available (%s); libsemb has no CPU fallback",
+                   e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    cudaGetLastError();
+    return SEMB_ECUDA;
+  }
+  SEMB_REQUIRE(device >= 0 && device < ndev, "semb_init: device %d out of range (have %d)", device, ndev);
+  SEMB_CHECK_CUDA(cudaSetDevice(device));
+  semb_ctx* c = new semb_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  SEMB_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  SEMB_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  SEMB_CHECK_CUDA(cudaEventCreate(&c->ev0));
+  SEMB_CHECK_CUDA(cudaEventCreate(&c->ev1));
+  SEMB_CHECK_CUDA(cudaMalloc(&c->d_sync, 64));
+  SEMB_CHECK_CUDA(cudaMemset(c->d_sync, 0, 64));
+  *out = c;
+  return SEMB_OK;
+}
+
+static int ctx_enter(semb_ctx* c) {
+  SEMB_REQUIRE(c, "null context");
+  SEMB_CHECK_CUDA(cudaSetDevice(c->device));
+  return SEMB_OK;
+}
+
+extern "C" int semb_finalize(semb_ctx* c) {
+  if (!c) return SEMB_OK;
+  SEMB_TRY(ctx_enter(c));
+  cudaStreamSynchronize(c->stream);
+  if (c->comm) ncclCommDestroy(c->comm);
+  if (c->flush_buf) cudaFree(c->flush_buf);
+  if (c->d_sync) cudaFree(c->d_sync);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return SEMB_OK;
+}
+
+extern "C" int semb_sync(semb_ctx* c) {
+  SEMB_TRY(ctx_enter(c));
+  SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  return SEMB_OK;
+}
+
+extern "C" int semb_stream(semb_ctx* c, void** s) {
+  SEMB_REQUIRE(c && s, "semb_stream: null argument");
+  *s = (void*)c->stream;
+  return SEMB_OK;
+}
+
+extern "C" int semb_timer_start(semb_ctx* c) {
+  SEMB_TRY(ctx_enter(c));
+  SEMB_CHECK_CUDA(cudaEventRecord(c->ev0, c->stream));
+  return SEMB_OK;
+}
+
+extern "C" int semb_timer_stop(semb_ctx* c, double* ms) {
+  SEMB_TRY(ctx_enter(c));
+  SEMB_CHECK_CUDA(cudaEventRecord(c->ev1, c->stream));
+  SEMB_CHECK_CUDA(cudaEventSynchronize(c->ev1));
+  float f = 0.f;
+  SEMB_CHECK_CUDA(cudaEventElapsedTime(&f, c->ev0, c->ev1));
+  if (ms) *ms = (double)f;
+  return SEMB_OK;
+}
+
+extern "C" int semb_launch_count(semb_ctx* c, long long* n) {
+  SEMB_REQUIRE(c && n, "semb_launch_count: null argument");
+  *n = c->launches;
+  return SEMB_OK;
+}
+
+extern "C" int semb_flush_l2(semb_ctx* c) {
+  SEMB_TRY(ctx_enter(c));
+  if (!c->flush_buf) {
+    c->flush_bytes = (size_t)256 << 20;  // 2x the 126 MB L2
+    SEMB_CHECK_CUDA(cudaMalloc(&c->flush_buf, c->flush_bytes));
+  }
+  SEMB_CHECK_CUDA(cudaMemsetAsync(c->flush_buf, 0, c->flush_bytes, c->stream));
+  return SEMB_OK;
+}
+
+// ---- NCCL plumbing ---------------------------------------------------------------------------------------
+extern "C" int semb_comm_unique_id(char id[128]) {
+  SEMB_REQUIRE(id, "semb_comm_unique_id: null");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId u;
+  SEMB_CHECK_NCCL(ncclGetUniqueId(&u));
+  memcpy(id, &u, 128);
+  return SEMB_OK;
+}
+
+extern "C" int semb_comm_init(semb_ctx* c, int nranks, int rank, const char id[128]) {
+  SEMB_TRY(ctx_enter(c));
+  SEMB_REQUIRE(nranks >= 1 && nranks <= SEMB_MAX_RANKS && rank >= 0 && rank < nranks,
+               "semb_comm_init: bad nranks/rank %d/%d", nranks, rank);
+  SEMB_REQUIRE(!c->comm, "semb_comm_init: communicator already initialised");
+  if (nranks > 1) {
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    SEMB_CHECK_NCCL(ncclCommInitRank(&c->comm, nranks, u, rank));
+  }
+  c->nranks = nranks;
+  c->rank = rank;
+  return SEMB_OK;
+}
+
+extern "C" int semb_comm_info(semb_ctx* c, int* nranks, int* rank) {
+  SEMB_REQUIRE(c, "null context");
+  if (nranks) *nranks = c->nranks;
+  if (rank) *rank = c->rank;
+  return SEMB_OK;
+}
+
+extern "C" int semb_comm_barrier(semb_ctx* c) {
+  SEMB_TRY(ctx_enter(c));
+  if (c->comm) SEMB_CHECK_NCCL(ncclAllReduce(c->d_sync, c->d_sync, 1, ncclDouble, ncclSum, c->comm, c->stream));
+  SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  return SEMB_OK;
+}
+
+extern "C" int semb_comm_allreduce_max(semb_ctx* c, double* v, int n) {
+  SEMB_TRY(ctx_enter(c));
+  SEMB_REQUIRE(v && n >= 1 && n <= 7, "semb_comm_allreduce_max: 1..7 values");
+  if (!c->comm) return SEMB_OK;
+  SEMB_CHECK_CUDA(cudaMemcpyAsync(c->d_sync + 1, v, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  SEMB_CHECK_NCCL(ncclAllReduce(c->d_sync + 1, c->d_sync + 1, n, ncclDouble, ncclMax, c->comm, c->stream));
+  SEMB_CHECK_CUDA(cudaMemcpyAsync(v, c->d_sync + 1, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  return SEMB_OK;
+}
+
+// ---- mesh --------------------------------------------------------------------------------------------------
+static int mesh_alloc_array(semb_mesh* m, int which) {
+  if (m->arr[which]) return SEMB_OK;
+  SEMB_CHECK_CUDA(cudaMalloc(&m->arr[which], m->nalloc * sizeof(double)));
+  SEMB_CHECK_CUDA(cudaMemsetAsync(m->arr[which], 0, m->nalloc * sizeof(double), m->ctx->stream));
+  return SEMB_OK;
+}
+
+static int upload_pitched(semb_mesh* m, double* dst, const double* host) {
+  SEMB_CHECK_CUDA(cudaMemcpy2DAsync(dst, m->pitch * sizeof(double), host, (size_t)m->nxl * sizeof(double),
+                                    (size_t)m->nxl * sizeof(double), m->nyl, cudaMemcpyHostToDevice,
+                                    m->ctx->stream));
+  SEMB_CHECK_CUDA(cudaStreamSynchronize(m->ctx->stream));  // never retain a host pointer after return
+  return SEMB_OK;
+}
+
+static int download_pitched(semb_mesh* m, const double* src, double* host) {
+  SEMB_CHECK_CUDA(cudaMemcpy2DAsync(host, (size_t)m->nxl * sizeof(double), src, m->pitch * sizeof(double),
+                                    (size_t)m->nxl * sizeof(double), m->nyl, cudaMemcpyDeviceToHost,
+                                    m->ctx->stream));
+  SEMB_CHECK_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return SEMB_OK;
+}
+
+// Launch plan of the fused operator: strips x chunks, seam lists, halo neighbours.
+static int mesh_build_plan(semb_mesh* m) {
+  semb_ctx* c = m->ctx;
+  const int N = m->ns;  // y-direction points per element
+  m->fast = (m->nr == m->ns && m->nr >= 2 && m->nr <= SEMB_MAXN);
+  m->nstrips = (m->Ex + SEMB_BX - 1) / SEMB_BX;
+  int occ = 1;
+  if (m->fast) SEMB_TRY(semb_strip_regs(m->nr, false, false, nullptr, nullptr, &occ));
+  if (occ < 1) occ = 1;
+  // chunks: pick the count in [1 wave, 4 waves] with the best wave efficiency, >= 2 element rows each
+  const int slots = c->sm_count * occ;
+  int best = 1;
+  double best_eff = -1.0;
+  const int lo = std::max(1, slots / m->nstrips), hi = std::max(lo, 4 * slots / m->nstrips);
+  for (int nc = lo; nc <= hi; ++nc) {
+    if (nc > m->ney) break;
+    if (nc > 1 && m->ney / nc < 2) break;
+    const long long ctas = (long long)nc * m->nstrips;
+    const long long waves = (ctas + slots - 1) / slots;
+    const double eff = (double)ctas / (double)(waves * slots) - 1e-4 * nc;  // prefer fewer seams on ties
+    if (eff > best_eff) {
+      best_eff = eff;
+      best = nc;
+    }
+  }
+  if (best > m->ney) best = m->ney;
+  if ((long long)best * m->nstrips > SEMB_NPARTIALS) best = SEMB_NPARTIALS / m->nstrips;
+  if (best < 1) best = 1;
+  m->nchunks = best;
+  m->h_chunk_r0.resize(m->nchunks + 1);
+  for (int k = 0; k <= m->nchunks; ++k) m->h_chunk_r0[k] = (int)((long long)k * m->ney / m->nchunks);
+  // halo neighbours
+  const int P = c->nranks, rk = c->rank;
+  m->halo_lo = (rk > 0) || (m->pery && P > 1);
+  m->halo_hi = (rk < P - 1) || (m->pery && P > 1);
+  m->rank_lo = (rk - 1 + P) % P;
+  m->rank_hi = (rk + 1) % P;
+  const bool wrap_local = m->pery && P == 1;
+  // y seam flags per element row
+  m->h_ystart.assign(m->ney + 1, 0);
+  for (int k = 1; k < m->nchunks; ++k) m->h_ystart[m->h_chunk_r0[k]] = 1;
+  m->h_ystart[0] = (m->halo_lo || wrap_local) ? 1 : 0;
+  m->h_ystart[m->ney] = (m->halo_hi || wrap_local) ? 1 : 0;
+  std::vector<int> xs, ys;
+  for (int s = 1; s < m->nstrips; ++s) {
+    xs.push_back(s * SEMB_BX * m->nr - 1);
+    xs.push_back(s * SEMB_BX * m->nr);
+  }
+  if (m->perx) {
+    xs.push_back(m->nxl - 1);
+    xs.push_back(0);
+  }
+  for (int k = 1; k < m->nchunks; ++k) {
+    ys.push_back(m->h_chunk_r0[k] * N - 1);
+    ys.push_back(m->h_chunk_r0[k] * N);
+  }
+  if (wrap_local) {
+    ys.push_back(m->nyl - 1);
+    ys.push_back(0);
+  }
+  m->nxseam = (int)xs.size() / 2;
+  m->nyseam = (int)ys.size() / 2;
+  // all y interfaces (stand-alone gatherScatter), appended after the chunk seams
+  std::vector<int> yall;
+  for (int r = 1; r < m->ney; ++r) {
+    yall.push_back(r * N - 1);
+    yall.push_back(r * N);
+  }
+  if (wrap_local) {
+    yall.push_back(m->nyl - 1);
+    yall.push_back(0);
+  }
+  const size_t nys = ys.size();
+  ys.insert(ys.end(), yall.begin(), yall.end());
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_chunk_r0, (m->nchunks + 1) * sizeof(int)));
+  SEMB_CHECK_CUDA(cudaMemcpy(m->d_chunk_r0, m->h_chunk_r0.data(), (m->nchunks + 1) * sizeof(int),
+                             cudaMemcpyHostToDevice));
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_ystart, m->ney + 1));
+  SEMB_CHECK_CUDA(cudaMemcpy(m->d_ystart, m->h_ystart.data(), m->ney + 1, cudaMemcpyHostToDevice));
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_xseam, std::max<size_t>(xs.size(), 2) * sizeof(int)));
+  if (!xs.empty())
+    SEMB_CHECK_CUDA(cudaMemcpy(m->d_xseam, xs.data(), xs.size() * sizeof(int), cudaMemcpyHostToDevice));
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_yseam, std::max<size_t>(ys.size(), 2) * sizeof(int)));
+  if (!ys.empty())
+    SEMB_CHECK_CUDA(cudaMemcpy(m->d_yseam, ys.data(), ys.size() * sizeof(int), cudaMemcpyHostToDevice));
+  (void)nys;
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_halo_lo, (size_t)m->pitch * sizeof(double)));
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_halo_hi, (size_t)m->pitch * sizeof(double)));
+  m->npartials = SEMB_NPARTIALS;
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_partials, 3 * (size_t)m->npartials * sizeof(double)));
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_counters, 8 * sizeof(unsigned)));
+  SEMB_CHECK_CUDA(cudaMemset(m->d_counters, 0, 8 * sizeof(unsigned)));
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_scal, sizeof(SembScal)));
+  SEMB_CHECK_CUDA(cudaMallocHost(&m->h_scal, sizeof(SembScal)));
+  memset(m->h_scal, 0, sizeof(SembScal));
+  m->h_scal->nranks = P;
+  m->h_scal->rank = rk;
+  m->h_scal->done = 1;
+  SEMB_CHECK_CUDA(cudaMemcpy(m->d_scal, m->h_scal, sizeof(SembScal), cudaMemcpyHostToDevice));
+  return SEMB_OK;
+}
+
+static int mesh_new(semb_ctx* c, int nr, int ns, int Ex, int Ey, int perx, int pery, const double* Dr,
+                    const double* Ds, const double* wr, const double* ws, semb_mesh** out) {
+  SEMB_TRY(ctx_enter(c));
+  SEMB_REQUIRE(out, "mesh: null output");
+  SEMB_REQUIRE(nr >= 2 && ns >= 2 && nr <= 64 && ns <= 64, "mesh: need 2 <= nr, ns <= 64 (got %d, %d)", nr, ns);
+  SEMB_REQUIRE(Ex >= 1 && Ey >= 1, "mesh: need Ex, Ey >= 1");
+  SEMB_REQUIRE(c->nranks <= Ey, "mesh: more ranks (%d) than element rows (%d)", c->nranks, Ey);
+  SEMB_REQUIRE((long long)nr * Ex < (1ll << 30) && (long long)ns * Ey < (1ll << 30), "mesh: too large");
+  semb_mesh* m = new semb_mesh();
+  m->ctx = c;
+  m->nr = nr;
+  m->ns = ns;
+  m->Ex = Ex;
+  m->Ey = Ey;
+  m->perx = perx ? 1 : 0;
+  m->pery = pery ? 1 : 0;
+  SEMB_TRY(semb_partition(Ey, c->nranks, c->rank, &m->ey0, &m->ney));
+  m->nxl = nr * Ex;
+  m->nyl = ns * m->ney;
+  m->pitch = semb_pitch_for(m->nxl);
+  m->nalloc = (size_t)m->pitch * m->nyl;
+  m->hDr.assign((size_t)nr * nr, 0.0);
+  m->hDs.assign((size_t)ns * ns, 0.0);
+  m->hwr.assign(nr, 0.0);
+  m->hws.assign(ns, 0.0);
+  if (Dr) {
+    std::copy(Dr, Dr + (size_t)nr * nr, m->hDr.begin());
+  } else {
+    std::vector<double> z(nr), w(nr);
+    SEMB_TRY(semb_gausslobatto(nr, z.data(), w.data()));
+    SEMB_TRY(semb_deriv_mat(nr, z.data(), m->hDr.data()));
+  }
+  if (Ds) {
+    std::copy(Ds, Ds + (size_t)ns * ns, m->hDs.begin());
+  } else {
+    std::vector<double> z(ns), w(ns);
+    SEMB_TRY(semb_gausslobatto(ns, z.data(), w.data()));
+    SEMB_TRY(semb_deriv_mat(ns, z.data(), m->hDs.data()));
+  }
+  {
+    std::vector<double> z(std::max(nr, ns)), w(std::max(nr, ns));
+    if (wr) std::copy(wr, wr + nr, m->hwr.begin());
+    else {
+      SEMB_TRY(semb_gausslobatto(nr, z.data(), w.data()));
+      std::copy(w.begin(), w.begin() + nr, m->hwr.begin());
+    }
+    if (ws) std::copy(ws, ws + ns, m->hws.begin());
+    else {
+      SEMB_TRY(semb_gausslobatto(ns, z.data(), w.data()));
+      std::copy(w.begin(), w.begin() + ns, m->hws.begin());
+    }
+  }
+  // row-major device copies for the generic kernels
+  std::vector<double> rm((size_t)nr * nr);
+  for (int i = 0; i < nr; ++i)
+    for (int k = 0; k < nr; ++k) rm[(size_t)i * nr + k] = m->hDr[i + (size_t)k * nr];
+  SEMB_CHECK_CUDA(cudaMalloc(&m->dDr, rm.size() * sizeof(double)));
+  SEMB_CHECK_CUDA(cudaMemcpy(m->dDr, rm.data(), rm.size() * sizeof(double), cudaMemcpyHostToDevice));
+  rm.assign((size_t)ns * ns, 0.0);
+  for (int i = 0; i < ns; ++i)
+    for (int k = 0; k < ns; ++k) rm[(size_t)i * ns + k] = m->hDs[i + (size_t)k * ns];
+  SEMB_CHECK_CUDA(cudaMalloc(&m->dDs, rm.size() * sizeof(double)));
+  SEMB_CHECK_CUDA(cudaMemcpy(m->dDs, rm.data(), rm.size() * sizeof(double), cudaMemcpyHostToDevice));
+  SEMB_TRY(mesh_build_plan(m));
+  SEMB_TRY(mesh_alloc_array(m, SEMB_MULT));
+  SEMB_TRY(semb_launch_mult(c, m->arr[SEMB_MULT], m->pitch, nr, ns, Ex, Ey, m->ey0, m->ney, m->perx, m->pery));
+  *out = m;
+  return SEMB_OK;
+}
+
+static int mesh_geometry(semb_mesh* m) {
+  semb_ctx* c = m->ctx;
+  double *d_wr = nullptr, *d_ws = nullptr;
+  SEMB_CHECK_CUDA(cudaMalloc(&d_wr, m->nr * sizeof(double)));
+  SEMB_CHECK_CUDA(cudaMalloc(&d_ws, m->ns * sizeof(double)));
+  SEMB_CHECK_CUDA(cudaMemcpyAsync(d_wr, m->hwr.data(), m->nr * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  SEMB_CHECK_CUDA(cudaMemcpyAsync(d_ws, m->hws.data(), m->ns * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  for (int w = SEMB_JAC; w <= SEMB_G22; ++w) SEMB_TRY(mesh_alloc_array(m, w));
+  SEMB_TRY(semb_launch_geom(c, m->arr[SEMB_X], m->arr[SEMB_Y], m->pitch, m->nr, m->ns, m->Ex, m->ney, m->dDr,
+                            m->dDs, d_wr, d_ws, m->arr[SEMB_JAC], m->arr[SEMB_JACI], m->arr[SEMB_RX],
+                            m->arr[SEMB_RY], m->arr[SEMB_SX], m->arr[SEMB_SY], m->arr[SEMB_B], m->arr[SEMB_BI],
+                            m->arr[SEMB_G11], m->arr[SEMB_G12], m->arr[SEMB_G22]));
+  SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_wr);
+  cudaFree(d_ws);
+  return SEMB_OK;
+}
+
+extern "C" int semb_mesh_create_xy(semb_ctx* c, int nr, int ns, int Ex, int Ey, int perx, int pery,
+                                   const double* Dr, const double* Ds, const double* wr, const double* ws,
+                                   const double* x, const double* y, semb_mesh** out) {
+  SEMB_REQUIRE(x && y, "semb_mesh_create_xy: x and y are required");
+  semb_mesh* m = nullptr;
+  SEMB_TRY(mesh_new(c, nr, ns, Ex, Ey, perx, pery, Dr, Ds, wr, ws, &m));
+  int rc = mesh_alloc_array(m, SEMB_X);
+  if (!rc) rc = mesh_alloc_array(m, SEMB_Y);
+  if (!rc) rc = upload_pitched(m, m->arr[SEMB_X], x);
+  if (!rc) rc = upload_pitched(m, m->arr[SEMB_Y], y);
+  if (!rc) rc = mesh_geometry(m);
+  if (rc) {
+    semb_mesh_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return SEMB_OK;
+}
+
+extern "C" int semb_mesh_create_deform(semb_ctx* c, int nr, int ns, int Ex, int Ey, int perx, int pery, int kind,
+                                       const double* params, int nparams, semb_mesh** out) {
+  SEMB_REQUIRE(kind >= SEMB_DEFORM_IDENTITY && kind <= SEMB_DEFORM_WAVY, "semb_mesh_create_deform: unknown kind %d",
+               kind);
+  double p[3] = {0.0, 0.0, 0.0};
+  if (kind == SEMB_DEFORM_ANNULUS) {
+    p[0] = 0.5;
+    p[1] = 1.0;
+    p[2] = 2.0 * 3.14159265358979323846;
+  }
+  if (kind == SEMB_DEFORM_WAVY) p[0] = 0.1;
+  for (int i = 0; i < nparams && i < 3; ++i) p[i] = params[i];
+  semb_mesh* m = nullptr;
+  SEMB_TRY(mesh_new(c, nr, ns, Ex, Ey, perx, pery, nullptr, nullptr, nullptr, nullptr, &m));
+  std::vector<double> z0r(nr), z0s(ns), w(std::max(nr, ns));
+  semb_gausslobatto(nr, z0r.data(), w.data());
+  semb_gausslobatto(ns, z0s.data(), w.data());
+  for (auto& v : z0r) v = 0.5 * (v + 1.0);  // semmesh.jl:13
+  for (auto& v : z0s) v = 0.5 * (v + 1.0);
+  double *dzr = nullptr, *dzs = nullptr;
+  int rc = SEMB_OK;
+  auto body = [&]() -> int {
+    SEMB_CHECK_CUDA(cudaMalloc(&dzr, nr * sizeof(double)));
+    SEMB_CHECK_CUDA(cudaMalloc(&dzs, ns * sizeof(double)));
+    SEMB_CHECK_CUDA(cudaMemcpy(dzr, z0r.data(), nr * sizeof(double), cudaMemcpyHostToDevice));
+    SEMB_CHECK_CUDA(cudaMemcpy(dzs, z0s.data(), ns * sizeof(double), cudaMemcpyHostToDevice));
+    SEMB_TRY(mesh_alloc_array(m, SEMB_X));
+    SEMB_TRY(mesh_alloc_array(m, SEMB_Y));
+    SEMB_TRY(semb_launch_grid(c, m->arr[SEMB_X], m->arr[SEMB_Y], m->pitch, nr, ns, Ex, Ey, m->ey0, m->ney, dzr, dzs,
+                              kind, p));
+    SEMB_TRY(mesh_geometry(m));
+    return SEMB_OK;
+  };
+  rc = body();
+  if (dzr) cudaFree(dzr);
+  if (dzs) cudaFree(dzs);
+  if (rc) {
+    semb_mesh_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return SEMB_OK;
+}
+
+extern "C" int semb_mesh_create_arrays(semb_ctx* c, int nr, int ns, int Ex, int Ey, int perx, int pery,
+                                       const double* Dr, const double* Ds, const double* G11, const double* G12,
+                                       const double* G22, const double* B, semb_mesh** out) {
+  SEMB_REQUIRE(Dr && Ds && G11 && G12 && G22, "semb_mesh_create_arrays: Dr, Ds, G11, G12, G22 are required");
+  semb_mesh* m = nullptr;
+  SEMB_TRY(mesh_new(c, nr, ns, Ex, Ey, perx, pery, Dr, Ds, nullptr, nullptr, &m));
+  const double* src[4] = {G11, G12, G22, B};
+  const int which[4] = {SEMB_G11, SEMB_G12, SEMB_G22, SEMB_B};
+  for (int i = 0; i < 4; ++i) {
+    if (!src[i]) continue;
+    int rc = mesh_alloc_array(m, which[i]);
+    if (!rc) rc = upload_pitched(m, m->arr[which[i]], src[i]);
+    if (rc) {
+      semb_mesh_destroy(m);
+      return rc;
+    }
+  }
+  *out = m;
+  return SEMB_OK;
+}
+
+extern "C" int semb_mesh_destroy(semb_mesh* m) {
+  if (!m) return SEMB_OK;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  std::vector<semb_field*> fs = m->fields;
+  for (semb_field* f : fs) semb_field_destroy(f);
+  for (int i = 0; i < SEMB_MESH_ARRAY_COUNT; ++i)
+    if (m->arr[i]) cudaFree(m->arr[i]);
+  cudaFree(m->dDr);
+  cudaFree(m->dDs);
+  cudaFree(m->d_chunk_r0);
+  cudaFree(m->d_ystart);
+  cudaFree(m->d_xseam);
+  cudaFree(m->d_yseam);
+  cudaFree(m->d_halo_lo);
+  cudaFree(m->d_halo_hi);
+  cudaFree(m->d_partials);
+  cudaFree(m->d_counters);
+  cudaFree(m->d_scal);
+  if (m->h_scal) cudaFreeHost(m->h_scal);
+  delete m;
+  return SEMB_OK;
+}
+
+extern "C" int semb_mesh_dims(semb_mesh* m, int* nr, int* ns, int* Ex, int* Ey, int* nxl, int* nyl, int* ey0,
+                              int* ney) {
+  SEMB_REQUIRE(m, "null mesh");
+  if (nr) *nr = m->nr;
+  if (ns) *ns = m->ns;
+  if (Ex) *Ex = m->Ex;
+  if (Ey) *Ey = m->Ey;
+  if (nxl) *nxl = m->nxl;
+  if (nyl) *nyl = m->nyl;
+  if (ey0) *ey0 = m->ey0;
+  if (ney) *ney = m->ney;
+  return SEMB_OK;
+}
+
+extern "C" int semb_mesh_plan(semb_mesh* m, int* nstrips, int* nchunks, int* nxseam, int* nyseam, int* fast) {
+  SEMB_REQUIRE(m, "null mesh");
+  if (nstrips) *nstrips = m->nstrips;
+  if (nchunks) *nchunks = m->nchunks;
+  if (nxseam) *nxseam = m->nxseam;
+  if (nyseam) *nyseam = m->nyseam;
+  if (fast) *fast = m->fast ? 1 : 0;
+  return SEMB_OK;
+}
+
+// test / tuning hook: override the number of y chunks of the strip kernel
+extern "C" int semb_mesh_set_chunks(semb_mesh* m, int nchunks) {
+  SEMB_REQUIRE(m && nchunks >= 1 && nchunks <= m->ney, "semb_mesh_set_chunks: 1 <= nchunks <= ney");
+  SEMB_REQUIRE((long long)nchunks * m->nstrips <= SEMB_NPARTIALS, "semb_mesh_set_chunks: too many CTAs");
+  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_CHECK_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  const int N = m->ns;
+  m->nchunks = nchunks;
+  m->h_chunk_r0.resize(nchunks + 1);
+  for (int k = 0; k <= nchunks; ++k) m->h_chunk_r0[k] = (int)((long long)k * m->ney / nchunks);
+  const unsigned char b0 = m->h_ystart[0], b1 = m->h_ystart[m->ney];
+  m->h_ystart.assign(m->ney + 1, 0);
+  m->h_ystart[0] = b0;
+  m->h_ystart[m->ney] = b1;
+  for (int k = 1; k < nchunks; ++k) m->h_ystart[m->h_chunk_r0[k]] = 1;
+  std::vector<int> ys;
+  for (int k = 1; k < nchunks; ++k) {
+    ys.push_back(m->h_chunk_r0[k] * N - 1);
+    ys.push_back(m->h_chunk_r0[k] * N);
+  }
+  const bool wrap_local = m->pery && m->ctx->nranks == 1;
+  if (wrap_local) {
+    ys.push_back(m->nyl - 1);
+    ys.push_back(0);
+  }
+  m->nyseam = (int)ys.size() / 2;
+  for (int r = 1; r < m->ney; ++r) {
+    ys.push_back(r * N - 1);
+    ys.push_back(r * N);
+  }
+  if (wrap_local) {
+    ys.push_back(m->nyl - 1);
+    ys.push_back(0);
+  }
+  cudaFree(m->d_chunk_r0);
+  cudaFree(m->d_yseam);
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_chunk_r0, (nchunks + 1) * sizeof(int)));
+  SEMB_CHECK_CUDA(cudaMemcpy(m->d_chunk_r0, m->h_chunk_r0.data(), (nchunks + 1) * sizeof(int),
+                             cudaMemcpyHostToDevice));
+  SEMB_CHECK_CUDA(cudaMemcpy(m->d_ystart, m->h_ystart.data(), m->ney + 1, cudaMemcpyHostToDevice));
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_yseam, std::max<size_t>(ys.size(), 2) * sizeof(int)));
+  if (!ys.empty())
+    SEMB_CHECK_CUDA(cudaMemcpy(m->d_yseam, ys.data(), ys.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return SEMB_OK;
+}
+
+extern "C" int semb_mesh_get(semb_mesh* m, int which, double* host) {
+  SEMB_REQUIRE(m && host, "semb_mesh_get: null argument");
+  SEMB_REQUIRE(which >= 0 && which < SEMB_MESH_ARRAY_COUNT, "semb_mesh_get: bad selector %d", which);
+  SEMB_REQUIRE(m->arr[which], "semb_mesh_get: array %d is not held by this mesh", which);
+  SEMB_TRY(ctx_enter(m->ctx));
+  return download_pitched(m, m->arr[which], host);
+}
+
+extern "C" int semb_mesh_get_D(semb_mesh* m, double* Dr, double* Ds) {
+  SEMB_REQUIRE(m, "null mesh");
+  if (Dr) std::copy(m->hDr.begin(), m->hDr.end(), Dr);
+  if (Ds) std::copy(m->hDs.begin(), m->hDs.end(), Ds);
+  return SEMB_OK;
+}
+
+struct MaskFlags {
+  int mx0, mx1, my0, my1;
+};
+static int parse_bc(semb_mesh* m, const char* bc, MaskFlags* f) {
+  f->mx0 = f->mx1 = f->my0 = f->my1 = 0;
+  if (!bc) return SEMB_OK;
+  for (int i = 0; i < 4; ++i)
+    SEMB_REQUIRE(bc[i] == 'D' || bc[i] == 'N', "bc must be 4 chars of 'D'/'N' (mesh.jl:138), got '%c'", bc[i]);
+  // mesh.jl:159-165: periodic direction overrides 'D'; only slabs on the global boundary carry y flags
+  f->mx0 = (bc[0] == 'D') && !m->perx;
+  f->mx1 = (bc[1] == 'D') && !m->perx;
+  f->my0 = (bc[2] == 'D') && !m->pery && m->ey0 == 0;
+  f->my1 = (bc[3] == 'D') && !m->pery && (m->ey0 + m->ney == m->Ey);
+  return SEMB_OK;
+}
+
+extern "C" int semb_generate_mask(semb_mesh* m, const char bc[4], double* host) {
+  SEMB_REQUIRE(m && bc && host, "semb_generate_mask: null argument");
+  SEMB_TRY(ctx_enter(m->ctx));
+  MaskFlags f;
+  SEMB_TRY(parse_bc(m, bc, &f));
+  double* d = nullptr;
+  SEMB_CHECK_CUDA(cudaMalloc(&d, m->nalloc * sizeof(double)));
+  int rc = semb_launch_mask_gen(m->ctx, d, m->pitch, m->nxl, m->nyl, f.mx0, f.mx1, f.my0, f.my1);
+  if (!rc) rc = download_pitched(m, d, host);
+  cudaFree(d);
+  return rc;
+}
+
+// ---- fields ------------------------------------------------------------------------------------------------
+extern "C" int semb_field_create(semb_mesh* m, semb_field** out) {
+  SEMB_REQUIRE(m && out, "semb_field_create: null argument");
+  SEMB_TRY(ctx_enter(m->ctx));
+  semb_field* f = new semb_field();
+  f->mesh = m;
+  cudaError_t e = cudaMalloc(&f->d, m->nalloc * sizeof(double));
+  if (e != cudaSuccess) {
+    delete f;
+    semb_set_error("semb_field_create: cudaMalloc of %zu bytes failed: %s", m->nalloc * sizeof(double),
+                   cudaGetErrorString(e));
+    return SEMB_ENOMEM;
+  }
+  SEMB_CHECK_CUDA(cudaMemsetAsync(f->d, 0, m->nalloc * sizeof(double), m->ctx->stream));
+  m->fields.push_back(f);
+  *out = f;
+  return SEMB_OK;
+}
+
+extern "C" int semb_field_destroy(semb_field* f) {
+  if (!f) return SEMB_OK;
+  semb_mesh* m = f->mesh;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  auto it = std::find(m->fields.begin(), m->fields.end(), f);
+  if (it != m->fields.end()) m->fields.erase(it);
+  cudaFree(f->d);
+  delete f;
+  return SEMB_OK;
+}
+
+extern "C" int semb_field_upload(semb_field* f, const double* host) {
+  SEMB_REQUIRE(f && host, "semb_field_upload: null argument");
+  SEMB_TRY(ctx_enter(f->mesh->ctx));
+  return upload_pitched(f->mesh, f->d, host);
+}
+
+extern "C" int semb_field_download(semb_field* f, double* host) {
+  SEMB_REQUIRE(f && host, "semb_field_download: null argument");
+  SEMB_TRY(ctx_enter(f->mesh->ctx));
+  return download_pitched(f->mesh, f->d, host);
+}
+
+extern "C" int semb_field_fill(semb_field* f, double v) {
+  SEMB_REQUIRE(f, "null field");
+  semb_mesh* m = f->mesh;
+  SEMB_TRY(ctx_enter(m->ctx));
+  return semb_launch_fill(m->ctx, f->d, v, m->pitch, m->nxl, m->nyl);
+}
+
+extern "C" int semb_field_copy(semb_field* dst, const semb_field* src) {
+  SEMB_REQUIRE(dst && src && dst->mesh == src->mesh, "semb_field_copy: fields must share a mesh");
+  semb_mesh* m = dst->mesh;
+  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_CHECK_CUDA(cudaMemcpyAsync(dst->d, src->d, m->nalloc * sizeof(double), cudaMemcpyDeviceToDevice,
+                                  m->ctx->stream));
+  return SEMB_OK;
+}
+
+extern "C" int semb_field_fill_random(semb_field* f, uint64_t seed) {
+  SEMB_REQUIRE(f, "null field");
+  semb_mesh* m = f->mesh;
+  SEMB_TRY(ctx_enter(m->ctx));
+  return semb_launch_fill_random(m->ctx, f->d, m->pitch, m->nxl, m->nyl, m->nxl, (long long)m->ey0 * m->ns, seed);
+}
+
+extern "C" int semb_field_axpby(double a, const semb_field* x, double b, semb_field* y) {
+  SEMB_REQUIRE(x && y && x->mesh == y->mesh, "semb_field_axpby: fields must share a mesh");
+  semb_mesh* m = y->mesh;
+  SEMB_TRY(ctx_enter(m->ctx));
+  return semb_launch_axpby(m->ctx, a, x->d, b, y->d, m->nalloc);
+}
+
+extern "C" int semb_field_devptr(semb_field* f, void** dptr, long long* pitch) {
+  SEMB_REQUIRE(f, "null field");
+  if (dptr) *dptr = f->d;
+  if (pitch) *pitch = f->mesh->pitch;
+  return SEMB_OK;
+}
+
+// ---- operators ------------------------------------------------------------------------------------------------
+static int check_field(semb_mesh* m, const semb_field* f, const char* what, bool optional = false) {
+  if (!f) {
+    SEMB_REQUIRE(optional, "%s: null field", what);
+    return SEMB_OK;
+  }
+  SEMB_REQUIRE(f->mesh == m, "%s: field belongs to another mesh (DimensionMismatch)", what);
+  return SEMB_OK;
+}
+
+static int halo_exchange(semb_mesh* m, double* field) {
+  semb_ctx* c = m->ctx;
+  if (!m->halo_lo && !m->halo_hi) return SEMB_OK;
+  SEMB_REQUIRE(c->comm, "halo exchange without a communicator");
+  SEMB_CHECK_NCCL(ncclGroupStart());
+  // order matters only when both neighbours are the same rank (2 ranks, periodic y): sends go
+  // {last row -> hi, first row -> lo}, receives {lo, hi}
+  if (m->halo_hi)
+    SEMB_CHECK_NCCL(ncclSend(field + (size_t)(m->nyl - 1) * m->pitch, m->nxl, ncclDouble, m->rank_hi, c->comm,
+                             c->stream));
+  if (m->halo_lo) SEMB_CHECK_NCCL(ncclSend(field, m->nxl, ncclDouble, m->rank_lo, c->comm, c->stream));
+  if (m->halo_lo) SEMB_CHECK_NCCL(ncclRecv(m->d_halo_lo, m->nxl, ncclDouble, m->rank_lo, c->comm, c->stream));
+  if (m->halo_hi) SEMB_CHECK_NCCL(ncclRecv(m->d_halo_hi, m->nxl, ncclDouble, m->rank_hi, c->comm, c->stream));
+  SEMB_CHECK_NCCL(ncclGroupEnd());
+  return SEMB_OK;
+}
+
+static int ensure_tmp(semb_mesh* m, semb_field** slot) {
+  if (*slot) return SEMB_OK;
+  return semb_field_create(m, slot);
+}
+
+struct OpSpec {
+  const semb_field* nu_arr = nullptr;
+  double nu = 1.0;
+  const semb_field* k_arr = nullptr;
+  double k = 0.0;
+  const char* bc = nullptr;
+  const semb_field* M_arr = nullptr;
+  bool gs = true;
+};
+
+static void fill_common(semb_mesh* m, OpArgs& a) {
+  a.G11 = m->arr[SEMB_G11];
+  a.G12 = m->arr[SEMB_G12];
+  a.G22 = m->arr[SEMB_G22];
+  a.B = m->arr[SEMB_B];
+  a.mult = m->arr[SEMB_MULT];
+  a.pitch = m->pitch;
+  a.N = m->ns;
+  a.Ex = m->Ex;
+  a.ney = m->ney;
+  a.nxl = m->nxl;
+  a.nyl = m->nyl;
+  a.perx = m->perx;
+  a.chunk_r0 = m->d_chunk_r0;
+  a.nchunks = m->nchunks;
+  a.ystart = m->d_ystart;
+  a.xseam = m->d_xseam;
+  a.nxseam = m->nxseam;
+  a.yseam = m->d_yseam;
+  a.nyseam = m->nyseam;
+  a.scal = m->d_scal;
+  a.halo_lo = m->d_halo_lo;
+  a.halo_hi = m->d_halo_hi;
+}
+
+// out = [mask(gs(]  nu .* laplace(u) + k .* B .* u  [))]   -- the one place operators are composed
+static int run_operator(semb_mesh* m, const double* u, double* out, const OpSpec& sp, bool pcg, double* p_inout,
+                        int precond, double prec_b0) {
+  semb_ctx* c = m->ctx;
+  SEMB_REQUIRE(m->arr[SEMB_G11] && m->arr[SEMB_G12] && m->arr[SEMB_G22], "operator: mesh has no G11/G12/G22");
+  const bool massterm = (sp.k_arr != nullptr) || (sp.k != 0.0);
+  SEMB_REQUIRE(!massterm || m->arr[SEMB_B], "operator: mass term requested but the mesh has no B");
+  SEMB_REQUIRE(!precond || m->arr[SEMB_B], "operator: preconditioner needs B");
+  OpArgs a;
+  fill_common(m, a);
+  a.u = u;
+  a.out = out;
+  a.nu_arr = sp.nu_arr ? sp.nu_arr->d : nullptr;
+  a.k_arr = sp.k_arr ? sp.k_arr->d : nullptr;
+  a.M_arr = sp.M_arr ? sp.M_arr->d : nullptr;
+  a.nu = sp.nu;
+  a.k = sp.k;
+  a.gs = sp.gs ? 1 : 0;
+  a.pcg = pcg ? 1 : 0;
+  a.precond = precond;
+  a.prec_b0 = prec_b0;
+  if (pcg) {
+    a.pold = p_inout;
+    a.pout = p_inout;
+  }
+  MaskFlags f;
+  SEMB_TRY(parse_bc(m, sp.bc, &f));
+  a.mx0 = f.mx0;
+  a.mx1 = f.mx1;
+  a.my0 = f.my0;
+  a.my1 = f.my1;
+  if (m->fast) {
+    a.partials = m->d_partials;
+    a.counters = m->d_counters + 0;
+    SEMB_TRY(semb_launch_strip(c, a, m->hDr.data(), m->hDs.data(), m->nstrips, m->nchunks, pcg, massterm));
+    if (!sp.gs) return SEMB_OK;
+    a.partials = m->d_partials + m->npartials;
+    a.counters = m->d_counters + 1;
+    SEMB_TRY(semb_launch_seam_x(c, a));
+    SEMB_TRY(halo_exchange(m, out));
+    a.partials = m->d_partials + 2 * (size_t)m->npartials;
+    a.counters = m->d_counters + 2;
+    SEMB_TRY(semb_launch_seam_y(c, a, m->halo_lo, m->halo_hi, true));
+    return SEMB_OK;
+  }
+  // generic path (nr != ns, or outside 2..17): separate passes, same arithmetic per node
+  SEMB_TRY(ensure_tmp(m, &m->w_tmp));
+  SEMB_TRY(ensure_tmp(m, &m->w_t1));
+  SEMB_TRY(ensure_tmp(m, &m->w_t2));
+  semb_field *t1 = m->w_t1, *t2 = m->w_t2;
+  int rc = SEMB_OK;
+  auto body = [&]() -> int {
+    if (pcg) SEMB_TRY(semb_launch_pcg_dir(c, m, u, p_inout, precond, prec_b0));
+    OpArgs g = a;
+    g.u = pcg ? p_inout : u;
+    g.out = sp.gs ? m->w_tmp->d : out;
+    SEMB_TRY(semb_launch_generic_local(c, g, m->nr, m->ns, m->dDr, m->dDs, t1->d, t2->d, massterm));
+    if (!sp.gs) return SEMB_OK;
+    SEMB_TRY(semb_launch_gs_x(c, m->w_tmp->d, out, m->pitch, m->nr, m->Ex, m->nxl, m->nyl, m->perx));
+    SEMB_TRY(halo_exchange(m, out));
+    OpArgs y = a;
+    y.pcg = 0;
+    y.yseam = m->d_yseam + 2 * m->nyseam;  // all y interfaces
+    y.nyseam = (m->ney - 1) + ((m->pery && c->nranks == 1) ? 1 : 0);
+    SEMB_TRY(semb_launch_seam_y(c, y, m->halo_lo, m->halo_hi, false));
+    OpArgs md = a;
+    md.partials = m->d_partials;
+    md.counters = m->d_counters + 0;
+    SEMB_TRY(semb_launch_mask_dot(c, m, md));
+    return SEMB_OK;
+  };
+  rc = body();
+  return rc;
+}
+
+extern "C" int semb_lapl(semb_mesh* m, const semb_field* u, semb_field* out) {
+  return semb_hlmz(m, u, nullptr, 1.0, nullptr, 0.0, out);
+}
+
+extern "C" int semb_hlmz(semb_mesh* m, const semb_field* u, const semb_field* nu_arr, double nu,
+                         const semb_field* k_arr, double k, semb_field* out) {
+  SEMB_REQUIRE(m, "null mesh");
+  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_TRY(check_field(m, u, "hlmz(u)"));
+  SEMB_TRY(check_field(m, out, "hlmz(out)"));
+  SEMB_TRY(check_field(m, nu_arr, "hlmz(nu)", true));
+  SEMB_TRY(check_field(m, k_arr, "hlmz(k)", true));
+  SEMB_REQUIRE(u != out, "hlmz: out must not alias u");
+  OpSpec sp;
+  sp.nu_arr = nu_arr;
+  sp.nu = nu;
+  sp.k_arr = k_arr;
+  sp.k = k;
+  sp.gs = false;
+  return run_operator(m, u->d, out->d, sp, false, nullptr, 0, 1.0);
+}
+
+extern "C" int semb_mass(semb_mesh* m, const semb_field* u, semb_field* out) {
+  SEMB_REQUIRE(m, "null mesh");
+  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_TRY(check_field(m, u, "mass(u)"));
+  SEMB_TRY(check_field(m, out, "mass(out)"));
+  SEMB_REQUIRE(m->arr[SEMB_B], "mass: mesh has no B");
+  return semb_launch_mask(m->ctx, u->d, m->arr[SEMB_B], out->d, m->nalloc);  // B .* u, mass.jl:17
+}
+
+extern "C" int semb_gather_scatter(semb_mesh* m, const semb_field* u, semb_field* out) {
+  SEMB_REQUIRE(m, "null mesh");
+  semb_ctx* c = m->ctx;
+  SEMB_TRY(ctx_enter(c));
+  SEMB_TRY(check_field(m, u, "gatherScatter(u)"));
+  SEMB_TRY(check_field(m, out, "gatherScatter(out)"));
+  SEMB_REQUIRE(u != out, "gatherScatter: out must not alias u");
+  SEMB_TRY(semb_launch_gs_x(c, u->d, out->d, m->pitch, m->nr, m->Ex, m->nxl, m->nyl, m->perx));
+  SEMB_TRY(halo_exchange(m, out->d));
+  OpArgs y;
+  fill_common(m, y);
+  y.out = out->d;
+  y.yseam = m->d_yseam + 2 * m->nyseam;
+  y.nyseam = (m->ney - 1) + ((m->pery && c->nranks == 1) ? 1 : 0);
+  return semb_launch_seam_y(c, y, m->halo_lo, m->halo_hi, false);
+}
+
+extern "C" int semb_mask(semb_mesh* m, const semb_field* u, const semb_field* M, semb_field* out) {
+  SEMB_REQUIRE(m, "null mesh");
+  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_TRY(check_field(m, u, "mask(u)"));
+  SEMB_TRY(check_field(m, out, "mask(out)"));
+  SEMB_TRY(check_field(m, M, "mask(M)", true));
+  return semb_launch_mask(m->ctx, u->d, M ? M->d : nullptr, out->d, m->nalloc);
+}
+
+extern "C" int semb_oplhs(semb_mesh* m, const semb_field* u, const semb_field* nu_arr, double nu,
+                          const semb_field* k_arr, double k, const char* bc, const semb_field* M_arr,
+                          semb_field* out) {
+  SEMB_REQUIRE(m, "null mesh");
+  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_TRY(check_field(m, u, "opLHS(u)"));
+  SEMB_TRY(check_field(m, out, "opLHS(out)"));
+  SEMB_TRY(check_field(m, nu_arr, "opLHS(nu)", true));
+  SEMB_TRY(check_field(m, k_arr, "opLHS(k)", true));
+  SEMB_TRY(check_field(m, M_arr, "opLHS(M)", true));
+  SEMB_REQUIRE(u != out, "opLHS: out must not alias u");
+  OpSpec sp;
+  sp.nu_arr = nu_arr;
+  sp.nu = nu;
+  sp.k_arr = k_arr;
+  sp.k = k;
+  sp.bc = bc;
+  sp.M_arr = M_arr;
+  sp.gs = true;
+  return run_operator(m, u->d, out->d, sp, false, nullptr, 0, 1.0);
+}
+
+extern "C" int semb_jac(semb_mesh* m, const semb_field* x, const semb_field* y, semb_field* J, semb_field* Ji,
+                        semb_field* rx, semb_field* ry, semb_field* sx, semb_field* sy) {
+  SEMB_REQUIRE(m, "null mesh");
+  semb_ctx* c = m->ctx;
+  SEMB_TRY(ctx_enter(c));
+  SEMB_TRY(check_field(m, x, "jac(x)"));
+  SEMB_TRY(check_field(m, y, "jac(y)"));
+  double *d_wr = nullptr, *d_ws = nullptr;
+  SEMB_CHECK_CUDA(cudaMalloc(&d_wr, m->nr * sizeof(double)));
+  SEMB_CHECK_CUDA(cudaMalloc(&d_ws, m->ns * sizeof(double)));
+  SEMB_CHECK_CUDA(cudaMemcpy(d_wr, m->hwr.data(), m->nr * sizeof(double), cudaMemcpyHostToDevice));
+  SEMB_CHECK_CUDA(cudaMemcpy(d_ws, m->hws.data(), m->ns * sizeof(double), cudaMemcpyHostToDevice));
+  int rc = semb_launch_geom(c, x->d, y->d, m->pitch, m->nr, m->ns, m->Ex, m->ney, m->dDr, m->dDs, d_wr, d_ws,
+                            J ? J->d : nullptr, Ji ? Ji->d : nullptr, rx ? rx->d : nullptr, ry ? ry->d : nullptr,
+                            sx ? sx->d : nullptr, sy ? sy->d : nullptr, nullptr, nullptr, nullptr, nullptr,
+                            nullptr);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(d_wr);
+  cudaFree(d_ws);
+  return rc;
+}
+
+static int gather_scalars(semb_mesh* m, double* xchg, int per_rank) {
+  semb_ctx* c = m->ctx;
+  if (c->nranks == 1) return SEMB_OK;
+  SEMB_REQUIRE(c->comm, "multi-rank reduction without a communicator");
+  SEMB_CHECK_NCCL(ncclAllGather(xchg + (size_t)c->rank * per_rank, xchg, per_rank, ncclDouble, c->comm, c->stream));
+  return SEMB_OK;
+}
+
+static int read_scal(semb_mesh* m) {
+  SEMB_CHECK_CUDA(cudaMemcpyAsync(m->h_scal, m->d_scal, sizeof(SembScal), cudaMemcpyDeviceToHost, m->ctx->stream));
+  SEMB_CHECK_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  return SEMB_OK;
+}
+
+static int reduce_common(semb_mesh* m, int which, const semb_field* a, const semb_field* b, double* result) {
+  semb_ctx* c = m->ctx;
+  SEMB_TRY(ctx_enter(c));
+  SEMB_REQUIRE(result, "reduction: null result");
+  SEMB_TRY(semb_launch_reduce(c, m, which, a->d, b ? b->d : nullptr));
+  if (c->nranks > 1) {
+    SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_red), 1));
+    SEMB_TRY(semb_launch_reduce_finalize(c, m, which));
+  }
+  SEMB_TRY(read_scal(m));
+  *result = m->h_scal->red[which];
+  return SEMB_OK;
+}
+
+extern "C" int semb_dot_mult(semb_mesh* m, const semb_field* a, const semb_field* b, double* result) {
+  SEMB_REQUIRE(m, "null mesh");
+  SEMB_TRY(check_field(m, a, "dot(a)"));
+  SEMB_TRY(check_field(m, b, "dot(b)"));
+  return reduce_common(m, 0, a, b, result);
+}
+
+extern "C" int semb_norm_inf(semb_mesh* m, const semb_field* a, double* result) {
+  SEMB_REQUIRE(m, "null mesh");
+  SEMB_TRY(check_field(m, a, "norm(a)"));
+  return reduce_common(m, 1, a, nullptr, result);
+}
+
+// ---- PCG ---------------------------------------------------------------------------------------------------------
+extern "C" int semb_pcg_begin(semb_mesh* m, const semb_pcg_opts* o, const semb_field* b, semb_field* x) {
+  SEMB_REQUIRE(m && o, "semb_pcg_begin: null argument");
+  semb_ctx* c = m->ctx;
+  SEMB_TRY(ctx_enter(c));
+  SEMB_TRY(check_field(m, b, "pcg(b)"));
+  SEMB_TRY(check_field(m, x, "pcg(x)"));
+  SEMB_TRY(check_field(m, o->nu_arr, "pcg(nu)", true));
+  SEMB_TRY(check_field(m, o->k_arr, "pcg(k)", true));
+  SEMB_TRY(check_field(m, o->M_arr, "pcg(M)", true));
+  SEMB_REQUIRE(b != x, "pcg: x must not alias b");
+  SEMB_REQUIRE(!o->precond || m->arr[SEMB_B], "pcg: diagonal preconditioner needs B");
+  MaskFlags f;
+  SEMB_TRY(parse_bc(m, o->bc, &f));
+  SEMB_TRY(ensure_tmp(m, &m->w_r));
+  SEMB_TRY(ensure_tmp(m, &m->w_p));
+  SEMB_TRY(ensure_tmp(m, &m->w_Ap));
+  m->pcg_opts = *o;
+  m->pcg_x = x;
+  long long maxiter = o->maxiter;
+  if (maxiter < 0) maxiter = (long long)m->nxl * ((long long)m->ns * m->Ey);  // length(b), pcg.jl:21
+  // reset the device scalars
+  memset(m->h_scal, 0, sizeof(SembScal));
+  m->h_scal->nranks = c->nranks;
+  m->h_scal->rank = c->rank;
+  SEMB_CHECK_CUDA(cudaMemcpyAsync(m->d_scal, m->h_scal, sizeof(SembScal), cudaMemcpyHostToDevice, c->stream));
+  SEMB_TRY(semb_launch_pcg_init(c, m, b->d, x->d, m->w_r->d, m->w_p->d, o->precond, o->prec_b0, o->tol, maxiter));
+  if (c->nranks > 1) {
+    SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_t), 2));
+    SEMB_TRY(semb_launch_pcg_finalize(c, m, 1));
+  }
+  m->pcg_active = true;
+  return SEMB_OK;
+}
+
+static int pcg_one_iteration(semb_mesh* m) {
+  semb_ctx* c = m->ctx;
+  const semb_pcg_opts& o = m->pcg_opts;
+  OpSpec sp;
+  sp.nu_arr = o.nu_arr;
+  sp.nu = o.nu;
+  sp.k_arr = o.k_arr;
+  sp.k = o.k;
+  sp.bc = o.bc;
+  sp.M_arr = o.M_arr;
+  sp.gs = true;
+  SEMB_TRY(run_operator(m, m->w_r->d, m->w_Ap->d, sp, true, m->w_p->d, o.precond, o.prec_b0));
+  if (c->nranks > 1) {
+    SEMB_TRY(semb_launch_pcg_pack_pap(c, m));
+    SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_pap), 1));
+  }
+  SEMB_TRY(semb_launch_pcg_update(c, m, m->pcg_x->d, m->w_r->d, m->w_p->d, m->w_Ap->d, o.precond, o.prec_b0));
+  if (c->nranks > 1) {
+    SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_t), 2));
+    SEMB_TRY(semb_launch_pcg_finalize(c, m, 0));
+  }
+  return SEMB_OK;
+}
+
+extern "C" int semb_pcg_iterate(semb_mesh* m, int n) {
+  SEMB_REQUIRE(m && m->pcg_active, "semb_pcg_iterate: call semb_pcg_begin first");
+  SEMB_TRY(ctx_enter(m->ctx));
+  for (int i = 0; i < n; ++i) SEMB_TRY(pcg_one_iteration(m));
+  return SEMB_OK;
+}
+
+extern "C" int semb_pcg_status(semb_mesh* m, long long* iters, double* resinf, int* done) {
+  SEMB_REQUIRE(m, "null mesh");
+  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_TRY(read_scal(m));
+  if (iters) *iters = m->h_scal->iters;
+  if (resinf) *resinf = m->h_scal->rmax;
+  if (done) *done = m->h_scal->done;
+  return m->h_scal->warned ? SEMB_NOT_CONVERGED : SEMB_OK;
+}
+
+extern "C" int semb_pcg(semb_mesh* m, const semb_pcg_opts* o, const semb_field* b, semb_field* x, long long* iters,
+                        double* resinf) {
+  SEMB_TRY(semb_pcg_begin(m, o, b, x));
+  int every = o->check_every > 0 ? o->check_every : 16;
+  for (;;) {
+    SEMB_TRY(read_scal(m));
+    if (m->h_scal->done) break;
+    if (!std::isfinite(m->h_scal->t) || !std::isfinite(m->h_scal->rmax)) {
+      semb_set_error("pcg: non-finite residual (t=%g, rmax=%g) at iteration %lld", m->h_scal->t, m->h_scal->rmax,
+                     m->h_scal->iters);
+      m->pcg_active = false;
+      return SEMB_EINVAL;
+    }
+    SEMB_TRY(semb_pcg_iterate(m, every));
+  }
+  m->pcg_active = false;
+  if (iters) *iters = m->h_scal->iters;
+  if (resinf) *resinf = m->h_scal->rmax;
+  return m->h_scal->warned ? SEMB_NOT_CONVERGED : SEMB_OK;
+}
+
+// ---- host-pointer twins -----------------------------------------------------------------------------------------
+struct TmpFields {
+  semb_mesh* m;
+  std::vector<semb_field*> f;
+  explicit TmpFields(semb_mesh* mm) : m(mm) {}
+  ~TmpFields() {
+    for (semb_field* p : f) semb_field_destroy(p);
+  }
+  int make(const double* host, semb_field** out) {
+    *out = nullptr;
+    semb_field* p = nullptr;
+    SEMB_TRY(semb_field_create(m, &p));
+    f.push_back(p);
+    if (host) SEMB_TRY(semb_field_upload(p, host));
+    *out = p;
+    return SEMB_OK;
+  }
+  int maybe(const double* host, semb_field** out) {
+    *out = nullptr;
+    return host ? make(host, out) : SEMB_OK;
+  }
+};
+
+extern "C" int semb_lapl_host(semb_mesh* m, const double* u, double* out) {
+  return semb_hlmz_host(m, u, nullptr, 1.0, nullptr, 0.0, out);
+}
+
+extern "C" int semb_hlmz_host(semb_mesh* m, const double* u, const double* nu_arr, double nu, const double* k_arr,
+                              double k, double* out) {
+  SEMB_REQUIRE(m && u && out, "hlmz_host: null argument");
+  TmpFields t(m);
+  semb_field *fu, *fo, *fn, *fk;
+  SEMB_TRY(t.make(u, &fu));
+  SEMB_TRY(t.make(nullptr, &fo));
+  SEMB_TRY(t.maybe(nu_arr, &fn));
+  SEMB_TRY(t.maybe(k_arr, &fk));
+  SEMB_TRY(semb_hlmz(m, fu, fn, nu, fk, k, fo));
+  return semb_field_download(fo, out);
+}
+
+extern "C" int semb_mass_host(semb_mesh* m, const double* u, double* out) {
+  SEMB_REQUIRE(m && u && out, "mass_host: null argument");
+  TmpFields t(m);
+  semb_field *fu, *fo;
+  SEMB_TRY(t.make(u, &fu));
+  SEMB_TRY(t.make(nullptr, &fo));
+  SEMB_TRY(semb_mass(m, fu, fo));
+  return semb_field_download(fo, out);
+}
+
+extern "C" int semb_gather_scatter_host(semb_mesh* m, const double* u, double* out) {
+  SEMB_REQUIRE(m && u && out, "gatherScatter_host: null argument");
+  TmpFields t(m);
+  semb_field *fu, *fo;
+  SEMB_TRY(t.make(u, &fu));
+  SEMB_TRY(t.make(nullptr, &fo));
+  SEMB_TRY(semb_gather_scatter(m, fu, fo));
+  return semb_field_download(fo, out);
+}
+
+extern "C" int semb_mask_host(semb_mesh* m, const double* u, const double* M, double* out) {
+  SEMB_REQUIRE(m && u && out, "mask_host: null argument");
+  TmpFields t(m);
+  semb_field *fu, *fo, *fm;
+  SEMB_TRY(t.make(u, &fu));
+  SEMB_TRY(t.make(nullptr, &fo));
+  SEMB_TRY(t.maybe(M, &fm));
+  SEMB_TRY(semb_mask(m, fu, fm, fo));
+  return semb_field_download(fo, out);
+}
+
+extern "C" int semb_oplhs_host(semb_mesh* m, const double* u, const double* nu_arr, double nu, const double* k_arr,
+                               double k, const char* bc, const double* M_arr, double* out) {
+  SEMB_REQUIRE(m && u && out, "oplhs_host: null argument");
+  TmpFields t(m);
+  semb_field *fu, *fo, *fn, *fk, *fm;
+  SEMB_TRY(t.make(u, &fu));
+  SEMB_TRY(t.make(nullptr, &fo));
+  SEMB_TRY(t.maybe(nu_arr, &fn));
+  SEMB_TRY(t.maybe(k_arr, &fk));
+  SEMB_TRY(t.maybe(M_arr, &fm));
+  SEMB_TRY(semb_oplhs(m, fu, fn, nu, fk, k, bc, fm, fo));
+  return semb_field_download(fo, out);
+}
+
+extern "C" int semb_pcg_host(semb_mesh* m, const semb_pcg_opts* o, const double* nu_arr, const double* k_arr,
+                             const double* M_arr, const double* b, double* x, long long* iters, double* resinf) {
+  SEMB_REQUIRE(m && o && b && x, "pcg_host: null argument");
+  TmpFields t(m);
+  semb_field *fb, *fx, *fn, *fk, *fm;
+  SEMB_TRY(t.make(b, &fb));
+  SEMB_TRY(t.make(nullptr, &fx));
+  SEMB_TRY(t.maybe(nu_arr, &fn));
+  SEMB_TRY(t.maybe(k_arr, &fk));
+  SEMB_TRY(t.maybe(M_arr, &fm));
+  semb_pcg_opts oo = *o;
+  oo.nu_arr = fn;
+  oo.k_arr = fk;
+  oo.M_arr = fm;
+  int rc = semb_pcg(m, &oo, fb, fx, iters, resinf);
+  if (rc < 0) return rc;
+  SEMB_TRY(semb_field_download(fx, x));
+  return rc;
+}
+
+extern "C" int semb_abu_host(semb_ctx* c, const double* As, int ma, int na, const double* Br, int mb, int nb,
+                             const double* u, int mrows, int ncols, double* out) {
+  SEMB_TRY(ctx_enter(c));
+  SEMB_REQUIRE(u && out && mrows >= 1 && ncols >= 1, "ABu: bad u");
+  const bool hasB = Br && mb > 0 && nb > 0, hasA = As && ma > 0 && na > 0;
+  // Julia: Int(m*mb/nb) / Int(Ey*ma) throw InexactError when not integral (ABu.jl:16,26)
+  SEMB_REQUIRE(!hasB || mrows % nb == 0, "ABu: InexactError: rows %d not a multiple of size(Br,2)=%d", mrows, nb);
+  SEMB_REQUIRE(!hasA || ncols % na == 0, "ABu: InexactError: cols %d not a multiple of size(As,2)=%d", ncols, na);
+  const int m1 = hasB ? mrows / nb * mb : mrows;
+  const int n1 = hasA ? ncols / na * ma : ncols;
+  double *du = nullptr, *dt = nullptr, *dout = nullptr, *dA = nullptr, *dB = nullptr;
+  int rc = SEMB_OK;
+  auto body = [&]() -> int {
+    SEMB_CHECK_CUDA(cudaMalloc(&du, (size_t)mrows * ncols * sizeof(double)));
+    SEMB_CHECK_CUDA(cudaMemcpyAsync(du, u, (size_t)mrows * ncols * sizeof(double), cudaMemcpyHostToDevice,
+                                    c->stream));
+    const double* cur = du;
+    if (hasB) {
+      SEMB_CHECK_CUDA(cudaMalloc(&dB, (size_t)mb * nb * sizeof(double)));
+      SEMB_CHECK_CUDA(cudaMemcpyAsync(dB, Br, (size_t)mb * nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      SEMB_CHECK_CUDA(cudaMalloc(&dt, (size_t)m1 * ncols * sizeof(double)));
+      SEMB_TRY(semb_launch_abu_r(c, dB, mb, nb, cur, mrows, ncols, dt));
+      cur = dt;
+    }
+    if (hasA) {
+      SEMB_CHECK_CUDA(cudaMalloc(&dA, (size_t)ma * na * sizeof(double)));
+      SEMB_CHECK_CUDA(cudaMemcpyAsync(dA, As, (size_t)ma * na * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      SEMB_CHECK_CUDA(cudaMalloc(&dout, (size_t)m1 * n1 * sizeof(double)));
+      SEMB_TRY(semb_launch_abu_s(c, dA, ma, na, cur, m1, ncols, dout));
+      cur = dout;
+    }
+    SEMB_CHECK_CUDA(cudaMemcpyAsync(out, cur, (size_t)m1 * n1 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+    return SEMB_OK;
+  };
+  rc = body();
+  cudaFree(du);
+  cudaFree(dt);
+  cudaFree(dout);
+  cudaFree(dA);
+  cudaFree(dB);
+  return rc;
+}

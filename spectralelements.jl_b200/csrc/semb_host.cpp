@@ -1,0 +1,171 @@
+// Host-side 1-D set-up routines of libsemb (no GPU): Gauss-Lobatto-Legendre rule, Lagrange
+// derivative / interpolation matrices, the 1-D SEM grid, BDF/EXT coefficients, slab partition.
+// They restate (reference /root/reference/src): FastGaussQuadrature.gausslobatto as called at
+// mesh.jl:70-71; derivMat.jl:9-35; interp.jl:10-35; semmesh.jl:9-27; time.jl:31-53.
+#include <cmath>
+#include <vector>
+
+#include "../../include/semb.h"
+
+void semb_set_error(const char* fmt, ...);
+
+namespace {
+// Legendre P_n(x) and P_{n-1}(x) via Bonnet's recurrence
+void legendre_pair(int n, double x, double* pn, double* pnm1) {
+  double a = 1.0, b = x;
+  if (n == 0) {
+    *pn = 1.0;
+    *pnm1 = 0.0;
+    return;
+  }
+  for (int k = 2; k <= n; ++k) {
+    const double c = ((2.0 * k - 1.0) * x * b - (k - 1.0) * a) / k;
+    a = b;
+    b = c;
+  }
+  *pn = b;
+  *pnm1 = a;
+}
+}  // namespace
+
+extern "C" int semb_gausslobatto(int n, double* z, double* w) {
+  if (n < 2 || !z || !w) {
+    semb_set_error("semb_gausslobatto: need n >= 2 and non-null outputs");
+    return SEMB_EINVAL;
+  }
+  const int N = n - 1;
+  const double pi = 3.14159265358979323846;
+  for (int i = 0; i < n; ++i) {
+    double x = -std::cos(pi * i / N);  // Chebyshev-Gauss-Lobatto start
+    if (i > 0 && i < N) {
+      for (int it = 0; it < 100; ++it) {
+        double pn, pm;
+        legendre_pair(N, x, &pn, &pm);
+        // q = (1-x^2) P_N' = N (P_{N-1} - x P_N),  q' = -N (N+1) P_N
+        const double q = N * (pm - x * pn);
+        const double dq = -1.0 * N * (N + 1) * pn;
+        const double dx = q / dq;
+        x -= dx;
+        if (std::fabs(dx) < 1e-16) break;
+      }
+    }
+    z[i] = x;
+  }
+  z[0] = -1.0;
+  z[N] = 1.0;
+  for (int i = 0; i < n / 2; ++i) {  // enforce antisymmetry
+    const double a = 0.5 * (z[i] - z[N - i]);
+    z[i] = a;
+    z[N - i] = -a;
+  }
+  if (n % 2 == 1) z[N / 2] = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double pn, pm;
+    legendre_pair(N, z[i], &pn, &pm);
+    w[i] = 2.0 / (N * (N + 1.0) * pn * pn);
+  }
+  return SEMB_OK;
+}
+
+extern "C" int semb_deriv_mat(int n, const double* x, double* D) {
+  if (n < 1 || !x || !D) {
+    semb_set_error("semb_deriv_mat: bad arguments");
+    return SEMB_EINVAL;
+  }
+  std::vector<double> a(n, 1.0);
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j)
+      if (j != i) a[i] *= (x[i] - x[j]);
+    a[i] = 1.0 / a[i];  // barycentric weights (derivMat.jl:13-18)
+  }
+  for (int i = 0; i < n; ++i) {
+    double diag = 0.0;  // derivMat.jl:24-27: row sum of 1/(xi-xj)
+    for (int j = 0; j < n; ++j) {
+      if (j == i) continue;
+      diag += 1.0 / (x[i] - x[j]);
+      D[i + (size_t)j * n] = a[j] / (a[i] * (x[i] - x[j]));  // derivMat.jl:31
+    }
+    D[i + (size_t)i * n] = diag;
+  }
+  return SEMB_OK;
+}
+
+extern "C" int semb_interp_mat(int no, const double* xo, int ni, const double* xi, double* J) {
+  if (no < 0 || ni < 0 || (no && !xo) || (ni && !xi) || (no && ni && !J)) {
+    semb_set_error("semb_interp_mat: bad arguments");
+    return SEMB_EINVAL;
+  }
+  std::vector<double> a(ni, 1.0), s(ni, 1.0), t(ni, 1.0);
+  for (int i = 0; i < ni; ++i) {
+    for (int j = 0; j < ni; ++j)
+      if (j != i) a[i] *= (xi[i] - xi[j]);
+    a[i] = 1.0 / a[i];
+  }
+  for (int i = 0; i < no; ++i) {
+    const double x = xo[i];
+    for (int j = 1; j < ni; ++j) {  // interp.jl:27-30 prefix / suffix products
+      s[j] = s[j - 1] * (x - xi[j - 1]);
+      t[ni - 1 - j] = t[ni - j] * (x - xi[ni - j]);
+    }
+    for (int j = 0; j < ni; ++j) J[i + (size_t)j * no] = a[j] * s[j] * t[j];
+  }
+  return SEMB_OK;
+}
+
+extern "C" int semb_semmesh(int E, int n, double* z, double* w) {
+  if (E < 1 || n < 2 || !z || !w) {
+    semb_set_error("semb_semmesh: bad arguments");
+    return SEMB_EINVAL;
+  }
+  std::vector<double> z0(n), w0(n);
+  int rc = semb_gausslobatto(n, z0.data(), w0.data());
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    z0[i] = 0.5 * (z0[i] + 1.0);
+    w0[i] = 0.5 * w0[i];
+  }
+  const double step = 2.0 / E;
+  for (int e = 0; e < E; ++e) {
+    const double ze0 = (double)e * step + -1.0;
+    const double ze1 = (e + 1 == E) ? 1.0 : (double)(e + 1) * step + -1.0;
+    const double dz = ze1 - ze0;
+    for (int i = 0; i < n; ++i) {
+      z[e * n + i] = dz * z0[i] + ze0;
+      w[e * n + i] = dz * w0[i];
+    }
+  }
+  return SEMB_OK;
+}
+
+extern "C" int semb_bdf_ext_k(int nt, const double* t, int k, double* a, double* b) {
+  if (nt < 1 || !t || k < 1 || !a || !b) {
+    semb_set_error("semb_bdf_ext_k: bad arguments");
+    return SEMB_EINVAL;
+  }
+  std::vector<double> tu;  // unique(t), first-occurrence order (time.jl:32)
+  for (int i = 0; i < nt; ++i) {
+    bool seen = false;
+    for (double v : tu) seen = seen || (v == t[i]);
+    if (!seen) tu.push_back(t[i]);
+  }
+  const int kk = (int)tu.size() - 1;
+  std::vector<double> aa(kk > 0 ? kk : 0), D((size_t)(kk + 1) * (kk + 1));
+  if (kk > 0) semb_interp_mat(1, &tu[0], kk, &tu[1], aa.data());  // a = interpMat(t1, t0)
+  semb_deriv_mat(kk + 1, tu.data(), D.data());                     // b = derivMat(t)[1,:]
+  for (int i = 0; i < k; ++i) a[i] = (i < kk) ? aa[i] : 0.0;
+  for (int i = 0; i < k + 1; ++i) b[i] = (i < kk + 1) ? D[0 + (size_t)i * (kk + 1)] : 0.0;
+  if (kk == 0) a[0] = 1.0;  // steady state, time.jl:48-50
+  return SEMB_OK;
+}
+
+extern "C" int semb_partition(int Ey, int nranks, int rank, int* ey0, int* ney) {
+  if (Ey < 1 || nranks < 1 || rank < 0 || rank >= nranks || nranks > Ey) {
+    semb_set_error("semb_partition: need 1 <= nranks <= Ey and 0 <= rank < nranks (Ey=%d nranks=%d rank=%d)", Ey,
+                   nranks, rank);
+    return SEMB_EINVAL;
+  }
+  const long long lo = (long long)rank * Ey / nranks, hi = (long long)(rank + 1) * Ey / nranks;
+  if (ey0) *ey0 = (int)lo;
+  if (ney) *ney = (int)(hi - lo);
+  return SEMB_OK;
+}

@@ -1,0 +1,178 @@
+// Internal definitions of libsemb (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/semb.h"
+
+#define SEMB_MAXN 17       // largest nr == ns served by the templated strip kernel
+#define SEMB_BX 32         // elements per strip (one warp lane per element in the x-line phase)
+#define SEMB_MAX_RANKS 16
+
+void semb_set_error(const char* fmt, ...);
+
+#define SEMB_CHECK_CUDA(expr)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      semb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                     cudaGetErrorString(_e));                                              \
+      return SEMB_ECUDA;                                                                   \
+    }                                                                                      \
+  } while (0)
+
+#define SEMB_CHECK_NCCL(expr)                                                         \
+  do {                                                                                \
+    ncclResult_t _r = (expr);                                                         \
+    if (_r != ncclSuccess) {                                                          \
+      semb_set_error("NCCL error at %s:%d: %s", __FILE__, __LINE__, ncclGetErrorString(_r)); \
+      return SEMB_ENCCL;                                                              \
+    }                                                                                 \
+  } while (0)
+
+#define SEMB_REQUIRE(cond, ...)      \
+  do {                               \
+    if (!(cond)) {                   \
+      semb_set_error(__VA_ARGS__);   \
+      return SEMB_EINVAL;            \
+    }                                \
+  } while (0)
+
+#define SEMB_TRY(expr)          \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc < 0) return _rc;    \
+  } while (0)
+
+// Device-resident PCG / reduction scalars.  One per mesh.
+struct SembScal {
+  double t;        // sum(r .* h .* mult) of the current residual   (pcg.jl:45)
+  double t_prev;   // previous t (the reference recomputes it, pcg.jl:49; same bits)
+  double rmax;     // norm(r, Inf)                                    (pcg.jl:36)
+  double pap[3];   // partial sum(p .* Ap .* mult): strip kernel, x-seam kernel, y-seam kernel
+  double red[4];   // generic reduction results (dot / norm)
+  double tol;
+  long long iters;
+  long long maxiter;
+  int done;        // 1 once norm(r,Inf) <= tol or iters == maxiter
+  int warned;      // 1 if stopped by maxiter (pcg.jl:39)
+  // multi-GPU gathered scalars: slot r = rank r's local contribution
+  double xchg_pap[SEMB_MAX_RANKS];
+  double xchg_t[2 * SEMB_MAX_RANKS];  // {t_local, rmax_local} per rank
+  double xchg_red[2 * SEMB_MAX_RANKS];
+  int nranks, rank;
+};
+
+struct semb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  long long launches = 0;
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+  double* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  double* d_sync = nullptr;  // 1-double scratch for barrier
+};
+
+struct semb_field {
+  semb_mesh* mesh = nullptr;
+  double* d = nullptr;
+};
+
+struct semb_mesh {
+  semb_ctx* ctx = nullptr;
+  int nr = 0, ns = 0, Ex = 0, Ey = 0;  // Ey global
+  int ey0 = 0, ney = 0;                // this rank's slab of element rows
+  int perx = 0, pery = 0;
+  int nxl = 0, nyl = 0;                // local node counts
+  long long pitch = 0;                 // row pitch in doubles (multiple of 16)
+  size_t nalloc = 0;                   // doubles per field allocation (pitch * nyl)
+  std::vector<double> hDr, hDs, hwr, hws;  // column-major host copies
+  double* dDr = nullptr;               // device copies (row-major: D[i*n+k] = D(i,k)) for generic kernels
+  double* dDs = nullptr;
+  double* arr[SEMB_MESH_ARRAY_COUNT] = {nullptr};
+  bool fast = false;                   // nr == ns in [2, SEMB_MAXN]: templated strip kernel
+  // launch plan of the strip kernel
+  int nstrips = 0, nchunks = 0;
+  std::vector<int> h_chunk_r0;         // nchunks+1 element-row offsets
+  int* d_chunk_r0 = nullptr;
+  unsigned char* d_ystart = nullptr;   // ney+1 flags: element row r starts a y-seam (chunk / periodic / halo)
+  std::vector<unsigned char> h_ystart;
+  int nxseam = 0;                      // x seams (strip boundaries + periodic wrap): column pairs
+  int* d_xseam = nullptr;              // 2*nxseam ints (xa, xb)
+  int nyseam = 0;                      // local y seams (row pairs); halo seams handled separately
+  int* d_yseam = nullptr;              // 2*nyseam ints (ya, yb)
+  int halo_lo = 0, halo_hi = 0;        // 1 if the slab has a neighbour rank below / above
+  int rank_lo = -1, rank_hi = -1;
+  double* d_halo_lo = nullptr;         // nxl doubles each (received neighbour rows)
+  double* d_halo_hi = nullptr;
+  // reductions
+  int npartials = 0;
+  double* d_partials = nullptr;        // 3 * npartials doubles
+  unsigned* d_counters = nullptr;      // 8 tickets
+  SembScal* d_scal = nullptr;
+  SembScal* h_scal = nullptr;          // pinned mirror
+  // pcg state
+  semb_field* w_r = nullptr;
+  semb_field* w_p = nullptr;
+  semb_field* w_Ap = nullptr;
+  semb_field* w_tmp = nullptr;
+  semb_field* w_t1 = nullptr;
+  semb_field* w_t2 = nullptr;
+  semb_field* pcg_x = nullptr;
+  semb_pcg_opts pcg_opts;
+  bool pcg_active = false;
+  std::vector<semb_field*> fields;     // live fields (for leak-free destroy)
+};
+
+// Arguments shared by the operator kernels (strip kernel, seam kernels, generic kernels).
+struct OpArgs {
+  const double* u = nullptr;      // input field (PCG mode: the residual r)
+  const double* pold = nullptr;   // PCG mode: previous search direction
+  double* pout = nullptr;         // PCG mode: new search direction p = h + beta*pold
+  const double* G11 = nullptr;
+  const double* G12 = nullptr;
+  const double* G22 = nullptr;
+  const double* B = nullptr;
+  const double* nu_arr = nullptr;
+  const double* k_arr = nullptr;
+  const double* M_arr = nullptr;
+  const double* mult = nullptr;
+  double* out = nullptr;
+  const double* halo_lo = nullptr;
+  const double* halo_hi = nullptr;
+  double nu = 1.0, k = 0.0, prec_b0 = 1.0;
+  long long pitch = 0;
+  int N = 0, Ex = 0, ney = 0, nxl = 0, nyl = 0;
+  int perx = 0;
+  int gs = 0;          // 1: fused QQ^T + mask; 0: local operator only
+  int precond = 0;     // PCG mode: h = (r ./ B) ./ b0
+  int mx0 = 0, mx1 = 0, my0 = 0, my1 = 0;  // Dirichlet flags that apply to THIS slab's boundary lines
+  const int* chunk_r0 = nullptr;
+  int nchunks = 0;
+  const unsigned char* ystart = nullptr;
+  const int* xseam = nullptr;
+  int nxseam = 0;
+  const int* yseam = nullptr;
+  int nyseam = 0;
+  SembScal* scal = nullptr;
+  double* partials = nullptr;
+  unsigned* counters = nullptr;
+  int pcg = 0;         // 1: PCG mode (read scal, fuse p update and dot)
+};
+
+// launchers implemented in the .cu files
+int semb_launch_strip(semb_ctx* ctx, const OpArgs& a, const double* hDr, const double* hDs, int nstrips,
+                      int nchunks, bool pcg, bool massterm);
+int semb_strip_regs(int N, bool pcg, bool massterm, int* regs, int* smem, int* occ);
+
+// helpers
+static inline long long semb_pitch_for(int nxl) { return ((long long)nxl + 15) / 16 * 16; }

@@ -1,0 +1,43 @@
+// Launch wrappers of the streaming kernels in semb_vec.cu (seams, gather-scatter, mask, PCG vector
+// updates, reductions, geometry set-up, generic fallbacks).
+#pragma once
+#include "semb_internal.cuh"
+
+int semb_launch_seam_x(semb_ctx* ctx, const OpArgs& a);
+int semb_launch_seam_y(semb_ctx* ctx, const OpArgs& a, int nhalo_lo, int nhalo_hi, bool domask);
+
+int semb_launch_gs_x(semb_ctx* ctx, const double* u, double* out, long long pitch, int N, int Ex, int nxl,
+                     int nyl, int perx);
+int semb_launch_mask(semb_ctx* ctx, const double* u, const double* M, double* out, size_t n);
+int semb_launch_axpby(semb_ctx* ctx, double a, const double* x, double b, double* y, size_t n);
+int semb_launch_fill(semb_ctx* ctx, double* x, double v, long long pitch, int nxl, int nyl);
+int semb_launch_fill_random(semb_ctx* ctx, double* x, long long pitch, int nxl, int nyl, long long gnxl,
+                            long long gy0, uint64_t seed);
+int semb_launch_mult(semb_ctx* ctx, double* mult, long long pitch, int nr, int ns, int Ex, int Ey, int ey0,
+                     int ney, int perx, int pery);
+int semb_launch_mask_gen(semb_ctx* ctx, double* M, long long pitch, int nxl, int nyl, int mx0, int mx1, int my0,
+                         int my1);
+int semb_launch_grid(semb_ctx* ctx, double* x, double* y, long long pitch, int nr, int ns, int Ex, int Ey,
+                     int ey0, int ney, const double* d_z0r, const double* d_z0s, int kind, const double* params);
+int semb_launch_geom(semb_ctx* ctx, const double* x, const double* y, long long pitch, int nr, int ns, int Ex,
+                     int ney, const double* dDr, const double* dDs, const double* d_wr, const double* d_ws,
+                     double* J, double* Ji, double* rx, double* ry, double* sx, double* sy, double* B, double* Bi,
+                     double* G11, double* G12, double* G22);
+// generic (any nr, ns) local operator: two passes through wr/ws temporaries
+int semb_launch_generic_local(semb_ctx* ctx, const OpArgs& a, int nr, int ns, const double* dDr,
+                              const double* dDs, double* tmp_wr, double* tmp_ws, bool massterm);
+// reductions (deterministic): which = 0 dot_mult(a,b,mult), 1 norm_inf(a)
+int semb_launch_reduce(semb_ctx* ctx, semb_mesh* m, int which, const double* a, const double* b);
+// PCG vector kernels
+int semb_launch_pcg_init(semb_ctx* ctx, semb_mesh* m, const double* b, double* x, double* r, double* p,
+                         int precond, double prec_b0, double tol, long long maxiter);
+int semb_launch_pcg_update(semb_ctx* ctx, semb_mesh* m, double* x, double* r, const double* p, const double* Ap,
+                           int precond, double prec_b0);
+int semb_launch_pcg_dir(semb_ctx* ctx, semb_mesh* m, const double* r, double* p, int precond, double prec_b0);
+int semb_launch_mask_dot(semb_ctx* ctx, semb_mesh* m, const OpArgs& a);
+int semb_launch_pcg_pack_pap(semb_ctx* ctx, semb_mesh* m);
+int semb_launch_pcg_finalize(semb_ctx* ctx, semb_mesh* m, int first);
+int semb_launch_reduce_finalize(semb_ctx* ctx, semb_mesh* m, int which);
+// generic ABu (ABu.jl:9-37)
+int semb_launch_abu_r(semb_ctx* ctx, const double* Br, int mb, int nb, const double* u, int m, int n, double* out);
+int semb_launch_abu_s(semb_ctx* ctx, const double* As, int ma, int na, const double* u, int m, int n, double* out);

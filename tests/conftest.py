@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def sem():
+    """The product package (ctypes over libsemb.so).  Fails loudly if the library is not built."""
+    import spectralelements_jl_b200 as sem
+    return sem
+
+
+@pytest.fixture(scope="session")
+def ctx(sem):
+    c = sem.init(0)
+    yield c
+    sem.finalize()

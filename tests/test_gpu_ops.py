@@ -1,0 +1,213 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI of libsemb.so) against the CPU oracle on
+the same seeded inputs.  Tolerance: 1e-12 relative, normwise (||y - y_ref||inf / ||y_ref||inf), the
+figure BASELINE.json's north_star states for FP64 operator applies; gather-scatter, mask and mult
+are required to be BIT-exact (their sums are 2-term)."""
+import numpy as np
+import pytest
+
+import sem_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+DEFORMS = {"box": so.fixU, "wavy": so.wavy, "annulus": so.annulus}
+
+# (nr, Ex, Ey, periodic, deform)
+CASES = [
+    (9, 8, 8, (False, False), "wavy"),     # BASELINE cfg1 (8x8, order 8)
+    (8, 5, 5, (False, True), "annulus"),   # examples/p2d.jl as shipped
+    (8, 8, 8, (False, False), "box"),
+    (5, 3, 4, (True, False), "wavy"),
+    (4, 1, 1, (False, False), "wavy"),     # single element
+    (2, 3, 3, (False, False), "box"),      # smallest order
+    (13, 2, 3, (False, False), "wavy"),    # order 12 (cfg3's order)
+    (17, 2, 2, (True, True), "wavy"),      # largest templated size
+    (9, 40, 6, (False, False), "wavy"),    # two strips (strip seam + partial strip)
+    (6, 70, 3, (True, False), "wavy"),     # three strips, periodic x
+    (7, 33, 5, (False, True), "annulus"),  # strip of one element
+]
+
+
+def make_pair(sem, ctx, nr, Ex, Ey, per, deform):
+    om = so.make_mesh(nr, nr, Ex, Ey, per, DEFORMS[deform])
+    gm = sem.Mesh.from_arrays(nr, nr, Ex, Ey, per, om.Dr, om.Ds, om.G11, om.G12, om.G22, om.B, ctx=ctx)
+    return om, gm
+
+
+@pytest.mark.parametrize("nr,Ex,Ey,per,deform", CASES)
+def test_local_operators(sem, ctx, nr, Ex, Ey, per, deform):
+    om, gm = make_pair(sem, ctx, nr, Ex, Ey, per, deform)
+    try:
+        u = so.splitmix_uniform(gm.shape)
+        assert relerr(sem.lapl(u, gm), so.lapl(u, om)) < TOL
+        nu = 1.0 + 0.5 * so.splitmix_uniform(gm.shape, seed=7) ** 2
+        k = 2.0 + so.splitmix_uniform(gm.shape, seed=9)
+        assert relerr(sem.hlmz(u, 0.7, 1.3, gm), so.hlmz(u, 0.7, 1.3, om)) < TOL
+        assert relerr(sem.hlmz(u, nu, k, gm), so.hlmz(u, nu, k, om)) < TOL
+        assert relerr(sem.lapl(u, nu, gm), so.lapl(u, om, nu)) < TOL
+        assert np.array_equal(sem.mass(u, gm), so.mass(u, om))
+    finally:
+        gm.free()
+
+
+@pytest.mark.parametrize("nr,Ex,Ey,per,deform", CASES)
+def test_gather_scatter_mask_bitexact(sem, ctx, nr, Ex, Ey, per, deform):
+    om, gm = make_pair(sem, ctx, nr, Ex, Ey, per, deform)
+    try:
+        u = so.splitmix_uniform(gm.shape, seed=3)
+        assert np.array_equal(sem.gatherScatter(u, gm), so.gatherScatter(u, om))
+        assert np.array_equal(gm.mult, om.mult)
+        for bc in ("DDDD", "DDNN", "NDND", "NNNN"):
+            Mo = so.generateMask(list(bc), om)
+            Mg = sem.generateMask(list(bc), gm)
+            assert np.array_equal(Mg, Mo)
+            assert np.array_equal(sem.mask(u, Mg, gm), so.mask(u, Mo))
+        assert np.array_equal(sem.mask(u, None, gm), u)
+    finally:
+        gm.free()
+
+
+@pytest.mark.parametrize("nr,Ex,Ey,per,deform", CASES)
+def test_fused_oplhs(sem, ctx, nr, Ex, Ey, per, deform):
+    """opLHS = mask(gs(hlmz(u))) (diffusion.jl:36-45): fused strip + seam kernels vs the oracle, for
+    every seam configuration (1 chunk ... one chunk per element row)."""
+    om, gm = make_pair(sem, ctx, nr, Ex, Ey, per, deform)
+    try:
+        u = so.splitmix_uniform(gm.shape, seed=11)
+        nu = 1.0 + 0.5 * so.splitmix_uniform(gm.shape, seed=7) ** 2
+        for bc in ("DDDD", "DDNN"):
+            M = so.generateMask(list(bc), om).astype(np.float64)
+            ref0 = so.opLHS(u, 1.0, 0.0, M, om)
+            ref1 = so.opLHS(u, nu, 1.5, M, om)
+            for nch in sorted({1, 2, max(1, Ey // 2), Ey}):
+                if nch > Ey:
+                    continue
+                gm.set_chunks(nch)
+                out0 = sem.OpLHS(gm, 1.0, 0.0, bc=bc)(u)
+                assert relerr(out0, ref0) < TOL, (bc, nch)
+                out1 = sem.OpLHS(gm, nu, 1.5, M=M)(u)
+                assert relerr(out1, ref1) < TOL, (bc, nch)
+                # the result must be continuous across duplicated nodes and honour the mask exactly
+                assert np.all(out0[M == 0.0] == 0.0)
+                gsd = so.gatherScatter(out0 * om.mult, om)
+                assert relerr(gsd, out0) < 1e-14
+    finally:
+        gm.free()
+
+
+def test_fused_is_deterministic(sem, ctx):
+    om, gm = make_pair(sem, ctx, 9, 40, 8, (False, False), "wavy")
+    try:
+        u = so.splitmix_uniform(gm.shape, seed=5)
+        a = sem.OpLHS(gm, 1.0, 0.0, bc="DDDD")(u)
+        for _ in range(3):
+            assert np.array_equal(sem.OpLHS(gm, 1.0, 0.0, bc="DDDD")(u), a)
+        # chunking must not change a single bit (interface sums are commutative 2-term sums)
+        gm.set_chunks(4)
+        assert np.array_equal(sem.OpLHS(gm, 1.0, 0.0, bc="DDDD")(u), a)
+    finally:
+        gm.free()
+
+
+@pytest.mark.parametrize("nr,ns,Ex,Ey,per", [(5, 7, 3, 2, (False, False)), (8, 6, 4, 3, (True, True)),
+                                            (20, 20, 2, 2, (False, False))])
+def test_generic_path(sem, ctx, nr, ns, Ex, Ey, per):
+    """nr != ns (or nr > 17) takes the generic kernels: same contract."""
+    om = so.make_mesh(nr, ns, Ex, Ey, per, so.wavy)
+    gm = sem.Mesh.from_arrays(nr, ns, Ex, Ey, per, om.Dr, om.Ds, om.G11, om.G12, om.G22, om.B, ctx=ctx)
+    try:
+        assert gm.plan()["fast"] == 0
+        u = so.splitmix_uniform(gm.shape, seed=13)
+        assert relerr(sem.lapl(u, gm), so.lapl(u, om)) < TOL
+        assert relerr(sem.hlmz(u, 0.5, 2.0, gm), so.hlmz(u, 0.5, 2.0, om)) < TOL
+        assert np.array_equal(sem.gatherScatter(u, gm), so.gatherScatter(u, om))
+        M = so.generateMask(list("DDDD"), om).astype(np.float64)
+        assert relerr(sem.OpLHS(gm, 1.0, 0.3, bc="DDDD")(u), so.opLHS(u, 1.0, 0.3, M, om)) < TOL
+    finally:
+        gm.free()
+
+
+@pytest.mark.parametrize("nr,Ex,Ey,per,deform", [(9, 8, 8, (False, False), "wavy"),
+                                                 (8, 5, 5, (False, True), "annulus"),
+                                                 (5, 3, 4, (True, False), "box")])
+def test_mesh_geometry(sem, ctx, nr, Ex, Ey, per, deform):
+    """Mesh(...) with a host deform closure: jac + B/G factors computed on device (jac.jl, mesh.jl:114-123).
+    Differentiating coordinates amplifies rounding by ~N^2*Ex, hence the looser (still tiny) bound."""
+    om = so.make_mesh(nr, nr, Ex, Ey, per, DEFORMS[deform])
+    fn = {"box": sem.fixU, "wavy": sem.wavy, "annulus": sem.annulus}[deform]
+    gm = sem.Mesh(nr, nr, Ex, Ey, per, fn, ctx=ctx)
+    try:
+        for name in ("x", "y"):
+            assert relerr(getattr(gm, name), getattr(om, name)) < 1e-15
+        for name in ("Jac", "Jaci", "rx", "ry", "sx", "sy", "B", "Bi", "G11", "G12", "G22"):
+            assert relerr(getattr(gm, name), getattr(om, name)) < 2e-12, name
+        assert np.array_equal(gm.mult, om.mult)
+        J, Ji, rx, ry, sx, sy = sem.jac(om.x, om.y, om.Dr, om.Ds, msh=gm)
+        assert relerr(J, om.Jac) < 2e-12 and relerr(sy, om.sy) < 2e-12
+        # built-in device deformation agrees with the host closure path
+        gd = sem.Mesh(nr, nr, Ex, Ey, per, {"box": "identity"}.get(deform, deform), ctx=ctx)
+        try:
+            for name in ("x", "y", "G11", "G12", "G22", "B"):
+                assert relerr(getattr(gd, name), getattr(om, name)) < 5e-12, name
+        finally:
+            gd.free()
+    finally:
+        gm.free()
+
+
+def test_abu_generic(sem, ctx):
+    """ABu(As,Br,u), ABu.jl:9-37, rectangular blocks and identities."""
+    rng = np.random.default_rng(0)
+    u = np.asfortranarray(rng.standard_normal((24, 18)))
+    Br = rng.standard_normal((5, 8))   # 8-row chunks -> 5
+    As = rng.standard_normal((4, 6))   # 6-col chunks -> 4
+    for A, B in ((As, Br), (so.EMPTY, Br), (As, so.EMPTY), (so.EMPTY, so.EMPTY)):
+        ref = so.ABu(A, B, u)
+        out = sem.ABu(A, B, u, ctx=ctx)
+        assert out.shape == ref.shape
+        assert relerr(out, ref) < TOL if ref.size else True
+    with pytest.raises(ValueError):
+        sem.ABu(so.EMPTY, rng.standard_normal((5, 7)), u, ctx=ctx)
+    # dense-QQt gather-scatter through ABu, gatherScatter.jl:13
+    om = so.make_mesh(5, 5, 3, 3, (False, True), so.wavy)
+    v = so.splitmix_uniform((15, 15))
+    assert np.array_equal(sem.gatherScatter(v, om.QQtx, om.QQty), so.gatherScatter(v, om.QQtx, om.QQty))
+
+
+def test_reductions(sem, ctx):
+    om, gm = make_pair(sem, ctx, 9, 8, 8, (False, False), "wavy")
+    try:
+        a = so.splitmix_uniform(gm.shape, seed=1)
+        b = so.splitmix_uniform(gm.shape, seed=2)
+        fa, fb = gm.field(a), gm.field(b)
+        ref = float(np.sum(a * b * om.mult))
+        assert abs(gm.dot_mult(fa, fb) - ref) <= 1e-13 * np.sum(np.abs(a * b * om.mult))
+        assert gm.norm_inf(fa) == float(np.max(np.abs(a)))
+        # deterministic: same bits every time
+        d0 = gm.dot_mult(fa, fb)
+        assert all(gm.dot_mult(fa, fb) == d0 for _ in range(3))
+        # device random fill reproduces the portable splitmix stream bit for bit
+        fr = gm.field().fill_random(0x5EED)
+        assert np.array_equal(fr.download(), so.splitmix_uniform(gm.shape, seed=0x5EED))
+    finally:
+        gm.free()
+
+
+def test_errors(sem, ctx):
+    om, gm = make_pair(sem, ctx, 4, 2, 2, (False, False), "box")
+    try:
+        with pytest.raises(ValueError):
+            sem.lapl(np.zeros((3, 3)), gm)  # DimensionMismatch
+        with pytest.raises(sem.SembError):
+            f = gm.field()
+            gm.lapl_device(f, f)  # aliasing
+        with pytest.raises(TypeError):
+            sem.pcg(np.zeros(gm.shape), lambda v: v)  # host closure: no CPU fallback
+    finally:
+        gm.free()
