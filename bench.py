@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SEM matrix-free operator hot path (BASELINE.json metric:
+"Laplacian+QQ^T apply GDOF/s and PCG iters/sec at 1/2/4/8 B200 (% HBM roof)").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl semb|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is ONE fused operator apply  out = mask(QQ^T(nu .* D^T G D u))  (opLHS, diffusion.jl:36-45,
+Poisson: nu = 1, k = 0) over the whole mesh: `value` = DOFs / time in GDOF/s with every input resident
+in HBM.  Default workload = the north-star target mesh: order 8 (nr = 9), 1112 x 1112 elements per GPU,
+wavy-deformed box, 1.0016e8 DOF per GPU (weak scaling: N GPUs hold 1112 x 1112N elements, split into
+y-slabs with an NCCL halo exchange per apply).  The same JSON line carries
+  extra.cfg2_helmholtz  BASELINE configs[1] (Helmholtz, 256x256 elements, order 8; L2 flushed per step)
+  extra.pcg             PCG iterations/s on the headline mesh (device-resident loop, pcg.jl:16-60)
+  e2e                   the same apply through the host-buffer C-ABI twin (semb_oplhs_host): pinned H2D
+                        of u + fused kernels + D2H of the result, every step
+  roofline              strip-kernel HBM roofline: 40 B/DOF algorithmic / CUDA-event kernel time
+  cpu_baseline          the NumPy/OpenBLAS restatement of the reference path (oracle/) on the host cores
+`--impl reference` times that CPU restatement alone (Julia is not installed, so the Julia reference
+itself cannot run here or on the GPU box: DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_POISSON = 40.0    # read u, G11, G12, G22; write Au
+ALG_BYTES_HELMHOLTZ = 48.0  # + B
+ALG_BYTES_PCG_ITER = 112.0
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def dist_setup(ngpus):
+    """One process per GPU; torch.distributed (NCCL) is plumbing: rendezvous, barriers, max-over-ranks."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local, dist
+
+
+def barrier(dist, ctx):
+    ctx.sync()
+    if dist is not None:
+        import torch
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+def max_over_ranks(dist, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def time_steps(ctx, dist, fn, steps, warmup, flush=False):
+    """W untimed steps, then exactly K steps bracketed by barrier+sync; CUDA events on the launch
+    stream; max over ranks.  With flush=True an L2-evicting memset precedes every step and its cost is
+    measured separately and subtracted."""
+    for _ in range(warmup):
+        if flush:
+            ctx.flush_l2()
+        fn()
+    barrier(dist, ctx)
+    ctx.timer_start()
+    for _ in range(steps):
+        if flush:
+            ctx.flush_l2()
+        fn()
+    ms = ctx.timer_stop()
+    barrier(dist, ctx)
+    if flush:
+        ctx.timer_start()
+        for _ in range(steps):
+            ctx.flush_l2()
+        ms -= ctx.timer_stop()
+    return max_over_ranks(dist, ms)
+
+
+def run_semb(args):
+    import numpy as np
+    import spectralelements_jl_b200 as sem
+
+    world, rank, local, dist = dist_setup(args.gpus)
+    ctx = sem.init(local)
+    if world > 1:
+        ctx.comm_init_torch()
+    nr, E = args.nr, args.elements
+    Ey_global = E * world if args.scaling == "weak" else E
+    msh = sem.Mesh(nr, nr, E, Ey_global, (False, False), "wavy", ctx=ctx)
+    ndof_local = msh.shape[0] * msh.shape[1]
+    ndof_global = msh.shape[0] * nr * Ey_global
+    u, out = msh.field().fill_random(0x5EED), msh.field()
+    bc = "DDDD"
+    peak, peak_src = measured_peak()
+
+    # ---- headline: fused Laplacian + QQ^T + mask apply, inputs resident in HBM ---------------------
+    apply_fn = lambda: msh.oplhs_device(u, out, nu=1.0, k=0.0, bc=bc)
+    sampler = ClockSampler(local)
+    for _ in range(args.warmup):
+        apply_fn()
+    barrier(dist, ctx)
+    sem._lib.check(ctx.lib.semb_profile_enable(ctx.h, args.steps))
+    sampler.start()
+    l0 = ctx.launch_count()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        apply_fn()
+    ms = ctx.timer_stop()
+    barrier(dist, ctx)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    kms, kn = C.c_double(), C.c_int()
+    ctx.lib.semb_profile_read(ctx.h, C.byref(kms), C.byref(kn))
+    ctx.lib.semb_profile_enable(ctx.h, 0)
+    ms = max_over_ranks(dist, ms)
+    ms_per_step = ms / args.steps
+    value = ndof_global / (ms_per_step * 1e-3) / 1e9
+    strip_ms = kms.value / max(kn.value, 1)
+    achieved = ALG_BYTES_POISSON * ndof_local / (strip_ms * 1e-3) / 1e9
+
+    extra = {}
+    # ---- PCG iterations/s on the same mesh (device-resident loop) -------------------------------------
+    if not args.skip_pcg:
+        b, x, rhs = msh.field().fill(1.0), msh.field(), msh.field()
+        msh.mass_device(b, rhs)           # B .* f, f = 1          (diffusion.jl:55)
+        msh.mask_bc_device(rhs, bc, b)    # mask(rhs, M)            (diffusion.jl:62)
+        msh.gs_device(b, rhs)             # gatherScatter(rhs, msh) (diffusion.jl:63)
+        msh.pcg_begin(rhs, x, nu=1.0, k=0.0, bc=bc, tol=0.0, maxiter=10 ** 9)
+        pcg_fn = lambda: msh.pcg_iterate(1)
+        for _ in range(args.warmup):
+            pcg_fn()
+        nit = max(min(args.steps, 100), 10)
+        barrier(dist, ctx)
+        ctx.timer_start()
+        msh.pcg_iterate(nit)
+        pms = max_over_ranks(dist, ctx.timer_stop()) / nit
+        barrier(dist, ctx)
+        extra["pcg"] = {"iters_per_s": 1e3 / pms, "ms_per_iter": pms, "gdof_iter_per_s": ndof_global / (pms * 1e-3) / 1e9,
+                        "hbm_frac_112B": ALG_BYTES_PCG_ITER * ndof_local / (pms * 1e-3) / 1e9 / peak}
+        for f in (b, x, rhs):
+            f.free()
+
+    # ---- end to end through the host-buffer C-ABI twin (pinned host memory) --------------------------
+    e2e = None
+    if not args.skip_e2e:
+        nbytes = ndof_local * 8
+        hp_in, hp_out = C.c_void_p(), C.c_void_p()
+        sem._lib.check(ctx.lib.semb_alloc_pinned(nbytes, C.byref(hp_in)))
+        sem._lib.check(ctx.lib.semb_alloc_pinned(nbytes, C.byref(hp_out)))
+        hin = np.ctypeslib.as_array(C.cast(hp_in, C.POINTER(C.c_double)), shape=(ndof_local,))
+        hin[:] = 0.25
+        din, dout = C.cast(hp_in, C.POINTER(C.c_double)), C.cast(hp_out, C.POINTER(C.c_double))
+        e2e_fn = lambda: sem._lib.check(ctx.lib.semb_oplhs_host(msh.h, din, None, 1.0, None, 0.0, bc.encode(), None, dout))
+        nst = max(3, min(args.steps, 5))
+        for _ in range(2):
+            e2e_fn()
+        barrier(dist, ctx)
+        t0 = time.perf_counter()
+        ctx.timer_start()
+        for _ in range(nst):
+            e2e_fn()
+        ems_dev = ctx.timer_stop()
+        ems = max(ems_dev, (time.perf_counter() - t0) * 1e3)  # host-blocking calls: wall clock bounds it
+        ems = max_over_ranks(dist, ems) / nst
+        e2e = {"value": ndof_global / (ems * 1e-3) / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": nbytes * world,
+               "d2h_bytes_per_step": nbytes * world, "ms_per_step": ems,
+               "api": "semb_oplhs_host (C ABI host-buffer twin of opLHS), pinned host buffers"}
+        ctx.lib.semb_free_pinned(hp_in)
+        ctx.lib.semb_free_pinned(hp_out)
+
+    # ---- BASELINE configs[1]: Helmholtz, 256x256 elements, order 8, 1 GPU (L2 flushed per step) --------
+    if rank == 0 and world == 1 and not args.skip_cfg2:
+        m2 = sem.Mesh(9, 9, 256, 256, (False, False), "wavy", ctx=ctx)
+        u2, o2 = m2.field().fill_random(1), m2.field()
+        n2 = m2.shape[0] * m2.shape[1]
+        f2 = lambda: m2.oplhs_device(u2, o2, nu=1.0, k=1.0, bc=bc)
+        n2s = max(min(args.steps, 100), 20)
+        ms2 = time_steps(ctx, None, f2, n2s, max(args.warmup, 3), flush=True) / n2s
+        extra["cfg2_helmholtz"] = {"workload": "Helmholtz opLHS, 256x256 elements, order 8, wavy box, 5308416 DOF",
+                                   "gdof_per_s": n2 / (ms2 * 1e-3) / 1e9, "ms_per_apply": ms2,
+                                   "hbm_frac_48B": ALG_BYTES_HELMHOLTZ * n2 / (ms2 * 1e-3) / 1e9 / peak,
+                                   "l2": "flushed before every apply (256 MB memset, cost subtracted)"}
+        m2.free()
+
+    # ---- CPU baseline beside it (rank 0, N = 1): bounded sample of the same workload -------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cpu = cpu_reference(nr, E, sample_rows=args.cpu_rows, reps=2)
+
+    plan = msh.plan()
+    if rank == 0:
+        line = {
+            "metric": "laplacian_gs_mask_apply_throughput", "value": value, "unit": "GDOF/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "fused Laplacian+QQ^T+mask apply (opLHS, Poisson nu=1 k=0, bc DDDD), order %d "
+                                   "(nr=%d), %dx%d elements per GPU, wavy-deformed box, %d DOF per GPU"
+                                   % (nr - 1, nr, E, msh.ney, ndof_local),
+                       "global_dofs": ndof_global, "partition": "y-slabs, %d rank(s), NCCL halo exchange" % world,
+                       "l2": "inputs (%.1f GB per apply) exceed the 126 MB L2" % (ALG_BYTES_POISSON * ndof_local / 1e9),
+                       "strips_x_chunks": [plan["nstrips"], plan["nchunks"]]},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "semb_strip_kernel<%d>" % nr,
+                         "algorithmic_bytes_per_dof": ALG_BYTES_POISSON, "kernel_ms": strip_ms,
+                         "kernel_share_of_step": strip_ms / ms_per_step, "peak_source": peak_src,
+                         "whole_apply_frac": ALG_BYTES_POISSON * ndof_local / (ms_per_step * 1e-3) / 1e9 / peak},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "cpu_baseline": cpu, "extra": extra,
+        }
+        print(json.dumps(line))
+    msh.free()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_reference(nr, E, sample_rows, reps):
+    """Time the oracle (NumPy/OpenBLAS restatement of the reference path) on a bounded y-slab sample of
+    the headline mesh: E x sample_rows elements, same order, same deformation, same fused opLHS."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import sem_oracle as so
+    t_setup = time.perf_counter()
+    om = so.make_mesh(nr, nr, E, sample_rows, (False, False), so.wavy, dense_qqt=False)
+    M = so.generateMask(list("DDDD"), om).astype(np.float64)
+    u = so.splitmix_uniform(om.x.shape)
+    t_setup = time.perf_counter() - t_setup
+    so.opLHS(u, 1.0, 0.0, M, om)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        so.opLHS(u, 1.0, 0.0, M, om)
+    dt = (time.perf_counter() - t0) / reps
+    try:
+        from threadpoolctl import threadpool_info
+        thr = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        thr = os.cpu_count()
+    return {"value": u.size / dt / 1e9, "unit": "GDOF/s", "cores": thr, "kind": "port",
+            "sample": "oracle/sem_oracle.py opLHS (NumPy/OpenBLAS restatement; Julia not installed) on a %dx%d-element "
+                      "y-slab of the headline mesh (%d DOF), %d applies, %.2f s each; index-form QQ^T (dense QQ^T "
+                      "does not fit); host cpu_count=%s" % (E, sample_rows, u.size, reps, dt, os.cpu_count()),
+            "seconds_per_apply_sample": dt}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (restated, oracle/) on the host cores, rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cpu = cpu_reference(args.nr, args.elements, args.cpu_rows, reps=1)
+    # K timed steps + W warm-up on the bounded sample
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import sem_oracle as so
+    om = so.make_mesh(args.nr, args.nr, args.elements, args.cpu_rows, (False, False), so.wavy, dense_qqt=False)
+    M = so.generateMask(list("DDDD"), om).astype(np.float64)
+    u = so.splitmix_uniform(om.x.shape)
+    steps, warm = min(args.steps, 5), min(args.warmup, 1)
+    for _ in range(warm):
+        so.opLHS(u, 1.0, 0.0, M, om)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        so.opLHS(u, 1.0, 0.0, M, om)
+    dt = (time.perf_counter() - t0) / steps
+    val = u.size / dt / 1e9
+    cpu["value"] = val
+    line = {"impl": "reference", "metric": "laplacian_gs_mask_apply_throughput", "value": val, "unit": "GDOF/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "fused Laplacian+QQ^T+mask apply (opLHS, Poisson), order %d (nr=%d), bounded sample: "
+                                   "%dx%d-element y-slab of the %dx%d headline mesh, throughput per DOF"
+                                   % (args.nr - 1, args.nr, args.elements, args.cpu_rows, args.elements, args.elements)},
+            "cpu_baseline": cpu,
+            "e2e": {"value": val, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference = NumPy/OpenBLAS restatement of the Julia CPU path (oracle/); Julia is not installed"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="semb", choices=["semb", "reference"])
+    ap.add_argument("--nr", type=int, default=9)
+    ap.add_argument("--elements", type=int, default=1112, help="elements per direction per GPU")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--cpu-rows", type=int, default=64, help="element rows of the CPU-baseline slab sample")
+    ap.add_argument("--skip-pcg", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cfg2", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "semb" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_semb(args)
+
+
+if __name__ == "__main__":
+    main()

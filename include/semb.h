@@ -68,6 +68,13 @@ int semb_timer_stop(semb_ctx* ctx, double* elapsed_ms); /* synchronises, returns
 int semb_launch_count(semb_ctx* ctx, long long* n);
 /* Writes >L2-size scratch to evict L2 between timed repetitions. */
 int semb_flush_l2(semb_ctx* ctx);
+/* Per-launch CUDA-event timing of the fused strip kernel (the dominant kernel): enable for up to
+ * max_launches launches (0 disables), then read the summed duration and the launch count. */
+int semb_profile_enable(semb_ctx* ctx, int max_launches);
+int semb_profile_read(semb_ctx* ctx, double* total_ms, int* launches);
+/* Page-locked host memory for the *_host twins (bench.py's end-to-end leg). */
+int semb_alloc_pinned(size_t bytes, void** p);
+int semb_free_pinned(void* p);
 
 /* ---- multi-GPU plumbing (new; the reference is single-process) ------------------ */
 /* Contiguous y-slab owned by `rank`: element rows [ey0, ey0+ney). No GPU needed. */
@@ -145,6 +152,8 @@ int semb_mass(semb_mesh* m, const semb_field* u, semb_field* out);
 int semb_gather_scatter(semb_mesh* m, const semb_field* u, semb_field* out);
 /* mask(u,M), mask.jl:10-18: out = M .* u; M = NULL copies (length(M)==0 branch). */
 int semb_mask(semb_mesh* m, const semb_field* u, const semb_field* M, semb_field* out);
+/* mask(u, generateMask(bc,msh)) without materialising M (mask.jl:14 with mesh.jl:149-175 flags). */
+int semb_mask_bc(semb_mesh* m, const semb_field* u, const char bc[4], semb_field* out);
 /* The fused unit opLHS(u,dfn), diffusion.jl:36-45 / convectionDiffusion.jl:76-85:
  * out = mask(gatherScatter(hlmz(u,nu,k,msh)), M).  Mask: bc = "DDNN"-style flags (NULL = no mask)
  * or an explicit 0/1 array M_arr (overrides bc).  One fused strip kernel + two seam kernels. */

@@ -365,6 +365,10 @@ class Mesh:
     def mask_device(self, u, M, out):
         check(self.lib.semb_mask(self.h, u.h, _fh(M), out.h))
 
+    def mask_bc_device(self, u, bc, out):
+        """out = generateMask(bc,msh) .* u without materialising the mask"""
+        check(self.lib.semb_mask_bc(self.h, u.h, _bc_bytes(bc), out.h))
+
     def oplhs_device(self, u, out, nu=1.0, k=0.0, bc=None, M=None):
         nua, nus = (nu, 1.0) if isinstance(nu, DeviceField) else (None, float(nu))
         ka, ks = (k, 0.0) if isinstance(k, DeviceField) else (None, float(k))

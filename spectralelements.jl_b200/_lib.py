@@ -45,6 +45,10 @@ _SIGS = {
     "semb_timer_stop": ([vp, c_double_p], C.c_int),
     "semb_launch_count": ([vp, c_ll_p], C.c_int),
     "semb_flush_l2": ([vp], C.c_int),
+    "semb_profile_enable": ([vp, C.c_int], C.c_int),
+    "semb_profile_read": ([vp, c_double_p, c_int_p], C.c_int),
+    "semb_alloc_pinned": ([C.c_size_t, C.POINTER(vp)], C.c_int),
+    "semb_free_pinned": ([vp], C.c_int),
     "semb_partition": ([C.c_int, C.c_int, C.c_int, c_int_p, c_int_p], C.c_int),
     "semb_comm_unique_id": ([C.c_char_p], C.c_int),
     "semb_comm_init": ([vp, C.c_int, C.c_int, C.c_char_p], C.c_int),
@@ -78,6 +82,7 @@ _SIGS = {
     "semb_mass": ([vp, vp, vp], C.c_int),
     "semb_gather_scatter": ([vp, vp, vp], C.c_int),
     "semb_mask": ([vp, vp, vp, vp], C.c_int),
+    "semb_mask_bc": ([vp, vp, C.c_char_p, vp], C.c_int),
     "semb_oplhs": ([vp, vp, vp, C.c_double, vp, C.c_double, C.c_char_p, vp, vp], C.c_int),
     "semb_jac": ([vp] * 9, C.c_int),
     "semb_dot_mult": ([vp, vp, vp, c_double_p], C.c_int),

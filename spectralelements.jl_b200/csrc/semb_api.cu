@@ -106,6 +106,7 @@ extern "C" int semb_finalize(semb_ctx* c) {
   if (c->comm) ncclCommDestroy(c->comm);
   if (c->flush_buf) cudaFree(c->flush_buf);
   if (c->d_sync) cudaFree(c->d_sync);
+  for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->stream);
@@ -154,6 +155,45 @@ extern "C" int semb_flush_l2(semb_ctx* c) {
     SEMB_CHECK_CUDA(cudaMalloc(&c->flush_buf, c->flush_bytes));
   }
   SEMB_CHECK_CUDA(cudaMemsetAsync(c->flush_buf, 0, c->flush_bytes, c->stream));
+  return SEMB_OK;
+}
+
+extern "C" int semb_profile_enable(semb_ctx* c, int max_launches) {
+  SEMB_TRY(ctx_enter(c));
+  SEMB_REQUIRE(max_launches >= 0 && max_launches <= 65536, "semb_profile_enable: 0..65536 launches");
+  while (c->prof_ev.size() < (size_t)2 * max_launches) {
+    cudaEvent_t e;
+    SEMB_CHECK_CUDA(cudaEventCreate(&e));
+    c->prof_ev.push_back(e);
+  }
+  c->prof_used = 0;
+  c->profile = max_launches > 0;
+  return SEMB_OK;
+}
+
+extern "C" int semb_profile_read(semb_ctx* c, double* total_ms, int* launches) {
+  SEMB_TRY(ctx_enter(c));
+  SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  double tot = 0.0;
+  for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
+    float f = 0.f;
+    SEMB_CHECK_CUDA(cudaEventElapsedTime(&f, c->prof_ev[i], c->prof_ev[i + 1]));
+    tot += f;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = (int)(c->prof_used / 2);
+  c->prof_used = 0;
+  return SEMB_OK;
+}
+
+extern "C" int semb_alloc_pinned(size_t bytes, void** p) {
+  SEMB_REQUIRE(p, "semb_alloc_pinned: null");
+  SEMB_CHECK_CUDA(cudaMallocHost(p, bytes));
+  return SEMB_OK;
+}
+
+extern "C" int semb_free_pinned(void* p) {
+  if (p) SEMB_CHECK_CUDA(cudaFreeHost(p));
   return SEMB_OK;
 }
 
@@ -922,6 +962,26 @@ extern "C" int semb_mask(semb_mesh* m, const semb_field* u, const semb_field* M,
   return semb_launch_mask(m->ctx, u->d, M ? M->d : nullptr, out->d, m->nalloc);
 }
 
+extern "C" int semb_mask_bc(semb_mesh* m, const semb_field* u, const char bc[4], semb_field* out) {
+  SEMB_REQUIRE(m && bc, "semb_mask_bc: null argument");
+  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_TRY(check_field(m, u, "mask(u)"));
+  SEMB_TRY(check_field(m, out, "mask(out)"));
+  if (u != out) SEMB_TRY(semb_field_copy(out, u));
+  MaskFlags f;
+  SEMB_TRY(parse_bc(m, bc, &f));
+  OpArgs a;
+  fill_common(m, a);
+  a.out = out->d;
+  a.mx0 = f.mx0;
+  a.mx1 = f.mx1;
+  a.my0 = f.my0;
+  a.my1 = f.my1;
+  a.partials = m->d_partials;
+  a.counters = m->d_counters + 0;
+  return semb_launch_mask_dot(m->ctx, m, a);
+}
+
 extern "C" int semb_oplhs(semb_mesh* m, const semb_field* u, const semb_field* nu_arr, double nu,
                           const semb_field* k_arr, double k, const char* bc, const semb_field* M_arr,
                           semb_field* out) {
@@ -1105,18 +1165,20 @@ extern "C" int semb_pcg(semb_mesh* m, const semb_pcg_opts* o, const semb_field* 
 }
 
 // ---- host-pointer twins -----------------------------------------------------------------------------------------
+// Device fields backing the *_host twins are cached on the mesh (slot order = request order), so a
+// twin call costs copies + kernels, not cudaMalloc/cudaFree.
 struct TmpFields {
   semb_mesh* m;
-  std::vector<semb_field*> f;
+  size_t next = 0;
   explicit TmpFields(semb_mesh* mm) : m(mm) {}
-  ~TmpFields() {
-    for (semb_field* p : f) semb_field_destroy(p);
-  }
   int make(const double* host, semb_field** out) {
     *out = nullptr;
-    semb_field* p = nullptr;
-    SEMB_TRY(semb_field_create(m, &p));
-    f.push_back(p);
+    if (next >= m->host_tmp.size()) {
+      semb_field* p = nullptr;
+      SEMB_TRY(semb_field_create(m, &p));
+      m->host_tmp.push_back(p);
+    }
+    semb_field* p = m->host_tmp[next++];
     if (host) SEMB_TRY(semb_field_upload(p, host));
     *out = p;
     return SEMB_OK;

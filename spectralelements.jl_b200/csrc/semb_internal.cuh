@@ -80,6 +80,10 @@ struct semb_ctx {
   double* flush_buf = nullptr;
   size_t flush_bytes = 0;
   double* d_sync = nullptr;  // 1-double scratch for barrier
+  // optional per-kernel timing of the strip kernel (bench.py's roofline leg)
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
+  size_t prof_used = 0;
 };
 
 struct semb_field {
@@ -131,6 +135,7 @@ struct semb_mesh {
   semb_pcg_opts pcg_opts;
   bool pcg_active = false;
   std::vector<semb_field*> fields;     // live fields (for leak-free destroy)
+  std::vector<semb_field*> host_tmp;   // cached device fields of the *_host twins
 };
 
 // Arguments shared by the operator kernels (strip kernel, seam kernels, generic kernels).

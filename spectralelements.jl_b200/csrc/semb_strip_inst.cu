@@ -29,8 +29,14 @@ int launch_variant(semb_ctx* ctx, const OpArgs& a, const double* hDr, const doub
     SEMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr_done = true;
   }
+  const bool prof = ctx->profile && ctx->prof_used + 2 <= ctx->prof_ev.size();
+  if (prof) SEMB_CHECK_CUDA(cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream));
   kern<<<dim3(nstrips, nchunks), C::T, C::SMEM, ctx->stream>>>(P);
   SEMB_CHECK_CUDA(cudaGetLastError());
+  if (prof) {
+    SEMB_CHECK_CUDA(cudaEventRecord(ctx->prof_ev[ctx->prof_used + 1], ctx->stream));
+    ctx->prof_used += 2;
+  }
   ctx->launches++;
   return SEMB_OK;
 }
