@@ -276,7 +276,8 @@ static int mesh_build_plan(semb_mesh* m) {
   semb_ctx* c = m->ctx;
   const int N = m->ns;  // y-direction points per element
   m->fast = (m->nr == m->ns && m->nr >= 2 && m->nr <= SEMB_MAXN);
-  m->nstrips = (m->Ex + SEMB_BX - 1) / SEMB_BX;
+  m->bx = m->fast ? semb_strip_bx(m->nr) : 32;
+  m->nstrips = (m->Ex + m->bx - 1) / m->bx;
   int occ = 1;
   if (m->fast) SEMB_TRY(semb_strip_regs(m->nr, false, false, nullptr, nullptr, &occ));
   if (occ < 1) occ = 1;
@@ -316,8 +317,8 @@ static int mesh_build_plan(semb_mesh* m) {
   m->h_ystart[m->ney] = (m->halo_hi || wrap_local) ? 1 : 0;
   std::vector<int> xs, ys;
   for (int s = 1; s < m->nstrips; ++s) {
-    xs.push_back(s * SEMB_BX * m->nr - 1);
-    xs.push_back(s * SEMB_BX * m->nr);
+    xs.push_back(s * m->bx * m->nr - 1);
+    xs.push_back(s * m->bx * m->nr);
   }
   if (m->perx) {
     xs.push_back(m->nxl - 1);
@@ -394,6 +395,11 @@ static int mesh_new(semb_ctx* c, int nr, int ns, int Ex, int Ey, int perx, int p
   m->nyl = ns * m->ney;
   m->pitch = semb_pitch_for(m->nxl);
   m->nalloc = (size_t)m->pitch * m->nyl;
+  if (m->nalloc >= ((size_t)1 << 31)) {
+    semb_set_error("mesh: %zu doubles per field on one GPU exceeds the 2^31 index range of the kernels; use more ranks", m->nalloc);
+    delete m;
+    return SEMB_EINVAL;
+  }
   m->hDr.assign((size_t)nr * nr, 0.0);
   m->hDs.assign((size_t)ns * ns, 0.0);
   m->hwr.assign(nr, 0.0);

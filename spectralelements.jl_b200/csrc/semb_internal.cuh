@@ -11,7 +11,11 @@
 #include "../../include/semb.h"
 
 #define SEMB_MAXN 17       // largest nr == ns served by the templated strip kernel
-#define SEMB_BX 32         // elements per strip (one warp lane per element in the x-line phase)
+#define SEMB_STRIP_THREADS 256  // CTA size of the strip kernel
+// elements per strip: as many as fit the CTA, with BX*N even so that every staged row is a multiple of 16 bytes
+constexpr int semb_strip_bx(int n) {
+  return ((SEMB_STRIP_THREADS / n) * n) % 2 == 0 ? SEMB_STRIP_THREADS / n : SEMB_STRIP_THREADS / n - 1;
+}
 #define SEMB_MAX_RANKS 16
 
 void semb_set_error(const char* fmt, ...);
@@ -105,6 +109,7 @@ struct semb_mesh {
   double* arr[SEMB_MESH_ARRAY_COUNT] = {nullptr};
   bool fast = false;                   // nr == ns in [2, SEMB_MAXN]: templated strip kernel
   // launch plan of the strip kernel
+  int bx = 0;                          // elements per strip (SEMB_STRIP_THREADS / nr)
   int nstrips = 0, nchunks = 0;
   std::vector<int> h_chunk_r0;         // nchunks+1 element-row offsets
   int* d_chunk_r0 = nullptr;

@@ -1,7 +1,7 @@
 // Streaming kernels of libsemb: seam completion of the fused operator, stand-alone gather-scatter and
 // mask, PCG vector updates with fused deterministic reductions, geometry set-up, generic fallbacks.
 // Reference citations are to /root/reference/src.
-#include "semb_strip.cuh"  // reduction helpers
+#include "semb_reduce.cuh"
 #include "semb_vec.cuh"
 
 #define SEMB_PI 3.14159265358979323846
