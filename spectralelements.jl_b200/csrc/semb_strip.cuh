@@ -41,7 +41,8 @@ struct StripCfg {
   static constexpr int PW = BX * S;              // row pitch of the transposition buffers S1/S2 (doubles)
   static constexpr int PWS = BX * N;             // row pitch of the TMA staging buffers (dense in x)
   static constexpr int NSTAGE = 4;               // u, G11, G12, G22
-  static constexpr int SMEM_DOUBLES = 2 * N * PW + NSTAGE * N * PWS + N * 2 * BX;
+  static constexpr int NP = N + (N & 1);         // padded row length of the D tables in smem (16-byte rows)
+  static constexpr int SMEM_DOUBLES = N * PW + NSTAGE * N * PWS + N * 2 * BX + 4 * N * NP;
   static constexpr int SMEM = SMEM_DOUBLES * 8 + 64;
   static constexpr int MINB = (2 * SMEM + 2048 <= 228 * 1024) ? ((3 * SMEM + 3072 <= 228 * 1024 && N <= 6) ? 3 : 2) : 1;
 };
@@ -81,14 +82,21 @@ template <int N, bool PCGM, bool MASS>
 __global__ void __launch_bounds__(StripCfg<N>::T, StripCfg<N>::MINB)
 semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
   using C = StripCfg<N>;
-  constexpr int S = C::S, PW = C::PW, PWS = C::PWS, BX = C::BX;
+  constexpr int S = C::S, PW = C::PW, PWS = C::PWS, BX = C::BX, NP = C::NP;
   extern __shared__ __align__(128) double smem[];
-  double* S1 = smem;                    // [N][PW] transposition buffer (u, then wr)
-  double* S2 = S1 + N * PW;             // [N][PW] transposition buffer (ur, then Dr^T wr)
-  double* SU = S2 + N * PW;             // [N][PWS] staged u rows (bulk copies)
+  // [N][PW] transposition buffer, updated IN PLACE by the alternating mappings (each phase touches
+  // every location from exactly one thread): u -> Dr u -> wr -> Dr^T wr
+  double* S1 = smem;
+  double* SU = S1 + N * PW;             // [N][PWS] staged u rows (bulk copies)
   double* SG = SU + N * PWS;            // [3][N][PWS] staged G11, G12, G22 rows
   double* S3 = SG + 3 * N * PWS;        // [N][2*BX] x-interface exchange
-  uint64_t* bars = (uint64_t*)(S3 + N * 2 * BX);  // bars[0]: u stage full, bars[1]: G stage full
+  // D tables, rows padded to NP: operands of the contractions are fetched with broadcast LDS.128
+  // (kernel-parameter constants end up as LDC + R2UR pairs, one pair per FMA, on sm_100)
+  double* sDr = S3 + N * 2 * BX;        // sDr [i][m] = Dr(i,m)
+  double* sDrT = sDr + N * NP;          // sDrT[i][m] = Dr(m,i)
+  double* sDs = sDrT + N * NP;          // sDs [j][m] = Ds(j,m)
+  double* sDsT = sDs + N * NP;          // sDsT[k][j] = Ds(j,k)
+  uint64_t* bars = (uint64_t*)(sDsT + N * NP);  // bars[0]: u stage full, bars[1]: G stage full
   __shared__ double red[32];
 
   const OpArgs& a = P.a;
@@ -141,6 +149,14 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
       semb_bulk_g2s(stage + (q * N + j) * PWS, src + (size_t)(r * N + j) * pitch + x0, row_bytes, bar);
     }
   };
+  for (int q = t; q < N * NP; q += C::T) {
+    const int i = q / NP, m = q - i * NP;
+    const bool ok = m < N;
+    sDr[q] = ok ? P.Dr[i * N + m] : 0.0;
+    sDrT[q] = ok ? P.Dr[m * N + i] : 0.0;
+    sDs[q] = ok ? P.Ds[i * N + m] : 0.0;
+    sDsT[q] = ok ? P.Ds[m * N + i] : 0.0;
+  }
   if (t == 0) {
     semb_mbar_init(&bars[0], 1);
     semb_mbar_init(&bars[1], 1);
@@ -181,28 +197,26 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
       if (inB) S1[j * PW + colB] = v;
     }
     if (PCGM && r + 1 < r1) issue_p(r + 1);
-    double us[N];
+    double us[N];  // us = Ds * u along y: us[j] = sum_k Ds(j,k) u[k]
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      double s = P.Ds[j * N] * u[0];
+    for (int k = 0; k < N; ++k) {
 #pragma unroll
-      for (int k = 1; k < N; ++k) s = fma(P.Ds[j * N + k], u[k], s);
-      us[j] = s;
+      for (int j = 0; j < N; ++j) us[j] = (k == 0) ? sDsT[j] * u[0] : fma(sDsT[k * NP + j], u[k], us[j]);
     }
     __syncthreads();
     if (t < 32 && r + 1 < r1) issue_rows(r + 1, 0, 1, SU, &bars[0]);  // u stage is free: prefetch row r+1
     // ---- step 2 (A): ur = Dr * u along x -------------------------------------------------------------
     if (actA) {
-      double c[N];
+      double c[N], o[N];  // ur[m] = sum_i Dr(m,i) u[i]
 #pragma unroll
       for (int i = 0; i < N; ++i) c[i] = S1[colA + i];
 #pragma unroll
-      for (int m = 0; m < N; ++m) {
-        double s = P.Dr[m * N] * c[0];
+      for (int i = 0; i < N; ++i) {
 #pragma unroll
-        for (int i = 1; i < N; ++i) s = fma(P.Dr[m * N + i], c[i], s);
-        S2[colA + m] = s;
+        for (int m = 0; m < N; ++m) o[m] = (i == 0) ? sDrT[m] * c[0] : fma(sDrT[i * NP + m], c[i], o[m]);
       }
+#pragma unroll
+      for (int m = 0; m < N; ++m) S1[colA + m] = o[m];
     }
     __syncthreads();
     // ---- step 3 (B): geometric factors, Ds^T contraction -------------------------------------------
@@ -210,36 +224,36 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     semb_mbar_wait(&bars[1], parity);
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      const double ur = inB ? S2[j * PW + colB] : 0.0;
+      const double ur = inB ? S1[j * PW + colB] : 0.0;
       const double g11 = inB ? SG[(0 * N + j) * PWS + t] : 0.0, g12 = inB ? SG[(1 * N + j) * PWS + t] : 0.0,
                    g22 = inB ? SG[(2 * N + j) * PWS + t] : 0.0;
       const double wr = fma(g11, ur, g12 * us[j]);  // lapl.jl:75
       const double ws = fma(g12, ur, g22 * us[j]);  // lapl.jl:76
       if (inB) S1[j * PW + colB] = wr;
 #pragma unroll
-      for (int m = 0; m < N; ++m) aus[m] = (j == 0) ? P.Ds[m] * ws : fma(P.Ds[j * N + m], ws, aus[m]);
+      for (int m = 0; m < N; ++m) aus[m] = (j == 0) ? sDs[m] * ws : fma(sDs[j * NP + m], ws, aus[m]);
     }
     __syncthreads();
     if (t < 32 && r + 1 < r1) issue_rows(r + 1, 1, 3, SG, &bars[1]);  // G stage is free: prefetch row r+1
     // ---- step 4 (A): Dr^T contraction ---------------------------------------------------------------
     if (actA) {
-      double c[N];
+      double c[N], o[N];  // (Dr^T wr)[m] = sum_i Dr(i,m) wr[i]
 #pragma unroll
       for (int i = 0; i < N; ++i) c[i] = S1[colA + i];
 #pragma unroll
-      for (int m = 0; m < N; ++m) {
-        double s = P.Dr[m] * c[0];
+      for (int i = 0; i < N; ++i) {
 #pragma unroll
-        for (int i = 1; i < N; ++i) s = fma(P.Dr[i * N + m], c[i], s);
-        S2[colA + m] = s;
+        for (int m = 0; m < N; ++m) o[m] = (i == 0) ? sDr[m] * c[0] : fma(sDr[i * NP + m], c[i], o[m]);
       }
+#pragma unroll
+      for (int m = 0; m < N; ++m) S1[colA + m] = o[m];
     }
     __syncthreads();
     // ---- step 5 (B): combine, hlmz, gather-scatter, mask, store -----------------------------------
     double v[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      double lap = __dadd_rn(inB ? S2[j * PW + colB] : 0.0, aus[j]);  // lapl.jl:78
+      double lap = __dadd_rn(inB ? S1[j * PW + colB] : 0.0, aus[j]);  // lapl.jl:78
       if (a.nu_arr) {
         if (actB) lap = __dmul_rn(a.nu_arr[base + j * pitch], lap);  // hlmz.jl:15
       } else {
