@@ -34,7 +34,7 @@ __all__ = [
     "init", "finalize", "default_context", "Context", "Mesh", "DeviceField", "generateMask", "ABu", "jac", "lapl",
     "hlmz", "mass", "gatherScatter", "mask", "pcg", "pcg_b", "OpLHS", "opLHS", "Diffusion", "makeRHS_b",
     "solve_b", "evolve_b", "simulate_b", "annulus", "wavy", "fixU", "gausslobatto", "derivMat", "interpMat",
-    "semmesh", "ndgrid", "bdfExtK", "partition", "SembError",
+    "semmesh", "ndgrid", "bdfExtK", "partition", "halo_plan", "SembError",
 ]
 
 SEMB_ARR = {"x": 0, "y": 1, "Jac": 2, "Jaci": 3, "rx": 4, "ry": 5, "sx": 6, "sy": 7, "B": 8, "Bi": 9, "G11": 10,
@@ -182,6 +182,13 @@ def partition(Ey: int, nranks: int, rank: int):
     e0, ne = C.c_int(), C.c_int()
     check(_lib.load().semb_partition(Ey, nranks, rank, C.byref(e0), C.byref(ne)))
     return e0.value, ne.value
+
+
+def halo_plan(nranks: int, rank: int, pery: bool):
+    """(halo_lo, halo_hi, rank_lo, rank_hi) of a y-slab"""
+    v = [C.c_int() for _ in range(4)]
+    check(_lib.load().semb_halo_plan(nranks, rank, int(bool(pery)), *[C.byref(a) for a in v]))
+    return tuple(a.value for a in v)
 
 
 # deformation maps (user-side closures in the reference: evaluated on the host, as there)

@@ -305,10 +305,7 @@ static int mesh_build_plan(semb_mesh* m) {
   for (int k = 0; k <= m->nchunks; ++k) m->h_chunk_r0[k] = (int)((long long)k * m->ney / m->nchunks);
   // halo neighbours
   const int P = c->nranks, rk = c->rank;
-  m->halo_lo = (rk > 0) || (m->pery && P > 1);
-  m->halo_hi = (rk < P - 1) || (m->pery && P > 1);
-  m->rank_lo = (rk - 1 + P) % P;
-  m->rank_hi = (rk + 1) % P;
+  SEMB_TRY(semb_halo_plan(P, rk, m->pery, &m->halo_lo, &m->halo_hi, &m->rank_lo, &m->rank_hi));
   const bool wrap_local = m->pery && P == 1;
   // y seam flags per element row
   m->h_ystart.assign(m->ney + 1, 0);

@@ -169,3 +169,21 @@ extern "C" int semb_partition(int Ey, int nranks, int rank, int* ey0, int* ney) 
   if (ney) *ney = (int)(hi - lo);
   return SEMB_OK;
 }
+
+// Halo plan of a y-slab: which neighbour ranks exist below / above (periodic wrap included).  The
+// exchange itself (semb_api.cu: halo_exchange) posts, in this order, send(last row -> hi),
+// send(first row -> lo), recv(lo), recv(hi): with two ranks and periodic y both neighbours are the
+// same peer and the order is what pairs the messages correctly.
+extern "C" int semb_halo_plan(int nranks, int rank, int pery, int* halo_lo, int* halo_hi, int* rank_lo,
+                              int* rank_hi) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) {
+    semb_set_error("semb_halo_plan: bad nranks/rank %d/%d", nranks, rank);
+    return SEMB_EINVAL;
+  }
+  const int lo = (rank > 0) || (pery && nranks > 1), hi = (rank < nranks - 1) || (pery && nranks > 1);
+  if (halo_lo) *halo_lo = lo;
+  if (halo_hi) *halo_hi = hi;
+  if (rank_lo) *rank_lo = lo ? (rank - 1 + nranks) % nranks : -1;
+  if (rank_hi) *rank_hi = hi ? (rank + 1) % nranks : -1;
+  return SEMB_OK;
+}

@@ -1,0 +1,80 @@
+"""Multi-GPU parity check, one process per GPU (run under torchrun by test_gpu_multi.py):
+y-slab partition + NCCL halo exchange + gathered PCG scalars against the single-domain CPU oracle."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import sem_oracle as so
+import spectralelements_jl_b200 as sem
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = sem.init(local)
+    ctx.comm_init_torch()
+    fails = []
+    cases = [(9, 8, 8, (False, False), so.wavy, "DDDD"), (8, 5, 6, (False, True), so.annulus, "DDNN"),
+             (6, 40, 5, (True, True), so.wavy, "NNNN"), (5, 7, 9, (False, False), so.wavy, "DDDD")]
+    if world > 5:
+        cases = [c for c in cases if c[2] >= world] + [(9, 8, 2 * world, (False, True), so.wavy, "DDNN")]
+    for nr, Ex, Ey, per, deform, bc in cases:
+        if Ey < world:
+            continue
+        om = so.make_mesh(nr, nr, Ex, Ey, per, deform)
+        e0, ne = sem.partition(Ey, world, rank)
+        sl = slice(e0 * nr, (e0 + ne) * nr)
+        loc = lambda a: np.asfortranarray(a[:, sl])
+        gm = sem.Mesh.from_arrays(nr, nr, Ex, Ey, per, om.Dr, om.Ds, loc(om.G11), loc(om.G12), loc(om.G22), loc(om.B),
+                                  ctx=ctx)
+        tag = "nr=%d %dx%d per=%s bc=%s" % (nr, Ex, Ey, per, bc)
+        u = so.splitmix_uniform(om.x.shape, seed=21)
+        M = so.generateMask(list(bc), om).astype(np.float64)
+        if not np.array_equal(gm.mult, loc(om.mult)):
+            fails.append(tag + " mult")
+        if not np.array_equal(sem.gatherScatter(loc(u), gm), loc(so.gatherScatter(u, om))):
+            fails.append(tag + " gatherScatter not bit-exact")
+        if not np.array_equal(sem.generateMask(list(bc), gm), loc(so.generateMask(list(bc), om))):
+            fails.append(tag + " mask")
+        e = relerr(sem.OpLHS(gm, 1.0, 0.7, bc=bc)(loc(u)), loc(so.opLHS(u, 1.0, 0.7, M, om)))
+        if e > 1e-12:
+            fails.append(tag + " opLHS %g" % e)
+        # device random fill uses the GLOBAL index: the slabs tile the single-domain stream
+        if not np.array_equal(gm.field().fill_random(5).download(), loc(so.splitmix_uniform(om.x.shape, seed=5))):
+            fails.append(tag + " fill_random")
+        fa, fb = gm.field(loc(u)), gm.field(loc(M * u))
+        ref = float(np.sum(u * (M * u) * om.mult))
+        if abs(gm.dot_mult(fa, fb) - ref) > 1e-12 * abs(ref) or gm.norm_inf(fa) != float(np.max(np.abs(u))):
+            fails.append(tag + " reductions")
+        b = so.gatherScatter(so.mask(so.mass(np.ones(om.x.shape), om), M), om)
+        io, ig = {}, {}
+        kk = 0.7 if bc == "NNNN" else 0.0
+        xo = so.pcg(b, lambda v: so.opLHS(v, 1.0, kk, M, om), mult=om.mult, tol=1e-12, info=io)
+        xg = sem.pcg(loc(b), sem.OpLHS(gm, 1.0, kk, bc=bc), tol=1e-12, info=ig)
+        e = relerr(xg, loc(xo)) if np.max(np.abs(loc(xo))) > 0 else 0.0
+        if e > 1e-9 or abs(ig["iters"] - io["iters"]) > max(3, 0.05 * io["iters"]):
+            fails.append(tag + " pcg err %g iters %d vs %d" % (e, ig["iters"], io["iters"]))
+        gm.free()
+    flag = torch.tensor([len(fails)], device="cuda")
+    dist.all_reduce(flag)
+    for f in fails:
+        print("[rank %d] FAIL %s" % (rank, f), flush=True)
+    if rank == 0:
+        print("DIST_CHECK", "OK" if int(flag.item()) == 0 else "FAILED", "world", world, flush=True)
+    sem.finalize()
+    dist.destroy_process_group()
+    sys.exit(1 if int(flag.item()) else 0)
+
+
+if __name__ == "__main__":
+    main()
