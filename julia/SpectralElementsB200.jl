@@ -1,0 +1,208 @@
+#
+# SpectralElementsB200.jl -- drop-in GPU methods for SpectralElements.jl's matrix-free hot path.
+#
+# `using SpectralElements, SpectralElementsB200` adds methods with the reference's own signatures
+# (ABu, lapl, hlmz, mass, gatherScatter, mask, pcg, pcg!, opLHS, solve!) that ccall libsemb.so
+# (include/semb.h).  Host code stays in Julia; the library owns every device buffer; there is no
+# CUDA.jl kernel generation and no CPU fallback.
+#
+# NOTE: Julia is not installed in the build container, so this file is written against the C ABI and
+# syntax-reviewed, but has NOT been executed.  tests/ drive the same ABI through Python ctypes.
+#
+module SpectralElementsB200
+
+using SpectralElements
+using SpectralElements: Mesh, Diffusion, ConvectionDiffusion
+import SpectralElements: ABu, lapl, hlmz, mass, gatherScatter, mask, pcg, pcg!, opLHS, solve!
+
+const libsemb = get(ENV, "LIBSEMB", joinpath(@__DIR__, "..", "spectralelements.jl_b200", "lib", "libsemb.so"))
+
+struct SembError <: Exception
+    code::Cint
+    msg::String
+end
+
+function check(rc::Cint)
+    rc < 0 && throw(SembError(rc, unsafe_string(ccall((:semb_last_error, libsemb), Cstring, ()))))
+    return rc
+end
+
+# ---- context (one per process / GPU) ------------------------------------------------------------
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+
+function context(device::Integer = parse(Int, get(ENV, "SEMB_DEVICE", "0")))
+    if CTX[] == C_NULL
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:semb_init, libsemb), Cint, (Cint, Ref{Ptr{Cvoid}}), device, h))
+        CTX[] = h[]
+        atexit(() -> ccall((:semb_finalize, libsemb), Cint, (Ptr{Cvoid},), CTX[]))
+    end
+    return CTX[]
+end
+
+"""Join the NCCL communicator: rank 0 creates the id, the caller broadcasts it (e.g. MPI.Bcast!)."""
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:semb_comm_unique_id, libsemb), Cint, (Ptr{UInt8},), id))
+    return id
+end
+comm_init(nranks, rank, id::Vector{UInt8}) =
+    check(ccall((:semb_comm_init, libsemb), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), context(), nranks, rank, id))
+
+# ---- device mesh cache: Mesh is immutable (mesh.jl:25), so objectid keys a semb_mesh* -------------
+const MESHES = Dict{UInt,Ptr{Cvoid}}()
+
+function devmesh(msh::Mesh)
+    get!(MESHES, objectid(msh)) do
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        # the Julia Mesh already holds the operator arrays: hand them over as they are
+        check(ccall((:semb_mesh_create_arrays, libsemb), Cint,
+                    (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, Cint,
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                     Ref{Ptr{Cvoid}}),
+                    context(), msh.nr, msh.ns, msh.Ex, msh.Ey, msh.ifperiodic[1], msh.ifperiodic[2],
+                    msh.Dr, msh.Ds, msh.G11, msh.G12, msh.G22, msh.B, h))
+        h[]
+    end
+end
+
+f64(a::Array{Float64}) = a
+f64(a::AbstractArray) = convert(Array{Float64}, a)   # BitMatrix masks (mesh.jl:171) are widened here
+coef(c::Number) = (Ptr{Float64}(C_NULL), Float64(c), nothing)
+coef(c::AbstractArray) = (a = f64(c); (pointer(a), 0.0, a))
+
+# ---- operators: arrays in, fresh Array{Float64,2} out ------------------------------------------------
+# lapl(u,msh), lapl.jl:26-36
+function lapl(u::Array, msh::Mesh)
+    out = similar(u, Float64)
+    check(ccall((:semb_lapl_host, libsemb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), devmesh(msh), f64(u), out))
+    return out
+end
+
+# hlmz(u,ν,k,msh), hlmz.jl:12-19 (ν, k scalar or array); lapl(u,ν,msh), lapl.jl:38-45
+function hlmz(u::Array, ν, k, msh::Mesh)
+    out = similar(u, Float64)
+    (pν, sν, kν) = coef(ν); (pk, sk, kk) = coef(k)
+    GC.@preserve kν kk check(ccall((:semb_hlmz_host, libsemb), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}, Cdouble, Ptr{Float64}),
+        devmesh(msh), f64(u), pν, sν, pk, sk, out))
+    return out
+end
+lapl(u::Array, ν::Array, msh::Mesh) = hlmz(u, ν, 0.0, msh)
+
+# mass(u,msh), mass.jl:12-22
+function mass(u::Array, msh::Mesh)
+    out = similar(u, Float64)
+    check(ccall((:semb_mass_host, libsemb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), devmesh(msh), f64(u), out))
+    return out
+end
+
+# gatherScatter(u,msh), gatherScatter.jl:18-21
+function gatherScatter(u, msh::Mesh)
+    out = similar(u, Float64)
+    check(ccall((:semb_gather_scatter_host, libsemb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+                devmesh(msh), f64(u), out))
+    return out
+end
+
+# ABu(As,Br,u), ABu.jl:9-37 (general rectangular blocks; [] = identity)
+function ABu(As::AbstractArray, Br::AbstractArray, u::AbstractArray)
+    (m, n) = size(u)
+    (ma, na) = length(As) == 0 ? (0, 0) : size(As)
+    (mb, nb) = length(Br) == 0 ? (0, 0) : size(Br)
+    mo = length(Br) == 0 ? m : Int(m * mb / nb)      # InexactError as in ABu.jl:16
+    no = length(As) == 0 ? n : Int(n / na * ma)      # ABu.jl:26
+    out = zeros(Float64, mo, no)
+    A = length(As) == 0 ? Float64[] : f64(As); B = length(Br) == 0 ? Float64[] : f64(Br)
+    check(ccall((:semb_abu_host, libsemb), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}),
+                context(), A, ma, na, B, mb, nb, f64(u), m, n, out))
+    return out
+end
+
+# mask(u,M), mask.jl:10-18 needs the device layout of u: the mesh whose size matches is looked up
+function mask(u::Array, M::Array, msh::Mesh)
+    out = similar(u, Float64)
+    Mf = length(M) == 0 ? Float64[] : f64(M)
+    check(ccall((:semb_mask_host, libsemb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                devmesh(msh), f64(u), length(M) == 0 ? C_NULL : pointer(Mf), out))
+    return out
+end
+
+# ---- the fused unit and the device-resident Krylov loop ------------------------------------------------
+"""opLHS as a callable struct: applying it runs the fused kernel; handing it to pcg runs the whole
+loop on the device (an arbitrary Julia closure cannot execute there)."""
+struct OpLHS
+    msh::Mesh
+    ν
+    k
+    M::Array{Float64}
+end
+function (op::OpLHS)(u::Array)
+    out = similar(u, Float64)
+    (pν, sν, kν) = coef(op.ν); (pk, sk, kk) = coef(op.k)
+    GC.@preserve kν kk check(ccall((:semb_oplhs_host, libsemb), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}, Cdouble, Cstring, Ptr{Float64}, Ptr{Float64}),
+        devmesh(op.msh), f64(u), pν, sν, pk, sk, C_NULL, op.M, out))
+    return out
+end
+Base.:*(op::OpLHS, u::AbstractArray) = op(u)
+
+# opLHS(u,dfn), diffusion.jl:36-45 / convectionDiffusion.jl:76-85
+opLHS(u::Array, dfn::Diffusion) = OpLHS(dfn.msh, dfn.ν, dfn.tstep.bdfB[1], dfn.fld.M)(u)
+opLHS(u::Array, cdn::ConvectionDiffusion) = OpLHS(cdn.mshV, cdn.ν, cdn.tstep.bdfB[1], cdn.fld.M)(u)
+
+# struct semb_pcg_opts (include/semb.h)
+struct PcgOpts
+    nu::Cdouble; nu_arr::Ptr{Cvoid}
+    k::Cdouble; k_arr::Ptr{Cvoid}
+    bc::Ptr{UInt8}; M_arr::Ptr{Cvoid}
+    precond::Cint; prec_b0::Cdouble
+    tol::Cdouble; maxiter::Clonglong
+    check_every::Cint
+end
+
+"""DiagPrecond(msh,b0): opPrecond(u) = u ./ B ./ b0, convectionDiffusion.jl:87-91"""
+struct DiagPrecond
+    msh::Mesh
+    b0::Float64
+end
+
+# pcg(b,opA;opM,mult,ifv,tol,maxiter), pcg.jl:16-60 -- device-resident
+function pcg(b, opA::OpLHS; opM = nothing, mult = nothing, ifv = false, tol = 1e-8, maxiter = length(b))
+    x = zeros(Float64, size(b))
+    (pν, sν, kν) = coef(opA.ν); (pk, sk, kk) = coef(opA.k)
+    prec = opM isa DiagPrecond
+    o = Ref(PcgOpts(sν, C_NULL, sk, C_NULL, C_NULL, C_NULL, prec ? 1 : 0, prec ? opM.b0 : 1.0, tol, maxiter, 0))
+    it = Ref{Clonglong}(0); res = Ref{Cdouble}(0.0)
+    rc = GC.@preserve kν kk check(ccall((:semb_pcg_host, libsemb), Cint,
+        (Ptr{Cvoid}, Ref{PcgOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ref{Clonglong}, Ref{Cdouble}),
+        devmesh(opA.msh), o, pν, pk, opA.M, f64(b), x, it, res))
+    rc == 1 && println("warning: res:", res[])           # pcg.jl:39
+    ifv && println("PCG iter: ", it[], ", res: ", res[])   # pcg.jl:57
+    return x
+end
+function pcg!(x, b, opA::OpLHS; kw...)
+    x .= pcg(b, opA; kw...)
+    return
+end
+
+# solve!(dfn), diffusion.jl:67-77 ; solve!(cdn), convectionDiffusion.jl:112-122
+function solve!(dfn::Diffusion)
+    fld = dfn.fld
+    pcg!(fld.u, dfn.rhs, OpLHS(dfn.msh, dfn.ν, dfn.tstep.bdfB[1], fld.M); mult = dfn.msh.mult)
+    fld.u .+= fld.ub
+    return
+end
+function solve!(cdn::ConvectionDiffusion)
+    fld = cdn.fld
+    b0 = cdn.tstep.bdfB[1]
+    pcg!(fld.u, cdn.rhs, OpLHS(cdn.mshV, cdn.ν, b0, fld.M); opM = DiagPrecond(cdn.mshV, b0), mult = cdn.mshV.mult)
+    fld.u .+= fld.ub
+    return
+end
+
+export OpLHS, DiagPrecond, comm_unique_id, comm_init
+
+end # module
