@@ -23,7 +23,8 @@ STRIP_N = list(range(2, 18))
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"] + \
+    os.environ.get("SEMB_EXTRA_FLAGS", "").split()
 
 
 def _sources_hash() -> str:
@@ -45,7 +46,7 @@ def _run(cmd):
     return p.stdout + p.stderr
 
 
-def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -> str:
+def build(force: bool = False, jobs: int | None = None, verbose: bool = False, lib: str = LIB) -> str:
     os.makedirs(BUILD, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(BUILD, "stamp")

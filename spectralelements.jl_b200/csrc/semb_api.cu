@@ -838,8 +838,10 @@ static int run_operator(semb_mesh* m, const double* u, double* out, const OpSpec
                         int precond, double prec_b0) {
   semb_ctx* c = m->ctx;
   SEMB_REQUIRE(m->arr[SEMB_G11] && m->arr[SEMB_G12] && m->arr[SEMB_G22], "operator: mesh has no G11/G12/G22");
-  const bool massterm = (sp.k_arr != nullptr) || (sp.k != 0.0);
-  SEMB_REQUIRE(!massterm || m->arr[SEMB_B], "operator: mass term requested but the mesh has no B");
+  const bool hasmass = (sp.k_arr != nullptr) || (sp.k != 0.0);
+  SEMB_REQUIRE(!hasmass || m->arr[SEMB_B], "operator: mass term requested but the mesh has no B");
+  // kernel variant with general coefficients: mass term and/or array viscosity
+  const bool massterm = hasmass || (sp.nu_arr != nullptr);
   SEMB_REQUIRE(!precond || m->arr[SEMB_B], "operator: preconditioner needs B");
   OpArgs a;
   fill_common(m, a);
@@ -889,7 +891,7 @@ static int run_operator(semb_mesh* m, const double* u, double* out, const OpSpec
     OpArgs g = a;
     g.u = pcg ? p_inout : u;
     g.out = sp.gs ? m->w_tmp->d : out;
-    SEMB_TRY(semb_launch_generic_local(c, g, m->nr, m->ns, m->dDr, m->dDs, t1->d, t2->d, massterm));
+    SEMB_TRY(semb_launch_generic_local(c, g, m->nr, m->ns, m->dDr, m->dDs, t1->d, t2->d, hasmass));
     if (!sp.gs) return SEMB_OK;
     SEMB_TRY(semb_launch_gs_x(c, m->w_tmp->d, out, m->pitch, m->nr, m->Ex, m->nxl, m->nyl, m->perx));
     SEMB_TRY(halo_exchange(m, out));

@@ -78,6 +78,30 @@ __device__ __forceinline__ void semb_bulk_g2s(void* dst_smem, const void* src_gm
 }
 __device__ __forceinline__ void semb_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Source of the D operands of the contractions.  Shared-memory tables (broadcast LDS.128) keep the
+// issue slots free but load the LSU/shared pipe; kernel-parameter constants (LDC) use the constant
+// cache instead.  The y-line phases (mapping B) and x-line phases (mapping A) can choose separately.
+#ifndef SEMB_DCONST_B
+#define SEMB_DCONST_B 0
+#endif
+#ifndef SEMB_DCONST_A
+#define SEMB_DCONST_A 0
+#endif
+#if SEMB_DCONST_B
+#define DS_T(k, j) P.Ds[(j) * N + (k)]
+#define DS_(j, m) P.Ds[(j) * N + (m)]
+#else
+#define DS_T(k, j) sDsT[(k) * NP + (j)]
+#define DS_(j, m) sDs[(j) * NP + (m)]
+#endif
+#if SEMB_DCONST_A
+#define DR_T(i, m) P.Dr[(m) * N + (i)]
+#define DR_(i, m) P.Dr[(i) * N + (m)]
+#else
+#define DR_T(i, m) sDrT[(i) * NP + (m)]
+#define DR_(i, m) sDr[(i) * NP + (m)]
+#endif
+
 template <int N, bool PCGM, bool MASS>
 __global__ void __launch_bounds__(StripCfg<N>::T, StripCfg<N>::MINB)
 semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
@@ -178,15 +202,37 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
   };
   if (PCGM && r0 < r1) issue_p(r0);
 
+  // inactive threads read through clamped indices (no selects in the inner loops); they never store
+  const int tr = inB ? t : 0, colBr = inB ? colB : 0;
+  // partner column of an in-strip x interface (element stride S, N nodes per element)
+  const int slotW = xl ? 2 * eB : 2 * (eB - 1) + 1, slotR = xl ? 2 * eB + 1 : 2 * (eB - 1);
+  const bool xi = xl || xr;
+  // nu .* (Dr^T wr + Ds^T ws) + k .* (B .* u)  (lapl.jl:78, hlmz.jl:15-16), un-fused like the reference
+  auto combine = [&](double aur, double ausj, double nuj, double mj) {
+    double lap = __dmul_rn(nuj, __dadd_rn(aur, ausj));
+    if (MASS) lap = __dadd_rn(lap, mj);
+    return lap;
+  };
+
   for (int r = r0; r < r1; ++r) {
     const int base = r * N * pitch + xg;
     const uint32_t parity = (uint32_t)((r - r0) & 1);
+    // coefficient columns that are not staged: issued now, consumed in step 3
+    double bq[N], nuq[N];
+    if (MASS) {  // MASS = "general coefficients": k != 0, array k, or array nu
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const int idx = base + j * pitch;
+        bq[j] = (a.B && actB) ? a.B[idx] : 0.0;
+        nuq[j] = (a.nu_arr && actB) ? a.nu_arr[idx] : a.nu;
+      }
+    }
     // ---- step 1 (B): the column of u (p in PCG mode), Ds contraction --------------------------------
     double u[N];
     semb_mbar_wait(&bars[0], parity);
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      double v = actB ? SU[j * PWS + t] : 0.0;
+      double v = SU[j * PWS + tr];
       if (PCGM && actB) {
         const int idx = base + j * pitch;
         if (a.precond) v = (v / a.B[idx]) / a.prec_b0;  // convectionDiffusion.jl:89
@@ -201,7 +247,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
 #pragma unroll
-      for (int j = 0; j < N; ++j) us[j] = (k == 0) ? sDsT[j] * u[0] : fma(sDsT[k * NP + j], u[k], us[j]);
+      for (int j = 0; j < N; ++j) us[j] = (k == 0) ? DS_T(0, j) * u[0] : fma(DS_T(k, j), u[k], us[j]);
     }
     __syncthreads();
     if (t < 32 && r + 1 < r1) issue_rows(r + 1, 0, 1, SU, &bars[0]);  // u stage is free: prefetch row r+1
@@ -213,7 +259,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
 #pragma unroll
       for (int i = 0; i < N; ++i) {
 #pragma unroll
-        for (int m = 0; m < N; ++m) o[m] = (i == 0) ? sDrT[m] * c[0] : fma(sDrT[i * NP + m], c[i], o[m]);
+        for (int m = 0; m < N; ++m) o[m] = (i == 0) ? DR_T(0, m) * c[0] : fma(DR_T(i, m), c[i], o[m]);
       }
 #pragma unroll
       for (int m = 0; m < N; ++m) S1[colA + m] = o[m];
@@ -224,14 +270,21 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     semb_mbar_wait(&bars[1], parity);
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      const double ur = inB ? S1[j * PW + colB] : 0.0;
-      const double g11 = inB ? SG[(0 * N + j) * PWS + t] : 0.0, g12 = inB ? SG[(1 * N + j) * PWS + t] : 0.0,
-                   g22 = inB ? SG[(2 * N + j) * PWS + t] : 0.0;
+      const double ur = S1[j * PW + colBr];
+      const double g11 = SG[(0 * N + j) * PWS + tr], g12 = SG[(1 * N + j) * PWS + tr], g22 = SG[(2 * N + j) * PWS + tr];
       const double wr = fma(g11, ur, g12 * us[j]);  // lapl.jl:75
       const double ws = fma(g12, ur, g22 * us[j]);  // lapl.jl:76
       if (inB) S1[j * PW + colB] = wr;
 #pragma unroll
-      for (int m = 0; m < N; ++m) aus[m] = (j == 0) ? sDs[m] * ws : fma(sDs[j * NP + m], ws, aus[m]);
+      for (int m = 0; m < N; ++m) aus[m] = (j == 0) ? DS_(0, m) * ws : fma(DS_(j, m), ws, aus[m]);
+    }
+    double mt[N];  // k .* (B .* u), hlmz.jl:16 / mass.jl:17
+    if (MASS) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const double kk = (a.k_arr && actB) ? a.k_arr[base + j * pitch] : a.k;
+        mt[j] = __dmul_rn(kk, __dmul_rn(bq[j], u[j]));
+      }
     }
     __syncthreads();
     if (t < 32 && r + 1 < r1) issue_rows(r + 1, 1, 3, SG, &bars[1]);  // G stage is free: prefetch row r+1
@@ -243,7 +296,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
 #pragma unroll
       for (int i = 0; i < N; ++i) {
 #pragma unroll
-        for (int m = 0; m < N; ++m) o[m] = (i == 0) ? sDr[m] * c[0] : fma(sDr[i * NP + m], c[i], o[m]);
+        for (int m = 0; m < N; ++m) o[m] = (i == 0) ? DR_(0, m) * c[0] : fma(DR_(i, m), c[i], o[m]);
       }
 #pragma unroll
       for (int m = 0; m < N; ++m) S1[colA + m] = o[m];
@@ -252,20 +305,8 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     // ---- step 5 (B): combine, hlmz, gather-scatter, mask, store -----------------------------------
     double v[N];
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      double lap = __dadd_rn(inB ? S1[j * PW + colB] : 0.0, aus[j]);  // lapl.jl:78
-      if (a.nu_arr) {
-        if (actB) lap = __dmul_rn(a.nu_arr[base + j * pitch], lap);  // hlmz.jl:15
-      } else {
-        lap = __dmul_rn(a.nu, lap);
-      }
-      if (MASS && actB) {
-        const int idx = base + j * pitch;
-        const double kk = a.k_arr ? a.k_arr[idx] : a.k;
-        lap = __dadd_rn(lap, __dmul_rn(kk, __dmul_rn(a.B[idx], u[j])));  // hlmz.jl:16, mass.jl:17
-      }
-      v[j] = lap;
-    }
+    for (int j = 0; j < N; ++j)
+      v[j] = combine(S1[j * PW + colBr], aus[j], MASS ? nuq[j] : a.nu, MASS ? mt[j] : 0.0);
     if (!gs) {
       if (actB) {
 #pragma unroll
@@ -273,23 +314,15 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
       }
       continue;
     }
-    // x pairs inside the strip
-    if (xl) {
+    // x pairs inside the strip: exchange the finished local values through S3
+    if (xi) {
 #pragma unroll
-      for (int j = 0; j < N; ++j) S3[j * 2 * BX + 2 * eB] = v[j];
-    }
-    if (xr) {
-#pragma unroll
-      for (int j = 0; j < N; ++j) S3[j * 2 * BX + 2 * (eB - 1) + 1] = v[j];
+      for (int j = 0; j < N; ++j) S3[j * 2 * BX + slotW] = v[j];
     }
     __syncthreads();
-    if (xl) {
+    if (xi) {
 #pragma unroll
-      for (int j = 0; j < N; ++j) v[j] = __dadd_rn(v[j], S3[j * 2 * BX + 2 * eB + 1]);
-    }
-    if (xr) {
-#pragma unroll
-      for (int j = 0; j < N; ++j) v[j] = __dadd_rn(v[j], S3[j * 2 * BX + 2 * (eB - 1)]);
+      for (int j = 0; j < N; ++j) v[j] = __dadd_rn(v[j], S3[j * 2 * BX + slotR]);
     }
     if (!actB) continue;
     if (xs) {
