@@ -1,6 +1,7 @@
 // C-ABI entry points of libsemb.so (see include/semb.h).  Host-side orchestration only: contexts,
 // meshes, fields, the launch plan of the fused operator, the device-resident PCG loop, NCCL plumbing.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <cmath>
@@ -27,19 +28,20 @@ extern "C" int semb_version(void) { return 100; }
 #define SEMB_NPARTIALS 4096
 
 // ---- strip-kernel dispatch -----------------------------------------------------------------------------
-#define SEMB_DECL_STRIP(n)                                                                                 \
-  int semb_launch_strip_n##n(semb_ctx*, const OpArgs&, const double*, const double*, int, int, bool, bool); \
+#define SEMB_DECL_STRIP(n)                                                                                       \
+  int semb_launch_strip_n##n(semb_ctx*, const OpArgs&, const double*, const double*, int, int, bool, bool, bool); \
+  double semb_strip_defect_n##n(const double*, const double*);                                                    \
   int semb_strip_attr_n##n(bool, bool, int*, int*, int*);
 SEMB_DECL_STRIP(2) SEMB_DECL_STRIP(3) SEMB_DECL_STRIP(4) SEMB_DECL_STRIP(5) SEMB_DECL_STRIP(6) SEMB_DECL_STRIP(7)
 SEMB_DECL_STRIP(8) SEMB_DECL_STRIP(9) SEMB_DECL_STRIP(10) SEMB_DECL_STRIP(11) SEMB_DECL_STRIP(12)
 SEMB_DECL_STRIP(13) SEMB_DECL_STRIP(14) SEMB_DECL_STRIP(15) SEMB_DECL_STRIP(16) SEMB_DECL_STRIP(17)
 
 int semb_launch_strip(semb_ctx* ctx, const OpArgs& a, const double* hDr, const double* hDs, int nstrips,
-                      int nchunks, bool pcg, bool massterm) {
+                      int nchunks, bool pcg, bool massterm, bool eo) {
   switch (a.N) {
 #define SEMB_CASE(n) \
   case n:            \
-    return semb_launch_strip_n##n(ctx, a, hDr, hDs, nstrips, nchunks, pcg, massterm);
+    return semb_launch_strip_n##n(ctx, a, hDr, hDs, nstrips, nchunks, pcg, massterm, eo);
     SEMB_CASE(2) SEMB_CASE(3) SEMB_CASE(4) SEMB_CASE(5) SEMB_CASE(6) SEMB_CASE(7) SEMB_CASE(8) SEMB_CASE(9)
     SEMB_CASE(10) SEMB_CASE(11) SEMB_CASE(12) SEMB_CASE(13) SEMB_CASE(14) SEMB_CASE(15) SEMB_CASE(16)
     SEMB_CASE(17)
@@ -47,6 +49,19 @@ int semb_launch_strip(semb_ctx* ctx, const OpArgs& a, const double* hDr, const d
   }
   semb_set_error("no strip kernel for N=%d", a.N);
   return SEMB_EINVAL;
+}
+
+double semb_strip_defect(int N, const double* hDr, const double* hDs) {
+  switch (N) {
+#define SEMB_CASE(n) \
+  case n:            \
+    return semb_strip_defect_n##n(hDr, hDs);
+    SEMB_CASE(2) SEMB_CASE(3) SEMB_CASE(4) SEMB_CASE(5) SEMB_CASE(6) SEMB_CASE(7) SEMB_CASE(8) SEMB_CASE(9)
+    SEMB_CASE(10) SEMB_CASE(11) SEMB_CASE(12) SEMB_CASE(13) SEMB_CASE(14) SEMB_CASE(15) SEMB_CASE(16)
+    SEMB_CASE(17)
+#undef SEMB_CASE
+  }
+  return 1.0;
 }
 
 int semb_strip_regs(int N, bool pcg, bool massterm, int* regs, int* smem, int* occ) {
@@ -277,6 +292,8 @@ static int mesh_build_plan(semb_mesh* m) {
   const int N = m->ns;  // y-direction points per element
   m->fast = (m->nr == m->ns && m->nr >= 2 && m->nr <= SEMB_MAXN);
   m->bx = m->fast ? semb_strip_bx(m->nr) : 32;
+  // derivative matrices on symmetric nodes are centro-antisymmetric: the even-odd kernel variant applies
+  m->eo = m->fast && semb_strip_defect(m->nr, m->hDr.data(), m->hDs.data()) < 1e-12 && !getenv("SEMB_NO_EVENODD");
   m->nstrips = (m->Ex + m->bx - 1) / m->bx;
   int occ = 1;
   if (m->fast) SEMB_TRY(semb_strip_regs(m->nr, false, false, nullptr, nullptr, &occ));
@@ -587,12 +604,13 @@ extern "C" int semb_mesh_dims(semb_mesh* m, int* nr, int* ns, int* Ex, int* Ey, 
 }
 
 extern "C" int semb_mesh_plan(semb_mesh* m, int* nstrips, int* nchunks, int* nxseam, int* nyseam, int* fast) {
+  if (m && fast) *fast = 0;
   SEMB_REQUIRE(m, "null mesh");
   if (nstrips) *nstrips = m->nstrips;
   if (nchunks) *nchunks = m->nchunks;
   if (nxseam) *nxseam = m->nxseam;
   if (nyseam) *nyseam = m->nyseam;
-  if (fast) *fast = m->fast ? 1 : 0;
+  if (fast) *fast = m->fast ? (m->eo ? 2 : 1) : 0;
   return SEMB_OK;
 }
 
@@ -869,7 +887,7 @@ static int run_operator(semb_mesh* m, const double* u, double* out, const OpSpec
   if (m->fast) {
     a.partials = m->d_partials;
     a.counters = m->d_counters + 0;
-    SEMB_TRY(semb_launch_strip(c, a, m->hDr.data(), m->hDs.data(), m->nstrips, m->nchunks, pcg, massterm));
+    SEMB_TRY(semb_launch_strip(c, a, m->hDr.data(), m->hDs.data(), m->nstrips, m->nchunks, pcg, massterm, m->eo));
     if (!sp.gs) return SEMB_OK;
     a.partials = m->d_partials + m->npartials;
     a.counters = m->d_counters + 1;

@@ -108,6 +108,7 @@ struct semb_mesh {
   double* dDs = nullptr;
   double* arr[SEMB_MESH_ARRAY_COUNT] = {nullptr};
   bool fast = false;                   // nr == ns in [2, SEMB_MAXN]: templated strip kernel
+  bool eo = false;                     // Dr, Ds centro-antisymmetric: even-odd contraction variant
   // launch plan of the strip kernel
   int bx = 0;                          // elements per strip (SEMB_STRIP_THREADS / nr)
   int nstrips = 0, nchunks = 0;
@@ -181,7 +182,7 @@ struct OpArgs {
 
 // launchers implemented in the .cu files
 int semb_launch_strip(semb_ctx* ctx, const OpArgs& a, const double* hDr, const double* hDs, int nstrips,
-                      int nchunks, bool pcg, bool massterm);
+                      int nchunks, bool pcg, bool massterm, bool eo);
 int semb_strip_regs(int N, bool pcg, bool massterm, int* regs, int* smem, int* occ);
 
 // helpers

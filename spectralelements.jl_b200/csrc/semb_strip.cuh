@@ -26,12 +26,102 @@
 #pragma once
 #include "semb_reduce.cuh"
 
+// Contraction tables.  Four N x N matrices are applied per element row: A1 = Ds (y-lines of u),
+// A2 = Dr (x-lines of u), A3 = Ds^T (y-lines of ws), A4 = Dr^T (x-lines of wr).  Each is shipped to the
+// kernel as a table in the exact layout the contraction reads with broadcast LDS.128:
+//   plain:    T[k][i] = A(i,k), rows padded to NP = N + (N&1)
+//   even-odd: for centro-antisymmetric A (A(N-1-i,N-1-k) = -A(i,k), true of derivative matrices on
+//             symmetric nodes) y = A x splits into two half-size products on e_k = x_k + x_{N-1-k} and
+//             o_k = x_k - x_{N-1-k}:  y_i = Se_i + So_i, y_{N-1-i} = So_i - Se_i  (about half the FMAs
+//             and half the table loads):  TP[k][i] = (A(i,k)+A(i,N-1-k))/2, TM[k][i] = (A(i,k)-A(i,N-1-k))/2
+template <int N>
+struct StripTab {
+  static constexpr int NP = N + (N & 1);
+  static constexpr int H = N / 2, ODD = N & 1;
+  static constexpr int RP = (H + 1) & ~1;          // padded row of TP (H entries)
+  static constexpr int RM = (H + ODD + 1) & ~1;    // padded row of TM (H + ODD entries)
+  static constexpr int EOSIZE = (H + ODD) * RP + H * RM;
+  static constexpr int SIZE = N * NP;              // >= EOSIZE
+  // A is row-major A[i*N+k] = A(i,k)
+  static void fill(const double* A, bool eo, double* T) {
+    for (int q = 0; q < SIZE; ++q) T[q] = 0.0;
+    if (!eo) {
+      for (int k = 0; k < N; ++k)
+        for (int i = 0; i < N; ++i) T[k * NP + i] = A[i * N + k];
+      return;
+    }
+    double* TP = T;
+    double* TM = T + (H + ODD) * RP;
+    for (int k = 0; k < H; ++k)
+      for (int i = 0; i < H; ++i) {
+        TP[k * RP + i] = 0.5 * (A[i * N + k] + A[i * N + (N - 1 - k)]);
+        TM[k * RM + i] = 0.5 * (A[i * N + k] - A[i * N + (N - 1 - k)]);
+      }
+    if (ODD) {
+      for (int i = 0; i < H; ++i) TP[H * RP + i] = 0.5 * (A[i * N + H] - A[(N - 1 - i) * N + H]);  // mid column
+      for (int k = 0; k < H; ++k) TM[k * RM + H] = 0.5 * (A[H * N + k] - A[H * N + (N - 1 - k)]);  // mid row
+    }
+  }
+  // max_ik |A(i,k) + A(N-1-i,N-1-k)| / max|A|
+  static double antisymmetry_defect(const double* A) {
+    double d = 0.0, mx = 0.0;
+    for (int i = 0; i < N; ++i)
+      for (int k = 0; k < N; ++k) {
+        const double s = A[i * N + k] + A[(N - 1 - i) * N + (N - 1 - k)];
+        d = s < 0 ? (-s > d ? -s : d) : (s > d ? s : d);
+        const double v = A[i * N + k] < 0 ? -A[i * N + k] : A[i * N + k];
+        mx = v > mx ? v : mx;
+      }
+    return mx > 0 ? d / mx : 0.0;
+  }
+};
+
 template <int N>
 struct StripParams {
-  double Dr[N * N];  // Dr[i*N+k] = Dr(i,k)
-  double Ds[N * N];
+  double tab[4][StripTab<N>::SIZE];  // A1 = Ds, A2 = Dr, A3 = Ds^T, A4 = Dr^T (StripTab layouts)
   OpArgs a;
 };
+
+// y = A x out of registers; T is the shared-memory table of A (StripTab layout), N independent accumulators
+template <int N, bool EO>
+__device__ __forceinline__ void semb_contract(const double* __restrict__ T, const double (&x)[N], double (&y)[N]) {
+  using TB = StripTab<N>;
+  if constexpr (!EO) {
+    constexpr int NP = TB::NP;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) y[i] = (k == 0) ? T[i] * x[0] : fma(T[k * NP + i], x[k], y[i]);
+    }
+  } else {
+    constexpr int H = TB::H, ODD = TB::ODD, RP = TB::RP, RM = TB::RM;
+    const double* TP = T;
+    const double* TM = T + (H + ODD) * RP;
+    double e[H > 0 ? H : 1], o[H > 0 ? H : 1], se[H > 0 ? H : 1], so[H + ODD];
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      e[k] = x[k] + x[N - 1 - k];
+      o[k] = x[k] - x[N - 1 - k];
+    }
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+#pragma unroll
+      for (int i = 0; i < H; ++i) se[i] = (k == 0) ? TP[i] * e[0] : fma(TP[k * RP + i], e[k], se[i]);
+#pragma unroll
+      for (int i = 0; i < H + ODD; ++i) so[i] = (k == 0) ? TM[i] * o[0] : fma(TM[k * RM + i], o[k], so[i]);
+    }
+    if (ODD) {
+#pragma unroll
+      for (int i = 0; i < H; ++i) se[i] = fma(TP[H * RP + i], x[H], se[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      y[i] = so[i] + se[i];
+      y[N - 1 - i] = so[i] - se[i];
+    }
+    if (ODD) y[H] = so[H];
+  }
+}
 
 template <int N>
 struct StripCfg {
@@ -41,8 +131,7 @@ struct StripCfg {
   static constexpr int PW = BX * S;              // row pitch of the transposition buffers S1/S2 (doubles)
   static constexpr int PWS = BX * N;             // row pitch of the TMA staging buffers (dense in x)
   static constexpr int NSTAGE = 4;               // u, G11, G12, G22
-  static constexpr int NP = N + (N & 1);         // padded row length of the D tables in smem (16-byte rows)
-  static constexpr int SMEM_DOUBLES = N * PW + NSTAGE * N * PWS + N * 2 * BX + 4 * N * NP;
+  static constexpr int SMEM_DOUBLES = N * PW + NSTAGE * N * PWS + N * 2 * BX + 4 * StripTab<N>::SIZE;
   static constexpr int SMEM = SMEM_DOUBLES * 8 + 64;
   static constexpr int MINB = (2 * SMEM + 2048 <= 228 * 1024) ? ((3 * SMEM + 3072 <= 228 * 1024 && N <= 6) ? 3 : 2) : 1;
 };
@@ -78,35 +167,11 @@ __device__ __forceinline__ void semb_bulk_g2s(void* dst_smem, const void* src_gm
 }
 __device__ __forceinline__ void semb_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Source of the D operands of the contractions.  Shared-memory tables (broadcast LDS.128) keep the
-// issue slots free but load the LSU/shared pipe; kernel-parameter constants (LDC) use the constant
-// cache instead.  The y-line phases (mapping B) and x-line phases (mapping A) can choose separately.
-#ifndef SEMB_DCONST_B
-#define SEMB_DCONST_B 0
-#endif
-#ifndef SEMB_DCONST_A
-#define SEMB_DCONST_A 0
-#endif
-#if SEMB_DCONST_B
-#define DS_T(k, j) P.Ds[(j) * N + (k)]
-#define DS_(j, m) P.Ds[(j) * N + (m)]
-#else
-#define DS_T(k, j) sDsT[(k) * NP + (j)]
-#define DS_(j, m) sDs[(j) * NP + (m)]
-#endif
-#if SEMB_DCONST_A
-#define DR_T(i, m) P.Dr[(m) * N + (i)]
-#define DR_(i, m) P.Dr[(i) * N + (m)]
-#else
-#define DR_T(i, m) sDrT[(i) * NP + (m)]
-#define DR_(i, m) sDr[(i) * NP + (m)]
-#endif
-
-template <int N, bool PCGM, bool MASS>
+template <int N, bool PCGM, bool MASS, bool EO>
 __global__ void __launch_bounds__(StripCfg<N>::T, StripCfg<N>::MINB)
 semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
   using C = StripCfg<N>;
-  constexpr int S = C::S, PW = C::PW, PWS = C::PWS, BX = C::BX, NP = C::NP;
+  constexpr int S = C::S, PW = C::PW, PWS = C::PWS, BX = C::BX, TSZ = StripTab<N>::SIZE;
   extern __shared__ __align__(128) double smem[];
   // [N][PW] transposition buffer, updated IN PLACE by the alternating mappings (each phase touches
   // every location from exactly one thread): u -> Dr u -> wr -> Dr^T wr
@@ -114,13 +179,10 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
   double* SU = S1 + N * PW;             // [N][PWS] staged u rows (bulk copies)
   double* SG = SU + N * PWS;            // [3][N][PWS] staged G11, G12, G22 rows
   double* S3 = SG + 3 * N * PWS;        // [N][2*BX] x-interface exchange
-  // D tables, rows padded to NP: operands of the contractions are fetched with broadcast LDS.128
-  // (kernel-parameter constants end up as LDC + R2UR pairs, one pair per FMA, on sm_100)
-  double* sDr = S3 + N * 2 * BX;        // sDr [i][m] = Dr(i,m)
-  double* sDrT = sDr + N * NP;          // sDrT[i][m] = Dr(m,i)
-  double* sDs = sDrT + N * NP;          // sDs [j][m] = Ds(j,m)
-  double* sDsT = sDs + N * NP;          // sDsT[k][j] = Ds(j,k)
-  uint64_t* bars = (uint64_t*)(sDsT + N * NP);  // bars[0]: u stage full, bars[1]: G stage full
+  // contraction tables (StripTab layouts), fetched with broadcast LDS.128: kernel-parameter constants
+  // end up as LDC + R2UR pairs, one pair per FMA, on sm_100 (profiles/r01_strip9_r1b.txt)
+  double* sT = S3 + N * 2 * BX;         // [4][TSZ]
+  uint64_t* bars = (uint64_t*)(sT + 4 * TSZ);  // bars[0]: u stage full, bars[1]: G stage full
   __shared__ double red[32];
 
   const OpArgs& a = P.a;
@@ -173,14 +235,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
       semb_bulk_g2s(stage + (q * N + j) * PWS, src + (size_t)(r * N + j) * pitch + x0, row_bytes, bar);
     }
   };
-  for (int q = t; q < N * NP; q += C::T) {
-    const int i = q / NP, m = q - i * NP;
-    const bool ok = m < N;
-    sDr[q] = ok ? P.Dr[i * N + m] : 0.0;
-    sDrT[q] = ok ? P.Dr[m * N + i] : 0.0;
-    sDs[q] = ok ? P.Ds[i * N + m] : 0.0;
-    sDsT[q] = ok ? P.Ds[m * N + i] : 0.0;
-  }
+  for (int q = t; q < 4 * TSZ; q += C::T) sT[q] = (&P.tab[0][0])[q];
   if (t == 0) {
     semb_mbar_init(&bars[0], 1);
     semb_mbar_init(&bars[1], 1);
@@ -244,11 +299,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     }
     if (PCGM && r + 1 < r1) issue_p(r + 1);
     double us[N];  // us = Ds * u along y: us[j] = sum_k Ds(j,k) u[k]
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-#pragma unroll
-      for (int j = 0; j < N; ++j) us[j] = (k == 0) ? DS_T(0, j) * u[0] : fma(DS_T(k, j), u[k], us[j]);
-    }
+    semb_contract<N, EO>(sT + 0 * TSZ, u, us);
     __syncthreads();
     if (t < 32 && r + 1 < r1) issue_rows(r + 1, 0, 1, SU, &bars[0]);  // u stage is free: prefetch row r+1
     // ---- step 2 (A): ur = Dr * u along x -------------------------------------------------------------
@@ -256,28 +307,23 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
       double c[N], o[N];  // ur[m] = sum_i Dr(m,i) u[i]
 #pragma unroll
       for (int i = 0; i < N; ++i) c[i] = S1[colA + i];
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-#pragma unroll
-        for (int m = 0; m < N; ++m) o[m] = (i == 0) ? DR_T(0, m) * c[0] : fma(DR_T(i, m), c[i], o[m]);
-      }
+      semb_contract<N, EO>(sT + 1 * TSZ, c, o);
 #pragma unroll
       for (int m = 0; m < N; ++m) S1[colA + m] = o[m];
     }
     __syncthreads();
     // ---- step 3 (B): geometric factors, Ds^T contraction -------------------------------------------
-    double aus[N];
+    double aus[N], ws[N];
     semb_mbar_wait(&bars[1], parity);
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       const double ur = S1[j * PW + colBr];
       const double g11 = SG[(0 * N + j) * PWS + tr], g12 = SG[(1 * N + j) * PWS + tr], g22 = SG[(2 * N + j) * PWS + tr];
       const double wr = fma(g11, ur, g12 * us[j]);  // lapl.jl:75
-      const double ws = fma(g12, ur, g22 * us[j]);  // lapl.jl:76
+      ws[j] = fma(g12, ur, g22 * us[j]);            // lapl.jl:76
       if (inB) S1[j * PW + colB] = wr;
-#pragma unroll
-      for (int m = 0; m < N; ++m) aus[m] = (j == 0) ? DS_(0, m) * ws : fma(DS_(j, m), ws, aus[m]);
     }
+    semb_contract<N, EO>(sT + 2 * TSZ, ws, aus);  // (Ds^T ws)[m] = sum_j Ds(j,m) ws[j]
     double mt[N];  // k .* (B .* u), hlmz.jl:16 / mass.jl:17
     if (MASS) {
 #pragma unroll
@@ -293,11 +339,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
       double c[N], o[N];  // (Dr^T wr)[m] = sum_i Dr(i,m) wr[i]
 #pragma unroll
       for (int i = 0; i < N; ++i) c[i] = S1[colA + i];
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-#pragma unroll
-        for (int m = 0; m < N; ++m) o[m] = (i == 0) ? DR_(0, m) * c[0] : fma(DR_(i, m), c[i], o[m]);
-      }
+      semb_contract<N, EO>(sT + 3 * TSZ, c, o);
 #pragma unroll
       for (int m = 0; m < N; ++m) S1[colA + m] = o[m];
     }

@@ -12,18 +12,27 @@
 namespace {
 constexpr int N = SEMB_INST_N;
 
-template <bool PCGM, bool MASS>
+// row-major copies of Dr, Ds and their transposes from the column-major host matrices
+void row_major_set(const double* hDr, const double* hDs, double (&A)[4][N * N]) {
+  for (int i = 0; i < N; ++i)
+    for (int k = 0; k < N; ++k) {
+      A[0][i * N + k] = hDs[i + k * N];  // A1 = Ds
+      A[1][i * N + k] = hDr[i + k * N];  // A2 = Dr
+      A[2][i * N + k] = hDs[k + i * N];  // A3 = Ds^T
+      A[3][i * N + k] = hDr[k + i * N];  // A4 = Dr^T
+    }
+}
+
+template <bool PCGM, bool MASS, bool EO>
 int launch_variant(semb_ctx* ctx, const OpArgs& a, const double* hDr, const double* hDs, int nstrips,
                    int nchunks) {
   using C = StripCfg<N>;
   StripParams<N> P;
-  for (int i = 0; i < N; ++i)
-    for (int k = 0; k < N; ++k) {
-      P.Dr[i * N + k] = hDr[i + k * N];  // host copies are column-major
-      P.Ds[i * N + k] = hDs[i + k * N];
-    }
+  double A[4][N * N];
+  row_major_set(hDr, hDs, A);
+  for (int q = 0; q < 4; ++q) StripTab<N>::fill(A[q], EO, P.tab[q]);
   P.a = a;
-  auto kern = semb_strip_kernel<N, PCGM, MASS>;
+  auto kern = semb_strip_kernel<N, PCGM, MASS, EO>;
   static bool attr_done = false;
   if (!attr_done) {
     SEMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -44,7 +53,7 @@ int launch_variant(semb_ctx* ctx, const OpArgs& a, const double* hDr, const doub
 template <bool PCGM, bool MASS>
 int attr_variant(int* regs, int* smem, int* occ) {
   using C = StripCfg<N>;
-  auto kern = semb_strip_kernel<N, PCGM, MASS>;
+  auto kern = semb_strip_kernel<N, PCGM, MASS, true>;
   cudaFuncAttributes fa;
   SEMB_CHECK_CUDA(cudaFuncGetAttributes(&fa, kern));
   SEMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -59,13 +68,23 @@ int attr_variant(int* regs, int* smem, int* occ) {
 
 int SEMB_CAT(semb_launch_strip_n, SEMB_INST_N)(semb_ctx* ctx, const OpArgs& a, const double* hDr,
                                                const double* hDs, int nstrips, int nchunks, bool pcg,
-                                               bool massterm) {
-  if (pcg) {
-    return massterm ? launch_variant<true, true>(ctx, a, hDr, hDs, nstrips, nchunks)
-                    : launch_variant<true, false>(ctx, a, hDr, hDs, nstrips, nchunks);
+                                               bool massterm, bool eo) {
+#define SEMB_GO(P_, M_, E_) return launch_variant<P_, M_, E_>(ctx, a, hDr, hDs, nstrips, nchunks)
+  if (eo) {
+    if (pcg) { if (massterm) SEMB_GO(true, true, true); else SEMB_GO(true, false, true); }
+    if (massterm) SEMB_GO(false, true, true); else SEMB_GO(false, false, true);
   }
-  return massterm ? launch_variant<false, true>(ctx, a, hDr, hDs, nstrips, nchunks)
-                  : launch_variant<false, false>(ctx, a, hDr, hDs, nstrips, nchunks);
+  if (pcg) { if (massterm) SEMB_GO(true, true, false); else SEMB_GO(true, false, false); }
+  if (massterm) SEMB_GO(false, true, false); else SEMB_GO(false, false, false);
+#undef SEMB_GO
+}
+
+// largest relative centro-antisymmetry defect of Dr and Ds (decides the even-odd kernel variant)
+double SEMB_CAT(semb_strip_defect_n, SEMB_INST_N)(const double* hDr, const double* hDs) {
+  double A[4][N * N];
+  row_major_set(hDr, hDs, A);
+  const double d0 = StripTab<N>::antisymmetry_defect(A[0]), d1 = StripTab<N>::antisymmetry_defect(A[1]);
+  return d0 > d1 ? d0 : d1;
 }
 
 int SEMB_CAT(semb_strip_attr_n, SEMB_INST_N)(bool pcg, bool massterm, int* regs, int* smem, int* occ) {
