@@ -458,6 +458,24 @@ static int mesh_new(semb_ctx* c, int nr, int ns, int Ex, int Ey, int perx, int p
   SEMB_CHECK_CUDA(cudaMemcpy(m->dDs, rm.data(), rm.size() * sizeof(double), cudaMemcpyHostToDevice));
   SEMB_TRY(mesh_build_plan(m));
   SEMB_TRY(mesh_alloc_array(m, SEMB_MULT));
+  {  // 1-D factors of mult (mesh.jl:94-96): 1/2 on duplicated lines, 1 elsewhere; pads are 0
+    std::vector<double> wx((size_t)m->pitch, 0.0), wy((size_t)m->nyl, 1.0);
+    for (int x = 0; x < m->nxl; ++x) {
+      const int e = x / nr, i = x % nr;
+      const bool d = (i == nr - 1 && e < Ex - 1) || (i == 0 && e > 0) || (m->perx && (x == 0 || x == m->nxl - 1));
+      wx[x] = d ? 0.5 : 1.0;
+    }
+    for (int y = 0; y < m->nyl; ++y) {
+      const int rg = m->ey0 + y / ns, j = y % ns;
+      const bool d = (j == ns - 1 && rg < Ey - 1) || (j == 0 && rg > 0) ||
+                     (m->pery && ((rg == 0 && j == 0) || (rg == Ey - 1 && j == ns - 1)));
+      wy[y] = d ? 0.5 : 1.0;
+    }
+    SEMB_CHECK_CUDA(cudaMalloc(&m->d_wx1d, wx.size() * sizeof(double)));
+    SEMB_CHECK_CUDA(cudaMalloc(&m->d_wy1d, wy.size() * sizeof(double)));
+    SEMB_CHECK_CUDA(cudaMemcpy(m->d_wx1d, wx.data(), wx.size() * sizeof(double), cudaMemcpyHostToDevice));
+    SEMB_CHECK_CUDA(cudaMemcpy(m->d_wy1d, wy.data(), wy.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   SEMB_TRY(semb_launch_mult(c, m->arr[SEMB_MULT], m->pitch, nr, ns, Ex, Ey, m->ey0, m->ney, m->perx, m->pery));
   *out = m;
   return SEMB_OK;
@@ -575,6 +593,8 @@ extern "C" int semb_mesh_destroy(semb_mesh* m) {
     if (m->arr[i]) cudaFree(m->arr[i]);
   cudaFree(m->dDr);
   cudaFree(m->dDs);
+  cudaFree(m->d_wx1d);
+  cudaFree(m->d_wy1d);
   cudaFree(m->d_chunk_r0);
   cudaFree(m->d_ystart);
   cudaFree(m->d_xseam);

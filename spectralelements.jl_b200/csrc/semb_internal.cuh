@@ -11,10 +11,12 @@
 #include "../../include/semb.h"
 
 #define SEMB_MAXN 17       // largest nr == ns served by the templated strip kernel
-#define SEMB_STRIP_THREADS 256  // CTA size of the strip kernel
+// CTA size of the strip kernel: 256 threads (8 warps, 2 per SM sub-partition); 192 for N = 12..14 so that two
+// CTAs still fit the 227 KB of shared memory (the staging buffers grow like N^2 per element)
+constexpr int semb_strip_threads(int n) { return (n >= 12 && n <= 14) ? 192 : 256; }
 // elements per strip: as many as fit the CTA, with BX*N even so that every staged row is a multiple of 16 bytes
 constexpr int semb_strip_bx(int n) {
-  return ((SEMB_STRIP_THREADS / n) * n) % 2 == 0 ? SEMB_STRIP_THREADS / n : SEMB_STRIP_THREADS / n - 1;
+  return ((semb_strip_threads(n) / n) * n) % 2 == 0 ? semb_strip_threads(n) / n : semb_strip_threads(n) / n - 1;
 }
 #define SEMB_MAX_RANKS 16
 
@@ -107,10 +109,12 @@ struct semb_mesh {
   double* dDr = nullptr;               // device copies (row-major: D[i*n+k] = D(i,k)) for generic kernels
   double* dDs = nullptr;
   double* arr[SEMB_MESH_ARRAY_COUNT] = {nullptr};
+  double* d_wx1d = nullptr;            // separable mult: mult(x,y) = wx1d[x] * wy1d[y] (pitch / nyl entries)
+  double* d_wy1d = nullptr;
   bool fast = false;                   // nr == ns in [2, SEMB_MAXN]: templated strip kernel
   bool eo = false;                     // Dr, Ds centro-antisymmetric: even-odd contraction variant
   // launch plan of the strip kernel
-  int bx = 0;                          // elements per strip (SEMB_STRIP_THREADS / nr)
+  int bx = 0;                          // elements per strip (semb_strip_bx(nr))
   int nstrips = 0, nchunks = 0;
   std::vector<int> h_chunk_r0;         // nchunks+1 element-row offsets
   int* d_chunk_r0 = nullptr;

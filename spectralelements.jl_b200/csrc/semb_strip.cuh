@@ -125,7 +125,7 @@ __device__ __forceinline__ void semb_contract(const double* __restrict__ T, cons
 
 template <int N>
 struct StripCfg {
-  static constexpr int T = SEMB_STRIP_THREADS;   // threads per CTA (8 warps: 2 per SM sub-partition)
+  static constexpr int T = semb_strip_threads(N);  // threads per CTA
   static constexpr int BX = semb_strip_bx(N);    // elements per strip (BX*N even: 16-byte bulk-copy rows)
   static constexpr int S = N | 1;                // element stride in smem (odd)
   static constexpr int PW = BX * S;              // row pitch of the transposition buffers S1/S2 (doubles)

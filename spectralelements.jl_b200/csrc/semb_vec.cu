@@ -351,11 +351,21 @@ __global__ void semb_generic_pass2(const OpArgs a, int nr, int ns, const double*
   }
 }
 
+// mult = 1 ./ gatherScatter(ones) (mesh.jl:94-96) is separable: mult(x,y) = wx(x) * wy(y) with weights in
+// {1, 1/2} (exact products), so the streaming kernels read two tiny 1-D tables instead of an n-sized array
+__device__ __forceinline__ double2 semb_mult2(const double2* __restrict__ wx1d, const double* __restrict__ wy1d,
+                                              int c2, int row) {
+  const double2 w = wx1d[c2];
+  const double wy = wy1d[row];
+  return make_double2(w.x * wy, w.y * wy);
+}
+
 // ---- deterministic reductions ------------------------------------------------------------------------
 // which = 0: sum(a .* b .* mult) (pcg.jl:45,52);  which = 1: norm(a, Inf) (pcg.jl:36)
 __global__ void __launch_bounds__(256) semb_reduce_kernel(int which, const double2* __restrict__ av,
                                                           const double2* __restrict__ bv,
-                                                          const double2* __restrict__ mv, int p2, int nyl,
+                                                          const double2* __restrict__ wx1d,
+                                                          const double* __restrict__ wy1d, int p2, int nyl,
                                                           double* partials, unsigned* counter, SembScal* scal) {
   __shared__ double red[32];
   double acc = 0.0;
@@ -363,7 +373,8 @@ __global__ void __launch_bounds__(256) semb_reduce_kernel(int which, const doubl
     const size_t i = (size_t)row * p2 + c2;
     const double2 a2 = av[i];
     if (which == 0) {
-      const double2 b2 = bv[i], m2 = mv[i];
+      const double2 b2 = bv[i];
+      const double2 m2 = semb_mult2(wx1d, wy1d, c2, row);
       acc += __dmul_rn(__dmul_rn(a2.x, b2.x), m2.x);
       acc += __dmul_rn(__dmul_rn(a2.y, b2.y), m2.y);
     } else {
@@ -422,7 +433,8 @@ __device__ __forceinline__ void semb_pcg_advance(SembScal* s, double tnew, doubl
 // x = 0, r = b, p = 0 (pcg.jl:25-33); t0, rmax0
 __global__ void __launch_bounds__(256) semb_pcg_init_kernel(const double2* __restrict__ b, double2* x, double2* r,
                                                             double2* p, const double2* __restrict__ Bm,
-                                                            const double2* __restrict__ mult, int p2, int nxl,
+                                                            const double2* __restrict__ wx1d,
+                                                            const double* __restrict__ wy1d, int p2, int nxl,
                                                             int nyl, int precond, double b0, double tol,
                                                             long long maxiter, double* partials,
                                                             unsigned* counter, SembScal* scal) {
@@ -435,7 +447,7 @@ __global__ void __launch_bounds__(256) semb_pcg_init_kernel(const double2* __res
     x[i] = z;
     p[i] = z;
     r[i] = bv;
-    const double2 m2 = mult[i];
+    const double2 m2 = semb_mult2(wx1d, wy1d, c2, row);
     double hx = bv.x, hy = bv.y;
     if (precond) {
       const double2 B2 = Bm[i];
@@ -463,7 +475,8 @@ __global__ void __launch_bounds__(256) semb_pcg_init_kernel(const double2* __res
 __global__ void __launch_bounds__(256) semb_pcg_update_kernel(double2* x, double2* r, const double2* __restrict__ p,
                                                               const double2* __restrict__ Ap,
                                                               const double2* __restrict__ Bm,
-                                                              const double2* __restrict__ mult, int p2, int nxl,
+                                                              const double2* __restrict__ wx1d,
+                                                              const double* __restrict__ wy1d, int p2, int nxl,
                                                               int nyl, int precond, double b0, double* partials,
                                                               unsigned* counter, SembScal* scal) {
   __shared__ double red[32];
@@ -479,7 +492,8 @@ __global__ void __launch_bounds__(256) semb_pcg_update_kernel(double2* x, double
   double acc = 0.0, amx = 0.0;
   SEMB_FOR_2D(p2, nyl) {
     const size_t i = (size_t)row * p2 + c2;
-    const double2 pv = p[i], av = Ap[i], m2 = mult[i];
+    const double2 pv = p[i], av = Ap[i];
+    const double2 m2 = semb_mult2(wx1d, wy1d, c2, row);
     double2 xv = x[i], rv = r[i];
     xv.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
     xv.y = __dadd_rn(xv.y, __dmul_rn(alpha, pv.y));
@@ -713,7 +727,7 @@ int semb_launch_generic_local(semb_ctx* ctx, const OpArgs& a, int nr, int ns, co
 int semb_launch_reduce(semb_ctx* ctx, semb_mesh* m, int which, const double* a, const double* b) {
   Grid2D g = grid2d(m->pitch, m->nyl, ctx->sm_count, m->npartials / 2);
   semb_reduce_kernel<<<g.grid, g.block, 0, ctx->stream>>>(which, (const double2*)a, (const double2*)b,
-                                                          (const double2*)m->arr[SEMB_MULT], (int)(m->pitch / 2),
+                                                          (const double2*)m->d_wx1d, m->d_wy1d, (int)(m->pitch / 2),
                                                           m->nyl, m->d_partials, m->d_counters + 4, m->d_scal);
   SEMB_POST_LAUNCH(ctx);
 }
@@ -728,7 +742,7 @@ int semb_launch_pcg_init(semb_ctx* ctx, semb_mesh* m, const double* b, double* x
   Grid2D g = grid2d(m->pitch, m->nyl, ctx->sm_count, m->npartials / 2);
   semb_pcg_init_kernel<<<g.grid, g.block, 0, ctx->stream>>>(
       (const double2*)b, (double2*)x, (double2*)r, (double2*)p, (const double2*)m->arr[SEMB_B],
-      (const double2*)m->arr[SEMB_MULT], (int)(m->pitch / 2), m->nxl, m->nyl, precond, prec_b0, tol, maxiter,
+      (const double2*)m->d_wx1d, m->d_wy1d, (int)(m->pitch / 2), m->nxl, m->nyl, precond, prec_b0, tol, maxiter,
       m->d_partials, m->d_counters + 3, m->d_scal);
   SEMB_POST_LAUNCH(ctx);
 }
@@ -738,7 +752,7 @@ int semb_launch_pcg_update(semb_ctx* ctx, semb_mesh* m, double* x, double* r, co
   Grid2D g = grid2d(m->pitch, m->nyl, ctx->sm_count, m->npartials / 2);
   semb_pcg_update_kernel<<<g.grid, g.block, 0, ctx->stream>>>(
       (double2*)x, (double2*)r, (const double2*)p, (const double2*)Ap, (const double2*)m->arr[SEMB_B],
-      (const double2*)m->arr[SEMB_MULT], (int)(m->pitch / 2), m->nxl, m->nyl, precond, prec_b0, m->d_partials,
+      (const double2*)m->d_wx1d, m->d_wy1d, (int)(m->pitch / 2), m->nxl, m->nyl, precond, prec_b0, m->d_partials,
       m->d_counters + 3, m->d_scal);
   SEMB_POST_LAUNCH(ctx);
 }
