@@ -36,6 +36,8 @@ sys.path.insert(0, ROOT)
 ALG_BYTES_POISSON = 40.0    # read u, G11, G12, G22; write Au
 ALG_BYTES_HELMHOLTZ = 48.0  # + B
 ALG_BYTES_PCG_ITER = 112.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one strip-kernel launch (ncu --set full), keyed by (nr, E)
+NCU_TRAFFIC_GB = {(9, 1112): 3.2096 + 0.7811}
 
 
 def measured_peak():
@@ -49,12 +51,19 @@ def measured_peak():
 
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device, self.proc, self.path = device, None, None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -78,11 +87,15 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         try:
+            import datetime
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
                 try:
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if self.t0 is not None and not (self.t0 - 0.02 <= ts <= self.t1 + 0.02):
+                        continue  # only samples taken DURING the timed region
                     sm.append(float(f[1]))
                     mx.append(float(f[2]))
                 except ValueError:
@@ -175,16 +188,19 @@ def run_semb(args):
     # ---- headline: fused Laplacian + QQ^T + mask apply, inputs resident in HBM ---------------------
     apply_fn = lambda: msh.oplhs_device(u, out, nu=1.0, k=0.0, bc=bc)
     sampler = ClockSampler(local)
+    sampler.start()  # nvidia-smi needs ~0.2 s to start sampling: launch it before the warm-up
     for _ in range(args.warmup):
         apply_fn()
     barrier(dist, ctx)
+    time.sleep(0.3)
     sem._lib.check(ctx.lib.semb_profile_enable(ctx.h, args.steps))
-    sampler.start()
     l0 = ctx.launch_count()
+    sampler.mark_begin()
     ctx.timer_start()
     for _ in range(args.steps):
         apply_fn()
     ms = ctx.timer_stop()
+    sampler.mark_end()
     barrier(dist, ctx)
     launches = ctx.launch_count() - l0
     clocks = sampler.stop()
@@ -279,7 +295,8 @@ def run_semb(args):
                        "l2": "inputs (%.1f GB per apply) exceed the 126 MB L2" % (ALG_BYTES_POISSON * ndof_local / 1e9),
                        "strips_x_chunks": [plan["nstrips"], plan["nchunks"]]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "semb_strip_kernel<%d>" % nr,
+                         "traffic": NCU_TRAFFIC_GB.get((nr, E)), "traffic_unit": "GB per launch (ncu --set full, profiles/r01_strip9_r1e.txt)",
+                         "kernel": "semb_strip_kernel<%d>" % nr,
                          "algorithmic_bytes_per_dof": ALG_BYTES_POISSON, "kernel_ms": strip_ms,
                          "kernel_share_of_step": strip_ms / ms_per_step, "peak_source": peak_src,
                          "whole_apply_frac": ALG_BYTES_POISSON * ndof_local / (ms_per_step * 1e-3) / 1e9 / peak},
@@ -355,7 +372,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="semb", choices=["semb", "reference"])
     ap.add_argument("--nr", type=int, default=9)
