@@ -26,6 +26,8 @@ extern "C" const char* semb_last_error(void) { return g_err; }
 extern "C" int semb_version(void) { return 100; }
 
 #define SEMB_NPARTIALS 4096
+// bytes of SembScal the host may overwrite: everything before the peer-written mailbox part
+#define SEMB_SCAL_HOST_BYTES offsetof(SembScal, flag_halo)
 
 // ---- strip-kernel dispatch -----------------------------------------------------------------------------
 #define SEMB_DECL_STRIP(n)                                                                                       \
@@ -378,13 +380,60 @@ static int mesh_build_plan(semb_mesh* m) {
   SEMB_CHECK_CUDA(cudaMalloc(&m->d_partials, 3 * (size_t)m->npartials * sizeof(double)));
   SEMB_CHECK_CUDA(cudaMalloc(&m->d_counters, 8 * sizeof(unsigned)));
   SEMB_CHECK_CUDA(cudaMemset(m->d_counters, 0, 8 * sizeof(unsigned)));
-  SEMB_CHECK_CUDA(cudaMalloc(&m->d_scal, sizeof(SembScal)));
+  // Mailbox = [SembScal][halo rows: 2 parities x 2 sides x pitch].  With more than one rank it is exported
+  // through CUDA IPC so that the neighbours' kernels can store into it over NVLink (P2P mode).
+  const size_t scal_bytes = (sizeof(SembScal) + 255) / 256 * 256;
+  const size_t mail_bytes = scal_bytes + 4 * (size_t)m->pitch * sizeof(double);
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_mailbox, mail_bytes));
+  SEMB_CHECK_CUDA(cudaMemset(m->d_mailbox, 0, mail_bytes));
+  m->d_scal = (SembScal*)m->d_mailbox;
+  m->d_mail_halo = (double*)((char*)m->d_mailbox + scal_bytes);
+  m->p2p = false;
+  if (P > 1 && m->fast && !getenv("SEMB_NO_P2P")) {
+    // exchange the IPC handles with the communicator itself, then map every peer's mailbox
+    cudaIpcMemHandle_t mine;
+    cudaError_t e = cudaIpcGetMemHandle(&mine, m->d_mailbox);
+    int ok = (e == cudaSuccess) ? 1 : 0;
+    if (!ok) cudaGetLastError();
+    char* d_h = nullptr;
+    SEMB_CHECK_CUDA(cudaMalloc(&d_h, (size_t)P * sizeof(cudaIpcMemHandle_t)));
+    SEMB_CHECK_CUDA(cudaMemcpy(d_h + (size_t)rk * sizeof(cudaIpcMemHandle_t), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    SEMB_CHECK_NCCL(ncclAllGather(d_h + (size_t)rk * sizeof(cudaIpcMemHandle_t), d_h, sizeof(cudaIpcMemHandle_t), ncclChar,
+                                  c->comm, c->stream));
+    std::vector<cudaIpcMemHandle_t> all(P);
+    SEMB_CHECK_CUDA(cudaMemcpyAsync(all.data(), d_h, (size_t)P * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost,
+                                    c->stream));
+    SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_h);
+    for (int r = 0; r < P && ok; ++r) {
+      if (r == rk) {
+        m->peer_mailbox[r] = m->d_mailbox;
+        continue;
+      }
+      e = cudaIpcOpenMemHandle(&m->peer_mailbox[r], all[r], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+      }
+    }
+    // every rank must take the same path: agree on success
+    double flag = ok ? 0.0 : 1.0;
+    SEMB_TRY(semb_comm_allreduce_max(c, &flag, 1));
+    m->p2p = (flag == 0.0);
+    if (!m->p2p)
+      for (int r = 0; r < P; ++r)
+        if (r != rk && m->peer_mailbox[r]) {
+          cudaIpcCloseMemHandle(m->peer_mailbox[r]);
+          m->peer_mailbox[r] = nullptr;
+        }
+  }
   SEMB_CHECK_CUDA(cudaMallocHost(&m->h_scal, sizeof(SembScal)));
   memset(m->h_scal, 0, sizeof(SembScal));
   m->h_scal->nranks = P;
   m->h_scal->rank = rk;
   m->h_scal->done = 1;
-  SEMB_CHECK_CUDA(cudaMemcpy(m->d_scal, m->h_scal, sizeof(SembScal), cudaMemcpyHostToDevice));
+  SEMB_CHECK_CUDA(cudaMemcpy(m->d_scal, m->h_scal, SEMB_SCAL_HOST_BYTES, cudaMemcpyHostToDevice));
+  if (P > 1) SEMB_TRY(semb_comm_barrier(c));  // every mailbox is mapped and initialised before anyone pushes
   return SEMB_OK;
 }
 
@@ -603,7 +652,13 @@ extern "C" int semb_mesh_destroy(semb_mesh* m) {
   cudaFree(m->d_halo_hi);
   cudaFree(m->d_partials);
   cudaFree(m->d_counters);
-  cudaFree(m->d_scal);
+  if (m->p2p) {
+    semb_comm_barrier(m->ctx);  // no peer may still be writing into (or mapping) this mailbox
+    for (int r = 0; r < m->ctx->nranks; ++r)
+      if (r != m->ctx->rank && m->peer_mailbox[r]) cudaIpcCloseMemHandle(m->peer_mailbox[r]);
+    semb_comm_barrier(m->ctx);
+  }
+  cudaFree(m->d_mailbox);
   if (m->h_scal) cudaFreeHost(m->h_scal);
   delete m;
   return SEMB_OK;
@@ -814,9 +869,41 @@ static int check_field(semb_mesh* m, const semb_field* f, const char* what, bool
   return SEMB_OK;
 }
 
-static int halo_exchange(semb_mesh* m, double* field) {
+static P2PArgs p2p_args(semb_mesh* m, unsigned long long epoch, unsigned long long epoch_b = 0) {
+  P2PArgs x;
+  x.on = m->p2p ? 1 : 0;
+  x.nranks = m->ctx->nranks;
+  x.rank = m->ctx->rank;
+  x.epoch = epoch;
+  x.epoch_b = epoch_b;
+  for (int r = 0; r < x.nranks; ++r) x.peer[r] = (SembScal*)m->peer_mailbox[r];
+  return x;
+}
+
+// local / peer halo rows inside a mailbox: [parity][side][pitch], side 0 = row from below, 1 = from above
+static double* mail_halo(semb_mesh* m, void* mailbox, int parity, int side) {
+  const size_t scal_bytes = (sizeof(SembScal) + 255) / 256 * 256;
+  return (double*)((char*)mailbox + scal_bytes) + (size_t)(2 * parity + side) * m->pitch;
+}
+
+// Exchange the slab's boundary rows with the neighbour ranks.  P2P mode: one small kernel stores the rows
+// straight into the neighbours' mailboxes over NVLink and releases an epoch flag (the consumer, the y-seam
+// kernel, waits on it).  Fallback: grouped ncclSend/ncclRecv.  Returns the epoch used in *epoch.
+static int halo_exchange(semb_mesh* m, double* field, int pcg, unsigned long long* epoch) {
   semb_ctx* c = m->ctx;
+  if (epoch) *epoch = 0;
   if (!m->halo_lo && !m->halo_hi) return SEMB_OK;
+  if (m->p2p) {
+    const unsigned long long ep = ++m->ep_halo;
+    const int par = (int)(ep & 1ull);
+    SembScal* plo = m->halo_lo ? (SembScal*)m->peer_mailbox[m->rank_lo] : nullptr;
+    SembScal* phi = m->halo_hi ? (SembScal*)m->peer_mailbox[m->rank_hi] : nullptr;
+    if (epoch) *epoch = ep;
+    return semb_launch_halo_push(c, field, m->pitch, m->nxl, m->nyl,
+                                 plo ? mail_halo(m, plo, par, 1) : nullptr, phi ? mail_halo(m, phi, par, 0) : nullptr,
+                                 plo ? &plo->flag_halo[1] : nullptr, phi ? &phi->flag_halo[0] : nullptr, ep,
+                                 m->d_counters + 5, m->d_scal, pcg);
+  }
   SEMB_REQUIRE(c->comm, "halo exchange without a communicator");
   SEMB_CHECK_NCCL(ncclGroupStart());
   // order matters only when both neighbours are the same rank (2 ranks, periodic y): sends go
@@ -912,10 +999,16 @@ static int run_operator(semb_mesh* m, const double* u, double* out, const OpSpec
     a.partials = m->d_partials + m->npartials;
     a.counters = m->d_counters + 1;
     SEMB_TRY(semb_launch_seam_x(c, a));
-    SEMB_TRY(halo_exchange(m, out));
+    unsigned long long eph = 0;
+    SEMB_TRY(halo_exchange(m, out, pcg ? 1 : 0, &eph));
+    if (m->p2p) {  // received rows live in the local mailbox, double-buffered by epoch parity
+      a.halo_lo = mail_halo(m, m->d_mailbox, (int)(eph & 1ull), 0);
+      a.halo_hi = mail_halo(m, m->d_mailbox, (int)(eph & 1ull), 1);
+    }
     a.partials = m->d_partials + 2 * (size_t)m->npartials;
     a.counters = m->d_counters + 2;
-    SEMB_TRY(semb_launch_seam_y(c, a, m->halo_lo, m->halo_hi, true));
+    // P2P + PCG: the y-seam kernel's last block also all-gathers sum(p.*Ap.*mult) over NVLink
+    SEMB_TRY(semb_launch_seam_y(c, a, m->halo_lo, m->halo_hi, true, p2p_args(m, eph, (m->p2p && pcg) ? ++m->ep_pap : 0)));
     return SEMB_OK;
   }
   // generic path (nr != ns, or outside 2..17): separate passes, same arithmetic per node
@@ -932,12 +1025,12 @@ static int run_operator(semb_mesh* m, const double* u, double* out, const OpSpec
     SEMB_TRY(semb_launch_generic_local(c, g, m->nr, m->ns, m->dDr, m->dDs, t1->d, t2->d, hasmass));
     if (!sp.gs) return SEMB_OK;
     SEMB_TRY(semb_launch_gs_x(c, m->w_tmp->d, out, m->pitch, m->nr, m->Ex, m->nxl, m->nyl, m->perx));
-    SEMB_TRY(halo_exchange(m, out));
+    SEMB_TRY(halo_exchange(m, out, 0, nullptr));  // generic meshes never use P2P
     OpArgs y = a;
     y.pcg = 0;
     y.yseam = m->d_yseam + 2 * m->nyseam;  // all y interfaces
     y.nyseam = (m->ney - 1) + ((m->pery && c->nranks == 1) ? 1 : 0);
-    SEMB_TRY(semb_launch_seam_y(c, y, m->halo_lo, m->halo_hi, false));
+    SEMB_TRY(semb_launch_seam_y(c, y, m->halo_lo, m->halo_hi, false, P2PArgs()));
     OpArgs md = a;
     md.partials = m->d_partials;
     md.counters = m->d_counters + 0;
@@ -987,13 +1080,18 @@ extern "C" int semb_gather_scatter(semb_mesh* m, const semb_field* u, semb_field
   SEMB_TRY(check_field(m, out, "gatherScatter(out)"));
   SEMB_REQUIRE(u != out, "gatherScatter: out must not alias u");
   SEMB_TRY(semb_launch_gs_x(c, u->d, out->d, m->pitch, m->nr, m->Ex, m->nxl, m->nyl, m->perx));
-  SEMB_TRY(halo_exchange(m, out->d));
+  unsigned long long eph = 0;
+  SEMB_TRY(halo_exchange(m, out->d, 0, &eph));
   OpArgs y;
   fill_common(m, y);
+  if (m->p2p) {
+    y.halo_lo = mail_halo(m, m->d_mailbox, (int)(eph & 1ull), 0);
+    y.halo_hi = mail_halo(m, m->d_mailbox, (int)(eph & 1ull), 1);
+  }
   y.out = out->d;
   y.yseam = m->d_yseam + 2 * m->nyseam;
   y.nyseam = (m->ney - 1) + ((m->pery && c->nranks == 1) ? 1 : 0);
-  return semb_launch_seam_y(c, y, m->halo_lo, m->halo_hi, false);
+  return semb_launch_seam_y(c, y, m->halo_lo, m->halo_hi, false, p2p_args(m, eph));
 }
 
 extern "C" int semb_mask(semb_mesh* m, const semb_field* u, const semb_field* M, semb_field* out) {
@@ -1087,8 +1185,8 @@ static int reduce_common(semb_mesh* m, int which, const semb_field* a, const sem
   semb_ctx* c = m->ctx;
   SEMB_TRY(ctx_enter(c));
   SEMB_REQUIRE(result, "reduction: null result");
-  SEMB_TRY(semb_launch_reduce(c, m, which, a->d, b ? b->d : nullptr));
-  if (c->nranks > 1) {
+  SEMB_TRY(semb_launch_reduce(c, m, which, a->d, b ? b->d : nullptr, p2p_args(m, m->p2p ? ++m->ep_red : 0)));
+  if (c->nranks > 1 && !m->p2p) {
     SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_red), 1));
     SEMB_TRY(semb_launch_reduce_finalize(c, m, which));
   }
@@ -1135,9 +1233,10 @@ extern "C" int semb_pcg_begin(semb_mesh* m, const semb_pcg_opts* o, const semb_f
   memset(m->h_scal, 0, sizeof(SembScal));
   m->h_scal->nranks = c->nranks;
   m->h_scal->rank = c->rank;
-  SEMB_CHECK_CUDA(cudaMemcpyAsync(m->d_scal, m->h_scal, sizeof(SembScal), cudaMemcpyHostToDevice, c->stream));
-  SEMB_TRY(semb_launch_pcg_init(c, m, b->d, x->d, m->w_r->d, m->w_p->d, o->precond, o->prec_b0, o->tol, maxiter));
-  if (c->nranks > 1) {
+  SEMB_CHECK_CUDA(cudaMemcpyAsync(m->d_scal, m->h_scal, SEMB_SCAL_HOST_BYTES, cudaMemcpyHostToDevice, c->stream));
+  SEMB_TRY(semb_launch_pcg_init(c, m, b->d, x->d, m->w_r->d, m->w_p->d, o->precond, o->prec_b0, o->tol, maxiter,
+                                p2p_args(m, m->p2p ? ++m->ep_t : 0)));
+  if (c->nranks > 1 && !m->p2p) {
     SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_t), 2));
     SEMB_TRY(semb_launch_pcg_finalize(c, m, 1));
   }
@@ -1157,12 +1256,15 @@ static int pcg_one_iteration(semb_mesh* m) {
   sp.M_arr = o.M_arr;
   sp.gs = true;
   SEMB_TRY(run_operator(m, m->w_r->d, m->w_Ap->d, sp, true, m->w_p->d, o.precond, o.prec_b0));
-  if (c->nranks > 1) {
+  if (c->nranks > 1 && !m->p2p) {
     SEMB_TRY(semb_launch_pcg_pack_pap(c, m));
     SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_pap), 1));
+    SEMB_TRY(semb_launch_pcg_combine_pap(c, m));
   }
-  SEMB_TRY(semb_launch_pcg_update(c, m, m->pcg_x->d, m->w_r->d, m->w_p->d, m->w_Ap->d, o.precond, o.prec_b0));
-  if (c->nranks > 1) {
+  // P2P: the update kernel's last block all-gathers {t, norm(r,Inf)} over NVLink and advances the state
+  SEMB_TRY(semb_launch_pcg_update(c, m, m->pcg_x->d, m->w_r->d, m->w_p->d, m->w_Ap->d, o.precond, o.prec_b0,
+                                  p2p_args(m, m->p2p ? ++m->ep_t : 0)));
+  if (c->nranks > 1 && !m->p2p) {
     SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_t), 2));
     SEMB_TRY(semb_launch_pcg_finalize(c, m, 0));
   }

@@ -72,6 +72,24 @@ struct SembScal {
   double xchg_t[2 * SEMB_MAX_RANKS];  // {t_local, rmax_local} per rank
   double xchg_red[2 * SEMB_MAX_RANKS];
   int nranks, rank;
+  double pap_total;  // multi-rank: combined sum(p .* Ap .* mult) of the current iteration
+  // ---- peer-memory mailbox (multi-GPU, P2P mode): written by the OTHER ranks over NVLink -----------
+  // flag_*[r] = epoch of the last value rank r pushed; data slots are double-buffered by epoch parity
+  unsigned long long flag_halo[2];  // [0]: row from the lower neighbour, [1]: from the upper neighbour
+  unsigned long long flag_pap[SEMB_MAX_RANKS];
+  unsigned long long flag_t[SEMB_MAX_RANKS];
+  unsigned long long flag_red[SEMB_MAX_RANKS];
+  double box_pap[2][SEMB_MAX_RANKS];
+  double box_t[2][2 * SEMB_MAX_RANKS];
+  double box_red[2][2 * SEMB_MAX_RANKS];
+};
+
+// Peer pointers handed to the kernels that exchange data through mapped peer memory (CUDA IPC).
+struct P2PArgs {
+  int on = 0, nranks = 1, rank = 0;
+  unsigned long long epoch = 0;    // epoch of the exchange this kernel takes part in
+  unsigned long long epoch_b = 0;  // second exchange in the same kernel (y-seam kernel: halo = epoch, pap = epoch_b)
+  SembScal* peer[SEMB_MAX_RANKS] = {nullptr};  // peer[r] = rank r's mailbox (r == rank: the local one)
 };
 
 struct semb_ctx {
@@ -126,8 +144,14 @@ struct semb_mesh {
   int* d_yseam = nullptr;              // 2*nyseam ints (ya, yb)
   int halo_lo = 0, halo_hi = 0;        // 1 if the slab has a neighbour rank below / above
   int rank_lo = -1, rank_hi = -1;
-  double* d_halo_lo = nullptr;         // nxl doubles each (received neighbour rows)
+  double* d_halo_lo = nullptr;         // nxl doubles each (received neighbour rows), NCCL path
   double* d_halo_hi = nullptr;
+  // P2P path: one IPC-exported allocation per mesh = [SembScal][halo rows: 2 parities x 2 sides x pitch]
+  bool p2p = false;
+  void* d_mailbox = nullptr;
+  double* d_mail_halo = nullptr;       // local halo rows inside the mailbox
+  void* peer_mailbox[SEMB_MAX_RANKS] = {nullptr};
+  unsigned long long ep_halo = 0, ep_pap = 0, ep_t = 0, ep_red = 0;
   // reductions
   int npartials = 0;
   double* d_partials = nullptr;        // 3 * npartials doubles

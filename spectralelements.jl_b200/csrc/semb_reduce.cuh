@@ -76,3 +76,95 @@ __device__ __forceinline__ double semb_pcg_beta(const SembScal* s) {
   return (s->iters == 0) ? 0.0 : s->t / s->t_prev;
 }
 
+
+// ---- peer-memory exchange (multi-GPU, P2P mode) ----------------------------------------------------------
+__device__ __forceinline__ unsigned long long semb_ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void semb_st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// All-gather of up to two doubles per rank through peer memory, executed by ONE block per rank (all of
+// its threads must call): thread r stores this rank's values into rank r's mailbox (NVLink st.global),
+// releases a flag, then waits for rank r's values to arrive in the local mailbox.  Afterwards thread 0
+// combines in rank order (v0: sum, v1: max) => bitwise identical results on every rank.  This is the
+// collective fused into the producing kernel: no NCCL launch.  kind: 0 = pap, 1 = {t, rmax}, 2 = reductions.
+__device__ __forceinline__ void semb_p2p_allgather(const P2PArgs& x, SembScal* me, int kind, double v0, double v1,
+                                                   double* sum0, double* max1, int tid) {
+  const int par = (int)(x.epoch & 1ull);
+  if (tid < x.nranks) {
+    SembScal* dst = x.peer[tid];
+    unsigned long long* fdst;
+    const unsigned long long* fsrc;
+    if (kind == 0) {
+      dst->box_pap[par][x.rank] = v0;
+      fdst = &dst->flag_pap[x.rank];
+      fsrc = &me->flag_pap[tid];
+    } else if (kind == 1) {
+      dst->box_t[par][2 * x.rank] = v0;
+      dst->box_t[par][2 * x.rank + 1] = v1;
+      fdst = &dst->flag_t[x.rank];
+      fsrc = &me->flag_t[tid];
+    } else {
+      dst->box_red[par][2 * x.rank] = v0;
+      dst->box_red[par][2 * x.rank + 1] = v1;
+      fdst = &dst->flag_red[x.rank];
+      fsrc = &me->flag_red[tid];
+    }
+    __threadfence_system();
+    semb_st_release_sys(fdst, x.epoch);
+    while (semb_ld_acquire_sys(fsrc) < x.epoch) {
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0, m = 0.0;
+    for (int r = 0; r < x.nranks; ++r) {
+      if (kind == 0) {
+        s += me->box_pap[par][r];
+      } else {
+        const double* b = (kind == 1) ? me->box_t[par] : me->box_red[par];
+        s += b[2 * r];
+        m = fmax(m, b[2 * r + 1]);
+      }
+    }
+    *sum0 = s;
+    if (max1) *max1 = m;
+  }
+}
+
+// like semb_last_block, but tells EVERY thread of the block whether it is the last one (block-uniform),
+// leaving the totals in shared memory (valid after the call in all threads of the last block)
+__device__ __forceinline__ bool semb_last_block_uniform(double bsum, double bmax, double* psum, double* pmax,
+                                                        unsigned* counter, int nblocks, int bid, double* red,
+                                                        int tid, int nthreads, double* sh_tot /* 2 shared doubles */) {
+  __shared__ int s_last2;
+  if (tid == 0) {
+    psum[bid] = bsum;
+    if (pmax) pmax[bid] = bmax;
+    __threadfence();
+    unsigned ticket = atomicAdd(counter, 1u);
+    s_last2 = (ticket == (unsigned)(nblocks - 1));
+  }
+  __syncthreads();
+  if (!s_last2) return false;
+  __threadfence();
+  double v = 0.0, mx = 0.0;
+  for (int i = tid; i < nblocks; i += nthreads) {
+    v += ((volatile double*)psum)[i];
+    if (pmax) mx = fmax(mx, ((volatile double*)pmax)[i]);
+  }
+  const double s = semb_block_sum(v, red, tid, nthreads);
+  double m2 = 0.0;
+  if (pmax) m2 = semb_block_max(mx, red, tid, nthreads);
+  if (tid == 0) {
+    sh_tot[0] = s;
+    sh_tot[1] = m2;
+    *counter = 0u;
+  }
+  __syncthreads();
+  return true;
+}

@@ -68,39 +68,91 @@ __global__ void __launch_bounds__(256) semb_seam_x_kernel(const OpArgs a) {
 // y seams: row pairs (ya, yb) (chunk boundaries, periodic wrap), then the halo rows received from the
 // neighbouring ranks.  Rows are contiguous => coalesced.  Applies the mask (mask.jl:14) last.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) semb_seam_y_kernel(const OpArgs a, int nhalo_lo, int nhalo_hi, int domask) {
+__global__ void __launch_bounds__(256) semb_seam_y_kernel(const OpArgs a, int nhalo_lo, int nhalo_hi, int domask,
+                                                          const P2PArgs x) {
   __shared__ double red[32];
+  __shared__ double sh_tot[2];
   if (a.pcg && a.scal->done) return;
+  if (x.on && (nhalo_lo || nhalo_hi)) {
+    // P2P halo: the neighbours' boundary rows arrive in the local mailbox over NVLink (semb_halo_push_kernel
+    // on the neighbour); wait for this apply's epoch before touching them
+    if (threadIdx.x == 0) {
+      if (nhalo_lo) while (semb_ld_acquire_sys(&a.scal->flag_halo[0]) < x.epoch) {
+        }
+      if (nhalo_hi) while (semb_ld_acquire_sys(&a.scal->flag_halo[1]) < x.epoch) {
+        }
+    }
+    __syncthreads();
+  }
   double acc = 0.0;
   const int nq = a.nyseam + nhalo_lo + nhalo_hi;
   const long long total = (long long)nq * a.nxl;
-  auto finish = [&](int x, int y, double val) {
-    const size_t idx = (size_t)y * a.pitch + x;
-    const double o = domask ? __dmul_rn(mask_at(a, x, y, idx), val) : val;
+  auto finish = [&](int x_, int y, double val) {
+    const size_t idx = (size_t)y * a.pitch + x_;
+    const double o = domask ? __dmul_rn(mask_at(a, x_, y, idx), val) : val;
     a.out[idx] = o;
     if (a.pcg) acc += __dmul_rn(__dmul_rn(a.pout[idx], o), a.mult[idx]);
   };
   for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total;
        id += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(id / a.nxl), x = (int)(id - (long long)q * a.nxl);
+    const int q = (int)(id / a.nxl), xx = (int)(id - (long long)q * a.nxl);
     if (q < a.nyseam) {
       const int ya = a.yseam[2 * q], yb = a.yseam[2 * q + 1];
-      const double s = __dadd_rn(a.out[(size_t)ya * a.pitch + x], a.out[(size_t)yb * a.pitch + x]);
-      finish(x, ya, s);
-      finish(x, yb, s);
+      const double s = __dadd_rn(a.out[(size_t)ya * a.pitch + xx], a.out[(size_t)yb * a.pitch + xx]);
+      finish(xx, ya, s);
+      finish(xx, yb, s);
     } else {
       const bool lo = (q == a.nyseam) && nhalo_lo;
       const int y = lo ? 0 : a.nyl - 1;
-      const double h = lo ? a.halo_lo[x] : a.halo_hi[x];
-      finish(x, y, __dadd_rn(a.out[(size_t)y * a.pitch + x], h));
+      const double h = lo ? a.halo_lo[xx] : a.halo_hi[xx];
+      finish(xx, y, __dadd_rn(a.out[(size_t)y * a.pitch + xx], h));
     }
   }
   if (a.pcg) {
     const double bs = semb_block_sum(acc, red, threadIdx.x, blockDim.x);
-    double tot;
-    if (semb_last_block(bs, 0.0, a.partials, nullptr, a.counters, gridDim.x, blockIdx.x, red, threadIdx.x,
-                        blockDim.x, &tot, nullptr))
-      a.scal->pap[2] = tot;
+    if (semb_last_block_uniform(bs, 0.0, a.partials, nullptr, a.counters, gridDim.x, blockIdx.x, red, threadIdx.x,
+                                blockDim.x, sh_tot)) {
+      if (threadIdx.x == 0) a.scal->pap[2] = sh_tot[0];
+      if (x.on) {
+        // sum(p .* Ap .* mult) over all ranks, fused here: this kernel is the last contributor
+        const double mine = __dadd_rn(__dadd_rn(a.scal->pap[0], a.scal->pap[1]), sh_tot[0]);
+        double tot;
+        P2PArgs xb = x;
+        xb.epoch = x.epoch_b;
+        semb_p2p_allgather(xb, a.scal, 0, mine, 0.0, &tot, nullptr, threadIdx.x);
+        if (threadIdx.x == 0) a.scal->pap_total = tot;
+      }
+    }
+  }
+}
+
+// P2P halo push: copy this slab's first / last row (x-summed by now) into the neighbours' mailboxes with
+// plain stores to mapped peer memory (NVLink), then release the epoch flag.  Replaces ncclSend/ncclRecv.
+__global__ void __launch_bounds__(256) semb_halo_push_kernel(const double* __restrict__ out, long long pitch, int nxl,
+                                                             int nyl, double* dst_lo, double* dst_hi,
+                                                             unsigned long long* flag_lo, unsigned long long* flag_hi,
+                                                             unsigned long long epoch, unsigned* counter,
+                                                             const SembScal* scal, int pcg) {
+  __shared__ int s_last;
+  if (pcg && scal->done) return;
+  const double* first = out;
+  const double* last = out + (size_t)(nyl - 1) * pitch;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nxl; i += gridDim.x * blockDim.x) {
+    if (dst_hi) dst_hi[i] = last[i];   // my last row is the upper neighbour's "row from below"
+    if (dst_lo) dst_lo[i] = first[i];  // my first row is the lower neighbour's "row from above"
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(counter, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence_system();
+    if (flag_hi) semb_st_release_sys(flag_hi, epoch);
+    if (flag_lo) semb_st_release_sys(flag_lo, epoch);
+    *counter = 0u;
   }
 }
 
@@ -366,7 +418,8 @@ __global__ void __launch_bounds__(256) semb_reduce_kernel(int which, const doubl
                                                           const double2* __restrict__ bv,
                                                           const double2* __restrict__ wx1d,
                                                           const double* __restrict__ wy1d, int p2, int nyl,
-                                                          double* partials, unsigned* counter, SembScal* scal) {
+                                                          double* partials, unsigned* counter, SembScal* scal,
+                                                          const P2PArgs x) {
   __shared__ double red[32];
   double acc = 0.0;
   SEMB_FOR_2D(p2, nyl) {
@@ -381,21 +434,27 @@ __global__ void __launch_bounds__(256) semb_reduce_kernel(int which, const doubl
       acc = fmax(acc, fmax(fabs(a2.x), fabs(a2.y)));
     }
   }
-  double bs, tot = 0.0, tmx = 0.0;
+  __shared__ double sh_tot[2];
   bool last;
   if (which == 0) {
-    bs = semb_block_sum(acc, red, SEMB_TID, SEMB_NT);
-    last = semb_last_block(bs, 0.0, partials, nullptr, counter, SEMB_NB, SEMB_BID, red, SEMB_TID, SEMB_NT, &tot,
-                           nullptr);
+    const double bs = semb_block_sum(acc, red, SEMB_TID, SEMB_NT);
+    last = semb_last_block_uniform(bs, 0.0, partials, nullptr, counter, SEMB_NB, SEMB_BID, red, SEMB_TID, SEMB_NT,
+                                   sh_tot);
   } else {
-    bs = semb_block_max(acc, red, SEMB_TID, SEMB_NT);
-    last = semb_last_block(0.0, bs, partials, partials + SEMB_NB, counter, SEMB_NB, SEMB_BID, red, SEMB_TID,
-                           SEMB_NT, &tot, &tmx);
+    const double bs = semb_block_max(acc, red, SEMB_TID, SEMB_NT);
+    last = semb_last_block_uniform(0.0, bs, partials, partials + SEMB_NB, counter, SEMB_NB, SEMB_BID, red, SEMB_TID,
+                                   SEMB_NT, sh_tot);
   }
   if (last) {
-    const double v = (which == 0) ? tot : tmx;
-    scal->red[which] = v;
-    scal->xchg_red[scal->rank] = v;
+    const double v = (which == 0) ? sh_tot[0] : sh_tot[1];
+    if (x.on) {
+      double s0, m1;
+      semb_p2p_allgather(x, scal, 2, which == 0 ? v : 0.0, which == 0 ? 0.0 : v, &s0, &m1, SEMB_TID);
+      if (SEMB_TID == 0) scal->red[which] = (which == 0) ? s0 : m1;
+    } else if (SEMB_TID == 0) {
+      scal->red[which] = v;
+      scal->xchg_red[scal->rank] = v;
+    }
   }
 }
 
@@ -437,7 +496,7 @@ __global__ void __launch_bounds__(256) semb_pcg_init_kernel(const double2* __res
                                                             const double* __restrict__ wy1d, int p2, int nxl,
                                                             int nyl, int precond, double b0, double tol,
                                                             long long maxiter, double* partials,
-                                                            unsigned* counter, SembScal* scal) {
+                                                            unsigned* counter, SembScal* scal, const P2PArgs xp) {
   __shared__ double red[32];
   double acc = 0.0, amx = 0.0;
   SEMB_FOR_2D(p2, nyl) {
@@ -458,16 +517,20 @@ __global__ void __launch_bounds__(256) semb_pcg_init_kernel(const double2* __res
     acc += __dmul_rn(__dmul_rn(bv.y, hy), m2.y);
     amx = fmax(amx, fmax(fabs(bv.x), fabs(bv.y)));
   }
+  __shared__ double sh_tot[2];
   const double bs = semb_block_sum(acc, red, SEMB_TID, SEMB_NT);
   const double bm = semb_block_max(amx, red, SEMB_TID, SEMB_NT);
-  double tot, tmx;
-  if (semb_last_block(bs, bm, partials, partials + SEMB_NB, counter, SEMB_NB, SEMB_BID, red, SEMB_TID, SEMB_NT,
-                      &tot, &tmx)) {
-    scal->tol = tol;
-    scal->maxiter = maxiter;
-    scal->xchg_t[2 * scal->rank] = tot;
-    scal->xchg_t[2 * scal->rank + 1] = tmx;
-    if (scal->nranks == 1) semb_pcg_advance(scal, tot, tmx, true);
+  if (semb_last_block_uniform(bs, bm, partials, partials + SEMB_NB, counter, SEMB_NB, SEMB_BID, red, SEMB_TID,
+                              SEMB_NT, sh_tot)) {
+    double tot = sh_tot[0], tmx = sh_tot[1];
+    if (SEMB_TID == 0) {
+      scal->tol = tol;
+      scal->maxiter = maxiter;
+      scal->xchg_t[2 * scal->rank] = tot;
+      scal->xchg_t[2 * scal->rank + 1] = tmx;
+    }
+    if (xp.on) semb_p2p_allgather(xp, scal, 1, tot, tmx, &tot, &tmx, SEMB_TID);
+    if (SEMB_TID == 0 && (scal->nranks == 1 || xp.on)) semb_pcg_advance(scal, tot, tmx, true);
   }
 }
 
@@ -478,15 +541,14 @@ __global__ void __launch_bounds__(256) semb_pcg_update_kernel(double2* x, double
                                                               const double2* __restrict__ wx1d,
                                                               const double* __restrict__ wy1d, int p2, int nxl,
                                                               int nyl, int precond, double b0, double* partials,
-                                                              unsigned* counter, SembScal* scal) {
+                                                              unsigned* counter, SembScal* scal, const P2PArgs xp) {
   __shared__ double red[32];
   if (scal->done) return;
   double pap;
   if (scal->nranks == 1) {
     pap = __dadd_rn(__dadd_rn(scal->pap[0], scal->pap[1]), scal->pap[2]);
   } else {
-    pap = 0.0;
-    for (int q = 0; q < scal->nranks; ++q) pap += scal->xchg_pap[q];
+    pap = scal->pap_total;  // combined over ranks by the y-seam kernel (P2P) or semb_pcg_combine_pap_kernel (NCCL)
   }
   const double alpha = scal->t / pap;
   double acc = 0.0, amx = 0.0;
@@ -511,14 +573,18 @@ __global__ void __launch_bounds__(256) semb_pcg_update_kernel(double2* x, double
     acc += __dmul_rn(__dmul_rn(rv.y, hy), m2.y);
     amx = fmax(amx, fmax(fabs(rv.x), fabs(rv.y)));
   }
+  __shared__ double sh_tot[2];
   const double bs = semb_block_sum(acc, red, SEMB_TID, SEMB_NT);
   const double bm = semb_block_max(amx, red, SEMB_TID, SEMB_NT);
-  double tot, tmx;
-  if (semb_last_block(bs, bm, partials, partials + SEMB_NB, counter, SEMB_NB, SEMB_BID, red, SEMB_TID, SEMB_NT,
-                      &tot, &tmx)) {
-    scal->xchg_t[2 * scal->rank] = tot;
-    scal->xchg_t[2 * scal->rank + 1] = tmx;
-    if (scal->nranks == 1) semb_pcg_advance(scal, tot, tmx, false);
+  if (semb_last_block_uniform(bs, bm, partials, partials + SEMB_NB, counter, SEMB_NB, SEMB_BID, red, SEMB_TID,
+                              SEMB_NT, sh_tot)) {
+    double tot = sh_tot[0], tmx = sh_tot[1];
+    if (SEMB_TID == 0) {
+      scal->xchg_t[2 * scal->rank] = tot;
+      scal->xchg_t[2 * scal->rank + 1] = tmx;
+    }
+    if (xp.on) semb_p2p_allgather(xp, scal, 1, tot, tmx, &tot, &tmx, SEMB_TID);  // fused all-gather over NVLink
+    if (SEMB_TID == 0 && (scal->nranks == 1 || xp.on)) semb_pcg_advance(scal, tot, tmx, false);
   }
 }
 
@@ -537,6 +603,14 @@ __global__ void semb_pcg_finalize_kernel(SembScal* scal, int first) {
 __global__ void semb_pcg_pack_pap_kernel(SembScal* scal) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   scal->xchg_pap[scal->rank] = __dadd_rn(__dadd_rn(scal->pap[0], scal->pap[1]), scal->pap[2]);
+}
+
+// NCCL path: after the all-gather of xchg_pap, combine in rank order
+__global__ void semb_pcg_combine_pap_kernel(SembScal* scal) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double pap = 0.0;
+  for (int q = 0; q < scal->nranks; ++q) pap += scal->xchg_pap[q];
+  scal->pap_total = pap;
 }
 
 // generic path: p = h + beta*p (pcg.jl:46-50)
@@ -646,13 +720,24 @@ int semb_launch_seam_x(semb_ctx* ctx, const OpArgs& a) {
   SEMB_POST_LAUNCH(ctx);
 }
 
-int semb_launch_seam_y(semb_ctx* ctx, const OpArgs& a, int nhalo_lo, int nhalo_hi, bool domask) {
+int semb_launch_seam_y(semb_ctx* ctx, const OpArgs& a, int nhalo_lo, int nhalo_hi, bool domask, const P2PArgs& x) {
   const int nq = a.nyseam + nhalo_lo + nhalo_hi;
   if (nq == 0) return SEMB_OK;
   const long long total = (long long)nq * a.nxl;
   int blocks = (int)((total + 255) / 256);
   if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-  semb_seam_y_kernel<<<blocks, 256, 0, ctx->stream>>>(a, nhalo_lo, nhalo_hi, domask ? 1 : 0);
+  semb_seam_y_kernel<<<blocks, 256, 0, ctx->stream>>>(a, nhalo_lo, nhalo_hi, domask ? 1 : 0, x);
+  SEMB_POST_LAUNCH(ctx);
+}
+
+int semb_launch_halo_push(semb_ctx* ctx, const double* out, long long pitch, int nxl, int nyl, double* dst_lo,
+                          double* dst_hi, unsigned long long* flag_lo, unsigned long long* flag_hi,
+                          unsigned long long epoch, unsigned* counter, const SembScal* scal, int pcg) {
+  int blocks = (nxl + 1023) / 1024;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 32) blocks = 32;
+  semb_halo_push_kernel<<<blocks, 256, 0, ctx->stream>>>(out, pitch, nxl, nyl, dst_lo, dst_hi, flag_lo, flag_hi, epoch,
+                                                         counter, scal, pcg);
   SEMB_POST_LAUNCH(ctx);
 }
 
@@ -724,11 +809,11 @@ int semb_launch_generic_local(semb_ctx* ctx, const OpArgs& a, int nr, int ns, co
   SEMB_POST_LAUNCH(ctx);
 }
 
-int semb_launch_reduce(semb_ctx* ctx, semb_mesh* m, int which, const double* a, const double* b) {
+int semb_launch_reduce(semb_ctx* ctx, semb_mesh* m, int which, const double* a, const double* b, const P2PArgs& x) {
   Grid2D g = grid2d(m->pitch, m->nyl, ctx->sm_count, m->npartials / 2);
   semb_reduce_kernel<<<g.grid, g.block, 0, ctx->stream>>>(which, (const double2*)a, (const double2*)b,
                                                           (const double2*)m->d_wx1d, m->d_wy1d, (int)(m->pitch / 2),
-                                                          m->nyl, m->d_partials, m->d_counters + 4, m->d_scal);
+                                                          m->nyl, m->d_partials, m->d_counters + 4, m->d_scal, x);
   SEMB_POST_LAUNCH(ctx);
 }
 
@@ -738,22 +823,22 @@ int semb_launch_reduce_finalize(semb_ctx* ctx, semb_mesh* m, int which) {
 }
 
 int semb_launch_pcg_init(semb_ctx* ctx, semb_mesh* m, const double* b, double* x, double* r, double* p,
-                         int precond, double prec_b0, double tol, long long maxiter) {
+                         int precond, double prec_b0, double tol, long long maxiter, const P2PArgs& xa) {
   Grid2D g = grid2d(m->pitch, m->nyl, ctx->sm_count, m->npartials / 2);
   semb_pcg_init_kernel<<<g.grid, g.block, 0, ctx->stream>>>(
       (const double2*)b, (double2*)x, (double2*)r, (double2*)p, (const double2*)m->arr[SEMB_B],
       (const double2*)m->d_wx1d, m->d_wy1d, (int)(m->pitch / 2), m->nxl, m->nyl, precond, prec_b0, tol, maxiter,
-      m->d_partials, m->d_counters + 3, m->d_scal);
+      m->d_partials, m->d_counters + 3, m->d_scal, xa);
   SEMB_POST_LAUNCH(ctx);
 }
 
 int semb_launch_pcg_update(semb_ctx* ctx, semb_mesh* m, double* x, double* r, const double* p, const double* Ap,
-                           int precond, double prec_b0) {
+                           int precond, double prec_b0, const P2PArgs& xa) {
   Grid2D g = grid2d(m->pitch, m->nyl, ctx->sm_count, m->npartials / 2);
   semb_pcg_update_kernel<<<g.grid, g.block, 0, ctx->stream>>>(
       (double2*)x, (double2*)r, (const double2*)p, (const double2*)Ap, (const double2*)m->arr[SEMB_B],
       (const double2*)m->d_wx1d, m->d_wy1d, (int)(m->pitch / 2), m->nxl, m->nyl, precond, prec_b0, m->d_partials,
-      m->d_counters + 3, m->d_scal);
+      m->d_counters + 3, m->d_scal, xa);
   SEMB_POST_LAUNCH(ctx);
 }
 
@@ -781,6 +866,11 @@ int semb_launch_mask_dot(semb_ctx* ctx, semb_mesh* m, const OpArgs& a) {
 
 int semb_launch_pcg_pack_pap(semb_ctx* ctx, semb_mesh* m) {
   semb_pcg_pack_pap_kernel<<<1, 32, 0, ctx->stream>>>(m->d_scal);
+  SEMB_POST_LAUNCH(ctx);
+}
+
+int semb_launch_pcg_combine_pap(semb_ctx* ctx, semb_mesh* m) {
+  semb_pcg_combine_pap_kernel<<<1, 32, 0, ctx->stream>>>(m->d_scal);
   SEMB_POST_LAUNCH(ctx);
 }
 

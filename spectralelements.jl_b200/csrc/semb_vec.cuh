@@ -4,7 +4,11 @@
 #include "semb_internal.cuh"
 
 int semb_launch_seam_x(semb_ctx* ctx, const OpArgs& a);
-int semb_launch_seam_y(semb_ctx* ctx, const OpArgs& a, int nhalo_lo, int nhalo_hi, bool domask);
+int semb_launch_seam_y(semb_ctx* ctx, const OpArgs& a, int nhalo_lo, int nhalo_hi, bool domask, const P2PArgs& x);
+int semb_launch_halo_push(semb_ctx* ctx, const double* out, long long pitch, int nxl, int nyl, double* dst_lo,
+                          double* dst_hi, unsigned long long* flag_lo, unsigned long long* flag_hi,
+                          unsigned long long epoch, unsigned* counter, const SembScal* scal, int pcg);
+int semb_launch_pcg_combine_pap(semb_ctx* ctx, semb_mesh* m);
 
 int semb_launch_gs_x(semb_ctx* ctx, const double* u, double* out, long long pitch, int N, int Ex, int nxl,
                      int nyl, int perx);
@@ -27,12 +31,12 @@ int semb_launch_geom(semb_ctx* ctx, const double* x, const double* y, long long 
 int semb_launch_generic_local(semb_ctx* ctx, const OpArgs& a, int nr, int ns, const double* dDr,
                               const double* dDs, double* tmp_wr, double* tmp_ws, bool massterm);
 // reductions (deterministic): which = 0 dot_mult(a,b,mult), 1 norm_inf(a)
-int semb_launch_reduce(semb_ctx* ctx, semb_mesh* m, int which, const double* a, const double* b);
+int semb_launch_reduce(semb_ctx* ctx, semb_mesh* m, int which, const double* a, const double* b, const P2PArgs& x);
 // PCG vector kernels
 int semb_launch_pcg_init(semb_ctx* ctx, semb_mesh* m, const double* b, double* x, double* r, double* p,
-                         int precond, double prec_b0, double tol, long long maxiter);
+                         int precond, double prec_b0, double tol, long long maxiter, const P2PArgs& xa);
 int semb_launch_pcg_update(semb_ctx* ctx, semb_mesh* m, double* x, double* r, const double* p, const double* Ap,
-                           int precond, double prec_b0);
+                           int precond, double prec_b0, const P2PArgs& xa);
 int semb_launch_pcg_dir(semb_ctx* ctx, semb_mesh* m, const double* r, double* p, int precond, double prec_b0);
 int semb_launch_mask_dot(semb_ctx* ctx, semb_mesh* m, const OpArgs& a);
 int semb_launch_pcg_pack_pap(semb_ctx* ctx, semb_mesh* m);
