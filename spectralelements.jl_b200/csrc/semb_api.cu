@@ -300,20 +300,26 @@ static int mesh_build_plan(semb_mesh* m) {
   int occ = 1;
   if (m->fast) SEMB_TRY(semb_strip_regs(m->nr, false, false, nullptr, nullptr, &occ));
   if (occ < 1) occ = 1;
-  // chunks: pick the count in [1 wave, 4 waves] with the best wave efficiency, >= 2 element rows each
+  // chunks: fill the resident CTA slots.  Small meshes (fewer element rows than slots) get one chunk per
+  // element row (parallelism beats seam overhead); large ones the count in [1 wave, 4 waves] with the best
+  // wave efficiency and at least 2 element rows per chunk.
   const int slots = c->sm_count * occ;
-  int best = 1;
-  double best_eff = -1.0;
   const int lo = std::max(1, slots / m->nstrips), hi = std::max(lo, 4 * slots / m->nstrips);
-  for (int nc = lo; nc <= hi; ++nc) {
-    if (nc > m->ney) break;
-    if (nc > 1 && m->ney / nc < 2) break;
-    const long long ctas = (long long)nc * m->nstrips;
-    const long long waves = (ctas + slots - 1) / slots;
-    const double eff = (double)ctas / (double)(waves * slots) - 1e-4 * nc;  // prefer fewer seams on ties
-    if (eff > best_eff) {
-      best_eff = eff;
-      best = nc;
+  int best = 1;
+  if (m->ney <= lo) {
+    best = m->ney;
+  } else if (m->ney / 2 <= lo) {
+    best = lo;
+  } else {
+    double best_eff = -1.0;
+    for (int nc = lo; nc <= hi && nc <= m->ney / 2; ++nc) {
+      const long long ctas = (long long)nc * m->nstrips;
+      const long long waves = (ctas + slots - 1) / slots;
+      const double eff = (double)ctas / (double)(waves * slots) - 1e-4 * nc;  // prefer fewer seams on ties
+      if (eff > best_eff) {
+        best_eff = eff;
+        best = nc;
+      }
     }
   }
   if (best > m->ney) best = m->ney;
@@ -1291,19 +1297,62 @@ extern "C" int semb_pcg_status(semb_mesh* m, long long* iters, double* resinf, i
 extern "C" int semb_pcg(semb_mesh* m, const semb_pcg_opts* o, const semb_field* b, semb_field* x, long long* iters,
                         double* resinf) {
   SEMB_TRY(semb_pcg_begin(m, o, b, x));
-  int every = o->check_every > 0 ? o->check_every : 16;
+  semb_ctx* c = m->ctx;
+  const int every = o->check_every > 0 ? o->check_every : 16;
+  // The loop is launch-bound on small meshes: capture `every` iterations (4 kernels each, all scalars live in
+  // device memory, so the arguments never change) into a CUDA graph and replay it between polls of the
+  // device-side done flag.  Multi-rank runs keep plain launches (per-iteration epochs / NCCL calls).
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  long long per_graph = 0;
+  const bool use_graph = c->nranks == 1 && every >= 2 && !getenv("SEMB_NO_GRAPH");
+  int rc = SEMB_OK;
   for (;;) {
-    SEMB_TRY(read_scal(m));
-    if (m->h_scal->done) break;
+    rc = read_scal(m);
+    if (rc < 0 || m->h_scal->done) break;
     if (!std::isfinite(m->h_scal->t) || !std::isfinite(m->h_scal->rmax)) {
       semb_set_error("pcg: non-finite residual (t=%g, rmax=%g) at iteration %lld", m->h_scal->t, m->h_scal->rmax,
                      m->h_scal->iters);
-      m->pcg_active = false;
-      return SEMB_EINVAL;
+      rc = SEMB_EINVAL;
+      break;
     }
-    SEMB_TRY(semb_pcg_iterate(m, every));
+    if (use_graph && !exec) {
+      const long long l0 = c->launches;
+      const bool prof = c->profile;
+      c->profile = false;
+      cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+      if (e == cudaSuccess) {
+        rc = semb_pcg_iterate(m, every);
+        e = cudaStreamEndCapture(c->stream, &graph);
+        if (rc >= 0 && e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+      }
+      c->profile = prof;
+      per_graph = c->launches - l0;
+      c->launches = l0;
+      if (rc < 0) break;
+      if (e != cudaSuccess || !exec) {
+        semb_set_error("pcg: CUDA graph capture failed: %s", cudaGetErrorString(e));
+        rc = SEMB_ECUDA;
+        break;
+      }
+    }
+    if (exec) {
+      cudaError_t e = cudaGraphLaunch(exec, c->stream);
+      if (e != cudaSuccess) {
+        semb_set_error("pcg: cudaGraphLaunch failed: %s", cudaGetErrorString(e));
+        rc = SEMB_ECUDA;
+        break;
+      }
+      c->launches += per_graph;
+    } else {
+      rc = semb_pcg_iterate(m, every);
+      if (rc < 0) break;
+    }
   }
+  if (exec) cudaGraphExecDestroy(exec);
+  if (graph) cudaGraphDestroy(graph);
   m->pcg_active = false;
+  if (rc < 0) return rc;
   if (iters) *iters = m->h_scal->iters;
   if (resinf) *resinf = m->h_scal->rmax;
   return m->h_scal->warned ? SEMB_NOT_CONVERGED : SEMB_OK;
