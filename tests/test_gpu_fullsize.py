@@ -1,0 +1,102 @@
+"""Parity at BASELINE.json's full sizes.  cfg2 (Helmholtz, 256x256 elements, order 8, 5.3 M DOF) is
+compared against the oracle node by node; the 1e8-DOF north-star mesh (order 8, 1112x1112) is checked
+through size-independent properties (linearity, self-adjointness in the mult inner product, constants in
+the null space, continuity / idempotence of QQ^T, mask) plus a node-by-node oracle comparison on a slab
+sample of element rows (the local operator is element-local, so a slab is self-contained once the
+boundary rows that couple to the rest of the mesh are excluded)."""
+import numpy as np
+import pytest
+
+import sem_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def test_cfg2_helmholtz_full_mesh_vs_oracle(sem, ctx):
+    nr, E = 9, 256
+    gm = sem.Mesh(nr, nr, E, E, (False, False), "wavy", ctx=ctx)  # grid, jac, factors generated on device
+    try:
+        om = so.make_mesh(nr, nr, E, E, (False, False), so.wavy)
+        # geometry generated on the device agrees with the oracle's (differentiation amplifies rounding ~N^2 E)
+        for name in ("G11", "G22", "B"):
+            assert relerr(getattr(gm, name), getattr(om, name)) < 2e-10, name
+        # operator parity proper: same factors on both sides
+        gm2 = sem.Mesh.from_arrays(nr, nr, E, E, (False, False), om.Dr, om.Ds, om.G11, om.G12, om.G22, om.B, ctx=ctx)
+        try:
+            u = so.splitmix_uniform(gm.shape)
+            M = so.generateMask(list("DDDD"), om).astype(np.float64)
+            ref = so.opLHS(u, 1.0, 1.0, M, om)
+            out = sem.OpLHS(gm2, 1.0, 1.0, bc="DDDD")(u)
+            assert relerr(out, ref) < 1e-12
+            assert np.array_equal(sem.gatherScatter(u, gm2), so.gatherScatter(u, om))
+            # 40 PCG iterations track the oracle (trajectory parity at full cfg2 size)
+            b = so.gatherScatter(so.mask(so.mass(np.ones(gm.shape), om), M), om)
+            io, ig = {}, {}
+            xo = so.pcg(b, lambda v: so.opLHS(v, 1.0, 1.0, M, om), mult=om.mult, maxiter=40, info=io)
+            xg = sem.pcg(b, sem.OpLHS(gm2, 1.0, 1.0, bc="DDDD"), maxiter=40, info=ig)
+            assert ig["iters"] == io["iters"] == 40
+            assert relerr(xg, xo) < 1e-9
+            assert abs(ig["resinf"] - io["resinf"]) < 1e-8 * io["resinf"]
+        finally:
+            gm2.free()
+    finally:
+        gm.free()
+
+
+def test_north_star_mesh_properties_and_slab_sample(sem, ctx):
+    nr, E = 9, 1112  # 1.0016e8 DOF
+    gm = sem.Mesh(nr, nr, E, E, (False, False), "wavy", ctx=ctx)
+    try:
+        n = gm.shape[0] * gm.shape[1]
+        assert n == 100160064
+        u, v, Au, Av, w, t = (gm.field() for _ in range(6))
+        u.fill_random(1)
+        v.fill_random(2)
+        # continuous, masked test functions: uc = mask(gs(u))
+        gm.gs_device(u, t); gm.mask_bc_device(t, "DDDD", u)
+        gm.gs_device(v, t); gm.mask_bc_device(t, "DDDD", v)
+        gm.oplhs_device(u, Au, nu=1.0, k=0.0, bc="DDDD")
+        gm.oplhs_device(v, Av, nu=1.0, k=0.0, bc="DDDD")
+        # self-adjoint in the mult inner product on continuous masked fields
+        a, b = gm.dot_mult(v, Au), gm.dot_mult(u, Av)
+        assert abs(a - b) < 1e-11 * abs(a)
+        assert gm.dot_mult(u, Au) > 0  # positive definite
+        # linearity: A(2u - 3v) = 2Au - 3Av
+        w.copy_from(u); w.axpby(-3.0, v, 2.0)
+        gm.oplhs_device(w, t, nu=1.0, k=0.0, bc="DDDD")
+        w.copy_from(Au); w.axpby(-3.0, Av, 2.0)
+        w.axpby(-1.0, t, 1.0)
+        assert gm.norm_inf(w) < 1e-12 * gm.norm_inf(t)
+        # constants are in the null space of the un-masked Poisson operator (Neumann everywhere)
+        w.fill(1.0)
+        gm.oplhs_device(w, t, nu=1.0, k=0.0, bc="NNNN")
+        assert gm.norm_inf(t) < 1e-9 * gm.norm_inf(Au)
+        # the result is continuous: gs(mult .* Au) == Au, and masked rows are exactly zero
+        hAu = Au.download()
+        assert np.all(hAu[0, :] == 0) and np.all(hAu[-1, :] == 0) and np.all(hAu[:, 0] == 0) and np.all(hAu[:, -1] == 0)
+        ia = np.arange(1, E) * nr - 1
+        assert np.array_equal(hAu[ia, :], hAu[ia + 1, :]) and np.array_equal(hAu[:, ia], hAu[:, ia + 1])
+        # determinism at full size: same bits on a second apply
+        gm.oplhs_device(u, t, nu=1.0, k=0.0, bc="DDDD")
+        assert np.array_equal(t.download(), hAu)
+        # slab sample against the oracle: element rows [r0, r0+R), all 1112 element columns
+        r0, R = 500, 24
+        sl = slice(r0 * nr, (r0 + R) * nr)
+        G11, G12, G22 = (np.asfortranarray(getattr(gm, k)[:, sl]) for k in ("G11", "G12", "G22"))
+        hu = u.download()
+        us = np.asfortranarray(hu[:, sl])
+        ref = so.laplace(us, gm.Dr, gm.Ds, G11, G12, G22)
+        ref = so.gatherScatter_index(ref, nr, nr, E, R, (False, False))
+        ref[0, :] = 0.0
+        ref[-1, :] = 0.0
+        got = hAu[:, sl]
+        inner = slice(1, R * nr - 1)  # the slab's first/last line also receive the neighbouring slabs
+        assert relerr(got[:, inner], ref[:, inner]) < 1e-12
+        for f in (u, v, Au, Av, w, t):
+            f.free()
+    finally:
+        gm.free()
