@@ -197,6 +197,25 @@ int semb_pcg_begin(semb_mesh* m, const semb_pcg_opts* opts, const semb_field* b,
 int semb_pcg_iterate(semb_mesh* m, int n);
 int semb_pcg_status(semb_mesh* m, long long* iters, double* resinf, int* done);
 
+/* ---- implicit diffusion driver, device resident (the caller that defines the fused unit) ---- */
+/* Diffusion(bc,msh;Ti,Tf,dt,k), diffusion.jl:20-34, with its Field (mesh.jl:179-195: u, uh[1..k], ub, M) and
+ * TimeStepper (time.jl:70-99) kept in HBM across steps.  The user closures setBC!/setForcing!/setVisc!
+ * (diffusion.jl:98-100) stay in the host language: between begin_step and finish_step the host uploads
+ * whatever they changed into the fields returned by semb_diffusion_field. */
+typedef struct semb_diffusion semb_diffusion;
+enum semb_diffusion_field_id { SEMB_DFN_U = 0, SEMB_DFN_UB, SEMB_DFN_NU, SEMB_DFN_F, SEMB_DFN_RHS, SEMB_DFN_UH0 /* + i */ };
+int semb_diffusion_create(semb_mesh* m, const char bc[4], double Ti, double Tf, double dt, int k, semb_diffusion** d);
+int semb_diffusion_destroy(semb_diffusion* d);
+int semb_diffusion_field(semb_diffusion* d, int which, semb_field** f);
+/* first half of evolve! (diffusion.jl:89-96): updateHist!(fld) (mesh.jl:199-215), time history (mesh.jl:217-224),
+ * istep += 1, time[1] += dt, bdfExtK! (time.jl:55-68).  Returns the new time for the host closures. */
+int semb_diffusion_begin_step(semb_diffusion* d, double* time, long long* istep);
+/* second half (diffusion.jl:102-103): makeRHS! (diffusion.jl:51-65: mass(f) - nu.*lapl(ub) - sum bdfB[1+i].*mass(uh[i]);
+ * mask THEN gatherScatter) and solve! (diffusion.jl:67-77: pcg! with opLHS, then u .+= ub). */
+int semb_diffusion_finish_step(semb_diffusion* d, double tol, long long* iters, double* resinf);
+/* time[k+1], bdfA[k], bdfB[k+1] (time.jl:70-82); any pointer may be NULL */
+int semb_diffusion_state(semb_diffusion* d, double* time, double* bdfA, double* bdfB, long long* istep);
+
 /* ---- host-pointer convenience twins (value semantics of the Julia functions) ------------------- */
 /* Each uploads its inputs, runs the device op, downloads `out` (fresh array in Julia). */
 int semb_lapl_host(semb_mesh* m, const double* u, double* out);

@@ -635,63 +635,94 @@ def pcg_b(x, b, opA, **kw):
 
 
 # ---------------------------------------------------------------------------------------------
-# Diffusion driver (diffusion.jl) -- "next" row 8f-1, thin host mirror over the device ops
+# Diffusion driver (diffusion.jl) -- "next" row 8f-1: fields, BDF history and RHS stay in HBM across steps
 # ---------------------------------------------------------------------------------------------
+_DFN_FIELDS = {"u": 0, "ub": 1, "nu": 2, "f": 3, "rhs": 4}
+
+
 class Diffusion:
-    """Diffusion(bc,msh;Ti,Tf,dt,k), diffusion.jl:20-34 (+ Field, mesh.jl:188-195; TimeStepper, time.jl:84-99)"""
+    """Diffusion(bc,msh;Ti,Tf,dt,k), diffusion.jl:20-34 (+ Field, mesh.jl:179-195; TimeStepper, time.jl:70-99).
+
+    Device resident (semb_diffusion_*): u, uh[1..k], ub, nu, f, rhs live in HBM; reading an attribute
+    downloads it, assigning uploads it.  The user closures are host functions of (x, y, t), as in the reference."""
 
     def __init__(self, bc, msh: Mesh, Ti=0.0, Tf=0.0, dt=0.0, k=3):
-        self.bc, self.msh = list(bc), msh
-        z = lambda: np.zeros(msh.shape, order="F")
-        self.u, self.ub, self.nu, self.f, self.rhs = z(), z(), z(), z(), z()
-        self.uh = [z() for _ in range(k)]
-        self.M = generateMask(bc, msh).astype(np.float64)
-        self.time = Ti * np.ones(k + 1)
-        self.bdfA, self.bdfB = bdfExtK(self.time, k)
-        self.istep, self.dt, self.Ti, self.Tf = 0, dt, Ti, Tf
+        self.__dict__["_ready"] = False
+        self.bc, self.msh, self.k = list(bc), msh, k
+        self.lib = msh.lib
+        h = C.c_void_p()
+        check(self.lib.semb_diffusion_create(msh.h, _bc_bytes(bc), float(Ti), float(Tf), float(dt), int(k), C.byref(h)))
+        self.h = h
+        self.dt, self.Ti, self.Tf = dt, Ti, Tf
+        self.M = generateMask(bc, msh).astype(np.float64)  # Field.M (mesh.jl:183,192)
         self.pcg_iters = []
+        self.__dict__["_ready"] = True
+
+    def _field(self, which: int) -> DeviceField:
+        fh = C.c_void_p()
+        check(self.lib.semb_diffusion_field(self.h, which, C.byref(fh)))
+        f = DeviceField.__new__(DeviceField)
+        f.msh, f.lib, f.h = self.msh, self.lib, fh
+        return f
+
+    def __getattr__(self, name):
+        if name in _DFN_FIELDS:
+            return self._field(_DFN_FIELDS[name]).download()
+        if name == "uh":
+            return [self._field(5 + i).download() for i in range(self.k)]
+        if name in ("time", "bdfA", "bdfB", "istep"):
+            t, a, b, i = np.zeros(self.k + 1), np.zeros(self.k), np.zeros(self.k + 1), C.c_longlong()
+            check(self.lib.semb_diffusion_state(self.h, dptr(t), dptr(a), dptr(b), C.byref(i)))
+            return {"time": t, "bdfA": a, "bdfB": b, "istep": i.value}[name]
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        if self.__dict__.get("_ready") and name in _DFN_FIELDS:
+            self._field(_DFN_FIELDS[name]).upload(value)
+        else:
+            self.__dict__[name] = value
+
+    def free(self):
+        if self.__dict__.get("h"):
+            self.lib.semb_diffusion_destroy(self.h)
+            self.__dict__["h"] = None
 
 
 def makeRHS_b(dfn: Diffusion):
-    """makeRHS!(dfn), diffusion.jl:51-65 (mask THEN gatherScatter)"""
+    """makeRHS!(dfn), diffusion.jl:51-65 -- host-composed from the device operators (the driver's own step uses
+    the fused device kernel; this form exists for callers that compose the pieces by hand)."""
     msh = dfn.msh
+    nu, bdfB = dfn.nu, dfn.bdfB
     rhs = mass(dfn.f, msh)
-    rhs = rhs - dfn.nu * lapl(dfn.ub, msh)
-    for i in range(len(dfn.uh)):
-        if dfn.bdfB[1 + i] != 0.0:
-            rhs = rhs - dfn.bdfB[1 + i] * mass(dfn.uh[i], msh)
+    rhs = rhs - nu * lapl(dfn.ub, msh)
+    for i, uh in enumerate(dfn.uh):
+        rhs = rhs - bdfB[1 + i] * mass(uh, msh)
     rhs = mask(rhs, dfn.M, msh)
     dfn.rhs = gatherScatter(rhs, msh)
 
 
 def solve_b(dfn: Diffusion, tol=1e-8):
-    """solve!(dfn), diffusion.jl:67-77"""
+    """solve!(dfn), diffusion.jl:67-77 (host-composed twin, see makeRHS_b)"""
     info = {}
     x = pcg(dfn.rhs, OpLHS(dfn.msh, dfn.nu, dfn.bdfB[0], dfn.M), mult=dfn.msh.mult, tol=tol, info=info)
     dfn.pcg_iters.append(info["iters"])
     dfn.u = x + dfn.ub
 
 
-def evolve_b(dfn: Diffusion, setBC=None, setForcing=None, setVisc=None):
-    """evolve!(dfn,...), diffusion.jl:81-106"""
-    for i in range(len(dfn.uh) - 1, 0, -1):
-        dfn.uh[i] = dfn.uh[i - 1].copy()
-    dfn.uh[0] = dfn.u.copy()
-    for i in range(dfn.time.size - 1, 0, -1):
-        dfn.time[i] = dfn.time[i - 1]
-    dfn.time[0] = dfn.time[1]
-    dfn.istep += 1
-    dfn.time[0] += dfn.dt
-    dfn.bdfA, dfn.bdfB = bdfExtK(dfn.time, dfn.time.size - 1)
-    x, y, t = dfn.msh.x, dfn.msh.y, dfn.time[0]
+def evolve_b(dfn: Diffusion, setBC=None, setForcing=None, setVisc=None, tol=1e-8):
+    """evolve!(dfn,setBC!,setForcing!,setVisc!), diffusion.jl:81-106"""
+    t, istep = C.c_double(), C.c_longlong()
+    check(dfn.lib.semb_diffusion_begin_step(dfn.h, C.byref(t), C.byref(istep)))  # updateHist!, bdfExtK!
+    x, y = dfn.msh.x, dfn.msh.y
     if setBC is not None:
-        dfn.ub = as_f64(setBC(x, y, t))
+        dfn.ub = as_f64(setBC(x, y, t.value))
     if setForcing is not None:
-        dfn.f = as_f64(setForcing(x, y, t))
+        dfn.f = as_f64(setForcing(x, y, t.value))
     if setVisc is not None:
-        dfn.nu = as_f64(setVisc(x, y, t))
-    makeRHS_b(dfn)
-    solve_b(dfn)
+        dfn.nu = as_f64(setVisc(x, y, t.value))
+    it, res = C.c_longlong(), C.c_double()
+    check(dfn.lib.semb_diffusion_finish_step(dfn.h, float(tol), C.byref(it), C.byref(res)))  # makeRHS!, solve!
+    dfn.pcg_iters.append(it.value)
 
 
 def simulate_b(dfn: Diffusion, callback=None, setIC=None, setBC=None, setForcing=None, setVisc=None, max_steps=None):

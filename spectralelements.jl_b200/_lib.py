@@ -92,6 +92,12 @@ _SIGS = {
     "semb_pcg_begin": ([vp, C.POINTER(PcgOpts), vp, vp], C.c_int),
     "semb_pcg_iterate": ([vp, C.c_int], C.c_int),
     "semb_pcg_status": ([vp, c_ll_p, c_double_p, c_int_p], C.c_int),
+    "semb_diffusion_create": ([vp, C.c_char_p, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(vp)], C.c_int),
+    "semb_diffusion_destroy": ([vp], C.c_int),
+    "semb_diffusion_field": ([vp, C.c_int, C.POINTER(vp)], C.c_int),
+    "semb_diffusion_begin_step": ([vp, c_double_p, c_ll_p], C.c_int),
+    "semb_diffusion_finish_step": ([vp, C.c_double, c_ll_p, c_double_p], C.c_int),
+    "semb_diffusion_state": ([vp, c_double_p, c_double_p, c_double_p, c_ll_p], C.c_int),
     "semb_lapl_host": ([vp, c_double_p, c_double_p], C.c_int),
     "semb_hlmz_host": ([vp, c_double_p, c_double_p, C.c_double, c_double_p, C.c_double, c_double_p], C.c_int),
     "semb_mass_host": ([vp, c_double_p, c_double_p], C.c_int),

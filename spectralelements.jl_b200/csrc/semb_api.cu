@@ -1358,6 +1358,127 @@ extern "C" int semb_pcg(semb_mesh* m, const semb_pcg_opts* o, const semb_field* 
   return m->h_scal->warned ? SEMB_NOT_CONVERGED : SEMB_OK;
 }
 
+// ---- device-resident Diffusion driver (diffusion.jl) --------------------------------------------------------------
+struct semb_diffusion {
+  semb_mesh* m = nullptr;
+  char bc[5] = {0, 0, 0, 0, 0};
+  int k = 3;
+  double Ti = 0, Tf = 0, dt = 0;
+  long long istep = 0;
+  std::vector<double> time, bdfA, bdfB;
+  semb_field *u = nullptr, *ub = nullptr, *nu = nullptr, *f = nullptr, *rhs = nullptr, *tmp = nullptr, *x = nullptr;
+  std::vector<semb_field*> uh;
+};
+
+extern "C" int semb_diffusion_create(semb_mesh* m, const char bc[4], double Ti, double Tf, double dt, int k,
+                                     semb_diffusion** out) {
+  SEMB_REQUIRE(m && bc && out, "semb_diffusion_create: null argument");
+  SEMB_REQUIRE(k >= 1 && k <= 4, "semb_diffusion_create: history length k must be 1..4 (got %d)", k);
+  SEMB_REQUIRE(m->arr[SEMB_B] && m->arr[SEMB_G11], "semb_diffusion_create: mesh needs B and G factors");
+  SEMB_TRY(ctx_enter(m->ctx));
+  MaskFlags fl;
+  SEMB_TRY(parse_bc(m, bc, &fl));
+  semb_diffusion* d = new semb_diffusion();
+  d->m = m;
+  memcpy(d->bc, bc, 4);
+  d->k = k;
+  d->Ti = Ti;
+  d->Tf = Tf;
+  d->dt = dt;
+  d->time.assign(k + 1, Ti);  // time.jl:87
+  d->bdfA.assign(k, 0.0);
+  d->bdfB.assign(k + 1, 0.0);
+  SEMB_TRY(semb_bdf_ext_k(k + 1, d->time.data(), k, d->bdfA.data(), d->bdfB.data()));
+  semb_field** all[] = {&d->u, &d->ub, &d->nu, &d->f, &d->rhs, &d->tmp, &d->x};
+  for (semb_field** p : all) SEMB_TRY(semb_field_create(m, p));
+  d->uh.resize(k);
+  for (int i = 0; i < k; ++i) SEMB_TRY(semb_field_create(m, &d->uh[i]));
+  *out = d;
+  return SEMB_OK;
+}
+
+extern "C" int semb_diffusion_destroy(semb_diffusion* d) {
+  if (!d) return SEMB_OK;
+  semb_field* all[] = {d->u, d->ub, d->nu, d->f, d->rhs, d->tmp, d->x};
+  for (semb_field* p : all) semb_field_destroy(p);
+  for (semb_field* p : d->uh) semb_field_destroy(p);
+  delete d;
+  return SEMB_OK;
+}
+
+extern "C" int semb_diffusion_field(semb_diffusion* d, int which, semb_field** f) {
+  SEMB_REQUIRE(d && f, "semb_diffusion_field: null argument");
+  semb_field* base[] = {d->u, d->ub, d->nu, d->f, d->rhs};
+  if (which >= 0 && which < 5) {
+    *f = base[which];
+    return SEMB_OK;
+  }
+  SEMB_REQUIRE(which >= SEMB_DFN_UH0 && which < SEMB_DFN_UH0 + d->k, "semb_diffusion_field: bad selector %d", which);
+  *f = d->uh[which - SEMB_DFN_UH0];
+  return SEMB_OK;
+}
+
+extern "C" int semb_diffusion_begin_step(semb_diffusion* d, double* time, long long* istep) {
+  SEMB_REQUIRE(d, "null diffusion");
+  SEMB_TRY(ctx_enter(d->m->ctx));
+  // updateHist!(fld), mesh.jl:207-215: uh[i] .= uh[i-1]; uh[1] .= u  (pointer rotation + one copy)
+  semb_field* last = d->uh[d->k - 1];
+  for (int i = d->k - 1; i >= 1; --i) d->uh[i] = d->uh[i - 1];
+  d->uh[0] = last;
+  SEMB_TRY(semb_field_copy(d->uh[0], d->u));
+  // updateHist!(time), mesh.jl:217-224; istep += 1; time[1] += dt; bdfExtK!, diffusion.jl:92-95
+  for (int i = d->k; i >= 1; --i) d->time[i] = d->time[i - 1];
+  d->time[0] = d->time[1];
+  d->istep += 1;
+  d->time[0] += d->dt;
+  SEMB_TRY(semb_bdf_ext_k(d->k + 1, d->time.data(), d->k, d->bdfA.data(), d->bdfB.data()));
+  if (time) *time = d->time[0];
+  if (istep) *istep = d->istep;
+  return SEMB_OK;
+}
+
+extern "C" int semb_diffusion_finish_step(semb_diffusion* d, double tol, long long* iters, double* resinf) {
+  SEMB_REQUIRE(d, "null diffusion");
+  semb_mesh* m = d->m;
+  semb_ctx* c = m->ctx;
+  SEMB_TRY(ctx_enter(c));
+  MaskFlags fl;
+  SEMB_TRY(parse_bc(m, d->bc, &fl));
+  // makeRHS!, diffusion.jl:51-65
+  SEMB_TRY(semb_lapl(m, d->ub, d->tmp));
+  const double* uh[4] = {nullptr, nullptr, nullptr, nullptr};
+  double b[4] = {0, 0, 0, 0};
+  for (int i = 0; i < d->k; ++i) {
+    uh[i] = d->uh[i]->d;
+    b[i] = d->bdfB[1 + i];
+  }
+  SEMB_TRY(semb_launch_rhs(c, m, d->f->d, d->nu->d, d->tmp->d, d->k, uh, b, fl.mx0, fl.mx1, fl.my0, fl.my1, d->x->d));
+  SEMB_TRY(semb_gather_scatter(m, d->x, d->rhs));
+  // solve!, diffusion.jl:67-77
+  semb_pcg_opts o;
+  memset(&o, 0, sizeof(o));
+  o.nu = 1.0;
+  o.nu_arr = d->nu;
+  o.k = d->bdfB[0];
+  o.bc = d->bc;
+  o.tol = tol;
+  o.maxiter = -1;
+  int rc = semb_pcg(m, &o, d->rhs, d->x, iters, resinf);
+  if (rc < 0) return rc;
+  SEMB_TRY(semb_field_copy(d->u, d->x));
+  SEMB_TRY(semb_field_axpby(1.0, d->ub, 1.0, d->u));  // u .+= ub
+  return rc;
+}
+
+extern "C" int semb_diffusion_state(semb_diffusion* d, double* time, double* bdfA, double* bdfB, long long* istep) {
+  SEMB_REQUIRE(d, "null diffusion");
+  if (time) std::copy(d->time.begin(), d->time.end(), time);
+  if (bdfA) std::copy(d->bdfA.begin(), d->bdfA.end(), bdfA);
+  if (bdfB) std::copy(d->bdfB.begin(), d->bdfB.end(), bdfB);
+  if (istep) *istep = d->istep;
+  return SEMB_OK;
+}
+
 // ---- host-pointer twins -----------------------------------------------------------------------------------------
 // Device fields backing the *_host twins are cached on the mesh (slot order = request order), so a
 // twin call costs copies + kernels, not cudaMalloc/cudaFree.

@@ -686,6 +686,29 @@ __global__ void semb_abu_s_kernel(const double* __restrict__ As, int ma, int na,
   }
 }
 
+struct RhsArgs {
+  const double* uh[4];
+  double b[4];
+  int k;
+};
+
+// makeRHS! (diffusion.jl:55-62), un-fused like the reference's broadcasts:
+//   rhs = B.*f ; rhs -= nu.*lapl(ub) ; rhs -= bdfB[1+i] .* (B.*uh[i]) ; rhs = M.*rhs
+__global__ void semb_rhs_kernel(const double* __restrict__ f, const double* __restrict__ nu,
+                                const double* __restrict__ lub, const double* __restrict__ B, RhsArgs h, long long pitch,
+                                int nxl, int nyl, int mx0, int mx1, int my0, int my1, double* rhs) {
+  for (int row = blockIdx.y; row < nyl; row += gridDim.y)
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < nxl; x += gridDim.x * blockDim.x) {
+      const size_t idx = (size_t)row * pitch + x;
+      const double Bv = B[idx];
+      double r = __dmul_rn(Bv, f[idx]);                               // mass(f), diffusion.jl:55
+      r = __dadd_rn(r, -__dmul_rn(nu[idx], lub[idx]));                // - nu .* lapl(ub), :56
+      for (int i = 0; i < h.k; ++i) r = __dadd_rn(r, -__dmul_rn(h.b[i], __dmul_rn(Bv, h.uh[i][idx])));  // :58-60
+      const bool z = (x == 0 && mx0) || (x == nxl - 1 && mx1) || (row == 0 && my0) || (row == nyl - 1 && my1);
+      rhs[idx] = __dmul_rn(z ? 0.0 : 1.0, r);                         // mask, :62
+    }
+}
+
 dim3 rows_grid(int ncols, int nrows, int threads) {
   int gx = (ncols + threads - 1) / threads;
   if (gx < 1) gx = 1;
@@ -886,5 +909,18 @@ int semb_launch_abu_r(semb_ctx* ctx, const double* Br, int mb, int nb, const dou
 
 int semb_launch_abu_s(semb_ctx* ctx, const double* As, int ma, int na, const double* u, int m, int n, double* out) {
   semb_abu_s_kernel<<<rows_grid(m, n / na * ma, 128), 128, 0, ctx->stream>>>(As, ma, na, u, m, n, out);
+  SEMB_POST_LAUNCH(ctx);
+}
+
+int semb_launch_rhs(semb_ctx* ctx, semb_mesh* m, const double* f, const double* nu, const double* lub, int k,
+                    const double* const* uh, const double* b, int mx0, int mx1, int my0, int my1, double* rhs) {
+  RhsArgs h;
+  h.k = k;
+  for (int i = 0; i < 4; ++i) {
+    h.uh[i] = i < k ? uh[i] : nullptr;
+    h.b[i] = i < k ? b[i] : 0.0;
+  }
+  semb_rhs_kernel<<<rows_grid(m->nxl, m->nyl, 256), 256, 0, ctx->stream>>>(f, nu, lub, m->arr[SEMB_B], h, m->pitch,
+                                                                          m->nxl, m->nyl, mx0, mx1, my0, my1, rhs);
   SEMB_POST_LAUNCH(ctx);
 }

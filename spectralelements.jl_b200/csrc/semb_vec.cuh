@@ -45,3 +45,6 @@ int semb_launch_reduce_finalize(semb_ctx* ctx, semb_mesh* m, int which);
 // generic ABu (ABu.jl:9-37)
 int semb_launch_abu_r(semb_ctx* ctx, const double* Br, int mb, int nb, const double* u, int m, int n, double* out);
 int semb_launch_abu_s(semb_ctx* ctx, const double* As, int ma, int na, const double* u, int m, int n, double* out);
+// makeRHS! pointwise part (diffusion.jl:55-62): rhs = M .* (B.*f - nu.*lub - sum_i b[i] .* (B.*uh[i]))
+int semb_launch_rhs(semb_ctx* ctx, semb_mesh* m, const double* f, const double* nu, const double* lub, int k,
+                    const double* const* uh, const double* b, int mx0, int mx1, int my0, int my1, double* rhs);
