@@ -203,7 +203,9 @@ int semb_pcg_status(semb_mesh* m, long long* iters, double* resinf, int* done);
  * (diffusion.jl:98-100) stay in the host language: between begin_step and finish_step the host uploads
  * whatever they changed into the fields returned by semb_diffusion_field. */
 typedef struct semb_diffusion semb_diffusion;
-enum semb_diffusion_field_id { SEMB_DFN_U = 0, SEMB_DFN_UB, SEMB_DFN_NU, SEMB_DFN_F, SEMB_DFN_RHS, SEMB_DFN_UH0 /* + i */ };
+enum semb_diffusion_field_id {
+  SEMB_DFN_U = 0, SEMB_DFN_UB, SEMB_DFN_NU, SEMB_DFN_F, SEMB_DFN_RHS, SEMB_DFN_VX, SEMB_DFN_VY, SEMB_DFN_UH0 = 8 /* + i */
+};
 int semb_diffusion_create(semb_mesh* m, const char bc[4], double Ti, double Tf, double dt, int k, semb_diffusion** d);
 int semb_diffusion_destroy(semb_diffusion* d);
 int semb_diffusion_field(semb_diffusion* d, int which, semb_field** f);
@@ -215,6 +217,22 @@ int semb_diffusion_begin_step(semb_diffusion* d, double* time, long long* istep)
 int semb_diffusion_finish_step(semb_diffusion* d, double tol, long long* iters, double* resinf);
 /* time[k+1], bdfA[k], bdfB[k+1] (time.jl:70-82); any pointer may be NULL */
 int semb_diffusion_state(semb_diffusion* d, double* time, double* bdfA, double* bdfB, long long* istep);
+
+/* ---- explicit dealiased convection and the ConvectionDiffusion driver -------------------- */
+/* grad(u,msh), grad.jl:94-113: ux = rx.*ur + sx.*us, uy = ry.*ur + sy.*us (needs a mesh built from x,y) */
+int semb_grad(semb_mesh* m, const semb_field* u, semb_field* ux, semb_field* uy);
+/* advect(T,ux,uy,mshV,mshD,Jr,Js), advect.jl:45-64: gradient on mshV, interpolation of Tx,Ty,ux,uy to the
+ * dealiasing mesh mshD (ABu(Js,Jr,.) with Jr = interpMat(mshD.zr,mshV.zr)), pointwise product with mshD.B,
+ * projection back (ABu(Js',Jr',.)).  mD = NULL: the un-dealiased form advect(T,ux,uy,msh), advect.jl:27-43.
+ * T, ux, uy, out are fields of mV.  mD must have the same Ex, Ey, periodicity (and partition) as mV. */
+int semb_advect(semb_mesh* mV, semb_mesh* mD, const semb_field* T, const semb_field* ux, const semb_field* uy,
+                semb_field* out);
+/* ConvectionDiffusion(name,fld,vx,vy,tstep,mshD,...), convectionDiffusion.jl:31-56: same handle type and
+ * begin/finish protocol as semb_diffusion; finish_step runs makeRHS! (convectionDiffusion.jl:93-110: the explicit
+ * term exH[i] = -advect(uh[i],vx,vy,...) enters with bdfA[i]) and solve! (:112-122, opM = u./B./bdfB[1]).
+ * Extra fields: SEMB_DFN_VX, SEMB_DFN_VY. */
+int semb_convdiff_create(semb_mesh* mV, semb_mesh* mD, const char bc[4], double Ti, double Tf, double dt, int k,
+                         semb_diffusion** d);
 
 /* ---- host-pointer convenience twins (value semantics of the Julia functions) ------------------- */
 /* Each uploads its inputs, runs the device op, downloads `out` (fresh array in Julia). */

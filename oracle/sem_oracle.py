@@ -607,6 +607,111 @@ def diffusion_simulate(dfn: Diffusion, setIC=None, setBC=None, setForcing=None, 
 
 
 # ----------------------------------------------------------------------------
+# grad.jl:94-113 and advect.jl:27-78 ("next" row 8f-2: the explicit convection term of cd2d)
+# ----------------------------------------------------------------------------
+def grad(u, msh: Mesh):
+    ur = ABu(EMPTY, msh.Dr, u)
+    us = ABu(msh.Ds, EMPTY, u)
+    ux = msh.rx * ur + msh.sx * us  # grad.jl:109-110
+    uy = msh.ry * ur + msh.sy * us
+    return ux, uy
+
+
+def advect(T, ux, uy, mshV: Mesh, mshD: Optional[Mesh] = None, Jr=None, Js=None):
+    if mshD is None:  # advect.jl:27-43
+        Tx, Ty = grad(T, mshV)
+        Cu = ux * Tx + uy * Ty
+        return Cu * mshV.B
+    if Jr is None:  # advect.jl:66-78
+        Jr = interpMat(mshD.zr, mshV.zr)
+        Js = interpMat(mshD.zs, mshV.zs)
+    Tx, Ty = grad(T, mshV)  # advect.jl:45-64
+    JTx = ABu(Js, Jr, Tx)
+    JTy = ABu(Js, Jr, Ty)
+    Jux = ABu(Js, Jr, ux)
+    Juy = ABu(Js, Jr, uy)
+    JCu = Jux * JTx + Juy * JTy
+    JCu = JCu * mshD.B
+    return ABu(Js.T, Jr.T, JCu)
+
+
+# ----------------------------------------------------------------------------
+# convectionDiffusion.jl:31-179 -- BDF-k implicit diffusion + EXT-k explicit dealiased convection
+# ----------------------------------------------------------------------------
+@dataclass
+class ConvectionDiffusion:
+    bc: Sequence[str]
+    mshV: Mesh
+    mshD: Mesh
+    vx: np.ndarray
+    vy: np.ndarray
+    Ti: float = 0.0
+    Tf: float = 0.0
+    dt: float = 0.0
+    k: int = 3
+    u: np.ndarray = field(default=None)
+    pcg_iters: list = field(default_factory=list)
+
+    def __post_init__(self):
+        z = lambda: _F(np.zeros_like(self.mshV.x))
+        self.u, self.ub, self.nu, self.f, self.rhs = z(), z(), z(), z(), z()
+        self.uh = [z() for _ in range(self.k)]
+        self.exH = [z() for _ in range(self.k)]
+        self.M = generateMask(self.bc, self.mshV).astype(np.float64)
+        self.time = self.Ti * np.ones(self.k + 1)
+        self.bdfA, self.bdfB = bdfExtK(self.time, self.k)
+        self.istep = 0
+        self.JrVD = interpMat(self.mshD.zr, self.mshV.zr)  # convectionDiffusion.jl:46-47
+        self.JsVD = interpMat(self.mshD.zs, self.mshV.zs)
+
+
+def convdiff_opLHS(u, cdn):  # convectionDiffusion.jl:76-85
+    return opLHS(u, cdn.nu, cdn.bdfB[0], cdn.M, cdn.mshV)
+
+
+def convdiff_makeRHS(cdn):  # convectionDiffusion.jl:93-110
+    m = cdn.mshV
+    rhs = mass(cdn.f, m)
+    rhs = rhs - cdn.nu * lapl(cdn.ub, m)
+    for i in range(len(cdn.uh)):
+        cdn.exH[i] = -advect(cdn.uh[i], cdn.vx, cdn.vy, m, cdn.mshD, cdn.JrVD, cdn.JsVD)
+        rhs = rhs - cdn.bdfB[1 + i] * mass(cdn.uh[i], m)
+        rhs = rhs + cdn.bdfA[i] * cdn.exH[i]
+    rhs = mask(rhs, cdn.M)
+    cdn.rhs = gatherScatter(rhs, m)
+
+
+def convdiff_solve(cdn, tol=1e-8):  # convectionDiffusion.jl:112-122
+    m = cdn.mshV
+    b0 = cdn.bdfB[0]
+    info = {}
+    x = pcg(cdn.rhs, lambda v: convdiff_opLHS(v, cdn), opM=lambda v: v / m.B / b0, mult=m.mult, tol=tol, info=info)
+    cdn.pcg_iters.append(info["iters"])
+    cdn.u = x + cdn.ub
+
+
+def convdiff_step(cdn, setBC=None, setForcing=None, setVisc=None):  # convectionDiffusion.jl:150-157
+    for i in range(len(cdn.uh) - 1, 0, -1):  # updateHist!(cdn)
+        cdn.uh[i] = cdn.uh[i - 1].copy()
+    cdn.uh[0] = cdn.u.copy()
+    for i in range(cdn.time.size - 1, 0, -1):  # updateHist!(tstep), time.jl:99-111
+        cdn.time[i] = cdn.time[i - 1]
+    cdn.time[0] = cdn.time[1]
+    cdn.istep += 1
+    cdn.time[0] += cdn.dt
+    cdn.bdfA, cdn.bdfB = bdfExtK(cdn.time, cdn.time.size - 1)
+    x, y, t = cdn.mshV.x, cdn.mshV.y, cdn.time[0]  # evolve!, convectionDiffusion.jl:133-146
+    if setBC is not None:
+        cdn.ub = _F(setBC(x, y, t))
+    if setForcing is not None:
+        cdn.f = _F(setForcing(x, y, t))
+    if setVisc is not None:
+        cdn.nu = _F(setVisc(x, y, t))
+    convdiff_makeRHS(cdn)
+    convdiff_solve(cdn)
+
+
+# ----------------------------------------------------------------------------
 # explicit Kronecker-assembled cross-check, examples/p2d_explicit.jl:142-180
 # (an independent construction used to PIN this oracle at small sizes)
 # ----------------------------------------------------------------------------

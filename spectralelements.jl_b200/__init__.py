@@ -33,7 +33,7 @@ from ._lib import PcgOpts, SembError, as_f64, check, dptr
 __all__ = [
     "init", "finalize", "default_context", "Context", "Mesh", "DeviceField", "generateMask", "ABu", "jac", "lapl",
     "hlmz", "mass", "gatherScatter", "mask", "pcg", "pcg_b", "OpLHS", "opLHS", "Diffusion", "makeRHS_b",
-    "solve_b", "evolve_b", "simulate_b", "annulus", "wavy", "fixU", "gausslobatto", "derivMat", "interpMat",
+    "solve_b", "evolve_b", "simulate_b", "grad", "advect", "ConvectionDiffusion", "step_b", "simulate_cd_b", "annulus", "wavy", "fixU", "gausslobatto", "derivMat", "interpMat",
     "semmesh", "ndgrid", "bdfExtK", "partition", "halo_plan", "SembError",
 ]
 
@@ -556,6 +556,29 @@ def mask(u, M, msh: Optional[Mesh] = None):
     return out
 
 
+def grad(u, msh: Mesh):
+    """grad(u,msh), grad.jl:94-113 -> (ux, uy)"""
+    fu, fx, fy = msh.field(u), msh.field(), msh.field()
+    try:
+        check(msh.lib.semb_grad(msh.h, fu.h, fx.h, fy.h))
+        return fx.download(), fy.download()
+    finally:
+        for f in (fu, fx, fy):
+            f.free()
+
+
+def advect(T, ux, uy, mshV: Mesh, mshD: Optional[Mesh] = None, Jr=None, Js=None):
+    """advect(T,ux,uy,msh) advect.jl:27-43 ; advect(T,ux,uy,mshV,mshD[,Jr,Js]) advect.jl:45-78 (dealiased).
+    Jr, Js are accepted for signature compatibility; the library builds interpMat(mshD.z*, mshV.z*) itself."""
+    fs = [mshV.field(a) for a in (T, ux, uy)] + [mshV.field()]
+    try:
+        check(mshV.lib.semb_advect(mshV.h, mshD.h if mshD is not None else None, fs[0].h, fs[1].h, fs[2].h, fs[3].h))
+        return fs[3].download()
+    finally:
+        for f in fs:
+            f.free()
+
+
 class OpLHS:
     """The fused unit opLHS(u,dfn) = mask(gatherScatter(hlmz(u,nu,b0,msh)),M), diffusion.jl:36-45.
 
@@ -637,7 +660,8 @@ def pcg_b(x, b, opA, **kw):
 # ---------------------------------------------------------------------------------------------
 # Diffusion driver (diffusion.jl) -- "next" row 8f-1: fields, BDF history and RHS stay in HBM across steps
 # ---------------------------------------------------------------------------------------------
-_DFN_FIELDS = {"u": 0, "ub": 1, "nu": 2, "f": 3, "rhs": 4}
+_DFN_FIELDS = {"u": 0, "ub": 1, "nu": 2, "f": 3, "rhs": 4, "vx": 5, "vy": 6}
+_DFN_UH0 = 8
 
 
 class Diffusion:
@@ -646,12 +670,16 @@ class Diffusion:
     Device resident (semb_diffusion_*): u, uh[1..k], ub, nu, f, rhs live in HBM; reading an attribute
     downloads it, assigning uploads it.  The user closures are host functions of (x, y, t), as in the reference."""
 
-    def __init__(self, bc, msh: Mesh, Ti=0.0, Tf=0.0, dt=0.0, k=3):
+    def __init__(self, bc, msh: Mesh, Ti=0.0, Tf=0.0, dt=0.0, k=3, mshD: Optional[Mesh] = None):
         self.__dict__["_ready"] = False
         self.bc, self.msh, self.k = list(bc), msh, k
         self.lib = msh.lib
         h = C.c_void_p()
-        check(self.lib.semb_diffusion_create(msh.h, _bc_bytes(bc), float(Ti), float(Tf), float(dt), int(k), C.byref(h)))
+        if mshD is None:
+            check(self.lib.semb_diffusion_create(msh.h, _bc_bytes(bc), float(Ti), float(Tf), float(dt), int(k), C.byref(h)))
+        else:  # ConvectionDiffusion: same protocol + explicit dealiased convection
+            check(self.lib.semb_convdiff_create(msh.h, mshD.h, _bc_bytes(bc), float(Ti), float(Tf), float(dt), int(k),
+                                                C.byref(h)))
         self.h = h
         self.dt, self.Ti, self.Tf = dt, Ti, Tf
         self.M = generateMask(bc, msh).astype(np.float64)  # Field.M (mesh.jl:183,192)
@@ -669,7 +697,7 @@ class Diffusion:
         if name in _DFN_FIELDS:
             return self._field(_DFN_FIELDS[name]).download()
         if name == "uh":
-            return [self._field(5 + i).download() for i in range(self.k)]
+            return [self._field(_DFN_UH0 + i).download() for i in range(self.k)]
         if name in ("time", "bdfA", "bdfB", "istep"):
             t, a, b, i = np.zeros(self.k + 1), np.zeros(self.k), np.zeros(self.k + 1), C.c_longlong()
             check(self.lib.semb_diffusion_state(self.h, dptr(t), dptr(a), dptr(b), C.byref(i)))
@@ -738,6 +766,42 @@ def simulate_b(dfn: Diffusion, callback=None, setIC=None, setBC=None, setForcing
         if callback:
             callback(dfn)
         if dfn.time[0] < 1e-12:
+            break
+        if max_steps is not None and steps >= max_steps:
+            break
+
+
+class ConvectionDiffusion(Diffusion):
+    """ConvectionDiffusion(name,fld,vx,vy,tstep,mshD,set0!,set∂!,setF!,setν!), convectionDiffusion.jl:31-56:
+    BDF-k implicit diffusion + EXT-k explicit dealiased convection, device resident."""
+
+    def __init__(self, name, bc, mshV: Mesh, mshD: Mesh, vx, vy, Ti=0.0, Tf=0.0, dt=0.0, k=3,
+                 set0=None, setBC=None, setF=None, setNu=None):
+        super().__init__(bc, mshV, Ti, Tf, dt, k, mshD=mshD)
+        self.name, self.mshV, self.mshD = name, mshV, mshD
+        self.set0, self.setBC, self.setF, self.setNu = set0, setBC, setF, setNu
+        self.vx = vx
+        self.vy = vy
+
+
+def step_b(cdn: ConvectionDiffusion, tol=1e-8):
+    """step!(cdn), convectionDiffusion.jl:150-157: updateHist!, updateHist!(tstep), evolve! (closures, makeRHS!, solve!)"""
+    evolve_b(cdn, cdn.setBC, cdn.setF, cdn.setNu, tol=tol)
+
+
+def simulate_cd_b(cdn: ConvectionDiffusion, callback=None, max_steps=None):
+    """simulate!(cdn,callback!), convectionDiffusion.jl:161-179"""
+    if cdn.set0 is not None:
+        cdn.u = as_f64(cdn.set0(cdn.msh.x, cdn.msh.y, cdn.time[0]))
+    if callback:
+        callback(cdn)
+    steps = 0
+    while cdn.time[0] <= cdn.Tf:
+        step_b(cdn)
+        steps += 1
+        if callback:
+            callback(cdn)
+        if cdn.time[0] < 1e-12:
             break
         if max_steps is not None and steps >= max_steps:
             break

@@ -1358,6 +1358,125 @@ extern "C" int semb_pcg(semb_mesh* m, const semb_pcg_opts* o, const semb_field* 
   return m->h_scal->warned ? SEMB_NOT_CONVERGED : SEMB_OK;
 }
 
+// ---- grad / dealiased advection (grad.jl, advect.jl) ---------------------------------------------------------------
+extern "C" int semb_grad(semb_mesh* m, const semb_field* u, semb_field* ux, semb_field* uy) {
+  SEMB_REQUIRE(m, "null mesh");
+  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_TRY(check_field(m, u, "grad(u)"));
+  SEMB_TRY(check_field(m, ux, "grad(ux)"));
+  SEMB_TRY(check_field(m, uy, "grad(uy)"));
+  SEMB_REQUIRE(u != ux && u != uy && ux != uy, "grad: outputs must not alias");
+  SEMB_REQUIRE(m->arr[SEMB_RX] && m->arr[SEMB_SY], "grad: mesh has no metric terms (create it from x,y)");
+  return semb_launch_grad(m->ctx, m, u->d, ux->d, uy->d);
+}
+
+// work space of advect for one (mshV, mshD) pair
+struct AdvectWork {
+  semb_mesh *V = nullptr, *D = nullptr;
+  double *dJr = nullptr, *dJs = nullptr, *dJrT = nullptr, *dJsT = nullptr;  // column-major interpolation matrices
+  semb_field *Tx = nullptr, *Ty = nullptr;                                 // on V
+  semb_field *JTx = nullptr, *JTy = nullptr, *Jux = nullptr, *Juy = nullptr, *JCu = nullptr;  // on D
+  double* mid = nullptr;  // mixed-resolution intermediate of the two-pass ABu
+};
+
+static int advect_work_free(AdvectWork* w) {
+  if (!w) return SEMB_OK;
+  cudaFree(w->dJr);
+  cudaFree(w->dJs);
+  cudaFree(w->dJrT);
+  cudaFree(w->dJsT);
+  cudaFree(w->mid);
+  semb_field* fs[] = {w->Tx, w->Ty, w->JTx, w->JTy, w->Jux, w->Juy, w->JCu};
+  for (semb_field* f : fs) semb_field_destroy(f);
+  delete w;
+  return SEMB_OK;
+}
+
+static int advect_work_create(semb_mesh* V, semb_mesh* D, AdvectWork** out) {
+  SEMB_REQUIRE(V->arr[SEMB_RX] && V->arr[SEMB_B], "advect: mshV has no metric terms / B");
+  AdvectWork* w = new AdvectWork();
+  w->V = V;
+  w->D = D;
+  SEMB_TRY(semb_field_create(V, &w->Tx));
+  SEMB_TRY(semb_field_create(V, &w->Ty));
+  if (D) {
+    SEMB_REQUIRE(D->ctx == V->ctx && D->Ex == V->Ex && D->Ey == V->Ey && D->ney == V->ney && D->perx == V->perx &&
+                     D->pery == V->pery,
+                 "advect: mshD must match mshV in Ex, Ey, periodicity and partition");
+    SEMB_REQUIRE(D->arr[SEMB_B], "advect: mshD has no B");
+    // Jr = interpMat(mshD.zr, mshV.zr), Js = interpMat(mshD.zs, mshV.zs)  (advect.jl:72-73)
+    auto nodes = [](int n, std::vector<double>& z) {
+      std::vector<double> wts(n);
+      z.resize(n);
+      return semb_gausslobatto(n, z.data(), wts.data());
+    };
+    std::vector<double> zrV, zsV, zrD, zsD;
+    SEMB_TRY(nodes(V->nr, zrV));
+    SEMB_TRY(nodes(V->ns, zsV));
+    SEMB_TRY(nodes(D->nr, zrD));
+    SEMB_TRY(nodes(D->ns, zsD));
+    std::vector<double> Jr((size_t)D->nr * V->nr), Js((size_t)D->ns * V->ns), JrT(Jr.size()), JsT(Js.size());
+    SEMB_TRY(semb_interp_mat(D->nr, zrD.data(), V->nr, zrV.data(), Jr.data()));
+    SEMB_TRY(semb_interp_mat(D->ns, zsD.data(), V->ns, zsV.data(), Js.data()));
+    for (int i = 0; i < D->nr; ++i)
+      for (int k = 0; k < V->nr; ++k) JrT[k + (size_t)i * V->nr] = Jr[i + (size_t)k * D->nr];
+    for (int i = 0; i < D->ns; ++i)
+      for (int k = 0; k < V->ns; ++k) JsT[k + (size_t)i * V->ns] = Js[i + (size_t)k * D->ns];
+    auto up = [&](const std::vector<double>& h, double** d) -> int {
+      SEMB_CHECK_CUDA(cudaMalloc(d, h.size() * sizeof(double)));
+      SEMB_CHECK_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+      return SEMB_OK;
+    };
+    SEMB_TRY(up(Jr, &w->dJr));
+    SEMB_TRY(up(Js, &w->dJs));
+    SEMB_TRY(up(JrT, &w->dJrT));
+    SEMB_TRY(up(JsT, &w->dJsT));
+    semb_field** fd[] = {&w->JTx, &w->JTy, &w->Jux, &w->Juy, &w->JCu};
+    for (semb_field** f : fd) SEMB_TRY(semb_field_create(D, f));
+    const size_t nmid = std::max((size_t)D->pitch * V->nyl, (size_t)V->pitch * D->nyl);
+    SEMB_CHECK_CUDA(cudaMalloc(&w->mid, nmid * sizeof(double)));
+  }
+  *out = w;
+  return SEMB_OK;
+}
+
+// out (on V) = advect(T, ux, uy, ...) ; advect.jl:45-64 (dealiased) or :27-43
+static int advect_run(AdvectWork* w, const double* T, const double* ux, const double* uy, double* out) {
+  semb_mesh *V = w->V, *D = w->D;
+  semb_ctx* c = V->ctx;
+  SEMB_TRY(semb_launch_grad(c, V, T, w->Tx->d, w->Ty->d));  // Tx,Ty = grad(T,mshV)
+  if (!D) return semb_launch_advect_pointwise(c, V, ux, w->Tx->d, uy, w->Ty->d, out);
+  auto interp = [&](const double* in, double* outD) -> int {  // ABu(Js,Jr,in): Br = Jr first, then As = Js (ABu.jl:14-33)
+    SEMB_TRY(semb_launch_abu_r(c, w->dJr, D->nr, V->nr, in, V->nxl, V->nyl, V->pitch, w->mid, D->pitch));
+    return semb_launch_abu_s(c, w->dJs, D->ns, V->ns, w->mid, D->nxl, V->nyl, D->pitch, outD, D->pitch);
+  };
+  SEMB_TRY(interp(w->Tx->d, w->JTx->d));
+  SEMB_TRY(interp(w->Ty->d, w->JTy->d));
+  SEMB_TRY(interp(ux, w->Jux->d));
+  SEMB_TRY(interp(uy, w->Juy->d));
+  SEMB_TRY(semb_launch_advect_pointwise(c, D, w->Jux->d, w->JTx->d, w->Juy->d, w->JTy->d, w->JCu->d));  // :59-60
+  // Cu = ABu(Js',Jr',JCu), advect.jl:61
+  SEMB_TRY(semb_launch_abu_r(c, w->dJrT, V->nr, D->nr, w->JCu->d, D->nxl, D->nyl, D->pitch, w->mid, V->pitch));
+  return semb_launch_abu_s(c, w->dJsT, V->ns, D->ns, w->mid, V->nxl, D->nyl, V->pitch, out, V->pitch);
+}
+
+extern "C" int semb_advect(semb_mesh* mV, semb_mesh* mD, const semb_field* T, const semb_field* ux, const semb_field* uy,
+                           semb_field* out) {
+  SEMB_REQUIRE(mV, "null mesh");
+  SEMB_TRY(ctx_enter(mV->ctx));
+  SEMB_TRY(check_field(mV, T, "advect(T)"));
+  SEMB_TRY(check_field(mV, ux, "advect(ux)"));
+  SEMB_TRY(check_field(mV, uy, "advect(uy)"));
+  SEMB_TRY(check_field(mV, out, "advect(out)"));
+  SEMB_REQUIRE(out != T && out != ux && out != uy, "advect: out must not alias an input");
+  AdvectWork* w = nullptr;
+  int rc = advect_work_create(mV, mD, &w);
+  if (rc >= 0) rc = advect_run(w, T->d, ux->d, uy->d, out->d);
+  cudaStreamSynchronize(mV->ctx->stream);
+  advect_work_free(w);
+  return rc;
+}
+
 // ---- device-resident Diffusion driver (diffusion.jl) --------------------------------------------------------------
 struct semb_diffusion {
   semb_mesh* m = nullptr;
@@ -1368,6 +1487,11 @@ struct semb_diffusion {
   std::vector<double> time, bdfA, bdfB;
   semb_field *u = nullptr, *ub = nullptr, *nu = nullptr, *f = nullptr, *rhs = nullptr, *tmp = nullptr, *x = nullptr;
   std::vector<semb_field*> uh;
+  // ConvectionDiffusion (convectionDiffusion.jl): advecting velocity, advect(uh[i]) and the dealiasing work space
+  bool conv = false;
+  semb_field *vx = nullptr, *vy = nullptr;
+  std::vector<semb_field*> adv;
+  AdvectWork* work = nullptr;
 };
 
 extern "C" int semb_diffusion_create(semb_mesh* m, const char bc[4], double Ti, double Tf, double dt, int k,
@@ -1397,8 +1521,32 @@ extern "C" int semb_diffusion_create(semb_mesh* m, const char bc[4], double Ti, 
   return SEMB_OK;
 }
 
+extern "C" int semb_convdiff_create(semb_mesh* mV, semb_mesh* mD, const char bc[4], double Ti, double Tf, double dt,
+                                    int k, semb_diffusion** out) {
+  SEMB_REQUIRE(mV && mD, "semb_convdiff_create: null mesh");
+  semb_diffusion* d = nullptr;
+  SEMB_TRY(semb_diffusion_create(mV, bc, Ti, Tf, dt, k, &d));
+  d->conv = true;
+  int rc = semb_field_create(mV, &d->vx);
+  if (rc >= 0) rc = semb_field_create(mV, &d->vy);
+  d->adv.assign(k, nullptr);
+  for (int i = 0; i < k && rc >= 0; ++i) rc = semb_field_create(mV, &d->adv[i]);
+  if (rc >= 0) rc = advect_work_create(mV, mD, &d->work);
+  if (rc < 0) {
+    semb_diffusion_destroy(d);
+    return rc;
+  }
+  *out = d;
+  return SEMB_OK;
+}
+
 extern "C" int semb_diffusion_destroy(semb_diffusion* d) {
   if (!d) return SEMB_OK;
+  cudaStreamSynchronize(d->m->ctx->stream);
+  semb_field_destroy(d->vx);
+  semb_field_destroy(d->vy);
+  for (semb_field* p : d->adv) semb_field_destroy(p);
+  advect_work_free(d->work);
   semb_field* all[] = {d->u, d->ub, d->nu, d->f, d->rhs, d->tmp, d->x};
   for (semb_field* p : all) semb_field_destroy(p);
   for (semb_field* p : d->uh) semb_field_destroy(p);
@@ -1408,8 +1556,9 @@ extern "C" int semb_diffusion_destroy(semb_diffusion* d) {
 
 extern "C" int semb_diffusion_field(semb_diffusion* d, int which, semb_field** f) {
   SEMB_REQUIRE(d && f, "semb_diffusion_field: null argument");
-  semb_field* base[] = {d->u, d->ub, d->nu, d->f, d->rhs};
-  if (which >= 0 && which < 5) {
+  semb_field* base[] = {d->u, d->ub, d->nu, d->f, d->rhs, d->vx, d->vy};
+  if (which >= 0 && which < 7) {
+    SEMB_REQUIRE(base[which], "semb_diffusion_field: field %d exists only for ConvectionDiffusion", which);
     *f = base[which];
     return SEMB_OK;
   }
@@ -1452,7 +1601,15 @@ extern "C" int semb_diffusion_finish_step(semb_diffusion* d, double tol, long lo
     uh[i] = d->uh[i]->d;
     b[i] = d->bdfB[1 + i];
   }
-  SEMB_TRY(semb_launch_rhs(c, m, d->f->d, d->nu->d, d->tmp->d, d->k, uh, b, fl.mx0, fl.mx1, fl.my0, fl.my1, d->x->d));
+  const double* adv[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (d->conv) {  // exH[i] = -advect(uh[i],vx,vy,mshV,mshD,JrVD,JsVD), convectionDiffusion.jl:102
+    for (int i = 0; i < d->k; ++i) {
+      SEMB_TRY(advect_run(d->work, d->uh[i]->d, d->vx->d, d->vy->d, d->adv[i]->d));
+      adv[i] = d->adv[i]->d;
+    }
+  }
+  SEMB_TRY(semb_launch_rhs(c, m, d->f->d, d->nu->d, d->tmp->d, d->k, uh, b, d->conv ? adv : nullptr,
+                           d->conv ? d->bdfA.data() : nullptr, fl.mx0, fl.mx1, fl.my0, fl.my1, d->x->d));
   SEMB_TRY(semb_gather_scatter(m, d->x, d->rhs));
   // solve!, diffusion.jl:67-77
   semb_pcg_opts o;
@@ -1463,6 +1620,10 @@ extern "C" int semb_diffusion_finish_step(semb_diffusion* d, double tol, long lo
   o.bc = d->bc;
   o.tol = tol;
   o.maxiter = -1;
+  if (d->conv) {  // opPrecond(u) = u ./ B ./ bdfB[1], convectionDiffusion.jl:87-91
+    o.precond = 1;
+    o.prec_b0 = d->bdfB[0];
+  }
   int rc = semb_pcg(m, &o, d->rhs, d->x, iters, resinf);
   if (rc < 0) return rc;
   SEMB_TRY(semb_field_copy(d->u, d->x));
@@ -1607,14 +1768,14 @@ extern "C" int semb_abu_host(semb_ctx* c, const double* As, int ma, int na, cons
       SEMB_CHECK_CUDA(cudaMalloc(&dB, (size_t)mb * nb * sizeof(double)));
       SEMB_CHECK_CUDA(cudaMemcpyAsync(dB, Br, (size_t)mb * nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
       SEMB_CHECK_CUDA(cudaMalloc(&dt, (size_t)m1 * ncols * sizeof(double)));
-      SEMB_TRY(semb_launch_abu_r(c, dB, mb, nb, cur, mrows, ncols, dt));
+      SEMB_TRY(semb_launch_abu_r(c, dB, mb, nb, cur, mrows, ncols, mrows, dt, m1));
       cur = dt;
     }
     if (hasA) {
       SEMB_CHECK_CUDA(cudaMalloc(&dA, (size_t)ma * na * sizeof(double)));
       SEMB_CHECK_CUDA(cudaMemcpyAsync(dA, As, (size_t)ma * na * sizeof(double), cudaMemcpyHostToDevice, c->stream));
       SEMB_CHECK_CUDA(cudaMalloc(&dout, (size_t)m1 * n1 * sizeof(double)));
-      SEMB_TRY(semb_launch_abu_s(c, dA, ma, na, cur, m1, ncols, dout));
+      SEMB_TRY(semb_launch_abu_s(c, dA, ma, na, cur, m1, ncols, m1, dout, m1));
       cur = dout;
     }
     SEMB_CHECK_CUDA(cudaMemcpyAsync(out, cur, (size_t)m1 * n1 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

@@ -661,34 +661,69 @@ __global__ void __launch_bounds__(256) semb_mask_dot_kernel(const OpArgs a) {
 // ---- generic ABu (ABu.jl:9-37) --------------------------------------------------------------------------
 // out (m*mb/nb x n) = (I (x) Br) u : Br (mb x nb, column-major) acts on each nb-row chunk of every column
 __global__ void semb_abu_r_kernel(const double* __restrict__ Br, int mb, int nb, const double* __restrict__ u,
-                                  int m, int n, double* out) {
+                                  int m, int n, long long ldu, double* out, long long ldo) {
   const int mo = m / nb * mb;
   for (int col = blockIdx.y; col < n; col += gridDim.y)
     for (int ro = blockIdx.x * blockDim.x + threadIdx.x; ro < mo; ro += gridDim.x * blockDim.x) {
       const int blk = ro / mb, i = ro - blk * mb;
-      const double* uc = u + (size_t)col * m + (size_t)blk * nb;
+      const double* uc = u + (size_t)col * ldu + (size_t)blk * nb;
       double s = 0.0;
       for (int k = 0; k < nb; ++k) s = fma(Br[i + (size_t)k * mb], uc[k], s);
-      out[(size_t)col * mo + ro] = s;
+      out[(size_t)col * ldo + ro] = s;
     }
 }
 // out (m x n*ma/na) : out[:, ii] = u[:, jj] * As'  (As ma x na)
 __global__ void semb_abu_s_kernel(const double* __restrict__ As, int ma, int na, const double* __restrict__ u,
-                                  int m, int n, double* out) {
+                                  int m, int n, long long ldu, double* out, long long ldo) {
   const int no = n / na * ma;
   for (int col = blockIdx.y; col < no; col += gridDim.y) {
     const int blk = col / ma, j = col - blk * ma;
     for (int ro = blockIdx.x * blockDim.x + threadIdx.x; ro < m; ro += gridDim.x * blockDim.x) {
       double s = 0.0;
-      for (int k = 0; k < na; ++k) s = fma(As[j + (size_t)k * ma], u[(size_t)(blk * na + k) * m + ro], s);
-      out[(size_t)col * m + ro] = s;
+      for (int k = 0; k < na; ++k) s = fma(As[j + (size_t)k * ma], u[(size_t)(blk * na + k) * ldu + ro], s);
+      out[(size_t)col * ldo + ro] = s;
     }
   }
 }
 
+// grad(u,msh), grad.jl:94-113: ux = rx.*ur + sx.*us, uy = ry.*ur + sy.*us with ur = (I (x) Dr) u, us = (Ds (x) I) u
+__global__ void semb_grad_kernel(const double* __restrict__ u, long long pitch, int nr, int ns, int Ex, int ney,
+                                 const double* __restrict__ Dr, const double* __restrict__ Ds,
+                                 const double* __restrict__ rx, const double* __restrict__ ry,
+                                 const double* __restrict__ sx, const double* __restrict__ sy, double* ux, double* uy) {
+  const int nxl = nr * Ex, nyl = ns * ney;
+  for (int row = blockIdx.y; row < nyl; row += gridDim.y) {
+    const int rl = row / ns, j = row - rl * ns;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nxl; c += gridDim.x * blockDim.x) {
+      const int e = c / nr, i = c - e * nr;
+      const size_t rowb = (size_t)row * pitch + (size_t)e * nr, colb = (size_t)rl * ns * pitch + c;
+      double ur = 0, us = 0;
+      for (int k = 0; k < nr; ++k) ur = fma(Dr[i * nr + k], u[rowb + k], ur);
+      for (int k = 0; k < ns; ++k) us = fma(Ds[j * ns + k], u[colb + (size_t)k * pitch], us);
+      const size_t idx = (size_t)row * pitch + c;
+      ux[idx] = __dadd_rn(__dmul_rn(rx[idx], ur), __dmul_rn(sx[idx], us));  // grad.jl:109
+      uy[idx] = __dadd_rn(__dmul_rn(ry[idx], ur), __dmul_rn(sy[idx], us));  // grad.jl:110
+    }
+  }
+}
+
+// advect.jl:59-60 (dealiased) / :36-37 (plain): Cu = (ux.*Tx + uy.*Ty) .* B ; sign = -1 stores exH = -advect
+__global__ void semb_advect_pointwise_kernel(const double* __restrict__ jux, const double* __restrict__ jtx,
+                                             const double* __restrict__ juy, const double* __restrict__ jty,
+                                             const double* __restrict__ B, long long pitch, int nxl, int nyl,
+                                             double* out) {
+  for (int row = blockIdx.y; row < nyl; row += gridDim.y)
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < nxl; x += gridDim.x * blockDim.x) {
+      const size_t idx = (size_t)row * pitch + x;
+      const double c = __dadd_rn(__dmul_rn(jux[idx], jtx[idx]), __dmul_rn(juy[idx], jty[idx]));
+      out[idx] = __dmul_rn(c, B[idx]);
+    }
+}
+
 struct RhsArgs {
   const double* uh[4];
-  double b[4];
+  const double* adv[4];  // advect(uh[i],...) (convectionDiffusion.jl:102); exH[i] = -adv[i]
+  double b[4], a[4];
   int k;
 };
 
@@ -703,7 +738,10 @@ __global__ void semb_rhs_kernel(const double* __restrict__ f, const double* __re
       const double Bv = B[idx];
       double r = __dmul_rn(Bv, f[idx]);                               // mass(f), diffusion.jl:55
       r = __dadd_rn(r, -__dmul_rn(nu[idx], lub[idx]));                // - nu .* lapl(ub), :56
-      for (int i = 0; i < h.k; ++i) r = __dadd_rn(r, -__dmul_rn(h.b[i], __dmul_rn(Bv, h.uh[i][idx])));  // :58-60
+      for (int i = 0; i < h.k; ++i) {
+        r = __dadd_rn(r, -__dmul_rn(h.b[i], __dmul_rn(Bv, h.uh[i][idx])));  // :58-60 / convectionDiffusion.jl:103
+        if (h.adv[i]) r = __dadd_rn(r, __dmul_rn(h.a[i], -h.adv[i][idx]));   // rhs .+= bdfA[i] .* exH[i], :104
+      }
       const bool z = (x == 0 && mx0) || (x == nxl - 1 && mx1) || (row == 0 && my0) || (row == nyl - 1 && my1);
       rhs[idx] = __dmul_rn(z ? 0.0 : 1.0, r);                         // mask, :62
     }
@@ -902,23 +940,42 @@ int semb_launch_pcg_finalize(semb_ctx* ctx, semb_mesh* m, int first) {
   SEMB_POST_LAUNCH(ctx);
 }
 
-int semb_launch_abu_r(semb_ctx* ctx, const double* Br, int mb, int nb, const double* u, int m, int n, double* out) {
-  semb_abu_r_kernel<<<rows_grid(m / nb * mb, n, 128), 128, 0, ctx->stream>>>(Br, mb, nb, u, m, n, out);
+int semb_launch_abu_r(semb_ctx* ctx, const double* Br, int mb, int nb, const double* u, int m, int n, long long ldu,
+                      double* out, long long ldo) {
+  semb_abu_r_kernel<<<rows_grid(m / nb * mb, n, 128), 128, 0, ctx->stream>>>(Br, mb, nb, u, m, n, ldu, out, ldo);
   SEMB_POST_LAUNCH(ctx);
 }
 
-int semb_launch_abu_s(semb_ctx* ctx, const double* As, int ma, int na, const double* u, int m, int n, double* out) {
-  semb_abu_s_kernel<<<rows_grid(m, n / na * ma, 128), 128, 0, ctx->stream>>>(As, ma, na, u, m, n, out);
+int semb_launch_abu_s(semb_ctx* ctx, const double* As, int ma, int na, const double* u, int m, int n, long long ldu,
+                      double* out, long long ldo) {
+  semb_abu_s_kernel<<<rows_grid(m, n / na * ma, 128), 128, 0, ctx->stream>>>(As, ma, na, u, m, n, ldu, out, ldo);
+  SEMB_POST_LAUNCH(ctx);
+}
+
+int semb_launch_grad(semb_ctx* ctx, semb_mesh* m, const double* u, double* ux, double* uy) {
+  semb_grad_kernel<<<rows_grid(m->nxl, m->nyl, 256), 256, 0, ctx->stream>>>(
+      u, m->pitch, m->nr, m->ns, m->Ex, m->ney, m->dDr, m->dDs, m->arr[SEMB_RX], m->arr[SEMB_RY], m->arr[SEMB_SX],
+      m->arr[SEMB_SY], ux, uy);
+  SEMB_POST_LAUNCH(ctx);
+}
+
+int semb_launch_advect_pointwise(semb_ctx* ctx, semb_mesh* m, const double* jux, const double* jtx, const double* juy,
+                                 const double* jty, double* out) {
+  semb_advect_pointwise_kernel<<<rows_grid(m->nxl, m->nyl, 256), 256, 0, ctx->stream>>>(
+      jux, jtx, juy, jty, m->arr[SEMB_B], m->pitch, m->nxl, m->nyl, out);
   SEMB_POST_LAUNCH(ctx);
 }
 
 int semb_launch_rhs(semb_ctx* ctx, semb_mesh* m, const double* f, const double* nu, const double* lub, int k,
-                    const double* const* uh, const double* b, int mx0, int mx1, int my0, int my1, double* rhs) {
+                    const double* const* uh, const double* b, const double* const* adv, const double* a, int mx0,
+                    int mx1, int my0, int my1, double* rhs) {
   RhsArgs h;
   h.k = k;
   for (int i = 0; i < 4; ++i) {
     h.uh[i] = i < k ? uh[i] : nullptr;
     h.b[i] = i < k ? b[i] : 0.0;
+    h.adv[i] = (adv && i < k) ? adv[i] : nullptr;
+    h.a[i] = (a && i < k) ? a[i] : 0.0;
   }
   semb_rhs_kernel<<<rows_grid(m->nxl, m->nyl, 256), 256, 0, ctx->stream>>>(f, nu, lub, m->arr[SEMB_B], h, m->pitch,
                                                                           m->nxl, m->nyl, mx0, mx1, my0, my1, rhs);

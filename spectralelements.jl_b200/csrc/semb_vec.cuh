@@ -43,8 +43,14 @@ int semb_launch_pcg_pack_pap(semb_ctx* ctx, semb_mesh* m);
 int semb_launch_pcg_finalize(semb_ctx* ctx, semb_mesh* m, int first);
 int semb_launch_reduce_finalize(semb_ctx* ctx, semb_mesh* m, int which);
 // generic ABu (ABu.jl:9-37)
-int semb_launch_abu_r(semb_ctx* ctx, const double* Br, int mb, int nb, const double* u, int m, int n, double* out);
-int semb_launch_abu_s(semb_ctx* ctx, const double* As, int ma, int na, const double* u, int m, int n, double* out);
+int semb_launch_abu_r(semb_ctx* ctx, const double* Br, int mb, int nb, const double* u, int m, int n, long long ldu,
+                      double* out, long long ldo);
+int semb_launch_abu_s(semb_ctx* ctx, const double* As, int ma, int na, const double* u, int m, int n, long long ldu,
+                      double* out, long long ldo);
+int semb_launch_grad(semb_ctx* ctx, semb_mesh* m, const double* u, double* ux, double* uy);
+int semb_launch_advect_pointwise(semb_ctx* ctx, semb_mesh* m, const double* jux, const double* jtx, const double* juy,
+                                 const double* jty, double* out);
 // makeRHS! pointwise part (diffusion.jl:55-62): rhs = M .* (B.*f - nu.*lub - sum_i b[i] .* (B.*uh[i]))
 int semb_launch_rhs(semb_ctx* ctx, semb_mesh* m, const double* f, const double* nu, const double* lub, int k,
-                    const double* const* uh, const double* b, int mx0, int mx1, int my0, int my1, double* rhs);
+                    const double* const* uh, const double* b, const double* const* adv, const double* a, int mx0,
+                    int mx1, int my0, int my1, double* rhs);
