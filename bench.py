@@ -277,10 +277,43 @@ def run_semb(args):
                                    "l2": "flushed before every apply (256 MB memset, cost subtracted)"}
         m2.free()
 
+    # ---- BASELINE configs[3]: convection-diffusion implicit stepping, order 8, 512x512 elements (cd2d) ------------
+    if rank == 0 and world == 1 and not args.skip_cfg4:
+        E4 = args.cfg4_elements
+        mV = sem.Mesh(9, 9, E4, E4, (True, False), "identity", ctx=ctx)
+        mD = sem.Mesh(14, 14, E4, E4, (True, False), "identity", ctx=ctx)   # 3/2 rule (examples/semPS.jl:31)
+        nV = mV.shape[0] * mV.shape[1]
+        cdn = sem.ConvectionDiffusion("ps", list("NNDD"), mV, mD, None, None, Tf=1.0, dt=5e-3)
+        for name, val in (("vx", 1.0), ("vy", 0.0), ("nu", 1e-3)):
+            cdn._field(sem._DFN_FIELDS[name]).fill(val)
+        cdn.u = np.sin(np.pi * mV.x) * np.sin(np.pi * mV.y)   # examples/cd2d.jl:11-16 initial condition
+        for _ in range(3):
+            sem.step_b(cdn)   # closures are constant: nothing is uploaded per step, everything stays in HBM
+        ctx.sync()
+        t0 = time.perf_counter()
+        nst = 10
+        for _ in range(nst):
+            sem.step_b(cdn)
+        ctx.sync()
+        dt4 = (time.perf_counter() - t0) / nst
+        fT, fo = mV.field().fill_random(5), mV.field()
+        vxf, vyf = cdn._field(sem._DFN_FIELDS["vx"]), cdn._field(sem._DFN_FIELDS["vy"])
+        sem._lib.check(ctx.lib.semb_advect(mV.h, mD.h, fT.h, vxf.h, vyf.h, fo.h))
+        ctx.sync()
+        t0 = time.perf_counter()
+        sem._lib.check(ctx.lib.semb_advect(mV.h, mD.h, fT.h, vxf.h, vyf.h, fo.h))
+        ctx.sync()
+        dta = time.perf_counter() - t0
+        extra["cfg4_cd2d"] = {"workload": "ConvectionDiffusion step (BDF3/EXT3: 3 dealiased advects nr=9->14, makeRHS!, "
+                                          "diag-preconditioned PCG), %dx%d elements, order 8, %d DOF" % (E4, E4, nV),
+                              "steps_per_s": 1.0 / dt4, "ms_per_step": dt4 * 1e3, "pcg_iters_last": cdn.pcg_iters[-1],
+                              "gdof_steps_per_s": nV / dt4 / 1e9, "ms_per_dealiased_advect_incl_alloc": dta * 1e3}
+        cdn.free(); mV.free(); mD.free()
+
     # ---- CPU baseline beside it (rank 0, N = 1): bounded sample of the same workload -------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        cpu = cpu_reference(nr, E, sample_rows=args.cpu_rows, reps=2)
+        cpu = cpu_reference(nr, E, sample_rows=min(args.cpu_rows, E), reps=5)
 
     plan = msh.plan()
     if rank == 0:
@@ -340,6 +373,7 @@ def run_reference(args):
     """--impl reference: the reference's CPU path (restated, oracle/) on the host cores, rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    args.cpu_rows = min(args.cpu_rows, args.elements)
     cpu = cpu_reference(args.nr, args.elements, args.cpu_rows, reps=1)
     # K timed steps + W warm-up on the bounded sample
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -378,11 +412,13 @@ def main():
     ap.add_argument("--nr", type=int, default=9)
     ap.add_argument("--elements", type=int, default=1112, help="elements per direction per GPU")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--cpu-rows", type=int, default=64, help="element rows of the CPU-baseline slab sample")
+    ap.add_argument("--cpu-rows", type=int, default=278, help="element rows of the CPU-baseline slab sample (1/4 mesh)")
     ap.add_argument("--skip-pcg", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cfg2", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-cfg4", action="store_true")
+    ap.add_argument("--cfg4-elements", type=int, default=512)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "semb" else args.warmup
     if args.impl == "reference":

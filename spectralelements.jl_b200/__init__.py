@@ -780,8 +780,10 @@ class ConvectionDiffusion(Diffusion):
         super().__init__(bc, mshV, Ti, Tf, dt, k, mshD=mshD)
         self.name, self.mshV, self.mshD = name, mshV, mshD
         self.set0, self.setBC, self.setF, self.setNu = set0, setBC, setF, setNu
-        self.vx = vx
-        self.vy = vy
+        if vx is not None:
+            self.vx = vx
+        if vy is not None:
+            self.vy = vy
 
 
 def step_b(cdn: ConvectionDiffusion, tol=1e-8):
