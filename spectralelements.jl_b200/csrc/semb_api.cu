@@ -116,9 +116,21 @@ static int ctx_enter(semb_ctx* c) {
   return SEMB_OK;
 }
 
+// A context is not re-entrant: one in-flight call per ctx (callable from any host thread).  The lock is
+// recursive because entry points are composed of each other.
+struct CtxGuard {
+  std::unique_lock<std::recursive_mutex> lock;
+  explicit CtxGuard(semb_ctx* c) {
+    if (c) lock = std::unique_lock<std::recursive_mutex>(c->mutex);
+  }
+};
+#define SEMB_ENTER(c)       \
+  CtxGuard _semb_guard(c);  \
+  SEMB_TRY(ctx_enter(c))
+
 extern "C" int semb_finalize(semb_ctx* c) {
   if (!c) return SEMB_OK;
-  SEMB_TRY(ctx_enter(c));
+  SEMB_TRY(ctx_enter(c));  // no guard: the context (and its mutex) is destroyed here
   cudaStreamSynchronize(c->stream);
   if (c->comm) ncclCommDestroy(c->comm);
   if (c->flush_buf) cudaFree(c->flush_buf);
@@ -132,7 +144,7 @@ extern "C" int semb_finalize(semb_ctx* c) {
 }
 
 extern "C" int semb_sync(semb_ctx* c) {
-  SEMB_TRY(ctx_enter(c));
+  SEMB_ENTER(c);
   SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
   return SEMB_OK;
 }
@@ -144,13 +156,13 @@ extern "C" int semb_stream(semb_ctx* c, void** s) {
 }
 
 extern "C" int semb_timer_start(semb_ctx* c) {
-  SEMB_TRY(ctx_enter(c));
+  SEMB_ENTER(c);
   SEMB_CHECK_CUDA(cudaEventRecord(c->ev0, c->stream));
   return SEMB_OK;
 }
 
 extern "C" int semb_timer_stop(semb_ctx* c, double* ms) {
-  SEMB_TRY(ctx_enter(c));
+  SEMB_ENTER(c);
   SEMB_CHECK_CUDA(cudaEventRecord(c->ev1, c->stream));
   SEMB_CHECK_CUDA(cudaEventSynchronize(c->ev1));
   float f = 0.f;
@@ -166,7 +178,7 @@ extern "C" int semb_launch_count(semb_ctx* c, long long* n) {
 }
 
 extern "C" int semb_flush_l2(semb_ctx* c) {
-  SEMB_TRY(ctx_enter(c));
+  SEMB_ENTER(c);
   if (!c->flush_buf) {
     c->flush_bytes = (size_t)256 << 20;  // 2x the 126 MB L2
     SEMB_CHECK_CUDA(cudaMalloc(&c->flush_buf, c->flush_bytes));
@@ -176,7 +188,7 @@ extern "C" int semb_flush_l2(semb_ctx* c) {
 }
 
 extern "C" int semb_profile_enable(semb_ctx* c, int max_launches) {
-  SEMB_TRY(ctx_enter(c));
+  SEMB_ENTER(c);
   SEMB_REQUIRE(max_launches >= 0 && max_launches <= 65536, "semb_profile_enable: 0..65536 launches");
   while (c->prof_ev.size() < (size_t)2 * max_launches) {
     cudaEvent_t e;
@@ -189,7 +201,7 @@ extern "C" int semb_profile_enable(semb_ctx* c, int max_launches) {
 }
 
 extern "C" int semb_profile_read(semb_ctx* c, double* total_ms, int* launches) {
-  SEMB_TRY(ctx_enter(c));
+  SEMB_ENTER(c);
   SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
   double tot = 0.0;
   for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
@@ -225,7 +237,7 @@ extern "C" int semb_comm_unique_id(char id[128]) {
 }
 
 extern "C" int semb_comm_init(semb_ctx* c, int nranks, int rank, const char id[128]) {
-  SEMB_TRY(ctx_enter(c));
+  SEMB_ENTER(c);
   SEMB_REQUIRE(nranks >= 1 && nranks <= SEMB_MAX_RANKS && rank >= 0 && rank < nranks,
                "semb_comm_init: bad nranks/rank %d/%d", nranks, rank);
   SEMB_REQUIRE(!c->comm, "semb_comm_init: communicator already initialised");
@@ -247,14 +259,14 @@ extern "C" int semb_comm_info(semb_ctx* c, int* nranks, int* rank) {
 }
 
 extern "C" int semb_comm_barrier(semb_ctx* c) {
-  SEMB_TRY(ctx_enter(c));
+  SEMB_ENTER(c);
   if (c->comm) SEMB_CHECK_NCCL(ncclAllReduce(c->d_sync, c->d_sync, 1, ncclDouble, ncclSum, c->comm, c->stream));
   SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
   return SEMB_OK;
 }
 
 extern "C" int semb_comm_allreduce_max(semb_ctx* c, double* v, int n) {
-  SEMB_TRY(ctx_enter(c));
+  SEMB_ENTER(c);
   SEMB_REQUIRE(v && n >= 1 && n <= 7, "semb_comm_allreduce_max: 1..7 values");
   if (!c->comm) return SEMB_OK;
   SEMB_CHECK_CUDA(cudaMemcpyAsync(c->d_sync + 1, v, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -445,7 +457,7 @@ static int mesh_build_plan(semb_mesh* m) {
 
 static int mesh_new(semb_ctx* c, int nr, int ns, int Ex, int Ey, int perx, int pery, const double* Dr,
                     const double* Ds, const double* wr, const double* ws, semb_mesh** out) {
-  SEMB_TRY(ctx_enter(c));
+  SEMB_ENTER(c);
   SEMB_REQUIRE(out, "mesh: null output");
   SEMB_REQUIRE(nr >= 2 && ns >= 2 && nr <= 64 && ns <= 64, "mesh: need 2 <= nr, ns <= 64 (got %d, %d)", nr, ns);
   SEMB_REQUIRE(Ex >= 1 && Ey >= 1, "mesh: need Ex, Ey >= 1");
@@ -699,7 +711,7 @@ extern "C" int semb_mesh_plan(semb_mesh* m, int* nstrips, int* nchunks, int* nxs
 extern "C" int semb_mesh_set_chunks(semb_mesh* m, int nchunks) {
   SEMB_REQUIRE(m && nchunks >= 1 && nchunks <= m->ney, "semb_mesh_set_chunks: 1 <= nchunks <= ney");
   SEMB_REQUIRE((long long)nchunks * m->nstrips <= SEMB_NPARTIALS, "semb_mesh_set_chunks: too many CTAs");
-  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_ENTER(m->ctx);
   SEMB_CHECK_CUDA(cudaStreamSynchronize(m->ctx->stream));
   const int N = m->ns;
   m->nchunks = nchunks;
@@ -745,7 +757,7 @@ extern "C" int semb_mesh_get(semb_mesh* m, int which, double* host) {
   SEMB_REQUIRE(m && host, "semb_mesh_get: null argument");
   SEMB_REQUIRE(which >= 0 && which < SEMB_MESH_ARRAY_COUNT, "semb_mesh_get: bad selector %d", which);
   SEMB_REQUIRE(m->arr[which], "semb_mesh_get: array %d is not held by this mesh", which);
-  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_ENTER(m->ctx);
   return download_pitched(m, m->arr[which], host);
 }
 
@@ -774,7 +786,7 @@ static int parse_bc(semb_mesh* m, const char* bc, MaskFlags* f) {
 
 extern "C" int semb_generate_mask(semb_mesh* m, const char bc[4], double* host) {
   SEMB_REQUIRE(m && bc && host, "semb_generate_mask: null argument");
-  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_ENTER(m->ctx);
   MaskFlags f;
   SEMB_TRY(parse_bc(m, bc, &f));
   double* d = nullptr;
@@ -788,7 +800,7 @@ extern "C" int semb_generate_mask(semb_mesh* m, const char bc[4], double* host) 
 // ---- fields ------------------------------------------------------------------------------------------------
 extern "C" int semb_field_create(semb_mesh* m, semb_field** out) {
   SEMB_REQUIRE(m && out, "semb_field_create: null argument");
-  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_ENTER(m->ctx);
   semb_field* f = new semb_field();
   f->mesh = m;
   cudaError_t e = cudaMalloc(&f->d, m->nalloc * sizeof(double));
@@ -818,27 +830,27 @@ extern "C" int semb_field_destroy(semb_field* f) {
 
 extern "C" int semb_field_upload(semb_field* f, const double* host) {
   SEMB_REQUIRE(f && host, "semb_field_upload: null argument");
-  SEMB_TRY(ctx_enter(f->mesh->ctx));
+  SEMB_ENTER(f->mesh->ctx);
   return upload_pitched(f->mesh, f->d, host);
 }
 
 extern "C" int semb_field_download(semb_field* f, double* host) {
   SEMB_REQUIRE(f && host, "semb_field_download: null argument");
-  SEMB_TRY(ctx_enter(f->mesh->ctx));
+  SEMB_ENTER(f->mesh->ctx);
   return download_pitched(f->mesh, f->d, host);
 }
 
 extern "C" int semb_field_fill(semb_field* f, double v) {
   SEMB_REQUIRE(f, "null field");
   semb_mesh* m = f->mesh;
-  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_ENTER(m->ctx);
   return semb_launch_fill(m->ctx, f->d, v, m->pitch, m->nxl, m->nyl);
 }
 
 extern "C" int semb_field_copy(semb_field* dst, const semb_field* src) {
   SEMB_REQUIRE(dst && src && dst->mesh == src->mesh, "semb_field_copy: fields must share a mesh");
   semb_mesh* m = dst->mesh;
-  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_ENTER(m->ctx);
   SEMB_CHECK_CUDA(cudaMemcpyAsync(dst->d, src->d, m->nalloc * sizeof(double), cudaMemcpyDeviceToDevice,
                                   m->ctx->stream));
   return SEMB_OK;
@@ -847,14 +859,14 @@ extern "C" int semb_field_copy(semb_field* dst, const semb_field* src) {
 extern "C" int semb_field_fill_random(semb_field* f, uint64_t seed) {
   SEMB_REQUIRE(f, "null field");
   semb_mesh* m = f->mesh;
-  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_ENTER(m->ctx);
   return semb_launch_fill_random(m->ctx, f->d, m->pitch, m->nxl, m->nyl, m->nxl, (long long)m->ey0 * m->ns, seed);
 }
 
 extern "C" int semb_field_axpby(double a, const semb_field* x, double b, semb_field* y) {
   SEMB_REQUIRE(x && y && x->mesh == y->mesh, "semb_field_axpby: fields must share a mesh");
   semb_mesh* m = y->mesh;
-  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_ENTER(m->ctx);
   return semb_launch_axpby(m->ctx, a, x->d, b, y->d, m->nalloc);
 }
 
@@ -1054,7 +1066,7 @@ extern "C" int semb_lapl(semb_mesh* m, const semb_field* u, semb_field* out) {
 extern "C" int semb_hlmz(semb_mesh* m, const semb_field* u, const semb_field* nu_arr, double nu,
                          const semb_field* k_arr, double k, semb_field* out) {
   SEMB_REQUIRE(m, "null mesh");
-  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_ENTER(m->ctx);
   SEMB_TRY(check_field(m, u, "hlmz(u)"));
   SEMB_TRY(check_field(m, out, "hlmz(out)"));
   SEMB_TRY(check_field(m, nu_arr, "hlmz(nu)", true));
@@ -1071,7 +1083,7 @@ extern "C" int semb_hlmz(semb_mesh* m, const semb_field* u, const semb_field* nu
 
 extern "C" int semb_mass(semb_mesh* m, const semb_field* u, semb_field* out) {
   SEMB_REQUIRE(m, "null mesh");
-  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_ENTER(m->ctx);
   SEMB_TRY(check_field(m, u, "mass(u)"));
   SEMB_TRY(check_field(m, out, "mass(out)"));
   SEMB_REQUIRE(m->arr[SEMB_B], "mass: mesh has no B");
@@ -1081,7 +1093,7 @@ extern "C" int semb_mass(semb_mesh* m, const semb_field* u, semb_field* out) {
 extern "C" int semb_gather_scatter(semb_mesh* m, const semb_field* u, semb_field* out) {
   SEMB_REQUIRE(m, "null mesh");
   semb_ctx* c = m->ctx;
-  SEMB_TRY(ctx_enter(c));
+  SEMB_ENTER(c);
   SEMB_TRY(check_field(m, u, "gatherScatter(u)"));
   SEMB_TRY(check_field(m, out, "gatherScatter(out)"));
   SEMB_REQUIRE(u != out, "gatherScatter: out must not alias u");
@@ -1102,7 +1114,7 @@ extern "C" int semb_gather_scatter(semb_mesh* m, const semb_field* u, semb_field
 
 extern "C" int semb_mask(semb_mesh* m, const semb_field* u, const semb_field* M, semb_field* out) {
   SEMB_REQUIRE(m, "null mesh");
-  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_ENTER(m->ctx);
   SEMB_TRY(check_field(m, u, "mask(u)"));
   SEMB_TRY(check_field(m, out, "mask(out)"));
   SEMB_TRY(check_field(m, M, "mask(M)", true));
@@ -1111,7 +1123,7 @@ extern "C" int semb_mask(semb_mesh* m, const semb_field* u, const semb_field* M,
 
 extern "C" int semb_mask_bc(semb_mesh* m, const semb_field* u, const char bc[4], semb_field* out) {
   SEMB_REQUIRE(m && bc, "semb_mask_bc: null argument");
-  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_ENTER(m->ctx);
   SEMB_TRY(check_field(m, u, "mask(u)"));
   SEMB_TRY(check_field(m, out, "mask(out)"));
   if (u != out) SEMB_TRY(semb_field_copy(out, u));
@@ -1133,7 +1145,7 @@ extern "C" int semb_oplhs(semb_mesh* m, const semb_field* u, const semb_field* n
                           const semb_field* k_arr, double k, const char* bc, const semb_field* M_arr,
                           semb_field* out) {
   SEMB_REQUIRE(m, "null mesh");
-  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_ENTER(m->ctx);
   SEMB_TRY(check_field(m, u, "opLHS(u)"));
   SEMB_TRY(check_field(m, out, "opLHS(out)"));
   SEMB_TRY(check_field(m, nu_arr, "opLHS(nu)", true));
@@ -1155,7 +1167,7 @@ extern "C" int semb_jac(semb_mesh* m, const semb_field* x, const semb_field* y, 
                         semb_field* rx, semb_field* ry, semb_field* sx, semb_field* sy) {
   SEMB_REQUIRE(m, "null mesh");
   semb_ctx* c = m->ctx;
-  SEMB_TRY(ctx_enter(c));
+  SEMB_ENTER(c);
   SEMB_TRY(check_field(m, x, "jac(x)"));
   SEMB_TRY(check_field(m, y, "jac(y)"));
   double *d_wr = nullptr, *d_ws = nullptr;
@@ -1189,7 +1201,7 @@ static int read_scal(semb_mesh* m) {
 
 static int reduce_common(semb_mesh* m, int which, const semb_field* a, const semb_field* b, double* result) {
   semb_ctx* c = m->ctx;
-  SEMB_TRY(ctx_enter(c));
+  SEMB_ENTER(c);
   SEMB_REQUIRE(result, "reduction: null result");
   SEMB_TRY(semb_launch_reduce(c, m, which, a->d, b ? b->d : nullptr, p2p_args(m, m->p2p ? ++m->ep_red : 0)));
   if (c->nranks > 1 && !m->p2p) {
@@ -1218,7 +1230,7 @@ extern "C" int semb_norm_inf(semb_mesh* m, const semb_field* a, double* result) 
 extern "C" int semb_pcg_begin(semb_mesh* m, const semb_pcg_opts* o, const semb_field* b, semb_field* x) {
   SEMB_REQUIRE(m && o, "semb_pcg_begin: null argument");
   semb_ctx* c = m->ctx;
-  SEMB_TRY(ctx_enter(c));
+  SEMB_ENTER(c);
   SEMB_TRY(check_field(m, b, "pcg(b)"));
   SEMB_TRY(check_field(m, x, "pcg(x)"));
   SEMB_TRY(check_field(m, o->nu_arr, "pcg(nu)", true));
@@ -1279,14 +1291,14 @@ static int pcg_one_iteration(semb_mesh* m) {
 
 extern "C" int semb_pcg_iterate(semb_mesh* m, int n) {
   SEMB_REQUIRE(m && m->pcg_active, "semb_pcg_iterate: call semb_pcg_begin first");
-  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_ENTER(m->ctx);
   for (int i = 0; i < n; ++i) SEMB_TRY(pcg_one_iteration(m));
   return SEMB_OK;
 }
 
 extern "C" int semb_pcg_status(semb_mesh* m, long long* iters, double* resinf, int* done) {
   SEMB_REQUIRE(m, "null mesh");
-  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_ENTER(m->ctx);
   SEMB_TRY(read_scal(m));
   if (iters) *iters = m->h_scal->iters;
   if (resinf) *resinf = m->h_scal->rmax;
@@ -1361,7 +1373,7 @@ extern "C" int semb_pcg(semb_mesh* m, const semb_pcg_opts* o, const semb_field* 
 // ---- grad / dealiased advection (grad.jl, advect.jl) ---------------------------------------------------------------
 extern "C" int semb_grad(semb_mesh* m, const semb_field* u, semb_field* ux, semb_field* uy) {
   SEMB_REQUIRE(m, "null mesh");
-  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_ENTER(m->ctx);
   SEMB_TRY(check_field(m, u, "grad(u)"));
   SEMB_TRY(check_field(m, ux, "grad(ux)"));
   SEMB_TRY(check_field(m, uy, "grad(uy)"));
@@ -1463,7 +1475,7 @@ static int advect_run(AdvectWork* w, const double* T, const double* ux, const do
 extern "C" int semb_advect(semb_mesh* mV, semb_mesh* mD, const semb_field* T, const semb_field* ux, const semb_field* uy,
                            semb_field* out) {
   SEMB_REQUIRE(mV, "null mesh");
-  SEMB_TRY(ctx_enter(mV->ctx));
+  SEMB_ENTER(mV->ctx);
   SEMB_TRY(check_field(mV, T, "advect(T)"));
   SEMB_TRY(check_field(mV, ux, "advect(ux)"));
   SEMB_TRY(check_field(mV, uy, "advect(uy)"));
@@ -1499,7 +1511,7 @@ extern "C" int semb_diffusion_create(semb_mesh* m, const char bc[4], double Ti, 
   SEMB_REQUIRE(m && bc && out, "semb_diffusion_create: null argument");
   SEMB_REQUIRE(k >= 1 && k <= 4, "semb_diffusion_create: history length k must be 1..4 (got %d)", k);
   SEMB_REQUIRE(m->arr[SEMB_B] && m->arr[SEMB_G11], "semb_diffusion_create: mesh needs B and G factors");
-  SEMB_TRY(ctx_enter(m->ctx));
+  SEMB_ENTER(m->ctx);
   MaskFlags fl;
   SEMB_TRY(parse_bc(m, bc, &fl));
   semb_diffusion* d = new semb_diffusion();
@@ -1569,7 +1581,7 @@ extern "C" int semb_diffusion_field(semb_diffusion* d, int which, semb_field** f
 
 extern "C" int semb_diffusion_begin_step(semb_diffusion* d, double* time, long long* istep) {
   SEMB_REQUIRE(d, "null diffusion");
-  SEMB_TRY(ctx_enter(d->m->ctx));
+  SEMB_ENTER(d->m->ctx);
   // updateHist!(fld), mesh.jl:207-215: uh[i] .= uh[i-1]; uh[1] .= u  (pointer rotation + one copy)
   semb_field* last = d->uh[d->k - 1];
   for (int i = d->k - 1; i >= 1; --i) d->uh[i] = d->uh[i - 1];
@@ -1590,7 +1602,7 @@ extern "C" int semb_diffusion_finish_step(semb_diffusion* d, double tol, long lo
   SEMB_REQUIRE(d, "null diffusion");
   semb_mesh* m = d->m;
   semb_ctx* c = m->ctx;
-  SEMB_TRY(ctx_enter(c));
+  SEMB_ENTER(c);
   MaskFlags fl;
   SEMB_TRY(parse_bc(m, d->bc, &fl));
   // makeRHS!, diffusion.jl:51-65
@@ -1749,7 +1761,7 @@ extern "C" int semb_pcg_host(semb_mesh* m, const semb_pcg_opts* o, const double*
 
 extern "C" int semb_abu_host(semb_ctx* c, const double* As, int ma, int na, const double* Br, int mb, int nb,
                              const double* u, int mrows, int ncols, double* out) {
-  SEMB_TRY(ctx_enter(c));
+  SEMB_ENTER(c);
   SEMB_REQUIRE(u && out && mrows >= 1 && ncols >= 1, "ABu: bad u");
   const bool hasB = Br && mb > 0 && nb > 0, hasA = As && ma > 0 && na > 0;
   // Julia: Int(m*mb/nb) / Int(Ey*ma) throw InexactError when not integral (ABu.jl:16,26)

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <nccl.h>
 #include <stdint.h>
+#include <mutex>
 #include <stdio.h>
 #include <string.h>
 #include <string>
@@ -93,6 +94,7 @@ struct P2PArgs {
 };
 
 struct semb_ctx {
+  std::recursive_mutex mutex;  // one in-flight call per context
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
