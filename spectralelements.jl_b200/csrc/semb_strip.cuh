@@ -258,7 +258,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
   if (PCGM && r0 < r1) issue_p(r0);
 
   // inactive threads read through clamped indices (no selects in the inner loops); they never store
-  const int tr = inB ? t : 0, colBr = inB ? colB : 0;
+  const int tr = inB ? t : 0;  // (the staging buffers are only written by the async proxy, between barriers)
   // partner column of an in-strip x interface (element stride S, N nodes per element)
   const int slotW = xl ? 2 * eB : 2 * (eB - 1) + 1, slotR = xl ? 2 * eB + 1 : 2 * (eB - 1);
   const bool xi = xl || xr;
@@ -317,7 +317,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     semb_mbar_wait(&bars[1], parity);
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      const double ur = S1[j * PW + colBr];
+      const double ur = inB ? S1[j * PW + colB] : 0.0;  // (threads BX*N..T-1 own no column)
       const double g11 = SG[(0 * N + j) * PWS + tr], g12 = SG[(1 * N + j) * PWS + tr], g22 = SG[(2 * N + j) * PWS + tr];
       const double wr = fma(g11, ur, g12 * us[j]);  // lapl.jl:75
       ws[j] = fma(g12, ur, g22 * us[j]);            // lapl.jl:76
@@ -348,7 +348,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     double v[N];
 #pragma unroll
     for (int j = 0; j < N; ++j)
-      v[j] = combine(S1[j * PW + colBr], aus[j], MASS ? nuq[j] : a.nu, MASS ? mt[j] : 0.0);
+      v[j] = combine(inB ? S1[j * PW + colB] : 0.0, aus[j], MASS ? nuq[j] : a.nu, MASS ? mt[j] : 0.0);
     if (!gs) {
       if (actB) {
 #pragma unroll
