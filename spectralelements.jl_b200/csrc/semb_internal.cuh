@@ -14,7 +14,10 @@
 #define SEMB_MAXN 17       // largest nr == ns served by the templated strip kernel
 // CTA size of the strip kernel: 256 threads (8 warps, 2 per SM sub-partition); 192 for N = 12..14 so that two
 // CTAs still fit the 227 KB of shared memory (the staging buffers grow like N^2 per element)
-constexpr int semb_strip_threads(int n) { return (n >= 12 && n <= 14) ? 192 : 256; }
+#ifndef SEMB_T9
+#define SEMB_T9 256
+#endif
+constexpr int semb_strip_threads(int n) { return (n >= 12 && n <= 14) ? 192 : (n == 9 ? SEMB_T9 : 256); }
 // elements per strip: as many as fit the CTA, with BX*N even so that every staged row is a multiple of 16 bytes
 constexpr int semb_strip_bx(int n) {
   return ((semb_strip_threads(n) / n) * n) % 2 == 0 ? semb_strip_threads(n) / n : semb_strip_threads(n) / n - 1;

@@ -133,7 +133,10 @@ struct StripCfg {
   static constexpr int NSTAGE = 4;               // u, G11, G12, G22
   static constexpr int SMEM_DOUBLES = N * PW + NSTAGE * N * PWS + N * 2 * BX + 4 * StripTab<N>::SIZE;
   static constexpr int SMEM = SMEM_DOUBLES * 8 + 64;
-  static constexpr int MINB = (2 * SMEM + 2048 <= 228 * 1024) ? ((3 * SMEM + 3072 <= 228 * 1024 && N <= 6) ? 3 : 2) : 1;
+  static constexpr int MAXB_SMEM = (228 * 1024) / (SMEM + 1024);              // CTAs/SM the shared memory allows
+  static constexpr int MAXB_REGS = 65536 / (T * 128) > 0 ? 65536 / (T * 128) : 1;  // ... at 128 registers per thread
+  static constexpr int MINB0 = MAXB_SMEM < MAXB_REGS ? MAXB_SMEM : MAXB_REGS;
+  static constexpr int MINB = (N <= 6 && 3 * SMEM + 3072 <= 228 * 1024 && T == 256) ? 3 : (MINB0 < 1 ? 1 : MINB0);
 };
 
 // ---- mbarrier / bulk-copy (TMA 1-D) PTX wrappers ------------------------------------------------------
