@@ -121,6 +121,9 @@ int semb_mesh_destroy(semb_mesh* mesh);
 int semb_mesh_dims(semb_mesh* mesh, int* nr, int* ns, int* Ex, int* Ey, int* nxl, int* nyl, int* ey0, int* ney);
 /* Copy one Mesh array (enum semb_mesh_array) to a host nxl x nyl buffer. */
 int semb_mesh_get(semb_mesh* mesh, int which, double* host_out);
+/* Upload one Mesh array (e.g. the rx, ry, sx, sy a Julia Mesh already holds; needed by semb_grad / semb_advect
+ * when the mesh was created with semb_mesh_create_arrays). */
+int semb_mesh_set(semb_mesh* mesh, int which, const double* host_in);
 /* Dr / Ds as held on the device side (column-major). */
 int semb_mesh_get_D(semb_mesh* mesh, double* Dr, double* Ds);
 /* generateMask(bc, msh), mesh.jl:149-175: bc = "DDNN" = [xmin,xmax,ymin,ymax]; writes 0/1 doubles. */

@@ -13,7 +13,7 @@ module SpectralElementsB200
 
 using SpectralElements
 using SpectralElements: Mesh, Diffusion, ConvectionDiffusion
-import SpectralElements: ABu, lapl, hlmz, mass, gatherScatter, mask, pcg, pcg!, opLHS, solve!
+import SpectralElements: ABu, lapl, hlmz, mass, gatherScatter, mask, pcg, pcg!, opLHS, solve!, grad, advect
 
 const libsemb = get(ENV, "LIBSEMB", joinpath(@__DIR__, "..", "spectralelements.jl_b200", "lib", "libsemb.so"))
 
@@ -62,6 +62,10 @@ function devmesh(msh::Mesh)
                      Ref{Ptr{Cvoid}}),
                     context(), msh.nr, msh.ns, msh.Ex, msh.Ey, msh.ifperiodic[1], msh.ifperiodic[2],
                     msh.Dr, msh.Ds, msh.G11, msh.G12, msh.G22, msh.B, h))
+        # metric terms for grad / advect (enum semb_mesh_array: RX = 4, RY = 5, SX = 6, SY = 7)
+        for (which, a) in ((4, msh.rx), (5, msh.ry), (6, msh.sx), (7, msh.sy))
+            check(ccall((:semb_mesh_set, libsemb), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h[], which, a))
+        end
         h[]
     end
 end
@@ -127,6 +131,33 @@ function mask(u::Array, M::Array, msh::Mesh)
     check(ccall((:semb_mask_host, libsemb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                 devmesh(msh), f64(u), length(M) == 0 ? C_NULL : pointer(Mf), out))
     return out
+end
+
+# grad(u,msh), grad.jl:94-102 ; advect(T,ux,uy,mshV,mshD,Jr,Js), advect.jl:45-64 (Jr, Js are rebuilt by the library)
+function devfield(msh::Mesh, a::Union{Array,Nothing} = nothing)
+    f = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:semb_field_create, libsemb), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), devmesh(msh), f))
+    a === nothing || check(ccall((:semb_field_upload, libsemb), Cint, (Ptr{Cvoid}, Ptr{Float64}), f[], f64(a)))
+    return f[]
+end
+function devget(f::Ptr{Cvoid}, like::Array)
+    out = similar(like, Float64)
+    check(ccall((:semb_field_download, libsemb), Cint, (Ptr{Cvoid}, Ptr{Float64}), f, out))
+    ccall((:semb_field_destroy, libsemb), Cint, (Ptr{Cvoid},), f)
+    return out
+end
+function grad(u::Array, msh::Mesh)
+    (fu, fx, fy) = (devfield(msh, u), devfield(msh), devfield(msh))
+    check(ccall((:semb_grad, libsemb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), devmesh(msh), fu, fx, fy))
+    ccall((:semb_field_destroy, libsemb), Cint, (Ptr{Cvoid},), fu)
+    return devget(fx, u), devget(fy, u)
+end
+function advect(T::Array, ux::Array, uy::Array, mshV::Mesh, mshD::Mesh, Jr, Js)
+    (fT, fx, fy, fo) = (devfield(mshV, T), devfield(mshV, ux), devfield(mshV, uy), devfield(mshV))
+    check(ccall((:semb_advect, libsemb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                devmesh(mshV), devmesh(mshD), fT, fx, fy, fo))
+    for f in (fT, fx, fy); ccall((:semb_field_destroy, libsemb), Cint, (Ptr{Cvoid},), f); end
+    return devget(fo, T)
 end
 
 # ---- the fused unit and the device-resident Krylov loop ------------------------------------------------

@@ -343,6 +343,12 @@ class Mesh:
             return c[name]
         raise AttributeError(name)
 
+    def set_array(self, name: str, host):
+        """upload one Mesh array (x, y, Jac, Jaci, rx, ry, sx, sy, B, Bi, G11, G12, G22)"""
+        a = as_f64(host, self.shape)
+        check(self.lib.semb_mesh_set(self.h, SEMB_ARR[name], dptr(a)))
+        self._cache.pop(name, None)
+
     def field(self, host=None) -> DeviceField:
         return DeviceField(self, host)
 

@@ -67,6 +67,7 @@ _SIGS = {
     "semb_mesh_destroy": ([vp], C.c_int),
     "semb_mesh_dims": ([vp] + [c_int_p] * 8, C.c_int),
     "semb_mesh_get": ([vp, C.c_int, c_double_p], C.c_int),
+    "semb_mesh_set": ([vp, C.c_int, c_double_p], C.c_int),
     "semb_mesh_get_D": ([vp, c_double_p, c_double_p], C.c_int),
     "semb_generate_mask": ([vp, C.c_char_p, c_double_p], C.c_int),
     "semb_field_create": ([vp, C.POINTER(vp)], C.c_int),

@@ -761,6 +761,14 @@ extern "C" int semb_mesh_get(semb_mesh* m, int which, double* host) {
   return download_pitched(m, m->arr[which], host);
 }
 
+extern "C" int semb_mesh_set(semb_mesh* m, int which, const double* host) {
+  SEMB_REQUIRE(m && host, "semb_mesh_set: null argument");
+  SEMB_REQUIRE(which >= 0 && which < SEMB_MESH_ARRAY_COUNT && which != SEMB_MULT, "semb_mesh_set: bad selector %d", which);
+  SEMB_ENTER(m->ctx);
+  SEMB_TRY(mesh_alloc_array(m, which));
+  return upload_pitched(m, m->arr[which], host);
+}
+
 extern "C" int semb_mesh_get_D(semb_mesh* m, double* Dr, double* Ds) {
   SEMB_REQUIRE(m, "null mesh");
   if (Dr) std::copy(m->hDr.begin(), m->hDr.end(), Dr);
