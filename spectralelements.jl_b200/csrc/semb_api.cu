@@ -102,6 +102,8 @@ extern "C" int semb_init(int device, semb_ctx** out) {
   SEMB_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   SEMB_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  SEMB_CHECK_CUDA(cudaStreamCreateWithFlags(&c->in_stream, cudaStreamNonBlocking));
+  SEMB_CHECK_CUDA(cudaStreamCreateWithFlags(&c->out_stream, cudaStreamNonBlocking));
   SEMB_CHECK_CUDA(cudaEventCreate(&c->ev0));
   SEMB_CHECK_CUDA(cudaEventCreate(&c->ev1));
   SEMB_CHECK_CUDA(cudaMalloc(&c->d_sync, 64));
@@ -139,6 +141,8 @@ extern "C" int semb_finalize(semb_ctx* c) {
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->in_stream);
+  cudaStreamDestroy(c->out_stream);
   delete c;
   return SEMB_OK;
 }
@@ -1733,11 +1737,118 @@ extern "C" int semb_mask_host(semb_mesh* m, const double* u, const double* M, do
   return semb_field_download(fo, out);
 }
 
+// Pipelined form of the host twin for large single-rank meshes: the element rows are cut into slabs of chunks;
+// slab s is uploaded (H2D stream) while slab s-1 is computed (strip + seam kernels restricted to the slab,
+// compute stream) and slab s-2 is downloaded (D2H stream), so the PCIe link is busy in both directions.
+// The operator is element-local and a slab's last line becomes final once the next slab's first line exists
+// (the y seam between them), hence the one-slab lag of the download.  Same kernels, same bits.
+static int oplhs_host_pipelined(semb_mesh* m, const double* u, double nu, double k, const char* bc, double* out,
+                                semb_field* fu, semb_field* fo) {
+  semb_ctx* c = m->ctx;
+  const int N = m->ns;
+  int nslab = std::min(8, m->nchunks);
+  OpArgs a;
+  fill_common(m, a);
+  a.u = fu->d;
+  a.out = fo->d;
+  a.nu = nu;
+  a.k = k;
+  a.gs = 1;
+  MaskFlags f;
+  SEMB_TRY(parse_bc(m, bc, &f));
+  a.mx0 = f.mx0;
+  a.mx1 = f.mx1;
+  a.my0 = f.my0;
+  a.my1 = f.my1;
+  a.partials = m->d_partials;
+  a.counters = m->d_counters;
+  const bool massterm = (k != 0.0);
+  std::vector<cudaEvent_t> ev_in(nslab), ev_cmp(nslab);
+  for (int s = 0; s < nslab; ++s) {
+    SEMB_CHECK_CUDA(cudaEventCreateWithFlags(&ev_in[s], cudaEventDisableTiming));
+    SEMB_CHECK_CUDA(cudaEventCreateWithFlags(&ev_cmp[s], cudaEventDisableTiming));
+  }
+  auto rows_of = [&](int s, int* y0, int* y1) {
+    const int c0 = (int)((long long)s * m->nchunks / nslab), c1 = (int)((long long)(s + 1) * m->nchunks / nslab);
+    *y0 = m->h_chunk_r0[c0] * N;
+    *y1 = m->h_chunk_r0[c1] * N;
+  };
+  auto copy_rows = [&](bool h2d, int y0, int y1, cudaStream_t st) -> int {
+    const size_t hw = (size_t)m->nxl * sizeof(double), dw = (size_t)m->pitch * sizeof(double);
+    if (h2d)
+      SEMB_CHECK_CUDA(cudaMemcpy2DAsync(fu->d + (size_t)y0 * m->pitch, dw, u + (size_t)y0 * m->nxl, hw, hw, y1 - y0,
+                                        cudaMemcpyHostToDevice, st));
+    else
+      SEMB_CHECK_CUDA(cudaMemcpy2DAsync(out + (size_t)y0 * m->nxl, hw, fo->d + (size_t)y0 * m->pitch, dw, hw, y1 - y0,
+                                        cudaMemcpyDeviceToHost, st));
+    return SEMB_OK;
+  };
+  int rc = SEMB_OK;
+  auto body = [&]() -> int {
+    SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < nslab; ++s) {
+      int y0, y1;
+      rows_of(s, &y0, &y1);
+      const int c0 = (int)((long long)s * m->nchunks / nslab), c1 = (int)((long long)(s + 1) * m->nchunks / nslab);
+      SEMB_TRY(copy_rows(true, y0, y1, c->in_stream));
+      SEMB_CHECK_CUDA(cudaEventRecord(ev_in[s], c->in_stream));
+      SEMB_CHECK_CUDA(cudaStreamWaitEvent(c->stream, ev_in[s], 0));
+      OpArgs b = a;
+      b.chunk0 = c0;
+      SEMB_TRY(semb_launch_strip(c, b, m->hDr.data(), m->hDs.data(), m->nstrips, c1 - c0, false, massterm, m->eo));
+      b.y_begin = y0;
+      b.y_end = y1;
+      SEMB_TRY(semb_launch_seam_x(c, b));
+      // y seams: q is the seam between chunk q and q+1; this slab closes seams c0-1 .. c1-2
+      const int q0 = std::max(c0 - 1, 0), q1 = c1 - 1;
+      if (q1 > q0) {
+        OpArgs y = a;
+        y.yseam = m->d_yseam + 2 * q0;
+        y.nyseam = q1 - q0;
+        SEMB_TRY(semb_launch_seam_y(c, y, 0, 0, true, P2PArgs()));
+      }
+      SEMB_CHECK_CUDA(cudaEventRecord(ev_cmp[s], c->stream));
+      if (s > 0) {  // slab s-1 is final now
+        int p0, p1;
+        rows_of(s - 1, &p0, &p1);
+        SEMB_CHECK_CUDA(cudaStreamWaitEvent(c->out_stream, ev_cmp[s], 0));
+        SEMB_TRY(copy_rows(false, p0, p1, c->out_stream));
+      }
+    }
+    int p0, p1;
+    rows_of(nslab - 1, &p0, &p1);
+    SEMB_CHECK_CUDA(cudaStreamWaitEvent(c->out_stream, ev_cmp[nslab - 1], 0));
+    SEMB_TRY(copy_rows(false, p0, p1, c->out_stream));
+    SEMB_CHECK_CUDA(cudaStreamSynchronize(c->out_stream));
+    SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+    return SEMB_OK;
+  };
+  rc = body();
+  if (rc < 0) {  // never leave copies in flight on the caller's buffers
+    cudaStreamSynchronize(c->in_stream);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->out_stream);
+  }
+  for (int s = 0; s < nslab; ++s) {
+    cudaEventDestroy(ev_in[s]);
+    cudaEventDestroy(ev_cmp[s]);
+  }
+  return rc;
+}
+
 extern "C" int semb_oplhs_host(semb_mesh* m, const double* u, const double* nu_arr, double nu, const double* k_arr,
                                double k, const char* bc, const double* M_arr, double* out) {
   SEMB_REQUIRE(m && u && out, "oplhs_host: null argument");
+  SEMB_ENTER(m->ctx);
   TmpFields t(m);
   semb_field *fu, *fo, *fn, *fk, *fm;
+  const bool pipe = m->fast && m->ctx->nranks == 1 && !m->pery && !nu_arr && !k_arr && !M_arr && m->nchunks >= 4 &&
+                    (size_t)m->nxl * m->nyl >= ((size_t)1 << 22) && (k == 0.0 || m->arr[SEMB_B]) && !getenv("SEMB_NO_PIPELINE");
+  if (pipe) {
+    SEMB_TRY(t.make(nullptr, &fu));
+    SEMB_TRY(t.make(nullptr, &fo));
+    return oplhs_host_pipelined(m, u, nu, k, bc, out, fu, fo);
+  }
   SEMB_TRY(t.make(u, &fu));
   SEMB_TRY(t.make(nullptr, &fo));
   SEMB_TRY(t.maybe(nu_arr, &fn));

@@ -101,7 +101,7 @@ struct semb_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
-  cudaStream_t comm_stream = nullptr;
+  cudaStream_t in_stream = nullptr, out_stream = nullptr;  // H2D / D2H streams of the pipelined host twin
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   long long launches = 0;
   ncclComm_t comm = nullptr;
@@ -202,6 +202,8 @@ struct OpArgs {
   int mx0 = 0, mx1 = 0, my0 = 0, my1 = 0;  // Dirichlet flags that apply to THIS slab's boundary lines
   const int* chunk_r0 = nullptr;
   int nchunks = 0;
+  int chunk0 = 0;               // first chunk of this launch (pipelined host twin: one slab of chunks per launch)
+  int y_begin = 0, y_end = 0;   // row range of the x-seam kernel (0, 0 = all rows)
   const unsigned char* ystart = nullptr;
   const int* xseam = nullptr;
   int nxseam = 0;

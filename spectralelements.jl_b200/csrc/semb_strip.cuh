@@ -205,7 +205,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
   const bool actB = eB < nbe;                   // (eB < BX is implied: nbe <= BX)
   const bool inB = t < BX * N;                  // threads BX*N..T-1 own no column (T need not divide by N)
   const bool actA = (jA < N) && (eA < nbe);
-  const int r0 = a.chunk_r0[blockIdx.y], r1 = a.chunk_r0[blockIdx.y + 1];
+  const int r0 = a.chunk_r0[a.chunk0 + blockIdx.y], r1 = a.chunk_r0[a.chunk0 + blockIdx.y + 1];
   const int pitch = (int)a.pitch;
   const int x0 = e0 * N;
   const int xg = x0 + t;

@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(256) semb_seam_x_kernel(const OpArgs a) {
   if (a.pcg && a.scal->done) return;
   const int N = a.N;
   double acc = 0.0;
-  const long long total = (long long)a.nxseam * a.nyl;
+  const int yb = a.y_begin, ny = (a.y_end > a.y_begin ? a.y_end : a.nyl) - yb;
+  const long long total = (long long)a.nxseam * ny;
   auto finish = [&](int x, int y, double val) {
     const size_t idx = (size_t)y * a.pitch + x;
     const double o = __dmul_rn(mask_at(a, x, y, idx), val);
@@ -34,7 +35,7 @@ __global__ void __launch_bounds__(256) semb_seam_x_kernel(const OpArgs a) {
   };
   for (long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x; id < total;
        id += (long long)gridDim.x * blockDim.x) {
-    const int s = (int)(id / a.nyl), y = (int)(id - (long long)s * a.nyl);
+    const int s = (int)(id / ny), y = yb + (int)(id - (long long)s * ny);
     const int xa = a.xseam[2 * s], xb = a.xseam[2 * s + 1];
     const int r = y / N, j = y - r * N;
     if (j == 0 && r > 0 && !a.ystart[r]) continue;  // lower line of an in-chunk pair: done by line y-1
@@ -772,7 +773,7 @@ int flat_blocks(size_t n, int sm_count) {
 
 int semb_launch_seam_x(semb_ctx* ctx, const OpArgs& a) {
   if (a.nxseam == 0) return SEMB_OK;
-  const long long total = (long long)a.nxseam * a.nyl;
+  const long long total = (long long)a.nxseam * ((a.y_end > a.y_begin ? a.y_end : a.nyl) - a.y_begin);
   int blocks = (int)((total + 255) / 256);
   if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
   OpArgs b = a;

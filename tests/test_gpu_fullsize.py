@@ -32,6 +32,11 @@ def test_cfg2_helmholtz_full_mesh_vs_oracle(sem, ctx):
             ref = so.opLHS(u, 1.0, 1.0, M, om)
             out = sem.OpLHS(gm2, 1.0, 1.0, bc="DDDD")(u)
             assert relerr(out, ref) < 1e-12
+            # the host twin pipelines upload / compute / download by slabs at this size: same bits as the
+            # device-resident single-launch path
+            fu, fo = gm2.field(u), gm2.field()
+            gm2.oplhs_device(fu, fo, nu=1.0, k=1.0, bc="DDDD")
+            assert np.array_equal(fo.download(), out)
             assert np.array_equal(sem.gatherScatter(u, gm2), so.gatherScatter(u, om))
             # 40 PCG iterations track the oracle (trajectory parity at full cfg2 size)
             b = so.gatherScatter(so.mask(so.mass(np.ones(gm.shape), om), M), om)
