@@ -1421,8 +1421,6 @@ static int advect_work_create(semb_mesh* V, semb_mesh* D, AdvectWork** out) {
   AdvectWork* w = new AdvectWork();
   w->V = V;
   w->D = D;
-  SEMB_TRY(semb_field_create(V, &w->Tx));
-  SEMB_TRY(semb_field_create(V, &w->Ty));
   if (D) {
     SEMB_REQUIRE(D->ctx == V->ctx && D->Ex == V->Ex && D->Ey == V->Ey && D->ney == V->ney && D->perx == V->perx &&
                      D->pery == V->pery,
@@ -1455,12 +1453,24 @@ static int advect_work_create(semb_mesh* V, semb_mesh* D, AdvectWork** out) {
     SEMB_TRY(up(Js, &w->dJs));
     SEMB_TRY(up(JrT, &w->dJrT));
     SEMB_TRY(up(JsT, &w->dJsT));
+  }
+  *out = w;
+  return SEMB_OK;
+}
+
+// intermediate fields of the multi-pass form, allocated on first use (the fused kernel needs none)
+static int advect_work_fields(AdvectWork* w) {
+  semb_mesh *V = w->V, *D = w->D;
+  if (!w->Tx) {
+    SEMB_TRY(semb_field_create(V, &w->Tx));
+    SEMB_TRY(semb_field_create(V, &w->Ty));
+  }
+  if (D && !w->JCu) {
     semb_field** fd[] = {&w->JTx, &w->JTy, &w->Jux, &w->Juy, &w->JCu};
     for (semb_field** f : fd) SEMB_TRY(semb_field_create(D, f));
     const size_t nmid = std::max((size_t)D->pitch * V->nyl, (size_t)V->pitch * D->nyl);
     SEMB_CHECK_CUDA(cudaMalloc(&w->mid, nmid * sizeof(double)));
   }
-  *out = w;
   return SEMB_OK;
 }
 
@@ -1468,6 +1478,12 @@ static int advect_work_create(semb_mesh* V, semb_mesh* D, AdvectWork** out) {
 static int advect_run(AdvectWork* w, const double* T, const double* ux, const double* uy, double* out) {
   semb_mesh *V = w->V, *D = w->D;
   semb_ctx* c = V->ctx;
+  if (D && !getenv("SEMB_NO_FUSED_ADVECT")) {  // one fused kernel when nr == ns and nrd == nsd
+    int done = 0;
+    SEMB_TRY(semb_launch_advect_fused(c, V, D, T, ux, uy, w->dJr, w->dJs, out, &done));
+    if (done) return SEMB_OK;
+  }
+  SEMB_TRY(advect_work_fields(w));
   SEMB_TRY(semb_launch_grad(c, V, T, w->Tx->d, w->Ty->d));  // Tx,Ty = grad(T,mshV)
   if (!D) return semb_launch_advect_pointwise(c, V, ux, w->Tx->d, uy, w->Ty->d, out);
   auto interp = [&](const double* in, double* outD) -> int {  // ABu(Js,Jr,in): Br = Jr first, then As = Js (ABu.jl:14-33)

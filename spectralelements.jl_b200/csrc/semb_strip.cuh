@@ -293,7 +293,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
       double v = SU[j * PWS + tr];
       if (PCGM && actB) {
         const int idx = base + j * pitch;
-        if (a.precond) v = (v / a.B[idx]) / a.prec_b0;  // convectionDiffusion.jl:89
+        if (a.precond) v = (v / (MASS ? bq[j] : a.B[idx])) / a.prec_b0;  // convectionDiffusion.jl:89
         v = __dadd_rn(v, __dmul_rn(beta, pn[j]));        // pcg.jl:49
         a.pout[idx] = v;
       }

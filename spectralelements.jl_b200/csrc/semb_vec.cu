@@ -748,6 +748,117 @@ __global__ void semb_rhs_kernel(const double* __restrict__ f, const double* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused dealiased advection, advect.jl:45-64, for nr == ns = N on mshV and nrd == nsd = M on mshD:
+//   Tx,Ty = grad(T) ; J* = ABu(Js,Jr,*) for Tx,Ty,ux,uy ; JCu = (Jux.*JTx + Juy.*JTy).*B_D ; Cu = ABu(Js',Jr',JCu)
+// One CTA works on EB x-consecutive elements of an element row at a time, everything between the loads
+// of T,ux,uy,rx,ry,sx,sy,B_D and the store of Cu stays in shared memory (no intermediate fields in HBM:
+// ~8 V-sized + 1 D-sized array of traffic instead of ~40).  Contraction order as the reference: the x
+// matrix (Br) before the y matrix (As) in both ABu calls (ABu.jl:14-33).
+// ------------------------------------------------------------------------------------------------
+struct AdvectFusedArgs {
+  const double *T, *ux, *uy, *rx, *ry, *sx, *sy, *BD;
+  const double *Dr, *Ds;  // row-major N x N
+  const double *Jr, *Js;  // column-major M x N (interpMat(mshD.z, mshV.z))
+  double* out;
+  long long pitchV, pitchD;
+  int N, M, Ex, ney, EB;
+};
+
+__global__ void __launch_bounds__(256) semb_advect_fused_kernel(const AdvectFusedArgs a) {
+  extern __shared__ double sh[];
+  const int N = a.N, M = a.M, EB = a.EB, NN = N * N, MN = M * N, MM = M * M;
+  double* sDr = sh;            // [N][N]   Dr(i,k)
+  double* sDs = sDr + NN;      // [N][N]   Ds(j,k)
+  double* sJr = sDs + NN;      // [M][N]   Jr(m,i)
+  double* sJs = sJr + MN;      // [M][N]   Js(n,j)
+  double* tT = sJs + MN;       // [EB][N][N] T, later unused
+  double* tF = tT + EB * NN;   // [4][EB][N][N]  Tx, Ty, ux, uy   (element tile: [j][i], i = x contiguous)
+  double* tB = tF + 4 * EB * NN;  // [4][EB][N][M] x-interpolated; later [EB][M][N] x-projected JCu
+  double* tD = tB + 4 * EB * MN;  // [4][EB][M][M] on the dealiasing grid; tD[0] becomes JCu
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int q = tid; q < NN; q += nt) {
+    sDr[q] = a.Dr[q];
+    sDs[q] = a.Ds[q];
+  }
+  for (int q = tid; q < MN; q += nt) {
+    const int m = q / N, i = q - m * N;
+    sJr[q] = a.Jr[m + (size_t)i * M];
+    sJs[q] = a.Js[m + (size_t)i * M];
+  }
+  const int e0 = blockIdx.x * EB;
+  const int nbe = min(EB, a.Ex - e0);
+  for (int r = blockIdx.y; r < a.ney; r += gridDim.y) {
+    __syncthreads();
+    // load T, ux, uy tiles (coalesced along x)
+    for (int q = tid; q < N * nbe * N; q += nt) {
+      const int j = q / (nbe * N), xx = q - j * (nbe * N), e = xx / N, i = xx - e * N;
+      const size_t g = (size_t)(r * N + j) * a.pitchV + (size_t)e0 * N + xx;
+      tT[e * NN + j * N + i] = a.T[g];
+      tF[(2 * EB + e) * NN + j * N + i] = a.ux[g];
+      tF[(3 * EB + e) * NN + j * N + i] = a.uy[g];
+    }
+    __syncthreads();
+    // grad: Tx = rx.*ur + sx.*us, Ty = ry.*ur + sy.*us (grad.jl:106-110)
+    for (int q = tid; q < N * nbe * N; q += nt) {
+      const int j = q / (nbe * N), xx = q - j * (nbe * N), e = xx / N, i = xx - e * N;
+      const double* t = tT + e * NN;
+      double ur = 0.0, us = 0.0;
+      for (int k = 0; k < N; ++k) ur = fma(sDr[i * N + k], t[j * N + k], ur);
+      for (int k = 0; k < N; ++k) us = fma(sDs[j * N + k], t[k * N + i], us);
+      const size_t g = (size_t)(r * N + j) * a.pitchV + (size_t)e0 * N + xx;
+      tF[(0 * EB + e) * NN + j * N + i] = __dadd_rn(__dmul_rn(a.rx[g], ur), __dmul_rn(a.sx[g], us));
+      tF[(1 * EB + e) * NN + j * N + i] = __dadd_rn(__dmul_rn(a.ry[g], ur), __dmul_rn(a.sy[g], us));
+    }
+    __syncthreads();
+    // interpolate along x: tB[f][e][j][m] = sum_i Jr(m,i) f[e][j][i]
+    for (int q = tid; q < 4 * nbe * N * M; q += nt) {
+      const int m = q % M, rest = q / M, j = rest % N, fe = rest / N, e = fe % nbe, f = fe / nbe;
+      const double* src = tF + (f * EB + e) * NN + j * N;
+      double s_ = 0.0;
+      for (int i = 0; i < N; ++i) s_ = fma(sJr[m * N + i], src[i], s_);
+      tB[(f * EB + e) * MN + j * M + m] = s_;
+    }
+    __syncthreads();
+    // interpolate along y: tD[f][e][n][m] = sum_j Js(n,j) tB[f][e][j][m]
+    for (int q = tid; q < 4 * nbe * M * M; q += nt) {
+      const int m = q % M, rest = q / M, n = rest % M, fe = rest / M, e = fe % nbe, f = fe / nbe;
+      const double* src = tB + (f * EB + e) * MN + m;
+      double s_ = 0.0;
+      for (int j = 0; j < N; ++j) s_ = fma(sJs[n * N + j], src[j * M], s_);
+      tD[(f * EB + e) * MM + n * M + m] = s_;
+    }
+    __syncthreads();
+    // JCu = (Jux.*JTx + Juy.*JTy) .* B_D (advect.jl:59-60), in place in tD[0]
+    for (int q = tid; q < M * nbe * M; q += nt) {
+      const int n = q / (nbe * M), xx = q - n * (nbe * M), e = xx / M, m = xx - e * M;
+      const int o = e * MM + n * M + m;
+      const double c = __dadd_rn(__dmul_rn(tD[2 * EB * MM + o], tD[0 * EB * MM + o]),
+                                 __dmul_rn(tD[3 * EB * MM + o], tD[1 * EB * MM + o]));
+      const size_t g = (size_t)(r * M + n) * a.pitchD + (size_t)e0 * M + xx;
+      tD[o] = __dmul_rn(c, a.BD[g]);
+    }
+    __syncthreads();
+    // project back along x (Br = Jr'): tB[e][n][i] = sum_m Jr(m,i) JCu[e][n][m]
+    for (int q = tid; q < nbe * M * N; q += nt) {
+      const int i = q % N, rest = q / N, n = rest % M, e = rest / M;
+      const double* src = tD + e * MM + n * M;
+      double s_ = 0.0;
+      for (int m = 0; m < M; ++m) s_ = fma(sJr[m * N + i], src[m], s_);
+      tB[e * MN + n * N + i] = s_;
+    }
+    __syncthreads();
+    // project back along y (As = Js'): Cu[e][j][i] = sum_n Js(n,j) tB[e][n][i] ; coalesced store
+    for (int q = tid; q < N * nbe * N; q += nt) {
+      const int j = q / (nbe * N), xx = q - j * (nbe * N), e = xx / N, i = xx - e * N;
+      const double* src = tB + e * MN + i;
+      double s_ = 0.0;
+      for (int n = 0; n < M; ++n) s_ = fma(sJs[n * N + j], src[n * N], s_);
+      a.out[(size_t)(r * N + j) * a.pitchV + (size_t)e0 * N + xx] = s_;
+    }
+  }
+}
+
 dim3 rows_grid(int ncols, int nrows, int threads) {
   int gx = (ncols + threads - 1) / threads;
   if (gx < 1) gx = 1;
@@ -981,4 +1092,52 @@ int semb_launch_rhs(semb_ctx* ctx, semb_mesh* m, const double* f, const double* 
   semb_rhs_kernel<<<rows_grid(m->nxl, m->nyl, 256), 256, 0, ctx->stream>>>(f, nu, lub, m->arr[SEMB_B], h, m->pitch,
                                                                           m->nxl, m->nyl, mx0, mx1, my0, my1, rhs);
   SEMB_POST_LAUNCH(ctx);
+}
+
+// returns SEMB_OK and *done = 1 if the fused kernel ran, *done = 0 if the sizes do not fit it
+int semb_launch_advect_fused(semb_ctx* ctx, semb_mesh* V, semb_mesh* D, const double* T, const double* ux,
+                             const double* uy, const double* dJr, const double* dJs, double* out, int* done) {
+  *done = 0;
+  if (V->nr != V->ns || D->nr != D->ns || D->nr < V->nr || D->nr > 32) return SEMB_OK;
+  const int N = V->nr, M = D->nr;
+  int EB = 4;
+  auto bytes = [&](int eb) { return (size_t)(2 * N * N + 2 * M * N + eb * (5 * N * N + 4 * M * N + 4 * M * M)) * 8; };
+  while (EB > 1 && bytes(EB) > 72 * 1024) EB >>= 1;
+  if (bytes(EB) > 200 * 1024) return SEMB_OK;
+  static size_t attr = 0;
+  if (bytes(EB) > attr) {
+    SEMB_CHECK_CUDA(cudaFuncSetAttribute(semb_advect_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)bytes(EB)));
+    attr = bytes(EB);
+  }
+  AdvectFusedArgs a;
+  a.T = T;
+  a.ux = ux;
+  a.uy = uy;
+  a.rx = V->arr[SEMB_RX];
+  a.ry = V->arr[SEMB_RY];
+  a.sx = V->arr[SEMB_SX];
+  a.sy = V->arr[SEMB_SY];
+  a.BD = D->arr[SEMB_B];
+  a.Dr = V->dDr;
+  a.Ds = V->dDs;
+  a.Jr = dJr;
+  a.Js = dJs;
+  a.out = out;
+  a.pitchV = V->pitch;
+  a.pitchD = D->pitch;
+  a.N = N;
+  a.M = M;
+  a.Ex = V->Ex;
+  a.ney = V->ney;
+  a.EB = EB;
+  const int gx = (V->Ex + EB - 1) / EB;
+  int gy = (ctx->sm_count * 12 + gx - 1) / gx;
+  if (gy > V->ney) gy = V->ney;
+  if (gy < 1) gy = 1;
+  semb_advect_fused_kernel<<<dim3(gx, gy), 256, bytes(EB), ctx->stream>>>(a);
+  SEMB_CHECK_CUDA(cudaGetLastError());
+  ctx->launches++;
+  *done = 1;
+  return SEMB_OK;
 }

@@ -54,3 +54,5 @@ int semb_launch_advect_pointwise(semb_ctx* ctx, semb_mesh* m, const double* jux,
 int semb_launch_rhs(semb_ctx* ctx, semb_mesh* m, const double* f, const double* nu, const double* lub, int k,
                     const double* const* uh, const double* b, const double* const* adv, const double* a, int mx0,
                     int mx1, int my0, int my1, double* rhs);
+int semb_launch_advect_fused(semb_ctx* ctx, semb_mesh* V, semb_mesh* D, const double* T, const double* ux,
+                             const double* uy, const double* dJr, const double* dJs, double* out, int* done);
