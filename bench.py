@@ -86,6 +86,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
+        allsm, allmx = [], []
         try:
             import datetime
             for line in open(self.path):
@@ -94,6 +95,8 @@ class ClockSampler:
                     continue
                 try:
                     ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    allsm.append(float(f[1]))
+                    allmx.append(float(f[2]))
                     if self.t0 is not None and not (self.t0 - 0.02 <= ts <= self.t1 + 0.02):
                         continue  # only samples taken DURING the timed region
                     sm.append(float(f[1]))
@@ -108,7 +111,12 @@ class ClockSampler:
             pass
         if sm:
             sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       window="timed region")
+        elif allsm:  # timed region shorter than the sampling period: report the warm-up + timed run instead
+            allsm.sort()
+            out.update(sm_mhz=allsm[len(allsm) // 2], sm_max_mhz=max(allmx), reasons=sorted(reasons),
+                       samples=len(allsm), window="warm-up + timed region (timed region too short to sample)")
         return out
 
 
