@@ -1211,11 +1211,12 @@ static int read_scal(semb_mesh* m) {
   return SEMB_OK;
 }
 
-static int reduce_common(semb_mesh* m, int which, const semb_field* a, const semb_field* b, double* result) {
+static int reduce_common(semb_mesh* m, int which, const semb_field* a, const semb_field* b, double* result,
+                         double ref = 0.0) {
   semb_ctx* c = m->ctx;
   SEMB_ENTER(c);
   SEMB_REQUIRE(result, "reduction: null result");
-  SEMB_TRY(semb_launch_reduce(c, m, which, a->d, b ? b->d : nullptr, p2p_args(m, m->p2p ? ++m->ep_red : 0)));
+  SEMB_TRY(semb_launch_reduce(c, m, which, a->d, b ? b->d : nullptr, p2p_args(m, m->p2p ? ++m->ep_red : 0), ref));
   if (c->nranks > 1 && !m->p2p) {
     SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_red), 1));
     SEMB_TRY(semb_launch_reduce_finalize(c, m, which));
@@ -1238,6 +1239,24 @@ extern "C" int semb_norm_inf(semb_mesh* m, const semb_field* a, double* result) 
   return reduce_common(m, 1, a, nullptr, result);
 }
 
+// Is an array coefficient (nu, k) really one constant, on every rank?  The reference's drivers always carry
+// nu as an array (diffusion.jl:11) that setVisc! fills with a constant (examples/p2d.jl:21-24, d2d.jl:35-38);
+// recognising that lets the solve run the scalar-coefficient kernel variant (same bits: nu .* x is the same
+// product either way) instead of streaming 8 more bytes per DOF per iteration.
+static int field_constant(semb_mesh* m, const semb_field* f, bool* is_const, double* value) {
+  semb_ctx* c = m->ctx;
+  double v0 = 0.0;
+  SEMB_CHECK_CUDA(cudaMemcpyAsync(&v0, f->d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  double spread = 0.0;
+  SEMB_TRY(reduce_common(m, 2, f, nullptr, &spread, v0));  // max |f - f[0,0]| over this rank's nodes (all-reduced)
+  double chk[3] = {spread, v0, -v0};
+  SEMB_TRY(semb_comm_allreduce_max(c, chk, 3));  // and every rank saw the same f[0,0]
+  *is_const = (chk[0] == 0.0) && (chk[1] == -chk[2]) && std::isfinite(v0);
+  *value = v0;
+  return SEMB_OK;
+}
+
 // ---- PCG ---------------------------------------------------------------------------------------------------------
 extern "C" int semb_pcg_begin(semb_mesh* m, const semb_pcg_opts* o, const semb_field* b, semb_field* x) {
   SEMB_REQUIRE(m && o, "semb_pcg_begin: null argument");
@@ -1257,6 +1276,24 @@ extern "C" int semb_pcg_begin(semb_mesh* m, const semb_pcg_opts* o, const semb_f
   SEMB_TRY(ensure_tmp(m, &m->w_Ap));
   m->pcg_opts = *o;
   m->pcg_x = x;
+  if (o->nu_arr) {
+    bool cst = false;
+    double v = 0.0;
+    SEMB_TRY(field_constant(m, o->nu_arr, &cst, &v));
+    if (cst) {
+      m->pcg_opts.nu_arr = nullptr;
+      m->pcg_opts.nu = v;
+    }
+  }
+  if (o->k_arr) {
+    bool cst = false;
+    double v = 0.0;
+    SEMB_TRY(field_constant(m, o->k_arr, &cst, &v));
+    if (cst) {
+      m->pcg_opts.k_arr = nullptr;
+      m->pcg_opts.k = v;
+    }
+  }
   long long maxiter = o->maxiter;
   if (maxiter < 0) maxiter = (long long)m->nxl * ((long long)m->ns * m->Ey);  // length(b), pcg.jl:21
   // reset the device scalars

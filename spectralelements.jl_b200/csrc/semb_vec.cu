@@ -414,13 +414,14 @@ __device__ __forceinline__ double2 semb_mult2(const double2* __restrict__ wx1d, 
 }
 
 // ---- deterministic reductions ------------------------------------------------------------------------
-// which = 0: sum(a .* b .* mult) (pcg.jl:45,52);  which = 1: norm(a, Inf) (pcg.jl:36)
+// which = 0: sum(a .* b .* mult) (pcg.jl:45,52);  which = 1: norm(a, Inf) (pcg.jl:36);
+// which = 2: max |a - ref| over the valid nodes (is an array coefficient really a constant?)
 __global__ void __launch_bounds__(256) semb_reduce_kernel(int which, const double2* __restrict__ av,
                                                           const double2* __restrict__ bv,
                                                           const double2* __restrict__ wx1d,
                                                           const double* __restrict__ wy1d, int p2, int nyl,
                                                           double* partials, unsigned* counter, SembScal* scal,
-                                                          const P2PArgs x) {
+                                                          const P2PArgs x, double ref, int nxl) {
   __shared__ double red[32];
   double acc = 0.0;
   SEMB_FOR_2D(p2, nyl) {
@@ -431,8 +432,11 @@ __global__ void __launch_bounds__(256) semb_reduce_kernel(int which, const doubl
       const double2 m2 = semb_mult2(wx1d, wy1d, c2, row);
       acc += __dmul_rn(__dmul_rn(a2.x, b2.x), m2.x);
       acc += __dmul_rn(__dmul_rn(a2.y, b2.y), m2.y);
-    } else {
+    } else if (which == 1) {
       acc = fmax(acc, fmax(fabs(a2.x), fabs(a2.y)));
+    } else {
+      if (2 * c2 < nxl) acc = fmax(acc, fabs(a2.x - ref));
+      if (2 * c2 + 1 < nxl) acc = fmax(acc, fabs(a2.y - ref));
     }
   }
   __shared__ double sh_tot[2];
@@ -982,11 +986,12 @@ int semb_launch_generic_local(semb_ctx* ctx, const OpArgs& a, int nr, int ns, co
   SEMB_POST_LAUNCH(ctx);
 }
 
-int semb_launch_reduce(semb_ctx* ctx, semb_mesh* m, int which, const double* a, const double* b, const P2PArgs& x) {
+int semb_launch_reduce(semb_ctx* ctx, semb_mesh* m, int which, const double* a, const double* b, const P2PArgs& x,
+                       double ref) {
   Grid2D g = grid2d(m->pitch, m->nyl, ctx->sm_count, m->npartials / 2);
   semb_reduce_kernel<<<g.grid, g.block, 0, ctx->stream>>>(which, (const double2*)a, (const double2*)b,
                                                           (const double2*)m->d_wx1d, m->d_wy1d, (int)(m->pitch / 2),
-                                                          m->nyl, m->d_partials, m->d_counters + 4, m->d_scal, x);
+                                                          m->nyl, m->d_partials, m->d_counters + 4, m->d_scal, x, ref, m->nxl);
   SEMB_POST_LAUNCH(ctx);
 }
 

@@ -31,7 +31,8 @@ int semb_launch_geom(semb_ctx* ctx, const double* x, const double* y, long long 
 int semb_launch_generic_local(semb_ctx* ctx, const OpArgs& a, int nr, int ns, const double* dDr,
                               const double* dDs, double* tmp_wr, double* tmp_ws, bool massterm);
 // reductions (deterministic): which = 0 dot_mult(a,b,mult), 1 norm_inf(a)
-int semb_launch_reduce(semb_ctx* ctx, semb_mesh* m, int which, const double* a, const double* b, const P2PArgs& x);
+int semb_launch_reduce(semb_ctx* ctx, semb_mesh* m, int which, const double* a, const double* b, const P2PArgs& x,
+                       double ref = 0.0);
 // PCG vector kernels
 int semb_launch_pcg_init(semb_ctx* ctx, semb_mesh* m, const double* b, double* x, double* r, double* p,
                          int precond, double prec_b0, double tol, long long maxiter, const P2PArgs& xa);
