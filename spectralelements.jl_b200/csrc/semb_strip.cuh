@@ -276,14 +276,10 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     const int base = r * N * pitch + xg;
     const uint32_t parity = (uint32_t)((r - r0) & 1);
     // coefficient columns that are not staged: issued now, consumed in step 3
-    double bq[N], nuq[N];
-    if (MASS) {  // MASS = "general coefficients": k != 0, array k, or array nu
+    double bq[N];
+    if (MASS) {  // MASS = "general coefficients": k != 0, array k, or (non-constant) array nu
 #pragma unroll
-      for (int j = 0; j < N; ++j) {
-        const int idx = base + j * pitch;
-        bq[j] = (a.B && actB) ? a.B[idx] : 0.0;
-        nuq[j] = (a.nu_arr && actB) ? a.nu_arr[idx] : a.nu;
-      }
+      for (int j = 0; j < N; ++j) bq[j] = (a.B && actB) ? a.B[base + j * pitch] : 0.0;
     }
     // ---- step 1 (B): the column of u (p in PCG mode), Ds contraction --------------------------------
     double u[N];
@@ -351,7 +347,9 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     double v[N];
 #pragma unroll
     for (int j = 0; j < N; ++j)
-      v[j] = combine(inB ? S1[j * PW + colB] : 0.0, aus[j], MASS ? nuq[j] : a.nu, MASS ? mt[j] : 0.0);
+      v[j] = combine(inB ? S1[j * PW + colB] : 0.0, aus[j],
+                     (MASS && a.nu_arr && actB) ? a.nu_arr[base + j * pitch] : a.nu,  // rare: loaded in place
+                     MASS ? mt[j] : 0.0);
     if (!gs) {
       if (actB) {
 #pragma unroll
