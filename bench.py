@@ -86,7 +86,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        allsm, allmx = [], []
+        allsm, allmx, allreasons = [], [], set()
         try:
             import datetime
             for line in open(self.path):
@@ -98,6 +98,9 @@ class ClockSampler:
                     allsm.append(float(f[1]))
                     allmx.append(float(f[2]))
                     if self.t0 is not None and not (self.t0 - 0.02 <= ts <= self.t1 + 0.02):
+                        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                            if v.lower().startswith("active"):
+                                allreasons.add(name)
                         continue  # only samples taken DURING the timed region
                     sm.append(float(f[1]))
                     mx.append(float(f[2]))
@@ -106,6 +109,7 @@ class ClockSampler:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
+                        allreasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
@@ -115,7 +119,7 @@ class ClockSampler:
                        window="timed region")
         elif allsm:  # timed region shorter than the sampling period: report the warm-up + timed run instead
             allsm.sort()
-            out.update(sm_mhz=allsm[len(allsm) // 2], sm_max_mhz=max(allmx), reasons=sorted(reasons),
+            out.update(sm_mhz=allsm[len(allsm) // 2], sm_max_mhz=max(allmx), reasons=sorted(allreasons),
                        samples=len(allsm), window="warm-up + timed region (timed region too short to sample)")
         return out
 
