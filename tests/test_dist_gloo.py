@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("world", [1, 2, 3])
-def test_slab_protocol_over_gloo(world):
+def test_slab_protocol_over_gloo(world, sem):  # `sem` makes sure libsemb.so exists for the spawned ranks
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(29600 + world),
            os.path.join(ROOT, "tests", "dist_cpu_protocol.py")]
