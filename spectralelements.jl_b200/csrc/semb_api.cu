@@ -459,7 +459,7 @@ static int mesh_build_plan(semb_mesh* m) {
   return SEMB_OK;
 }
 
-static int mesh_new(semb_ctx* c, int nr, int ns, int Ex, int Ey, int perx, int pery, const double* Dr,
+static int mesh_new_impl(semb_ctx* c, int nr, int ns, int Ex, int Ey, int perx, int pery, const double* Dr,
                     const double* Ds, const double* wr, const double* ws, semb_mesh** out) {
   SEMB_ENTER(c);
   SEMB_REQUIRE(out, "mesh: null output");
@@ -468,6 +468,7 @@ static int mesh_new(semb_ctx* c, int nr, int ns, int Ex, int Ey, int perx, int p
   SEMB_REQUIRE(c->nranks <= Ey, "mesh: more ranks (%d) than element rows (%d)", c->nranks, Ey);
   SEMB_REQUIRE((long long)nr * Ex < (1ll << 30) && (long long)ns * Ey < (1ll << 30), "mesh: too large");
   semb_mesh* m = new semb_mesh();
+  *out = m;  // handed to the caller at once: mesh_new destroys it if anything below fails
   m->ctx = c;
   m->nr = nr;
   m->ns = ns;
@@ -482,7 +483,6 @@ static int mesh_new(semb_ctx* c, int nr, int ns, int Ex, int Ey, int perx, int p
   m->nalloc = (size_t)m->pitch * m->nyl;
   if (m->nalloc >= ((size_t)1 << 31)) {
     semb_set_error("mesh: %zu doubles per field on one GPU exceeds the 2^31 index range of the kernels; use more ranks", m->nalloc);
-    delete m;
     return SEMB_EINVAL;
   }
   m->hDr.assign((size_t)nr * nr, 0.0);
@@ -548,9 +548,21 @@ static int mesh_new(semb_ctx* c, int nr, int ns, int Ex, int Ey, int perx, int p
     SEMB_CHECK_CUDA(cudaMemcpy(m->d_wy1d, wy.data(), wy.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
   SEMB_TRY(semb_launch_mult(c, m->arr[SEMB_MULT], m->pitch, nr, ns, Ex, Ey, m->ey0, m->ney, m->perx, m->pery));
-  *out = m;
   return SEMB_OK;
 }
+
+static int mesh_new(semb_ctx* c, int nr, int ns, int Ex, int Ey, int perx, int pery, const double* Dr,
+                    const double* Ds, const double* wr, const double* ws, semb_mesh** out) {
+  SEMB_REQUIRE(out, "mesh: null output");
+  *out = nullptr;
+  const int rc = mesh_new_impl(c, nr, ns, Ex, Ey, perx, pery, Dr, Ds, wr, ws, out);
+  if (rc < 0 && *out) {
+    semb_mesh_destroy(*out);
+    *out = nullptr;
+  }
+  return rc;
+}
+
 
 static int mesh_geometry(semb_mesh* m) {
   semb_ctx* c = m->ctx;

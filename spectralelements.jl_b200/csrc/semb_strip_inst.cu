@@ -33,10 +33,11 @@ int launch_variant(semb_ctx* ctx, const OpArgs& a, const double* hDr, const doub
   for (int q = 0; q < 4; ++q) StripTab<N>::fill(A[q], EO, P.tab[q]);
   P.a = a;
   auto kern = semb_strip_kernel<N, PCGM, MASS, EO>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {false};  // per device: function attributes belong to the device's context
+  const int dev = ctx->device & 63;
+  if (!attr_done[dev]) {
     SEMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr_done = true;
+    attr_done[dev] = true;
   }
   const bool prof = ctx->profile && ctx->prof_used + 2 <= ctx->prof_ev.size();
   if (prof) SEMB_CHECK_CUDA(cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream));

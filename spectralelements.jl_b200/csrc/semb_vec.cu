@@ -1109,11 +1109,12 @@ int semb_launch_advect_fused(semb_ctx* ctx, semb_mesh* V, semb_mesh* D, const do
   auto bytes = [&](int eb) { return (size_t)(2 * N * N + 2 * M * N + eb * (5 * N * N + 4 * M * N + 4 * M * M)) * 8; };
   while (EB > 1 && bytes(EB) > 72 * 1024) EB >>= 1;
   if (bytes(EB) > 200 * 1024) return SEMB_OK;
-  static size_t attr = 0;
-  if (bytes(EB) > attr) {
+  static size_t attr[64] = {0};  // per device
+  const int dev = ctx->device & 63;
+  if (bytes(EB) > attr[dev]) {
     SEMB_CHECK_CUDA(cudaFuncSetAttribute(semb_advect_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)bytes(EB)));
-    attr = bytes(EB);
+    attr[dev] = bytes(EB);
   }
   AdvectFusedArgs a;
   a.T = T;
