@@ -1529,6 +1529,8 @@ static int advect_run(AdvectWork* w, const double* T, const double* ux, const do
   semb_ctx* c = V->ctx;
   if (D && !getenv("SEMB_NO_FUSED_ADVECT")) {  // one fused kernel when nr == ns and nrd == nsd
     int done = 0;
+    if (!getenv("SEMB_NO_TILED_ADVECT")) SEMB_TRY(semb_launch_advect_tile(c, V, D, 1, &T, ux, uy, w->dJr, w->dJs, &out, &done));
+    if (done) return SEMB_OK;
     SEMB_TRY(semb_launch_advect_fused(c, V, D, T, ux, uy, w->dJr, w->dJs, out, &done));
     if (done) return SEMB_OK;
   }
@@ -1692,10 +1694,20 @@ extern "C" int semb_diffusion_finish_step(semb_diffusion* d, double tol, long lo
   }
   const double* adv[4] = {nullptr, nullptr, nullptr, nullptr};
   if (d->conv) {  // exH[i] = -advect(uh[i],vx,vy,mshV,mshD,JrVD,JsVD), convectionDiffusion.jl:102
+    // all k history levels share vx, vy: one launch of the tiled kernel when it serves (nr, nrd)
+    const double* Ts[4] = {nullptr, nullptr, nullptr, nullptr};
+    double* outs[4] = {nullptr, nullptr, nullptr, nullptr};
     for (int i = 0; i < d->k; ++i) {
-      SEMB_TRY(advect_run(d->work, d->uh[i]->d, d->vx->d, d->vy->d, d->adv[i]->d));
+      Ts[i] = d->uh[i]->d;
+      outs[i] = d->adv[i]->d;
       adv[i] = d->adv[i]->d;
     }
+    int done = 0;
+    if (d->work->D && d->k <= 4 && !getenv("SEMB_NO_FUSED_ADVECT") && !getenv("SEMB_NO_TILED_ADVECT"))
+      SEMB_TRY(semb_launch_advect_tile(c, d->work->V, d->work->D, d->k, Ts, d->vx->d, d->vy->d, d->work->dJr,
+                                       d->work->dJs, outs, &done));
+    if (!done)
+      for (int i = 0; i < d->k; ++i) SEMB_TRY(advect_run(d->work, Ts[i], d->vx->d, d->vy->d, outs[i]));
   }
   SEMB_TRY(semb_launch_rhs(c, m, d->f->d, d->nu->d, d->tmp->d, d->k, uh, b, d->conv ? adv : nullptr,
                            d->conv ? d->bdfA.data() : nullptr, fl.mx0, fl.mx1, fl.my0, fl.my1, d->x->d));

@@ -57,3 +57,6 @@ int semb_launch_rhs(semb_ctx* ctx, semb_mesh* m, const double* f, const double* 
                     int mx1, int my0, int my1, double* rhs);
 int semb_launch_advect_fused(semb_ctx* ctx, semb_mesh* V, semb_mesh* D, const double* T, const double* ux,
                              const double* uy, const double* dJr, const double* dJs, double* out, int* done);
+// register-tiled fused dealiased advection for the served (N, M) pairs (semb_advect_tile.cu); nT fields per launch
+int semb_launch_advect_tile(semb_ctx* ctx, semb_mesh* V, semb_mesh* D, int nT, const double* const* T, const double* ux,
+                            const double* uy, const double* dJr, const double* dJs, double* const* out, int* done);

@@ -12,8 +12,17 @@ def relerr(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
 
 
+# (nr, nrd) pairs served by the register-tiled kernel (semb_advect_tile.cu) with full and ragged element batches
+# (EB = 128 // nrd elements per CTA), and pairs only the generic fused / multi-pass kernels serve ((6, 8), (4, 9))
 @pytest.mark.parametrize("nr,nrd,Ex,Ey,per,deform", [(8, 12, 5, 5, (True, False), "box"), (6, 9, 3, 4, (False, False), "wavy"),
-                                                     (9, 14, 4, 3, (False, True), "annulus")])
+                                                     (9, 14, 4, 3, (False, True), "annulus"),
+                                                     (9, 14, 11, 2, (False, False), "wavy"), (9, 13, 19, 2, (True, False), "wavy"),
+                                                     (5, 8, 17, 3, (False, False), "wavy"), (12, 18, 8, 2, (False, False), "wavy"),
+                                                     (7, 10, 13, 2, (False, False), "wavy"), (10, 15, 9, 2, (False, False), "wavy"),
+                                                     (11, 16, 9, 2, (False, False), "wavy"), (11, 17, 3, 2, (False, False), "wavy"),
+                                                     (3, 5, 27, 2, (False, False), "wavy"), (4, 6, 22, 3, (True, True), "box"),
+                                                     (5, 7, 19, 2, (False, False), "wavy"), (7, 11, 12, 2, (False, False), "wavy"),
+                                                     (6, 8, 5, 3, (False, False), "wavy"), (4, 9, 5, 3, (False, False), "wavy")])
 def test_grad_and_advect(sem, ctx, nr, nrd, Ex, Ey, per, deform):
     od = {"box": so.fixU, "wavy": so.wavy, "annulus": so.annulus}[deform]
     gd = {"box": sem.fixU, "wavy": sem.wavy, "annulus": sem.annulus}[deform]
