@@ -222,7 +222,7 @@ int semb_diffusion_finish_step(semb_diffusion* d, double tol, long long* iters, 
 int semb_diffusion_state(semb_diffusion* d, double* time, double* bdfA, double* bdfB, long long* istep);
 
 /* ---- explicit dealiased convection and the ConvectionDiffusion driver -------------------- */
-/* grad(u,msh), grad.jl:94-113: ux = rx.*ur + sx.*us, uy = ry.*ur + sy.*us (needs a mesh built from x,y) */
+/* grad(u,msh), grad.jl:15-34: ux = rx.*ur + sx.*us, uy = ry.*ur + sy.*us (needs a mesh built from x,y) */
 int semb_grad(semb_mesh* m, const semb_field* u, semb_field* ux, semb_field* uy);
 /* advect(T,ux,uy,mshV,mshD,Jr,Js), advect.jl:45-64: gradient on mshV, interpolation of Tx,Ty,ux,uy to the
  * dealiasing mesh mshD (ABu(Js,Jr,.) with Jr = interpMat(mshD.zr,mshV.zr)), pointwise product with mshD.B,
@@ -236,6 +236,42 @@ int semb_advect(semb_mesh* mV, semb_mesh* mD, const semb_field* T, const semb_fi
  * Extra fields: SEMB_DFN_VX, SEMB_DFN_VY. */
 int semb_convdiff_create(semb_mesh* mV, semb_mesh* mD, const char bc[4], double Ti, double Tf, double dt, int k,
                          semb_diffusion** d);
+
+/* ---- Stokes pressure/velocity split ---------------------------------------------------------- */
+/* RECONSTRUCTION: the reference's diver.jl / stokes.jl are not executable as shipped (stokes.jl is not included,
+ * SpectralElements.jl:53; undefined names at diver.jl:22-27,96 and stokes.jl:114-120).  These entry points follow the
+ * docstring math (diver.jl:5-16,35-51,67-72; stokes.jl:5-51).  Deviations from the literal code, all flagged where
+ * they occur: gradT applies Dr' along r and Ds' along s (grad.jl:56-60 swaps them); `msh` in diver.jl:22-27 is mshV;
+ * `Mvx` in diver.jl:96,101 is the mask of the component, and approxHlmzInv's missing b0 argument (diver.jl:83-84) is
+ * the handle's b0; opStokesLHS returns Eq (stokes.jl:120 returns the undefined Eu); the right-hand side is gathered
+ * on mshP (stokes.jl:139 names mshV) and the pressure PCG weighs its inner products with mshP.mult (stokes.jl:151
+ * names mshV.mult): both live on the pressure mesh. */
+/* gradT(u,msh), grad.jl:44-63: ux = Dr'(rx.*u) + Ds'(sx.*u), uy = Dr'(ry.*u) + Ds'(sy.*u), Dr' along r and Ds' along s
+ * (grad.jl:56-60 swaps the directions; the docstring :38-42 does not) */
+int semb_gradT(semb_mesh* m, const semb_field* u, semb_field* ux, semb_field* uy);
+/* approxHlmzInv(u,b0,mshV), diver.jl:92-104: mask(gs( mask(gs(u)) .* Bi ./ b0 )); bc = the component's "DDNN" flags */
+int semb_approx_hlmz_inv(semb_mesh* m, const semb_field* u, double b0, const char bc[4], semb_field* out);
+/* Stokes(bcVX,bcVY,mshV,mshD,mshP), stokes.jl:75-108, reduced to the pressure system: JrPV = interpMat(mshV.zr,mshP.zr)
+ * (:101-102), the velocity masks, b0 (the bdfB[1] of approxHlmzInv, stokes.jl:133-134) and work fields.
+ * mshP must share Ex, Ey, periodicity and partition with mshV (pressure order nr-2, examples/semPS.jl:31). */
+typedef struct semb_stokes semb_stokes;
+int semb_stokes_create(semb_mesh* mV, semb_mesh* mP, const char bcVX[4], const char bcVY[4], double b0, semb_stokes** s);
+int semb_stokes_destroy(semb_stokes* s);
+/* diver(ux,uy,mshV,Jr,Js), diver.jl:17-31: ABu(Js',Jr', B .* (dx ux + dy uy)) -> field of mshP */
+int semb_diver(semb_stokes* s, const semb_field* ux, const semb_field* uy, semb_field* out);
+/* diverT(pr,mshV,Jr,Js), diver.jl:53-63: gradT(B .* ABu(Js,Jr,pr)) -> two fields of mshV */
+int semb_diverT(semb_stokes* s, const semb_field* pr, semb_field* qx, semb_field* qy);
+/* opStokesLHS(q,sks), stokes.jl:110-121: gatherScatter(stokesOp(q), mshP), stokesOp = -DD HH^-1 DD' (diver.jl:73-89) */
+int semb_stokes_op(semb_stokes* s, const semb_field* q, semb_field* out);
+/* makeStokesRHS!, stokes.jl:128-141: rhs = gatherScatter(diver(vx,vy), mshP) */
+int semb_stokes_rhs(semb_stokes* s, const semb_field* vx, const semb_field* vy, semb_field* rhs);
+/* solveStokes!, stokes.jl:143-154: pcg(rhs, opStokesLHS; mult = mshP.mult), pcg.jl:16-60.  Returns SEMB_NOT_CONVERGED
+ * at maxiter (<0: length(rhs)).  iters / resinf may be NULL. */
+int semb_stokes_solve(semb_stokes* s, const semb_field* rhs, semb_field* dp, double tol, long long maxiter,
+                      long long* iters, double* resinf);
+/* pressureProject!, stokes.jl:159-177: dp = solveStokes; vx += HH^-1 DD'x dp, vy += ..., pr += dp (pr may be NULL) */
+int semb_stokes_project(semb_stokes* s, semb_field* vx, semb_field* vy, semb_field* pr, double tol, long long maxiter,
+                        long long* iters, double* resinf);
 
 /* ---- host-pointer convenience twins (value semantics of the Julia functions) ------------------- */
 /* Each uploads its inputs, runs the device op, downloads `out` (fresh array in Julia). */

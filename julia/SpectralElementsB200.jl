@@ -133,7 +133,7 @@ function mask(u::Array, M::Array, msh::Mesh)
     return out
 end
 
-# grad(u,msh), grad.jl:94-102 ; advect(T,ux,uy,mshV,mshD,Jr,Js), advect.jl:45-64 (Jr, Js are rebuilt by the library)
+# grad(u,msh), grad.jl:15-34 ; advect(T,ux,uy,mshV,mshD,Jr,Js), advect.jl:45-64 (Jr, Js are rebuilt by the library)
 function devfield(msh::Mesh, a::Union{Array,Nothing} = nothing)
     f = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:semb_field_create, libsemb), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), devmesh(msh), f))

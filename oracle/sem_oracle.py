@@ -607,12 +607,12 @@ def diffusion_simulate(dfn: Diffusion, setIC=None, setBC=None, setForcing=None, 
 
 
 # ----------------------------------------------------------------------------
-# grad.jl:94-113 and advect.jl:27-78 ("next" row 8f-2: the explicit convection term of cd2d)
+# grad.jl:15-34 and advect.jl:27-78 ("next" row 8f-2: the explicit convection term of cd2d)
 # ----------------------------------------------------------------------------
 def grad(u, msh: Mesh):
     ur = ABu(EMPTY, msh.Dr, u)
     us = ABu(msh.Ds, EMPTY, u)
-    ux = msh.rx * ur + msh.sx * us  # grad.jl:109-110
+    ux = msh.rx * ur + msh.sx * us  # grad.jl:30-31
     uy = msh.ry * ur + msh.sy * us
     return ux, uy
 
@@ -709,6 +709,110 @@ def convdiff_step(cdn, setBC=None, setForcing=None, setVisc=None):  # convection
         cdn.nu = _F(setVisc(x, y, t))
     convdiff_makeRHS(cdn)
     convdiff_solve(cdn)
+
+
+# ----------------------------------------------------------------------------
+# SURVEY 8f-4 -- Stokes pressure/velocity split: a RECONSTRUCTION, parity unpinned.
+# The reference's diver.jl / stokes.jl are not executable as shipped: stokes.jl is not included
+# (SpectralElements.jl:53), does not parse (stokes.jl:91-92) and uses undefined names (`msh`
+# diver.jl:22-23,27; `Mvx` diver.jl:96,101 with an arity mismatch against :83-84; `vx`, `Eu`
+# stokes.jl:114-120).  What follows restates the docstring math (diver.jl:5-16,35-51,67-72,
+# stokes.jl:5-51) with the undefined names bound to the obvious arguments; every deviation is
+# flagged at the line.  Pinned only by identities (tests/test_oracle_pins.py): gradT is the exact
+# transpose of grad, diverT the transpose of diver, the Schur operator is symmetric negative
+# semi-definite in the mult inner product, and the projection leaves a divergence-free field.
+# ----------------------------------------------------------------------------
+def gradT(u, msh: Mesh):
+    """grad.jl:44-63.  Deviation, flagged: grad.jl:56-60 passes Dr' as `As` and Ds' as `Br`
+    (ABu's first matrix acts along s, ABu.jl:23-33), i.e. swaps the directions; the transpose of
+    grad.jl:25-34 -- what the docstring grad.jl:38-42 states -- applies Dr' along r and Ds' along s."""
+    ux = ABu(EMPTY, msh.Dr.T, msh.rx * u) + ABu(msh.Ds.T, EMPTY, msh.sx * u)
+    uy = ABu(EMPTY, msh.Dr.T, msh.ry * u) + ABu(msh.Ds.T, EMPTY, msh.sy * u)
+    return ux, uy
+
+
+def diver(ux, uy, mshV: Mesh, Jr, Js):
+    """diver.jl:17-31 (`msh` there is mshV): (q, div u) on the pressure grid.
+    Jr = interpMat(mshV.zr, mshP.zr) maps pressure -> velocity nodes (stokes.jl:101-102)."""
+    uxdx, _ = grad(ux, mshV)
+    _, uydy = grad(uy, mshV)
+    div = uxdx + uydy
+    Bdiv = mass(div, mshV)
+    return ABu(Js.T, Jr.T, Bdiv)
+
+
+def diverT(pr, mshV: Mesh, Jr, Js):
+    """diver.jl:53-63"""
+    Jp = ABu(Js, Jr, pr)
+    BJp = mass(Jp, mshV)
+    return gradT(BJp, mshV)
+
+
+def approxHlmzInv(u, b0, mshV: Mesh, M):
+    """diver.jl:92-104 (`Mvx` there is the mask of the component, passed here as M)"""
+    v = gatherScatter(u, mshV)
+    v = mask(v, M)
+    v = v * mshV.Bi / b0
+    v = gatherScatter(v, mshV)
+    v = mask(v, M)
+    return v
+
+
+def stokesOp(q, mshV: Mesh, Mvx, Mvy, Jr, Js, b0=1.0):
+    """diver.jl:73-89: EE q = -DD HH^-1 DD' q (b0: the missing second argument of approxHlmzInv, :83-84)"""
+    qx, qy = diverT(q, mshV, Jr, Js)
+    qx = approxHlmzInv(qx, b0, mshV, Mvx)
+    qy = approxHlmzInv(qy, b0, mshV, Mvy)
+    return -diver(qx, qy, mshV, Jr, Js)
+
+
+@dataclass
+class Stokes:
+    """stokes.jl:52-108, reduced to what the pressure solve needs"""
+    mshV: Mesh
+    mshP: Mesh
+    Mvx: np.ndarray
+    Mvy: np.ndarray
+    JrPV: np.ndarray
+    JsPV: np.ndarray
+    b0: float = 1.0
+    pcg_iters: list = field(default_factory=list)
+
+
+def make_stokes(bcVX, bcVY, mshV: Mesh, mshP: Mesh, b0=1.0) -> Stokes:
+    return Stokes(mshV, mshP, generateMask(bcVX, mshV).astype(np.float64), generateMask(bcVY, mshV).astype(np.float64),
+                  interpMat(mshV.zr, mshP.zr), interpMat(mshV.zs, mshP.zs), float(b0))  # stokes.jl:101-102
+
+
+def opStokesLHS(q, sks: Stokes):
+    """stokes.jl:110-121 (returns `Eq`; the reference returns the undefined `Eu`)"""
+    Eq = stokesOp(q, sks.mshV, sks.Mvx, sks.Mvy, sks.JrPV, sks.JsPV, sks.b0)
+    return gatherScatter(Eq, sks.mshP)
+
+
+def makeStokesRHS(vx, vy, sks: Stokes):
+    """stokes.jl:128-141 with fx, fy the velocity to be projected.  Deviation, flagged: :139 gathers with
+    mshV; the right-hand side lives on the pressure mesh."""
+    return gatherScatter(diver(vx, vy, sks.mshV, sks.JrPV, sks.JsPV), sks.mshP)
+
+
+def solveStokes(rhs, sks: Stokes, tol=1e-8, maxiter=None):
+    """stokes.jl:143-154.  Deviation, flagged: :151 weighs the inner products with mshV.mult; the iterates
+    live on the pressure mesh, so mshP.mult is used."""
+    info = {}
+    dp = pcg(rhs, lambda q: opStokesLHS(q, sks), mult=sks.mshP.mult, tol=tol, maxiter=maxiter, info=info)
+    sks.pcg_iters.append(info["iters"])
+    return dp
+
+
+def pressureProject(vx, vy, pr, sks: Stokes, tol=1e-8, maxiter=None):
+    """stokes.jl:159-177: returns the corrected (vx, vy, pr) instead of updating in place"""
+    rhs = makeStokesRHS(vx, vy, sks)
+    dp = solveStokes(rhs, sks, tol, maxiter)
+    px, py = diverT(dp, sks.mshV, sks.JrPV, sks.JsPV)
+    px = approxHlmzInv(px, sks.b0, sks.mshV, sks.Mvx)
+    py = approxHlmzInv(py, sks.b0, sks.mshV, sks.Mvy)
+    return vx + px, vy + py, pr + dp
 
 
 # ----------------------------------------------------------------------------

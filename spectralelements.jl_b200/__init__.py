@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import warnings
 from typing import Callable, Optional, Sequence
 
 import numpy as np
@@ -35,6 +36,7 @@ __all__ = [
     "hlmz", "mass", "gatherScatter", "mask", "pcg", "pcg_b", "OpLHS", "opLHS", "Diffusion", "makeRHS_b",
     "solve_b", "evolve_b", "simulate_b", "grad", "advect", "ConvectionDiffusion", "step_b", "simulate_cd_b", "annulus", "wavy", "fixU", "gausslobatto", "derivMat", "interpMat",
     "semmesh", "ndgrid", "bdfExtK", "partition", "halo_plan", "SembError",
+    "gradT", "approxHlmzInv", "Stokes", "diver", "diverT", "opStokesLHS", "makeStokesRHS", "solveStokes", "pressureProject",
 ]
 
 SEMB_ARR = {"x": 0, "y": 1, "Jac": 2, "Jaci": 3, "rx": 4, "ry": 5, "sx": 6, "sy": 7, "B": 8, "Bi": 9, "G11": 10,
@@ -563,7 +565,7 @@ def mask(u, M, msh: Optional[Mesh] = None):
 
 
 def grad(u, msh: Mesh):
-    """grad(u,msh), grad.jl:94-113 -> (ux, uy)"""
+    """grad(u,msh), grad.jl:15-34 -> (ux, uy)"""
     fu, fx, fy = msh.field(u), msh.field(), msh.field()
     try:
         check(msh.lib.semb_grad(msh.h, fu.h, fx.h, fy.h))
@@ -813,3 +815,121 @@ def simulate_cd_b(cdn: ConvectionDiffusion, callback=None, max_steps=None):
             break
         if max_steps is not None and steps >= max_steps:
             break
+
+
+# ---------------------------------------------------------------------------------------------
+# Stokes pressure/velocity split -- reconstruction of diver.jl / stokes.jl (not executable as shipped)
+# ---------------------------------------------------------------------------------------------
+def gradT(u, msh: Mesh):
+    """gradᵀ(u,msh), grad.jl:44-63 -> (ux, uy); Dr' along r, Ds' along s (the docstring's transpose of grad)"""
+    fu, fx, fy = msh.field(u), msh.field(), msh.field()
+    try:
+        check(msh.lib.semb_gradT(msh.h, fu.h, fx.h, fy.h))
+        return fx.download(), fy.download()
+    finally:
+        for f in (fu, fx, fy):
+            f.free()
+
+
+def approxHlmzInv(u, b0, mshV: Mesh, bc=None):
+    """approxHlmzInv(u,b0,mshV), diver.jl:92-104; bc = the "DDNN" flags of the component's mask (`Mvx` there)"""
+    fu, fo = mshV.field(u), mshV.field()
+    try:
+        check(mshV.lib.semb_approx_hlmz_inv(mshV.h, fu.h, float(b0), _bc_bytes(bc), fo.h))
+        return fo.download()
+    finally:
+        fu.free()
+        fo.free()
+
+
+class Stokes:
+    """Stokes(bcVX,bcVY,mshV,mshD,mshP), stokes.jl:52-108, reduced to the pressure system of the split:
+    JrPV/JsPV (stokes.jl:101-102), the velocity masks and b0 live in the library handle."""
+
+    def __init__(self, bcVX, bcVY, mshV: Mesh, mshP: Mesh, b0: float = 1.0):
+        self.mshV, self.mshP, self.lib, self.b0 = mshV, mshP, mshV.lib, float(b0)
+        self.bcVX, self.bcVY = bcVX, bcVY
+        h = C.c_void_p()
+        check(self.lib.semb_stokes_create(mshV.h, mshP.h, _bc_bytes(bcVX), _bc_bytes(bcVY), self.b0, C.byref(h)))
+        self.h = h
+        self.pcg_iters = []
+        self.resinf = None
+
+    def free(self):
+        if self.h:
+            self.lib.semb_stokes_destroy(self.h)
+            self.h = None
+
+    # device-resident forms (fields in, fields out)
+    def op_device(self, q: DeviceField, out: DeviceField):
+        check(self.lib.semb_stokes_op(self.h, q.h, out.h))
+        return out
+
+    def project_device(self, vx: DeviceField, vy: DeviceField, pr: Optional[DeviceField] = None, tol=1e-8, maxiter=-1):
+        it, res = C.c_longlong(), C.c_double()
+        rc = check(self.lib.semb_stokes_project(self.h, vx.h, vy.h, _fh(pr), float(tol), int(maxiter), C.byref(it),
+                                                C.byref(res)))
+        self.pcg_iters.append(it.value)
+        self.resinf = res.value
+        return rc
+
+
+def _with_fields(pairs, fn):
+    fs = [m.field(a) if a is not None else m.field() for m, a in pairs]
+    try:
+        return fn(*fs)
+    finally:
+        for f in fs:
+            f.free()
+
+
+def diver(ux, uy, sks: Stokes):
+    """diver(ux,uy,mshV,Jr,Js), diver.jl:17-31 -> array on the pressure mesh"""
+    V, P = sks.mshV, sks.mshP
+    return _with_fields([(V, ux), (V, uy), (P, None)],
+                        lambda a, b, o: (check(sks.lib.semb_diver(sks.h, a.h, b.h, o.h)), o.download())[1])
+
+
+def diverT(pr, sks: Stokes):
+    """diverᵀ(pr,mshV,Jr,Js), diver.jl:53-63 -> (qx, qy) on the velocity mesh"""
+    V, P = sks.mshV, sks.mshP
+    return _with_fields([(P, pr), (V, None), (V, None)],
+                        lambda p, a, b: (check(sks.lib.semb_diverT(sks.h, p.h, a.h, b.h)), a.download(), b.download())[1:])
+
+
+def opStokesLHS(q, sks: Stokes):
+    """opStokesLHS(q,sks), stokes.jl:110-121 = gatherScatter(stokesOp(q,...), mshP) (stokesOp: diver.jl:73-89)"""
+    P = sks.mshP
+    return _with_fields([(P, q), (P, None)], lambda a, o: sks.op_device(a, o).download())
+
+
+def makeStokesRHS(vx, vy, sks: Stokes):
+    """makeStokesRHS!, stokes.jl:128-141 for the velocity to be projected"""
+    V, P = sks.mshV, sks.mshP
+    return _with_fields([(V, vx), (V, vy), (P, None)],
+                        lambda a, b, o: (check(sks.lib.semb_stokes_rhs(sks.h, a.h, b.h, o.h)), o.download())[1])
+
+
+def solveStokes(rhs, sks: Stokes, tol=1e-8, maxiter=-1):
+    """solveStokes!, stokes.jl:143-154: pcg on the pressure mesh with opStokesLHS"""
+    P = sks.mshP
+
+    def run(r, x):
+        it, res = C.c_longlong(), C.c_double()
+        rc = check(sks.lib.semb_stokes_solve(sks.h, r.h, x.h, float(tol), int(maxiter), C.byref(it), C.byref(res)))
+        sks.pcg_iters.append(it.value)
+        sks.resinf = res.value
+        if rc == 1:
+            warnings.warn("pcg: maxiter reached (pcg.jl:39)")
+        return x.download()
+    return _with_fields([(P, rhs), (P, None)], run)
+
+
+def pressureProject(vx, vy, pr, sks: Stokes, tol=1e-8, maxiter=-1):
+    """pressureProject!, stokes.jl:159-177 -> corrected (vx, vy, pr)"""
+    V, P = sks.mshV, sks.mshP
+
+    def run(a, b, p):
+        sks.project_device(a, b, p, tol, maxiter)
+        return a.download(), b.download(), p.download()
+    return _with_fields([(V, vx), (V, vy), (P, pr)], run)

@@ -102,6 +102,16 @@ _SIGS = {
     "semb_grad": ([vp, vp, vp, vp], C.c_int),
     "semb_advect": ([vp, vp, vp, vp, vp, vp], C.c_int),
     "semb_convdiff_create": ([vp, vp, C.c_char_p, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(vp)], C.c_int),
+    "semb_gradT": ([vp, vp, vp, vp], C.c_int),
+    "semb_approx_hlmz_inv": ([vp, vp, C.c_double, C.c_char_p, vp], C.c_int),
+    "semb_stokes_create": ([vp, vp, C.c_char_p, C.c_char_p, C.c_double, C.POINTER(vp)], C.c_int),
+    "semb_stokes_destroy": ([vp], C.c_int),
+    "semb_diver": ([vp, vp, vp, vp], C.c_int),
+    "semb_diverT": ([vp, vp, vp, vp], C.c_int),
+    "semb_stokes_op": ([vp, vp, vp], C.c_int),
+    "semb_stokes_rhs": ([vp, vp, vp, vp], C.c_int),
+    "semb_stokes_solve": ([vp, vp, vp, C.c_double, C.c_longlong, c_ll_p, c_double_p], C.c_int),
+    "semb_stokes_project": ([vp, vp, vp, vp, C.c_double, C.c_longlong, c_ll_p, c_double_p], C.c_int),
     "semb_lapl_host": ([vp, c_double_p, c_double_p], C.c_int),
     "semb_hlmz_host": ([vp, c_double_p, c_double_p, C.c_double, c_double_p, C.c_double, c_double_p], C.c_int),
     "semb_mass_host": ([vp, c_double_p, c_double_p], C.c_int),

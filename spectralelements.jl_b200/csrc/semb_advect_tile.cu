@@ -1,7 +1,7 @@
 // Register-tiled fused dealiased advection, advect.jl:45-64, for nr == ns = N on mshV and nrd == nsd = M on mshD,
 // templated on (N, M) so that every contraction runs fully unrolled out of registers (one thread = one line):
 //
-//   Tx,Ty = grad(T,mshV)                       grad.jl:94-113
+//   Tx,Ty = grad(T,mshV)                       grad.jl:15-34
 //   JTx,JTy,Jux,Juy = ABu(Js,Jr,.)             advect.jl:54-57   (V grid -> dealiasing grid)
 //   JCu = (Jux.*JTx + Juy.*JTy) .* mshD.B      advect.jl:59-60
 //   Cu  = ABu(Js',Jr',JCu)                     advect.jl:61      (projection back to the V grid)
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(ADV_T, AdvCfg<N, M>::OCC) semb_advect_tile_ker
         for (int i = 0; i < N; ++i) row[i] = ur[i];
       }
       __syncthreads();
-      // ---- phase 3 (C): Tx, Ty (grad.jl:109-110), y-interpolation of Tx, Ty (and ux, uy for the first T) ----------------
+      // ---- phase 3 (C): Tx, Ty (grad.jl:30-31), y-interpolation of Tx, Ty (and ux, uy for the first T) ----------------
       if (actC) {
         // one field per trip (not unrolled: bounds the loads in flight and the live registers)
         const int nf = it == 0 ? 4 : 2;

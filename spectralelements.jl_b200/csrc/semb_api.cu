@@ -1998,3 +1998,5 @@ extern "C" int semb_abu_host(semb_ctx* c, const double* As, int ma, int na, cons
   cudaFree(dB);
   return rc;
 }
+
+#include "semb_stokes_api.cuh"

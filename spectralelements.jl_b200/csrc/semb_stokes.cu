@@ -1,0 +1,210 @@
+// Element-local kernels of the Stokes pressure/velocity split: grad^T (grad.jl:44-63), the velocity-grid
+// part of diver (diver.jl:17-31) and of diver^T (diver.jl:53-63), and the pointwise middle of approxHlmzInv
+// (diver.jl:92-104).  The reference's stokes.jl / diver.jl are not executable as shipped; these kernels
+// follow the docstring math; the deviations from the literal code are listed in include/semb.h (Stokes section).
+//
+// One CTA per batch of EB x-consecutive elements of an element row; the element tiles live in shared memory, so every
+// input array is read from HBM once and every output written once:
+//   gradT : 1 input (+B) + 4 metric arrays in, 2 out      (56 or 64 B/DOF)
+//   diver : 2 inputs + 4 metric arrays + B in, 1 out      (64 B/DOF)
+// Arithmetic order: products with the metric terms / B are formed and rounded first (the reference's broadcasts),
+// the contractions then accumulate with FMAs (the reference's BLAS calls: order unpinned).
+#include "semb_vec.cuh"
+
+namespace {
+
+struct StokesLocalArgs {
+  const double *a = nullptr, *b = nullptr;  // gradT: a = u ; diver: a = ux, b = uy
+  const double* W = nullptr;                // gradT: optional pointwise weight applied to u first (mass: B)
+  const double *rx, *ry, *sx, *sy, *B;
+  const double *Dr, *Ds;                    // row-major D[i*n+k] = D(i,k)
+  double *o1 = nullptr, *o2 = nullptr;
+  long long pitch;
+  int nr, ns, Ex, ney, EB;
+};
+
+// shared layout: Dr [nr*nr], Ds [ns*ns], then 4 tiles [EB][ns][nr|1]
+__device__ __forceinline__ int tile_idx(int e, int j, int i, int ns, int S) { return (e * ns + j) * S + i; }
+
+// out_x = Dr'_r (rx .* w) + Ds'_s (sx .* w),  out_y = Dr'_r (ry .* w) + Ds'_s (sy .* w),  w = W .* u  (or u)
+__global__ void __launch_bounds__(256) semb_gradT_kernel(const StokesLocalArgs a) {
+  extern __shared__ double sh[];
+  const int nr = a.nr, ns = a.ns, S = nr | 1, EB = a.EB, tile = EB * ns * S;
+  double* sDr = sh;
+  double* sDs = sDr + nr * nr;
+  double* t0 = sDs + ns * ns;  // rx .* w
+  double* t1 = t0 + tile;      // sx .* w
+  double* t2 = t1 + tile;      // ry .* w
+  double* t3 = t2 + tile;      // sy .* w
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int q = tid; q < nr * nr; q += nt) sDr[q] = a.Dr[q];
+  for (int q = tid; q < ns * ns; q += nt) sDs[q] = a.Ds[q];
+  const int nbx = (a.Ex + EB - 1) / EB;
+  for (int bidx = blockIdx.x; bidx < nbx * a.ney; bidx += gridDim.x) {
+    const int r = bidx / nbx, e0 = (bidx - r * nbx) * EB, nbe = min(EB, a.Ex - e0);
+    const int rowlen = nbe * nr;
+    __syncthreads();
+    for (int q = tid; q < ns * rowlen; q += nt) {
+      const int j = q / rowlen, xx = q - j * rowlen, e = xx / nr, i = xx - e * nr;
+      const size_t g = (size_t)(r * ns + j) * a.pitch + (size_t)e0 * nr + xx;
+      double w = a.a[g];
+      if (a.W) w = __dmul_rn(a.W[g], w);  // mass(Jp), mass.jl:17
+      const int o = tile_idx(e, j, i, ns, S);
+      t0[o] = __dmul_rn(a.rx[g], w);
+      t1[o] = __dmul_rn(a.sx[g], w);
+      t2[o] = __dmul_rn(a.ry[g], w);
+      t3[o] = __dmul_rn(a.sy[g], w);
+    }
+    __syncthreads();
+    for (int q = tid; q < ns * rowlen; q += nt) {
+      const int j = q / rowlen, xx = q - j * rowlen, e = xx / nr, i = xx - e * nr;
+      double ax = 0.0, bx = 0.0, ay = 0.0, by = 0.0;
+      for (int k = 0; k < nr; ++k) {  // (Dr' along r): sum_k Dr(k,i) v(k,j)
+        const double d = sDr[k * nr + i];
+        const int o = tile_idx(e, j, k, ns, S);
+        ax = fma(d, t0[o], ax);
+        ay = fma(d, t2[o], ay);
+      }
+      for (int k = 0; k < ns; ++k) {  // (Ds' along s): sum_k Ds(k,j) v(i,k)
+        const double d = sDs[k * ns + j];
+        const int o = tile_idx(e, k, i, ns, S);
+        bx = fma(d, t1[o], bx);
+        by = fma(d, t3[o], by);
+      }
+      const size_t g = (size_t)(r * ns + j) * a.pitch + (size_t)e0 * nr + xx;
+      a.o1[g] = __dadd_rn(ax, bx);
+      a.o2[g] = __dadd_rn(ay, by);
+    }
+  }
+}
+
+// out = B .* (dx(ux) + dy(uy)),  dx(u) = rx .* ur + sx .* us,  dy(u) = ry .* ur + sy .* us  (grad.jl:27-31, diver.jl:22-27)
+__global__ void __launch_bounds__(256) semb_diver_local_kernel(const StokesLocalArgs a) {
+  extern __shared__ double sh[];
+  const int nr = a.nr, ns = a.ns, S = nr | 1, EB = a.EB, tile = EB * ns * S;
+  double* sDr = sh;
+  double* sDs = sDr + nr * nr;
+  double* t0 = sDs + ns * ns;  // ux
+  double* t1 = t0 + tile;      // uy
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int q = tid; q < nr * nr; q += nt) sDr[q] = a.Dr[q];
+  for (int q = tid; q < ns * ns; q += nt) sDs[q] = a.Ds[q];
+  const int nbx = (a.Ex + EB - 1) / EB;
+  for (int bidx = blockIdx.x; bidx < nbx * a.ney; bidx += gridDim.x) {
+    const int r = bidx / nbx, e0 = (bidx - r * nbx) * EB, nbe = min(EB, a.Ex - e0);
+    const int rowlen = nbe * nr;
+    __syncthreads();
+    for (int q = tid; q < ns * rowlen; q += nt) {
+      const int j = q / rowlen, xx = q - j * rowlen, e = xx / nr, i = xx - e * nr;
+      const size_t g = (size_t)(r * ns + j) * a.pitch + (size_t)e0 * nr + xx;
+      const int o = tile_idx(e, j, i, ns, S);
+      t0[o] = a.a[g];
+      t1[o] = a.b[g];
+    }
+    __syncthreads();
+    for (int q = tid; q < ns * rowlen; q += nt) {
+      const int j = q / rowlen, xx = q - j * rowlen, e = xx / nr, i = xx - e * nr;
+      double urx = 0.0, ury = 0.0, usx = 0.0, usy = 0.0;
+      for (int k = 0; k < nr; ++k) {
+        const double d = sDr[i * nr + k];
+        const int o = tile_idx(e, j, k, ns, S);
+        urx = fma(d, t0[o], urx);
+        ury = fma(d, t1[o], ury);
+      }
+      for (int k = 0; k < ns; ++k) {
+        const double d = sDs[j * ns + k];
+        const int o = tile_idx(e, k, i, ns, S);
+        usx = fma(d, t0[o], usx);
+        usy = fma(d, t1[o], usy);
+      }
+      const size_t g = (size_t)(r * ns + j) * a.pitch + (size_t)e0 * nr + xx;
+      const double uxdx = __dadd_rn(__dmul_rn(a.rx[g], urx), __dmul_rn(a.sx[g], usx));
+      const double uydy = __dadd_rn(__dmul_rn(a.ry[g], ury), __dmul_rn(a.sy[g], usy));
+      a.o1[g] = __dmul_rn(a.B[g], __dadd_rn(uxdx, uydy));  // mass(div), diver.jl:25-27
+    }
+  }
+}
+
+// middle of approxHlmzInv (diver.jl:97-99): out = (M .* g) .* Bi ./ b0, M from the Dirichlet flags of this slab
+__global__ void semb_hinv_mid_kernel(const double* __restrict__ g, const double* __restrict__ Bi, double b0,
+                                     long long pitch, int nxl, int nyl, int mx0, int mx1, int my0, int my1, double* out) {
+  for (int row = blockIdx.y; row < nyl; row += gridDim.y)
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < nxl; x += gridDim.x * blockDim.x) {
+      const size_t idx = (size_t)row * pitch + x;
+      const bool z = (x == 0 && mx0) || (x == nxl - 1 && mx1) || (row == 0 && my0) || (row == nyl - 1 && my1);
+      const double v = __dmul_rn(z ? 0.0 : 1.0, g[idx]);
+      out[idx] = __ddiv_rn(__dmul_rn(v, Bi[idx]), b0);
+    }
+}
+
+int local_launch_cfg(semb_ctx* ctx, semb_mesh* m, int ntiles, StokesLocalArgs* a, size_t* smem, int* grid) {
+  const int S = m->nr | 1;
+  int EB = 256 / (m->nr * m->ns);  // about one node per thread
+  if (EB < 1) EB = 1;
+  if (EB > m->Ex) EB = m->Ex;
+  auto bytes = [&](int eb) { return (size_t)(m->nr * m->nr + m->ns * m->ns + ntiles * eb * m->ns * S) * 8; };
+  while (EB > 1 && bytes(EB) > 48 * 1024) --EB;
+  SEMB_REQUIRE(bytes(EB) <= 48 * 1024, "stokes: element tile of %d x %d nodes does not fit shared memory", m->nr, m->ns);
+  a->EB = EB;
+  a->nr = m->nr;
+  a->ns = m->ns;
+  a->Ex = m->Ex;
+  a->ney = m->ney;
+  a->pitch = m->pitch;
+  a->rx = m->arr[SEMB_RX];
+  a->ry = m->arr[SEMB_RY];
+  a->sx = m->arr[SEMB_SX];
+  a->sy = m->arr[SEMB_SY];
+  a->B = m->arr[SEMB_B];
+  a->Dr = m->dDr;
+  a->Ds = m->dDs;
+  *smem = bytes(EB);
+  const long long nb = (long long)((m->Ex + EB - 1) / EB) * m->ney;
+  long long g = (long long)ctx->sm_count * 8;
+  *grid = (int)(nb < g ? nb : g);
+  if (*grid < 1) *grid = 1;
+  return SEMB_OK;
+}
+
+}  // namespace
+
+int semb_launch_gradT(semb_ctx* ctx, semb_mesh* m, const double* u, const double* W, double* ox, double* oy) {
+  StokesLocalArgs a;
+  size_t smem;
+  int grid;
+  SEMB_TRY(local_launch_cfg(ctx, m, 4, &a, &smem, &grid));
+  a.a = u;
+  a.W = W;
+  a.o1 = ox;
+  a.o2 = oy;
+  semb_gradT_kernel<<<grid, 256, smem, ctx->stream>>>(a);
+  SEMB_CHECK_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return SEMB_OK;
+}
+
+int semb_launch_diver_local(semb_ctx* ctx, semb_mesh* m, const double* ux, const double* uy, double* out) {
+  StokesLocalArgs a;
+  size_t smem;
+  int grid;
+  SEMB_TRY(local_launch_cfg(ctx, m, 2, &a, &smem, &grid));
+  a.a = ux;
+  a.b = uy;
+  a.o1 = out;
+  semb_diver_local_kernel<<<grid, 256, smem, ctx->stream>>>(a);
+  SEMB_CHECK_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return SEMB_OK;
+}
+
+int semb_launch_hinv_mid(semb_ctx* ctx, semb_mesh* m, const double* g, double b0, int mx0, int mx1, int my0, int my1,
+                         double* out) {
+  int gx = (m->nxl + 255) / 256;
+  if (gx > 1024) gx = 1024;
+  const int gy = m->nyl > 32768 ? 32768 : m->nyl;
+  semb_hinv_mid_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(g, m->arr[SEMB_BI], b0, m->pitch, m->nxl, m->nyl, mx0, mx1,
+                                                             my0, my1, out);
+  SEMB_CHECK_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return SEMB_OK;
+}

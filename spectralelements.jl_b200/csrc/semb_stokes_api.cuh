@@ -1,0 +1,255 @@
+// C-ABI entry points of the Stokes pressure/velocity split; textually included at the end of semb_api.cu
+// (uses its static helpers).  The reference's diver.jl / stokes.jl are not executable as shipped: these
+// functions reconstruct gradT, diver, diverT, approxHlmzInv, stokesOp, opStokesLHS, makeStokesRHS, solveStokes and
+// pressureProject from the docstring math; the deviations from the literal code are listed in include/semb.h.
+#pragma once
+
+struct semb_stokes {
+  semb_mesh *V = nullptr, *P = nullptr;
+  char bcx[5] = {0}, bcy[5] = {0};
+  double b0 = 1.0;
+  // JrPV = interpMat(mshV.zr, mshP.zr), JsPV = interpMat(mshV.zs, mshP.zs) (stokes.jl:101-102), column-major, + transposes
+  double *dJr = nullptr, *dJs = nullptr, *dJrT = nullptr, *dJsT = nullptr;
+  double* mid = nullptr;                                      // mixed-resolution intermediate of the two-pass ABu
+  semb_field *v1 = nullptr, *v2 = nullptr, *v3 = nullptr, *v4 = nullptr;  // work fields on mshV
+  semb_field *p_r = nullptr, *p_u = nullptr, *p_Au = nullptr, *p_rhs = nullptr, *p_dp = nullptr;  // on mshP
+};
+
+extern "C" int semb_gradT(semb_mesh* m, const semb_field* u, semb_field* ux, semb_field* uy) {
+  SEMB_REQUIRE(m, "null mesh");
+  SEMB_ENTER(m->ctx);
+  SEMB_TRY(check_field(m, u, "gradT(u)"));
+  SEMB_TRY(check_field(m, ux, "gradT(ux)"));
+  SEMB_TRY(check_field(m, uy, "gradT(uy)"));
+  SEMB_REQUIRE(u != ux && u != uy && ux != uy, "gradT: outputs must not alias");
+  SEMB_REQUIRE(m->arr[SEMB_RX] && m->arr[SEMB_SY], "gradT: mesh has no metric terms (create it from x,y)");
+  return semb_launch_gradT(m->ctx, m, u->d, nullptr, ux->d, uy->d);
+}
+
+extern "C" int semb_approx_hlmz_inv(semb_mesh* m, const semb_field* u, double b0, const char bc[4], semb_field* out) {
+  SEMB_REQUIRE(m, "null mesh");
+  SEMB_ENTER(m->ctx);
+  SEMB_TRY(check_field(m, u, "approxHlmzInv(u)"));
+  SEMB_TRY(check_field(m, out, "approxHlmzInv(out)"));
+  SEMB_REQUIRE(u != out, "approxHlmzInv: out must not alias u");
+  SEMB_REQUIRE(m->arr[SEMB_BI], "approxHlmzInv: mesh has no Bi");
+  SEMB_REQUIRE(b0 != 0.0, "approxHlmzInv: b0 must be non-zero");
+  MaskFlags f;
+  SEMB_TRY(parse_bc(m, bc, &f));
+  if (!m->w_t1) SEMB_TRY(semb_field_create(m, &m->w_t1));
+  semb_field* t = m->w_t1;
+  SEMB_REQUIRE(t != u && t != out, "approxHlmzInv: argument aliases the mesh work field");
+  SEMB_TRY(semb_gather_scatter(m, u, t));                                                            // diver.jl:95
+  SEMB_TRY(semb_launch_hinv_mid(m->ctx, m, t->d, b0, f.mx0, f.mx1, f.my0, f.my1, out->d));           // :96-98
+  SEMB_TRY(semb_gather_scatter(m, out, t));                                                          // :100
+  return bc ? semb_mask_bc(m, t, bc, out) : semb_field_copy(out, t);                                 // :101
+}
+
+extern "C" int semb_stokes_destroy(semb_stokes* s) {
+  if (!s) return SEMB_OK;
+  cudaFree(s->dJr);
+  cudaFree(s->dJs);
+  cudaFree(s->dJrT);
+  cudaFree(s->dJsT);
+  cudaFree(s->mid);
+  semb_field* fs[] = {s->v1, s->v2, s->v3, s->v4, s->p_r, s->p_u, s->p_Au, s->p_rhs, s->p_dp};
+  for (semb_field* f : fs) semb_field_destroy(f);
+  delete s;
+  return SEMB_OK;
+}
+
+static int stokes_create_impl(semb_stokes* s) {
+  semb_mesh *V = s->V, *P = s->P;
+  auto nodes = [](int n, std::vector<double>& z) {
+    std::vector<double> wts(n);
+    z.resize(n);
+    return semb_gausslobatto(n, z.data(), wts.data());
+  };
+  std::vector<double> zrV, zsV, zrP, zsP;
+  SEMB_TRY(nodes(V->nr, zrV));
+  SEMB_TRY(nodes(V->ns, zsV));
+  SEMB_TRY(nodes(P->nr, zrP));
+  SEMB_TRY(nodes(P->ns, zsP));
+  std::vector<double> Jr((size_t)V->nr * P->nr), Js((size_t)V->ns * P->ns), JrT(Jr.size()), JsT(Js.size());
+  SEMB_TRY(semb_interp_mat(V->nr, zrV.data(), P->nr, zrP.data(), Jr.data()));
+  SEMB_TRY(semb_interp_mat(V->ns, zsV.data(), P->ns, zsP.data(), Js.data()));
+  for (int i = 0; i < V->nr; ++i)
+    for (int k = 0; k < P->nr; ++k) JrT[k + (size_t)i * P->nr] = Jr[i + (size_t)k * V->nr];
+  for (int i = 0; i < V->ns; ++i)
+    for (int k = 0; k < P->ns; ++k) JsT[k + (size_t)i * P->ns] = Js[i + (size_t)k * V->ns];
+  auto up = [&](const std::vector<double>& h, double** d) -> int {
+    SEMB_CHECK_CUDA(cudaMalloc(d, h.size() * sizeof(double)));
+    SEMB_CHECK_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return SEMB_OK;
+  };
+  SEMB_TRY(up(Jr, &s->dJr));
+  SEMB_TRY(up(Js, &s->dJs));
+  SEMB_TRY(up(JrT, &s->dJrT));
+  SEMB_TRY(up(JsT, &s->dJsT));
+  const size_t nmid = std::max((size_t)V->pitch * P->nyl, (size_t)P->pitch * V->nyl);
+  SEMB_CHECK_CUDA(cudaMalloc(&s->mid, nmid * sizeof(double)));
+  semb_field** fv[] = {&s->v1, &s->v2, &s->v3, &s->v4};
+  for (semb_field** f : fv) SEMB_TRY(semb_field_create(V, f));
+  semb_field** fp[] = {&s->p_r, &s->p_u, &s->p_Au, &s->p_rhs, &s->p_dp};
+  for (semb_field** f : fp) SEMB_TRY(semb_field_create(P, f));
+  return SEMB_OK;
+}
+
+extern "C" int semb_stokes_create(semb_mesh* mV, semb_mesh* mP, const char bcVX[4], const char bcVY[4], double b0,
+                                  semb_stokes** out) {
+  SEMB_REQUIRE(mV && mP && out, "semb_stokes_create: null argument");
+  *out = nullptr;
+  SEMB_ENTER(mV->ctx);
+  SEMB_REQUIRE(mP->ctx == mV->ctx && mP->Ex == mV->Ex && mP->Ey == mV->Ey && mP->ney == mV->ney && mP->perx == mV->perx &&
+                   mP->pery == mV->pery,
+               "Stokes: mshP must match mshV in Ex, Ey, periodicity and partition");
+  SEMB_REQUIRE(mV->arr[SEMB_RX] && mV->arr[SEMB_B] && mV->arr[SEMB_BI], "Stokes: mshV has no metric terms / B / Bi");
+  SEMB_REQUIRE(b0 != 0.0, "Stokes: b0 must be non-zero");
+  MaskFlags f;
+  SEMB_TRY(parse_bc(mV, bcVX, &f));
+  SEMB_TRY(parse_bc(mV, bcVY, &f));
+  semb_stokes* s = new semb_stokes();
+  s->V = mV;
+  s->P = mP;
+  s->b0 = b0;
+  if (bcVX) memcpy(s->bcx, bcVX, 4);
+  if (bcVY) memcpy(s->bcy, bcVY, 4);
+  const int rc = stokes_create_impl(s);
+  if (rc < 0) {
+    semb_stokes_destroy(s);
+    return rc;
+  }
+  *out = s;
+  return SEMB_OK;
+}
+
+// ABu(Js,Jr,p): pressure grid -> velocity grid (Br = Jr first, then As = Js, ABu.jl:14-33)
+static int stokes_interp_PV(semb_stokes* s, const double* p, double* outV) {
+  semb_mesh *V = s->V, *P = s->P;
+  semb_ctx* c = V->ctx;
+  SEMB_TRY(semb_launch_abu_r(c, s->dJr, V->nr, P->nr, p, P->nxl, P->nyl, P->pitch, s->mid, V->pitch));
+  return semb_launch_abu_s(c, s->dJs, V->ns, P->ns, s->mid, V->nxl, P->nyl, V->pitch, outV, V->pitch);
+}
+// ABu(Js',Jr',v): velocity grid -> pressure grid
+static int stokes_interp_VP(semb_stokes* s, const double* v, double* outP) {
+  semb_mesh *V = s->V, *P = s->P;
+  semb_ctx* c = V->ctx;
+  SEMB_TRY(semb_launch_abu_r(c, s->dJrT, P->nr, V->nr, v, V->nxl, V->nyl, V->pitch, s->mid, P->pitch));
+  return semb_launch_abu_s(c, s->dJsT, P->ns, V->ns, s->mid, P->nxl, V->nyl, P->pitch, outP, P->pitch);
+}
+
+// diver(ux,uy,mshV,Jr,Js), diver.jl:17-31
+extern "C" int semb_diver(semb_stokes* s, const semb_field* ux, const semb_field* uy, semb_field* out) {
+  SEMB_REQUIRE(s, "null Stokes handle");
+  SEMB_ENTER(s->V->ctx);
+  SEMB_TRY(check_field(s->V, ux, "diver(ux)"));
+  SEMB_TRY(check_field(s->V, uy, "diver(uy)"));
+  SEMB_TRY(check_field(s->P, out, "diver(out)"));
+  SEMB_REQUIRE(ux != s->v4 && uy != s->v4, "diver: argument aliases the work field");
+  SEMB_TRY(semb_launch_diver_local(s->V->ctx, s->V, ux->d, uy->d, s->v4->d));  // B .* (uxdx + uydy), :22-27
+  return stokes_interp_VP(s, s->v4->d, out->d);                                 // ABu(Js',Jr',Bdiv), :28
+}
+
+// diverT(pr,mshV,Jr,Js), diver.jl:53-63
+extern "C" int semb_diverT(semb_stokes* s, const semb_field* pr, semb_field* qx, semb_field* qy) {
+  SEMB_REQUIRE(s, "null Stokes handle");
+  SEMB_ENTER(s->V->ctx);
+  SEMB_TRY(check_field(s->P, pr, "diverT(pr)"));
+  SEMB_TRY(check_field(s->V, qx, "diverT(qx)"));
+  SEMB_TRY(check_field(s->V, qy, "diverT(qy)"));
+  SEMB_REQUIRE(qx != qy && qx != s->v4 && qy != s->v4, "diverT: outputs must not alias (each other or the work field)");
+  SEMB_TRY(stokes_interp_PV(s, pr->d, s->v4->d));                                                   // Jp, :57
+  return semb_launch_gradT(s->V->ctx, s->V, s->v4->d, s->V->arr[SEMB_B], qx->d, qy->d);            // mass, gradT, :58-60
+}
+
+// opStokesLHS(q,sks), stokes.jl:110-121 = gatherScatter(stokesOp(q,...), mshP), stokesOp: diver.jl:73-89
+extern "C" int semb_stokes_op(semb_stokes* s, const semb_field* q, semb_field* out) {
+  SEMB_REQUIRE(s, "null Stokes handle");
+  SEMB_ENTER(s->V->ctx);
+  SEMB_TRY(check_field(s->P, q, "stokesOp(q)"));
+  SEMB_TRY(check_field(s->P, out, "stokesOp(out)"));
+  SEMB_REQUIRE(q != out && q != s->p_rhs && out != s->p_rhs, "stokesOp: argument aliases a work field");
+  SEMB_TRY(semb_diverT(s, q, s->v1, s->v2));                                  // DD'
+  SEMB_TRY(semb_approx_hlmz_inv(s->V, s->v1, s->b0, s->bcx, s->v3));          // HH^-1
+  SEMB_TRY(semb_approx_hlmz_inv(s->V, s->v2, s->b0, s->bcy, s->v1));
+  SEMB_TRY(semb_diver(s, s->v3, s->v1, s->p_rhs));                            // DD
+  SEMB_TRY(semb_field_axpby(0.0, s->p_rhs, -1.0, s->p_rhs));                  // return -Eq, diver.jl:88 (0*x + (-1)*y)
+  return semb_gather_scatter(s->P, s->p_rhs, out);                           // stokes.jl:118
+}
+
+// makeStokesRHS!, stokes.jl:128-141, for the velocity (vx, vy) to be projected
+extern "C" int semb_stokes_rhs(semb_stokes* s, const semb_field* vx, const semb_field* vy, semb_field* rhs) {
+  SEMB_REQUIRE(s, "null Stokes handle");
+  SEMB_ENTER(s->V->ctx);
+  SEMB_TRY(check_field(s->P, rhs, "makeStokesRHS(rhs)"));
+  SEMB_REQUIRE(rhs != s->p_Au, "makeStokesRHS: rhs aliases a work field");
+  SEMB_TRY(semb_diver(s, vx, vy, s->p_Au));
+  return semb_gather_scatter(s->P, s->p_Au, rhs);
+}
+
+// solveStokes!, stokes.jl:143-154: pcg(rhs, opStokesLHS; mult = mshP.mult) with the loop of pcg.jl:16-60 driven from
+// the host over device vectors (the operator is a chain of ~25 launches; scalars come back per iteration)
+extern "C" int semb_stokes_solve(semb_stokes* s, const semb_field* rhs, semb_field* dp, double tol, long long maxiter,
+                                 long long* iters, double* resinf) {
+  SEMB_REQUIRE(s, "null Stokes handle");
+  semb_mesh* P = s->P;
+  SEMB_ENTER(P->ctx);
+  SEMB_TRY(check_field(P, rhs, "solveStokes(rhs)"));
+  SEMB_TRY(check_field(P, dp, "solveStokes(dp)"));
+  SEMB_REQUIRE(rhs != dp, "solveStokes: dp must not alias rhs");
+  if (maxiter < 0) maxiter = (long long)P->nxl * P->ns * P->Ey;  // length(b), pcg.jl:21
+  semb_field *r = s->p_r, *u = s->p_u, *Au = s->p_Au;
+  SEMB_TRY(semb_field_fill(dp, 0.0));     // x = zero(b), pcg.jl:25
+  SEMB_TRY(semb_field_copy(r, rhs));      // ra = b - opA*x = b
+  long long k = 0;
+  double rinf = 0.0, t_prev = 0.0;
+  int rc = SEMB_OK;
+  for (;;) {
+    SEMB_TRY(semb_norm_inf(P, r, &rinf));
+    if (!(rinf > tol)) break;             // pcg.jl:36
+    if (k == maxiter) {                   // pcg.jl:39
+      rc = SEMB_NOT_CONVERGED;
+      break;
+    }
+    ++k;
+    double t = 0.0, uAu = 0.0;
+    SEMB_TRY(semb_dot_mult(P, r, r, &t));                    // pcg.jl:45 with opM = identity (stokes.jl:123-126)
+    if (k == 1)
+      SEMB_TRY(semb_field_copy(u, r));                       // pcg.jl:47
+    else
+      SEMB_TRY(semb_field_axpby(1.0, r, t / t_prev, u));     // u = hp + beta*u, pcg.jl:49
+    SEMB_TRY(semb_stokes_op(s, u, Au));                      // pcg.jl:51
+    SEMB_TRY(semb_dot_mult(P, u, Au, &uAu));                 // pcg.jl:52
+    const double a = t / uAu;
+    SEMB_TRY(semb_field_axpby(a, u, 1.0, dp));               // pcg.jl:53
+    SEMB_TRY(semb_field_axpby(-a, Au, 1.0, r));              // pcg.jl:54
+    t_prev = t;
+  }
+  if (iters) *iters = k;
+  if (resinf) *resinf = rinf;
+  return rc;
+}
+
+// pressureProject!, stokes.jl:159-177: vx, vy, pr are updated in place
+extern "C" int semb_stokes_project(semb_stokes* s, semb_field* vx, semb_field* vy, semb_field* pr, double tol,
+                                   long long maxiter, long long* iters, double* resinf) {
+  SEMB_REQUIRE(s, "null Stokes handle");
+  SEMB_ENTER(s->V->ctx);
+  SEMB_TRY(check_field(s->V, vx, "pressureProject(vx)"));
+  SEMB_TRY(check_field(s->V, vy, "pressureProject(vy)"));
+  SEMB_TRY(check_field(s->P, pr, "pressureProject(pr)", true));
+  SEMB_TRY(semb_stokes_rhs(s, vx, vy, s->p_rhs));                          // makeStokesRHS!, :162
+  semb_field* rhs2 = nullptr;  // p_rhs is a work field of the operator: keep the right-hand side in its own field
+  SEMB_TRY(semb_field_create(s->P, &rhs2));
+  int rc = semb_field_copy(rhs2, s->p_rhs);
+  if (rc >= 0) rc = semb_stokes_solve(s, rhs2, s->p_dp, tol, maxiter, iters, resinf);  // :164
+  semb_field_destroy(rhs2);
+  if (rc < 0) return rc;
+  SEMB_TRY(semb_diverT(s, s->p_dp, s->v1, s->v2));                         // :166
+  SEMB_TRY(semb_approx_hlmz_inv(s->V, s->v1, s->b0, s->bcx, s->v3));       // :169
+  SEMB_TRY(semb_field_axpby(1.0, s->v3, 1.0, vx));                         // :173
+  SEMB_TRY(semb_approx_hlmz_inv(s->V, s->v2, s->b0, s->bcy, s->v3));       // :170
+  SEMB_TRY(semb_field_axpby(1.0, s->v3, 1.0, vy));                         // :174
+  if (pr) SEMB_TRY(semb_field_axpby(1.0, s->p_dp, 1.0, pr));               // :175
+  return rc;
+}

@@ -691,7 +691,7 @@ __global__ void semb_abu_s_kernel(const double* __restrict__ As, int ma, int na,
   }
 }
 
-// grad(u,msh), grad.jl:94-113: ux = rx.*ur + sx.*us, uy = ry.*ur + sy.*us with ur = (I (x) Dr) u, us = (Ds (x) I) u
+// grad(u,msh), grad.jl:15-34: ux = rx.*ur + sx.*us, uy = ry.*ur + sy.*us with ur = (I (x) Dr) u, us = (Ds (x) I) u
 __global__ void semb_grad_kernel(const double* __restrict__ u, long long pitch, int nr, int ns, int Ex, int ney,
                                  const double* __restrict__ Dr, const double* __restrict__ Ds,
                                  const double* __restrict__ rx, const double* __restrict__ ry,
@@ -706,8 +706,8 @@ __global__ void semb_grad_kernel(const double* __restrict__ u, long long pitch, 
       for (int k = 0; k < nr; ++k) ur = fma(Dr[i * nr + k], u[rowb + k], ur);
       for (int k = 0; k < ns; ++k) us = fma(Ds[j * ns + k], u[colb + (size_t)k * pitch], us);
       const size_t idx = (size_t)row * pitch + c;
-      ux[idx] = __dadd_rn(__dmul_rn(rx[idx], ur), __dmul_rn(sx[idx], us));  // grad.jl:109
-      uy[idx] = __dadd_rn(__dmul_rn(ry[idx], ur), __dmul_rn(sy[idx], us));  // grad.jl:110
+      ux[idx] = __dadd_rn(__dmul_rn(rx[idx], ur), __dmul_rn(sx[idx], us));  // grad.jl:30
+      uy[idx] = __dadd_rn(__dmul_rn(ry[idx], ur), __dmul_rn(sy[idx], us));  // grad.jl:31
     }
   }
 }
@@ -803,7 +803,7 @@ __global__ void __launch_bounds__(256) semb_advect_fused_kernel(const AdvectFuse
       tF[(3 * EB + e) * NN + j * N + i] = a.uy[g];
     }
     __syncthreads();
-    // grad: Tx = rx.*ur + sx.*us, Ty = ry.*ur + sy.*us (grad.jl:106-110)
+    // grad: Tx = rx.*ur + sx.*us, Ty = ry.*ur + sy.*us (grad.jl:27-31)
     for (int q = tid; q < N * nbe * N; q += nt) {
       const int j = q / (nbe * N), xx = q - j * (nbe * N), e = xx / N, i = xx - e * N;
       const double* t = tT + e * NN;

@@ -60,3 +60,8 @@ int semb_launch_advect_fused(semb_ctx* ctx, semb_mesh* V, semb_mesh* D, const do
 // register-tiled fused dealiased advection for the served (N, M) pairs (semb_advect_tile.cu); nT fields per launch
 int semb_launch_advect_tile(semb_ctx* ctx, semb_mesh* V, semb_mesh* D, int nT, const double* const* T, const double* ux,
                             const double* uy, const double* dJr, const double* dJs, double* const* out, int* done);
+// Stokes split, element-local kernels (semb_stokes.cu): grad^T (optionally of W .* u), B .* div(ux,uy), (M.*g).*Bi./b0
+int semb_launch_gradT(semb_ctx* ctx, semb_mesh* m, const double* u, const double* W, double* ox, double* oy);
+int semb_launch_diver_local(semb_ctx* ctx, semb_mesh* m, const double* ux, const double* uy, double* out);
+int semb_launch_hinv_mid(semb_ctx* ctx, semb_mesh* m, const double* g, double b0, int mx0, int mx1, int my0, int my1,
+                         double* out);

@@ -1,5 +1,5 @@
 """Next row 8f-2: grad, dealiased advection and the ConvectionDiffusion stepper (examples/cd2d.jl) against the
-oracle (oracle/sem_oracle.py: grad.jl:94-113, advect.jl:27-78, convectionDiffusion.jl:76-157)."""
+oracle (oracle/sem_oracle.py: grad.jl:15-34, advect.jl:27-78, convectionDiffusion.jl:76-157)."""
 import numpy as np
 import pytest
 

@@ -184,3 +184,61 @@ def test_pcg_reference_semantics():
     so.pcg(0 * b, op, mult=m.mult, info=info)
     assert info["iters"] == 0  # loop not entered, pcg.jl:36
     assert so.splitmix_uniform((3, 2))[0, 0] == so.splitmix_uniform((6, 1))[0, 0]  # column-major stream
+
+
+# ---- the Stokes reconstruction has no executable reference; these identities are what pins it ----------
+def _stokes_setup(nr=7, E=3, deform=None):
+    deform = deform or so.wavy
+    V = so.make_mesh(nr, nr, E, E, (False, False), deform)
+    P = so.make_mesh(nr - 2, nr - 2, E, E, (False, False), deform)
+    return V, P, so.make_stokes(list("DDDD"), list("DDDD"), V, P, 1.0)
+
+
+def test_gradT_and_diverT_are_exact_transposes():
+    V, P, sks = _stokes_setup()
+    rng = np.random.default_rng(0)
+    u, v, w = (rng.standard_normal(V.x.shape) for _ in range(3))
+    q = rng.standard_normal(P.x.shape)
+    gx, gy = so.grad(u, V)
+    tx, _ = so.gradT(v, V)
+    _, ty = so.gradT(w, V)
+    assert abs(np.sum(gx * v) - np.sum(u * tx)) < 1e-11 * np.sum(np.abs(gx * v))
+    assert abs(np.sum(gy * w) - np.sum(u * ty)) < 1e-11 * np.sum(np.abs(gy * w))
+    d = so.diver(u, v, V, sks.JrPV, sks.JsPV)
+    qx, qy = so.diverT(q, V, sks.JrPV, sks.JsPV)
+    assert abs(np.sum(d * q) - np.sum(qx * u) - np.sum(qy * v)) < 1e-11 * np.sum(np.abs(d * q))
+
+
+def test_diver_of_a_linear_field_is_its_divergence():
+    """diver integrates div(u) against the pressure basis: for u = (x, 2y) on the undeformed box, div = 3 and
+    sum(diver) = 3 * area (the pressure interpolants sum to one)."""
+    V, P, sks = _stokes_setup(deform=so.fixU)
+    d = so.diver(V.x.copy(), 2.0 * V.y, V, sks.JrPV, sks.JsPV)
+    assert abs(np.sum(d) - 3.0 * 4.0) < 1e-11
+
+
+def test_schur_operator_is_symmetric_negative_semidefinite():
+    V, P, sks = _stokes_setup()
+    rng = np.random.default_rng(1)
+    q = so.gatherScatter(rng.standard_normal(P.x.shape) * P.mult, P)
+    r = so.gatherScatter(rng.standard_normal(P.x.shape) * P.mult, P)
+    a = np.sum(r * so.opStokesLHS(q, sks) * P.mult)
+    b = np.sum(q * so.opStokesLHS(r, sks) * P.mult)
+    assert abs(a - b) < 1e-10 * abs(a)
+    assert np.sum(q * so.opStokesLHS(q, sks) * P.mult) < 0
+    one = np.ones(P.x.shape)  # constant pressure: in the null space for an enclosed (all-Dirichlet) flow
+    assert np.max(np.abs(so.opStokesLHS(one, sks))) < 1e-10
+
+
+def test_pressure_projection_removes_the_divergence():
+    V, P, sks = _stokes_setup()
+    rng = np.random.default_rng(2)
+    vx = so.mask(so.gatherScatter(rng.standard_normal(V.x.shape) * V.mult, V), sks.Mvx)
+    vy = so.mask(so.gatherScatter(rng.standard_normal(V.x.shape) * V.mult, V), sks.Mvy)
+    r0 = so.makeStokesRHS(vx, vy, sks)
+    nx, ny, p = so.pressureProject(vx, vy, np.zeros(P.x.shape), sks, tol=1e-10)
+    r1 = so.makeStokesRHS(nx, ny, sks)
+    assert np.max(np.abs(r1)) < 1e-8 and np.max(np.abs(r1)) < 1e-7 * np.max(np.abs(r0))
+    # the corrected velocity stays continuous and keeps its Dirichlet values
+    assert np.max(np.abs(so.gatherScatter(nx * V.mult, V) - nx)) < 1e-12
+    assert np.max(np.abs(nx * (1 - sks.Mvx))) == 0.0
