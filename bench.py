@@ -12,6 +12,8 @@ wavy-deformed box, 1.0016e8 DOF per GPU (weak scaling: N GPUs hold 1112 x 1112N 
 y-slabs with an NCCL halo exchange per apply).  The same JSON line carries
   extra.cfg2_helmholtz  BASELINE configs[1] (Helmholtz, 256x256 elements, order 8; L2 flushed per step)
   extra.pcg             PCG iterations/s on the headline mesh (device-resident loop, pcg.jl:16-60)
+  extra.cfg4_cd2d       BASELINE configs[3] (convection-diffusion BDF3/EXT3 step, 512x512 elements, order 8)
+  extra.cfg5_stokes     BASELINE configs[4] (Stokes split, 256x256 elements, order 10/8): Schur apply, pressure PCG
   e2e                   the same apply through the host-buffer C-ABI twin (semb_oplhs_host): pinned H2D
                         of u + fused kernels + D2H of the result, every step
   roofline              strip-kernel HBM roofline: 40 B/DOF algorithmic / CUDA-event kernel time
@@ -322,6 +324,38 @@ def run_semb(args):
                               "gdof_steps_per_s": nV / dt4 / 1e9, "ms_per_dealiased_advect_incl_alloc": dta * 1e3}
         cdn.free(); mV.free(); mD.free()
 
+    # ---- BASELINE configs[4]: Stokes pressure-velocity split, order 10 velocity / order 8 pressure ---------------------
+    if rank == 0 and world == 1 and not args.skip_cfg5:
+        E5 = args.cfg5_elements
+        mV = sem.Mesh(11, 11, E5, E5, (False, False), "wavy", ctx=ctx)
+        mP = sem.Mesh(9, 9, E5, E5, (False, False), "wavy", ctx=ctx)   # pressure order nr-2 (examples/semPS.jl:31)
+        sks = sem.Stokes("DDDD", "DDDD", mV, mP, 1.0)
+        nV5, nP5 = mV.shape[0] * mV.shape[1], mP.shape[0] * mP.shape[1]
+        q5, o5 = mP.field().fill_random(3), mP.field()
+        for _ in range(3):
+            sks.op_device(q5, o5)
+        ctx.timer_start()
+        nop = 20
+        for _ in range(nop):
+            sks.op_device(q5, o5)
+        ms5 = ctx.timer_stop() / nop
+        vx5, vy5, pr5 = mV.field().fill_random(5), mV.field().fill_random(6), mP.field()
+        sks.project_device(vx5, vy5, pr5, tol=0.0, maxiter=2)   # first-use allocations outside the timed call
+        ctx.sync()
+        t0 = time.perf_counter()
+        nit5 = 50
+        sks.project_device(vx5, vy5, pr5, tol=0.0, maxiter=nit5)
+        ctx.sync()
+        dt5 = time.perf_counter() - t0
+        extra["cfg5_stokes"] = {"workload": "Stokes split (reconstruction of diver.jl/stokes.jl): Schur operator -DD HH^-1 DD' + "
+                                            "QQ^T on the pressure mesh, %dx%d elements, velocity order 10 (%d DOF per component), "
+                                            "pressure order 8 (%d DOF), wavy box" % (E5, E5, nV5, nP5),
+                                "ms_per_schur_apply": ms5, "velocity_gdof_per_s": nV5 / ms5 / 1e6,
+                                "pressure_pcg_iters_per_s": nit5 / dt5,
+                                "note": "pressureProject timed over %d PCG iterations incl. the right-hand side and the "
+                                        "velocity correction; host-driven loop (3 scalar read-backs per iteration)" % nit5}
+        sks.free(); mV.free(); mP.free()
+
     # ---- CPU baseline beside it (rank 0, N = 1): bounded sample of the same workload -------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -430,6 +464,8 @@ def main():
     ap.add_argument("--skip-cfg2", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-cfg4", action="store_true")
+    ap.add_argument("--skip-cfg5", action="store_true")
+    ap.add_argument("--cfg5-elements", type=int, default=256)
     ap.add_argument("--cfg4-elements", type=int, default=512)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "semb" else args.warmup

@@ -292,6 +292,21 @@ int semb_pcg_host(semb_mesh* m, const semb_pcg_opts* opts_scalars, const double*
 int semb_abu_host(semb_ctx* ctx, const double* As, int ma, int na, const double* Br, int mb, int nb,
                   const double* u, int m, int n, double* out);
 
+/* ---- explicit-argument operator forms on plain arrays (no Mesh), host twins ---------------------------------- */
+/* laplace(u,Dr,Ds,G11,G12,G22), lapl.jl:70-81 (Jr = Js = NULL) and the dealiased laplace(u,Jr,Js,Dr,Ds,G11,G12,G22),
+ * lapl.jl:83-103, as examples/p2d_explicit.jl:183 and examples/semPS.jl:168 use them: u is m x n = (nr*Ex) x (ns*Ey);
+ * Jr is nrd x nr, Js nsd x ns (column-major); the G factors live on the (m*nrd/nr) x (n*nsd/ns) grid. */
+int semb_laplace_host(semb_ctx* ctx, int m, int n, const double* Dr, int nr, const double* Ds, int ns,
+                      const double* Jr, int nrd, const double* Js, int nsd, const double* G11, const double* G12,
+                      const double* G22, const double* u, double* out);
+/* core of mass(u,M,B,Jr,Js,QQtx,QQty,mult), mass.jl:32-50: out = ABu(Js',Jr', B .* ABu(Js,Jr,u)); NULL Jr/Js/B are
+ * Julia's `[]` (identity / no weight, mass.jl:38).  The mult hook, gatherScatter and mask that follow are ABu / a.*b. */
+int semb_mass_explicit_host(semb_ctx* ctx, int m, int n, const double* Jr, int nrd, int nr, const double* Js, int nsd,
+                            int ns, const double* B, const double* u, double* out);
+/* out = a .* b on n doubles: mask(u,M), mask.jl:14, and the `d .* mult` hooks (lapl.jl:62, mass.jl:44) for arrays
+ * that belong to no Mesh */
+int semb_mul_host(semb_ctx* ctx, size_t n, const double* a, const double* b, double* out);
+
 /* ---- diagnostics / tuning hooks (no reference counterpart) ------------------------------------- */
 /* registers / shared memory / resident CTAs per SM of the fused strip kernel for polynomial size N */
 int semb_strip_kernel_info(int N, int pcg, int massterm, int* regs, int* smem, int* occ);

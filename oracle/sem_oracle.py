@@ -228,6 +228,24 @@ def annulus(r, s, r0=0.5, r1=1.0, span=2 * math.pi):
     return R * np.cos(th), R * np.sin(th)
 
 
+def gordonHall(xrm, xrp, xsm, xsp, yrm, yrp, ysm, ysp, zr, zs, as_written=False):
+    """geom.jl:8-31, transfinite interpolation.  Deviation, flagged: the corner matrix of geom.jl:14-18 has its first
+    index along s but is interpolated with Jer along that index (:20-21); indexed [r, s] here (as_written=True: literal)."""
+    ze = np.array([-1.0, 1.0])
+    Jer, Jes = interpMat(zr, ze), interpMat(zs, ze)
+    col = lambda a: np.asarray(a, dtype=np.float64).reshape(-1)
+    xrm, xrp, xsm, xsp, yrm, yrp, ysm, ysp = map(col, (xrm, xrp, xsm, xsp, yrm, yrp, ysm, ysp))
+    corners = lambda m, p: np.array([[m[0], p[0]], [m[-1], p[-1]]])
+    xv, yv = corners(xrm, xrp), corners(yrm, yrp)
+    if not as_written:
+        xv, yv = xv.T, yv.T
+    xv = ABu(Jes, Jer, xv)
+    yv = ABu(Jes, Jer, yv)
+    x = ABu(EMPTY, Jer, np.vstack([xrm, xrp])) + ABu(Jes, EMPTY, np.column_stack([xsm, xsp])) - xv
+    y = ABu(EMPTY, Jer, np.vstack([yrm, yrp])) + ABu(Jes, EMPTY, np.column_stack([ysm, ysp])) - yv
+    return x, y
+
+
 def wavy(x, y, amp=0.1):
     """Synthetic deformation used by the bench: (x+d, y+d), d = amp sin(pi x) sin(pi y)."""
     d = amp * np.sin(np.pi * x) * np.sin(np.pi * y)
@@ -396,6 +414,7 @@ def laplace(u, Dr, Ds, G11, G12, G22):
 
 # lapl.jl:83-103 (dealiased)
 def laplace_dealias(u, Jr, Js, Dr, Ds, G11, G12, G22):
+    Jr, Js = np.asarray(Jr, dtype=np.float64), np.asarray(Js, dtype=np.float64)
     ur = ABu(EMPTY, Dr, u)
     us = ABu(Ds, EMPTY, u)
     Jur = ABu(Js, Jr, ur)
@@ -408,6 +427,22 @@ def laplace_dealias(u, Jr, Js, Dr, Ds, G11, G12, G22):
 
 
 # lapl.jl:26-45
+def lapl_explicit(u, M, Jr, Js, QQtx, QQty, Dr, Ds, G11, G12, G22, mult):
+    """lapl(u,M,Jr,Js,QQtx,QQty,Dr,Ds,G11,G12,G22,mult), lapl.jl:54-68; the mult hook (:62) is identity in the forward pass"""
+    Au = laplace_dealias(u, Jr, Js, Dr, Ds, G11, G12, G22)
+    Au = gatherScatter(Au, QQtx, QQty)
+    return mask(Au, M)
+
+
+def mass_explicit(u, M, B, Jr, Js, QQtx, QQty, mult):
+    """mass(u,M,B,Jr,Js,QQtx,QQty,mult), mass.jl:32-50"""
+    Ju = ABu(Js, Jr, u)
+    BJu = Ju if np.size(B) == 0 else B * Ju
+    Bu = ABu(np.asarray(Js).T if np.size(Js) else EMPTY, np.asarray(Jr).T if np.size(Jr) else EMPTY, BJu)
+    Bu = gatherScatter(Bu, QQtx, QQty)
+    return mask(Bu, M)
+
+
 def lapl(u, msh: Mesh, nu=None):
     Au = laplace(u, msh.Dr, msh.Ds, msh.G11, msh.G12, msh.G22)
     if nu is not None:

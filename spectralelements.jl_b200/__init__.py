@@ -36,7 +36,7 @@ __all__ = [
     "hlmz", "mass", "gatherScatter", "mask", "pcg", "pcg_b", "OpLHS", "opLHS", "Diffusion", "makeRHS_b",
     "solve_b", "evolve_b", "simulate_b", "grad", "advect", "ConvectionDiffusion", "step_b", "simulate_cd_b", "annulus", "wavy", "fixU", "gausslobatto", "derivMat", "interpMat",
     "semmesh", "ndgrid", "bdfExtK", "partition", "halo_plan", "SembError",
-    "gradT", "approxHlmzInv", "Stokes", "diver", "diverT", "opStokesLHS", "makeStokesRHS", "solveStokes", "pressureProject",
+    "laplace", "gordonHall", "gradT", "approxHlmzInv", "Stokes", "diver", "diverT", "opStokesLHS", "makeStokesRHS", "solveStokes", "pressureProject",
 ]
 
 SEMB_ARR = {"x": 0, "y": 1, "Jac": 2, "Jaci": 3, "rx": 4, "ry": 5, "sx": 6, "sy": 7, "B": 8, "Bi": 9, "G11": 10,
@@ -202,6 +202,28 @@ def annulus(r, s, r0=0.5, r1=1.0, span=2 * math.pi):  # geom.jl:40-49
     R = (r1 - r0) / 2 * (r + 1) + r0
     th = span / 2 * (s + 1) + 0.0
     return R * np.cos(th), R * np.sin(th)
+
+
+def gordonHall(xrm, xrp, xsm, xsp, yrm, yrp, ysm, ysp, zr, zs, as_written=False, ctx=None):
+    """gordonHall(xrm,xrp,xsm,xsp,yrm,yrp,ysm,ysp,zr,zs), geom.jl:8-31: transfinite interpolation of the four boundary
+    curves (x/y on the r = -1, r = +1 edges as functions of s, on the s = -1, s = +1 edges as functions of r) to the
+    (zr, zs) tensor grid; the ABu calls run on the device.
+    Deviation, flagged: geom.jl:14-18 writes the corner matrix with its first index running along s
+    (`[xrm[1] xrp[1]; xrm[end] xrp[end]]`) but interpolates that index with Jer (:20-21), which does not even reproduce
+    the identity map; the corner matrix here is indexed [r, s].  as_written=True gives the literal reference form."""
+    ze = np.array([-1.0, 1.0])
+    Jer, Jes = interpMat(zr, ze), interpMat(zs, ze)
+    col = lambda a: np.asarray(a, dtype=np.float64).reshape(-1)
+    xrm, xrp, xsm, xsp, yrm, yrp, ysm, ysp = map(col, (xrm, xrp, xsm, xsp, yrm, yrp, ysm, ysp))
+    corners = lambda m, p: np.array([[m[0], p[0]], [m[-1], p[-1]]])  # the Julia literal of geom.jl:14-18
+    xv, yv = corners(xrm, xrp), corners(yrm, yrp)
+    if not as_written:
+        xv, yv = xv.T, yv.T
+    xv = ABu(Jes, Jer, xv, ctx=ctx)
+    yv = ABu(Jes, Jer, yv, ctx=ctx)
+    x = ABu(None, Jer, np.vstack([xrm, xrp]), ctx=ctx) + ABu(Jes, None, np.column_stack([xsm, xsp]), ctx=ctx) - xv
+    y = ABu(None, Jer, np.vstack([yrm, yrp]), ctx=ctx) + ABu(Jes, None, np.column_stack([ysm, ysp]), ctx=ctx) - yv
+    return x, y
 
 
 def wavy(x, y, amp=0.1):
@@ -506,8 +528,79 @@ def jac(x, y, Dr, Ds, msh: Optional[Mesh] = None):
             f.free()
 
 
+def _none_if_empty(a):
+    return None if a is None or np.size(a) == 0 else as_f64(a)
+
+
+def laplace(u, *args, ctx: Optional[Context] = None):
+    """laplace(u,Dr,Ds,G11,G12,G22), lapl.jl:70-81 ; laplace(u,Jr,Js,Dr,Ds,G11,G12,G22), lapl.jl:83-103 (dealiased;
+    empty Jr, Js = the plain form, as ABu treats `[]`).  Plain arrays, no Mesh."""
+    if len(args) == 5:
+        Jr = Js = None
+        Dr, Ds, G11, G12, G22 = args
+    elif len(args) == 7:
+        Jr, Js, Dr, Ds, G11, G12, G22 = args
+        Jr, Js = _none_if_empty(Jr), _none_if_empty(Js)
+        if (Jr is None) != (Js is None):
+            raise ValueError("laplace: pass both Jr and Js, or neither")
+    else:
+        raise TypeError("laplace(u,Dr,Ds,G11,G12,G22) or laplace(u,Jr,Js,Dr,Ds,G11,G12,G22)")
+    ctx = ctx or default_context()
+    u, Dr, Ds = as_f64(u), as_f64(Dr), as_f64(Ds)
+    m, n = u.shape
+    nr, ns = Dr.shape[0], Ds.shape[0]
+    if m % nr or n % ns:
+        raise ValueError("InexactError: u is not a whole number of elements (ABu.jl:16,26)")
+    nrd, nsd = (Jr.shape[0], Js.shape[0]) if Jr is not None else (0, 0)
+    gshape = (m // nr * nrd, n // ns * nsd) if Jr is not None else (m, n)
+    G11, G12, G22 = as_f64(G11, gshape), as_f64(G12, gshape), as_f64(G22, gshape)
+    out = np.zeros((m, n), order="F")
+    check(ctx.lib.semb_laplace_host(ctx.h, m, n, dptr(Dr), nr, dptr(Ds), ns, dptr(Jr), nrd, dptr(Js), nsd, dptr(G11),
+                                    dptr(G12), dptr(G22), dptr(u), dptr(out)))
+    return out
+
+
+def _mul(a, b, ctx: Optional[Context] = None):
+    """a .* b on the device for arrays that belong to no Mesh (mask.jl:14, the mult hooks lapl.jl:62 / mass.jl:44)"""
+    ctx = ctx or default_context()
+    a = as_f64(a)
+    b = as_f64(b, a.shape)
+    out = np.zeros(a.shape, order="F")
+    check(ctx.lib.semb_mul_host(ctx.h, a.size, dptr(a), dptr(b), dptr(out)))
+    return out
+
+
+def _lapl_explicit(u, M, Jr, Js, QQtx, QQty, Dr, Ds, G11, G12, G22, mult, ctx=None):
+    """lapl(u,M,Jr,Js,QQtx,QQty,Dr,Ds,G11,G12,G22,mult), lapl.jl:54-68 (examples/p2d_explicit.jl:183, semPS.jl:168).
+    `mult` only enters the reverse pass (Zygote.hook, lapl.jl:62): the forward value ignores it."""
+    Au = laplace(u, Jr, Js, Dr, Ds, G11, G12, G22, ctx=ctx)
+    Au = ABu(QQty, QQtx, Au, ctx=ctx)  # gatherScatter(Au,QQtx,QQty), gatherScatter.jl:8-16
+    return Au if M is None or np.size(M) == 0 else _mul(M, Au, ctx)  # mask, mask.jl:10-18
+
+
+def _mass_explicit(u, M, B, Jr, Js, QQtx, QQty, mult, ctx=None):
+    """mass(u,M,B,Jr,Js,QQtx,QQty,mult), mass.jl:32-50 (examples/p2d_explicit.jl:186-188, semPS.jl:172)"""
+    ctx = ctx or default_context()
+    u = as_f64(u)
+    m, n = u.shape
+    Jr, Js, B = _none_if_empty(Jr), _none_if_empty(Js), _none_if_empty(B)
+    nrd, nr = Jr.shape if Jr is not None else (0, 0)
+    nsd, ns = Js.shape if Js is not None else (0, 0)
+    if (Jr is not None and m % nr) or (Js is not None and n % ns):
+        raise ValueError("InexactError: Int(m*mb/nb) (ABu.jl:16,26)")
+    if B is not None:
+        B = as_f64(B, (m // nr * nrd if Jr is not None else m, n // ns * nsd if Js is not None else n))
+    out = np.zeros((m, n), order="F")
+    check(ctx.lib.semb_mass_explicit_host(ctx.h, m, n, dptr(Jr), nrd, nr, dptr(Js), nsd, ns, dptr(B), dptr(u), dptr(out)))
+    Bu = ABu(QQty, QQtx, out, ctx=ctx)
+    return Bu if M is None or np.size(M) == 0 else _mul(M, Bu, ctx)
+
+
 def lapl(u, *args):
-    """lapl(u,msh) lapl.jl:26-36 ; lapl(u,nu,msh) lapl.jl:38-45 ; lapl(u,msh1,msh2) lapl.jl:47-52"""
+    """lapl(u,msh) lapl.jl:26-36 ; lapl(u,nu,msh) lapl.jl:38-45 ; lapl(u,msh1,msh2) lapl.jl:47-52 ;
+    lapl(u,M,Jr,Js,QQtx,QQty,Dr,Ds,G11,G12,G22,mult) lapl.jl:54-68 (explicit arrays)"""
+    if len(args) == 11:
+        return _lapl_explicit(u, *args)
     if len(args) == 1:
         msh, nu = args[0], None
     elif isinstance(args[0], Mesh):
@@ -534,8 +627,10 @@ def hlmz(u, nu, k, msh: Mesh, msh2: Optional[Mesh] = None):
     return out
 
 
-def mass(u, msh: Mesh, msh2: Optional[Mesh] = None):
-    """mass(u,msh), mass.jl:12-22"""
+def mass(u, msh, *args):
+    """mass(u,msh) mass.jl:12-22 ; mass(u,msh1,msh2) :25-30 ; mass(u,M,B,Jr,Js,QQtx,QQty,mult) :32-50 (explicit arrays)"""
+    if len(args) == 6:
+        return _mass_explicit(u, msh, *args)
     u = as_f64(u, msh.shape)
     out = np.zeros(msh.shape, order="F")
     check(msh.lib.semb_mass_host(msh.h, dptr(u), dptr(out)))
@@ -555,8 +650,8 @@ def gatherScatter(u, *args):
 
 def mask(u, M, msh: Optional[Mesh] = None):
     """mask(u,M), mask.jl:10-18.  Needs a mesh for the device layout: pass msh= or a masked-field owner."""
-    if msh is None:
-        raise ValueError("mask needs msh= (the device layout of u)")
+    if msh is None:  # plain arrays that belong to no Mesh (examples/p2d_explicit.jl)
+        return as_f64(u).copy(order="F") if M is None or np.size(M) == 0 else _mul(M, u)
     u = as_f64(u, msh.shape)
     Mf = None if M is None or np.size(M) == 0 else as_f64(M, msh.shape)
     out = np.zeros(msh.shape, order="F")

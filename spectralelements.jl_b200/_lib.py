@@ -123,6 +123,11 @@ _SIGS = {
                        c_double_p], C.c_int),
     "semb_abu_host": ([vp, c_double_p, C.c_int, C.c_int, c_double_p, C.c_int, C.c_int, c_double_p, C.c_int,
                        C.c_int, c_double_p], C.c_int),
+    "semb_laplace_host": ([vp, C.c_int, C.c_int, c_double_p, C.c_int, c_double_p, C.c_int, c_double_p, C.c_int, c_double_p,
+                           C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p], C.c_int),
+    "semb_mass_explicit_host": ([vp, C.c_int, C.c_int, c_double_p, C.c_int, C.c_int, c_double_p, C.c_int, C.c_int,
+                                 c_double_p, c_double_p, c_double_p], C.c_int),
+    "semb_mul_host": ([vp, C.c_size_t, c_double_p, c_double_p, c_double_p], C.c_int),
     "semb_strip_kernel_info": ([C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p], C.c_int),
     "semb_mesh_plan": ([vp] + [c_int_p] * 5, C.c_int),
     "semb_mesh_set_chunks": ([vp, C.c_int], C.c_int),

@@ -2000,3 +2000,4 @@ extern "C" int semb_abu_host(semb_ctx* c, const double* As, int ma, int na, cons
 }
 
 #include "semb_stokes_api.cuh"
+#include "semb_explicit_api.cuh"

@@ -65,6 +65,30 @@ def main():
         if e > 1e-9 or abs(ig["iters"] - io["iters"]) > max(3, 0.05 * io["iters"]):
             fails.append(tag + " pcg err %g iters %d vs %d" % (e, ig["iters"], io["iters"]))
         gm.free()
+    # Stokes split on slabs: element-local kernels + gatherScatter on both meshes + all-reduced PCG scalars
+    for nr, Ex, Ey in [(7, 3, 8), (9, 4, 2 * world)]:
+        if Ey < world:
+            continue
+        oV, oP = so.make_mesh(nr, nr, Ex, Ey, (False, False), so.wavy), so.make_mesh(nr - 2, nr - 2, Ex, Ey, (False, False), so.wavy)
+        gV = sem.Mesh(nr, nr, Ex, Ey, (False, False), "wavy", deform_params=(0.1,), ctx=ctx)
+        gP = sem.Mesh(nr - 2, nr - 2, Ex, Ey, (False, False), "wavy", deform_params=(0.1,), ctx=ctx)
+        osk, gsk = so.make_stokes(list("DDDD"), list("DDNN"), oV, oP, 1.0), sem.Stokes("DDDD", "DDNN", gV, gP, 1.0)
+        e0, ne = sem.partition(Ey, world, rank)
+        locV = lambda a: np.asfortranarray(a[:, e0 * nr:(e0 + ne) * nr])
+        locP = lambda a: np.asfortranarray(a[:, e0 * (nr - 2):(e0 + ne) * (nr - 2)])
+        tag = "stokes nr=%d %dx%d" % (nr, Ex, Ey)
+        q = so.splitmix_uniform(oP.x.shape, seed=3)
+        e = relerr(sem.opStokesLHS(locP(q), gsk), locP(so.opStokesLHS(q, osk)))
+        if e > 1e-11:
+            fails.append(tag + " opStokesLHS %g" % e)
+        vx = so.mask(so.gatherScatter(so.splitmix_uniform(oV.x.shape, seed=5) * oV.mult, oV), osk.Mvx)
+        vy = so.mask(so.gatherScatter(so.splitmix_uniform(oV.x.shape, seed=6) * oV.mult, oV), osk.Mvy)
+        ox, oy, op = so.pressureProject(vx, vy, np.zeros(oP.x.shape), osk, tol=1e-9)
+        gx, gy, gp = sem.pressureProject(locV(vx), locV(vy), locP(np.zeros(oP.x.shape)), gsk, tol=1e-9)
+        e = max(np.max(np.abs(gx - locV(ox))), np.max(np.abs(gy - locV(oy))))
+        if e > 1e-6 or abs(gsk.pcg_iters[-1] - osk.pcg_iters[-1]) > max(3, 0.05 * osk.pcg_iters[-1]):
+            fails.append(tag + " project err %g iters %d vs %d" % (e, gsk.pcg_iters[-1], osk.pcg_iters[-1]))
+        gsk.free(); gV.free(); gP.free()
     flag = torch.tensor([len(fails)], device="cuda")
     dist.all_reduce(flag)
     for f in fails:

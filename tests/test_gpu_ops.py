@@ -215,3 +215,40 @@ def test_errors(sem, ctx):
             sem.pcg(np.zeros(gm.shape), lambda v: v)  # host closure: no CPU fallback
     finally:
         gm.free()
+
+
+def test_explicit_argument_forms(sem, ctx):
+    """lapl(u,M,Jr,Js,QQtx,QQty,Dr,Ds,G11,G12,G22,mult) lapl.jl:54-68 (plain and dealiased, examples/p2d_explicit.jl:183,
+    semPS.jl:168), laplace(...) lapl.jl:70-103, mass(u,M,B,Jr,Js,QQtx,QQty,mult) mass.jl:32-50, mask on plain arrays."""
+    m = so.make_mesh(6, 6, 3, 2, (False, True), so.wavy)
+    md = so.make_mesh(9, 9, 3, 2, (False, True), so.wavy)
+    M = so.generateMask(list("DDNN"), m).astype(np.float64)
+    u = so.splitmix_uniform(m.x.shape, seed=9)
+    Jr, Js = so.interpMat(md.zr, m.zr), so.interpMat(md.zs, m.zs)
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+    assert rel(sem.laplace(u, m.Dr, m.Ds, m.G11, m.G12, m.G22), so.laplace(u, m.Dr, m.Ds, m.G11, m.G12, m.G22)) < 1e-12
+    assert rel(sem.laplace(u, Jr, Js, m.Dr, m.Ds, md.G11, md.G12, md.G22),
+               so.laplace_dealias(u, Jr, Js, m.Dr, m.Ds, md.G11, md.G12, md.G22)) < 1e-12
+    args = (M, [], [], m.QQtx, m.QQty, m.Dr, m.Ds, m.G11, m.G12, m.G22, m.mult)
+    assert rel(sem.lapl(u, *args), so.lapl_explicit(u, *args)) < 1e-12
+    args = (M, Jr, Js, m.QQtx, m.QQty, m.Dr, m.Ds, md.G11, md.G12, md.G22, m.mult)
+    assert rel(sem.lapl(u, *args), so.lapl_explicit(u, *args)) < 1e-12
+    for args in ((M, m.B, [], [], m.QQtx, m.QQty, m.mult), ([], md.B, Jr, Js, [], [], m.mult), (M, [], Jr, Js, m.QQtx, m.QQty, m.mult)):
+        assert rel(sem.mass(u, *args), so.mass_explicit(u, *args)) < 1e-12
+    assert np.array_equal(sem.mask(u, M), so.mask(u, M)) and np.array_equal(sem.mask(u, []), u)
+    with pytest.raises(ValueError):
+        sem.laplace(u[:-1], m.Dr, m.Ds, m.G11, m.G12, m.G22)
+
+
+def test_gordonHall(sem, ctx):
+    """geom.jl:8-31 on the device ABu kernels against the oracle, curved edges (a quarter annulus)"""
+    zr, _ = so.gausslobatto(7)
+    zs, _ = so.gausslobatto(6)
+    R = lambda r: 0.75 + 0.25 * r
+    th = lambda s: np.pi / 4 * (s + 1)
+    edges = (R(-1) * np.cos(th(zs)), R(1) * np.cos(th(zs)), R(zr) * np.cos(th(-1)), R(zr) * np.cos(th(1)),
+             R(-1) * np.sin(th(zs)), R(1) * np.sin(th(zs)), R(zr) * np.sin(th(-1)), R(zr) * np.sin(th(1)))
+    for lit in (False, True):
+        gx, gy = sem.gordonHall(*edges, zr, zs, as_written=lit)
+        ox, oy = so.gordonHall(*edges, zr, zs, as_written=lit)
+        assert np.max(np.abs(gx - ox)) < 1e-14 and np.max(np.abs(gy - oy)) < 1e-14

@@ -242,3 +242,38 @@ def test_pressure_projection_removes_the_divergence():
     # the corrected velocity stays continuous and keeps its Dirichlet values
     assert np.max(np.abs(so.gatherScatter(nx * V.mult, V) - nx)) < 1e-12
     assert np.max(np.abs(nx * (1 - sks.Mvx))) == 0.0
+
+
+def test_gordonHall_reproduces_bilinear_quadrilaterals():
+    """geom.jl:8-31 (with the corner matrix indexed [r, s]): exact for straight-sided quadrilaterals, identity included"""
+    zr, _ = so.gausslobatto(6)
+    zs, _ = so.gausslobatto(5)
+    R, S = np.meshgrid(zr, zs, indexing="ij")
+    for fx, fy in ((lambda r, s: r, lambda r, s: s),
+                   (lambda r, s: 1 + 2 * r + 0.3 * s + 0.2 * r * s, lambda r, s: -0.5 + 0.1 * r + 1.5 * s - 0.25 * r * s)):
+        x, y = so.gordonHall(fx(-1, zs), fx(1, zs), fx(zr, -1), fx(zr, 1), fy(-1, zs), fy(1, zs), fy(zr, -1), fy(zr, 1), zr, zs)
+        assert np.max(np.abs(x - fx(R, S))) < 1e-13 and np.max(np.abs(y - fy(R, S))) < 1e-13
+    # the literal reference form does not reproduce the identity map (the flagged deviation)
+    x, _ = so.gordonHall(-1 + 0 * zs, 1 + 0 * zs, zr, zr, zs, zs, -1 + 0 * zr, 1 + 0 * zr, zr, zs, as_written=True)
+    assert np.max(np.abs(x - R)) > 0.1
+
+
+def test_explicit_argument_forms_match_the_mesh_forms():
+    """lapl(u,M,Jr,Js,QQtx,QQty,...) lapl.jl:54-68 and mass(u,M,B,Jr,Js,QQtx,QQty,mult) mass.jl:32-50 with `[]` for
+    Jr, Js (examples/p2d_explicit.jl:183-188) are mask(gs(lapl(u,msh))) / mask(gs(mass(u,msh)))."""
+    m = so.make_mesh(6, 6, 3, 2, (False, True), so.wavy)
+    M = so.generateMask(list("DDNN"), m).astype(np.float64)
+    u = so.splitmix_uniform(m.x.shape, seed=9)
+    a = so.lapl_explicit(u, M, [], [], m.QQtx, m.QQty, m.Dr, m.Ds, m.G11, m.G12, m.G22, m.mult)
+    b = so.mask(so.gatherScatter(so.lapl(u, m), m), M)
+    assert np.array_equal(a, b)
+    a = so.mass_explicit(u, M, m.B, [], [], m.QQtx, m.QQty, m.mult)
+    assert np.array_equal(a, so.mask(so.gatherScatter(so.mass(u, m), m), M))
+    # dealiased: on the affine box mesh the integrand has degree 8 per direction, so every finer GLL rule with
+    # 2n-3 >= 8 integrates it exactly: over-integration on 8 and on 11 points agree (and differ from the 5-point rule)
+    mb, md, me = so.make_mesh(5, 5, 2, 2), so.make_mesh(8, 8, 2, 2), so.make_mesh(11, 11, 2, 2)
+    ub = so.splitmix_uniform(mb.x.shape, seed=10)
+    dea = [so.laplace_dealias(ub, so.interpMat(q.zr, mb.zr), so.interpMat(q.zs, mb.zs), mb.Dr, mb.Ds, q.G11, q.G12, q.G22)
+           for q in (md, me)]
+    assert np.max(np.abs(dea[0] - dea[1])) < 1e-11 * np.max(np.abs(dea[0]))
+    assert np.max(np.abs(dea[0] - so.laplace(ub, mb.Dr, mb.Ds, mb.G11, mb.G12, mb.G22))) > 1e-3
