@@ -313,6 +313,14 @@ static int mesh_build_plan(semb_mesh* m) {
   // derivative matrices on symmetric nodes are centro-antisymmetric: the even-odd kernel variant applies
   m->eo = m->fast && semb_strip_defect(m->nr, m->hDr.data(), m->hDs.data()) < 1e-12 && !getenv("SEMB_NO_EVENODD");
   m->nstrips = (m->Ex + m->bx - 1) / m->bx;
+  if (m->fast) {  // balanced strips (semb_strip_e0): the fewest strips whose widest member still fits the CTA
+    for (;; ++m->nstrips) {
+      int widest = 0;
+      for (int s = 0; s < m->nstrips; ++s)
+        widest = std::max(widest, semb_strip_e0(s + 1, m->nstrips, m->Ex, m->nr) - semb_strip_e0(s, m->nstrips, m->Ex, m->nr));
+      if (widest <= m->bx) break;
+    }
+  }
   int occ = 1;
   if (m->fast) SEMB_TRY(semb_strip_regs(m->nr, false, false, nullptr, nullptr, &occ));
   if (occ < 1) occ = 1;
@@ -355,8 +363,9 @@ static int mesh_build_plan(semb_mesh* m) {
   m->h_ystart[m->ney] = (m->halo_hi || wrap_local) ? 1 : 0;
   std::vector<int> xs, ys;
   for (int s = 1; s < m->nstrips; ++s) {
-    xs.push_back(s * m->bx * m->nr - 1);
-    xs.push_back(s * m->bx * m->nr);
+    const int e = m->fast ? semb_strip_e0(s, m->nstrips, m->Ex, m->nr) : s * m->bx;
+    xs.push_back(e * m->nr - 1);
+    xs.push_back(e * m->nr);
   }
   if (m->perx) {
     xs.push_back(m->nxl - 1);

@@ -22,6 +22,15 @@ constexpr int semb_strip_threads(int n) { return (n >= 12 && n <= 14) ? 192 : (n
 constexpr int semb_strip_bx(int n) {
   return ((semb_strip_threads(n) / n) * n) % 2 == 0 ? semb_strip_threads(n) / n : semb_strip_threads(n) / n - 1;
 }
+// First element of strip s when Ex elements are dealt to nstrips strips of (nearly) equal width: every CTA of a wave
+// then streams the same number of bytes (a fixed width of BX leaves a narrow last strip and BX-wide critical paths).
+// For odd N the start is rounded down to an even element so that x0 = e0*N doubles stays 16-byte aligned (bulk copies).
+__host__ __device__ inline int semb_strip_e0(int s, int nstrips, int Ex, int N) {
+  if (s >= nstrips) return Ex;
+  int e = (int)((long long)s * Ex / nstrips);
+  if (N & 1) e &= ~1;
+  return e;
+}
 #define SEMB_MAX_RANKS 16
 
 void semb_set_error(const char* fmt, ...);

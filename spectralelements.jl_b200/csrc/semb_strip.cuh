@@ -200,8 +200,8 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
   const int colB = eB * S + iB;
   const int jA = t / BX, eA = t - jA * BX;      // mapping A: row / element of this thread's x-line
   const int colA = jA * PW + eA * S;
-  const int e0 = blockIdx.x * BX;
-  const int nbe = min(BX, a.Ex - e0);
+  const int e0 = semb_strip_e0(blockIdx.x, gridDim.x, a.Ex, N);   // balanced strips (plan: mesh_build_plan)
+  const int nbe = semb_strip_e0(blockIdx.x + 1, gridDim.x, a.Ex, N) - e0;
   const bool actB = eB < nbe;                   // (eB < BX is implied: nbe <= BX)
   const bool inB = t < BX * N;                  // threads BX*N..T-1 own no column (T need not divide by N)
   const bool actA = (jA < N) && (eA < nbe);
