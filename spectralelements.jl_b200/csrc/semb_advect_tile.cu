@@ -11,18 +11,30 @@
 // (as in the strip kernel, semb_strip.cuh), exchanging lines through shared memory tiles [row][e*S + i], S odd:
 //   C (y-lines): thread c <-> column (e,i) of the batch: coalesced global loads/stores, Ds / Js / Js' contractions
 //   R (x-lines): thread p <-> (row, e):                                               Dr / Jr / Jr' contractions
+// All inputs are staged into shared memory with cp.async one pass / one batch AHEAD (issued right after the barrier that
+// retires the last read of their buffer), so HBM latency overlaps the contractions of the current pass.
 // Phases per batch (one __syncthreads between them):
-//   1 C: load T column, us = Ds*T, T -> tile            2 R: ur = Dr*T in place
+//   1 C: T column from the staged tile, us = Ds*T       2 R: ur = Dr*T in place
 //   3 C: Tx,Ty from ur,us and the metric terms; y-interpolation (Js) of Tx,Ty,ux,uy -> 4 tiles of M rows
 //   4 R: x-interpolation (Jr) of the 4 rows, pointwise product with B_D, x-projection (Jr') -> tile (in place)
 //   5 C: y-projection (Js'), coalesced store of Cu
+//
+// The kernel is bound by shared-memory wavefronts, not by FP64 issue or HBM (profiles/r01_advtile_r1h.txt: a broadcast
+// table load per FMA), so the contractions are organised to need as few table loads as possible:
+//   * even-odd: GLL interpolation matrices are centro-symmetric (J(M-1-m,N-1-k) = J(m,k)) and derivative matrices
+//     centro-antisymmetric, so y = A x splits into two half-size products on e_k = x_k + x_{N-1-k}, o_k = x_k - x_{N-1-k}
+//     (half the FMAs and half the table loads; same idea as StripTab in semb_strip.cuh, here for rectangular A);
+//   * pairing: two lines that take the same matrix (Tx,Ty / ux,uy) are contracted together, one table load feeds both.
+// The host launches this kernel only when the matrices pass the symmetry test (mesh `eo` flag; the J's are built by the
+// library from GLL nodes).
+//
 // The two interpolation directions commute exactly in exact arithmetic; the reference applies Jr first (ABu.jl:14-33),
 // here Js is applied first (the column mapping already holds the y-lines): results agree to rounding (~1e-16
 // relative), well inside the 1e-12 contract.  The projection is applied in the reference's order (Jr' then Js').
 //
 // Several T's that share the advecting velocity (makeRHS!: exH[i] = -advect(uh[i],vx,vy,...) for i = 1..k,
-// convectionDiffusion.jl:100-105) are processed in ONE launch: ux,uy,B_D are loaded and Jux,Juy interpolated once
-// per batch (kept in registers by the R mapping), each T then costs T + Cu of HBM traffic.
+// convectionDiffusion.jl:100-105) are processed in ONE launch: ux,uy,B_D and the metric terms are loaded and Jux,Juy
+// interpolated once per batch, each T then costs T + Cu of HBM traffic.
 #include "semb_vec.cuh"
 
 namespace {
@@ -40,18 +52,121 @@ struct AdvTileArgs {
   int nT, Ex, ney;
 };
 
+// Even-odd tables of A (NO x NI) with A(NO-1-m, NI-1-k) = SG * A(m,k), SG = +1 (interpolation) or -1 (derivative):
+//   s_m = (y_m + SG y_{NO-1-m})/2 = sum_{k<HI} P(m,k) e_k + [NI odd] A(m,c) x_c,   P = (A(m,k) + A(m,NI-1-k))/2
+//   d_m = (y_m - SG y_{NO-1-m})/2 = sum_{k<HI} Q(m,k) o_k,                          Q = (A(m,k) - A(m,NI-1-k))/2
+//   y_m = s_m + d_m,  y_{NO-1-m} = SG (s_m - d_m);  the middle output row (NO odd) lives in s (SG = +1) or d (SG = -1).
+// Layout: P[k][m], k < HI + (NI odd), m < NS, rows padded to LS (even: LDS.128); then Q[k][m], k < HI, m < ND, rows LQ.
+template <int NI, int NO, int SG>
+struct EoTab {
+  static constexpr int HI = NI / 2, OI = NI & 1, HO = NO / 2, OO = NO & 1;
+  static constexpr int NS = HO + ((OO && SG > 0) ? 1 : 0);
+  static constexpr int ND = HO + ((OO && SG < 0) ? 1 : 0);
+  static constexpr int LS = (NS + 1) & ~1, LQ = (ND + 1) & ~1;
+  static constexpr int KP = HI + OI;
+  static constexpr int OFFQ = KP * LS;
+  static constexpr int SIZE = OFFQ + HI * LQ;
+  // fill cooperatively; A(m,k) = getA(m, k)
+  template <typename F>
+  static __device__ void fill(double* T, int tid, int nt, F getA) {
+    for (int q = tid; q < KP * LS; q += nt) {
+      const int k = q / LS, m = q - k * LS;
+      double v = 0.0;
+      if (m < NS) v = k < HI ? 0.5 * (getA(m, k) + getA(m, NI - 1 - k)) : getA(m, HI);
+      T[q] = v;
+    }
+    for (int q = tid; q < HI * LQ; q += nt) {
+      const int k = q / LQ, m = q - k * LQ;
+      T[OFFQ + q] = m < ND ? 0.5 * (getA(m, k) - getA(m, NI - 1 - k)) : 0.0;
+    }
+  }
+};
+
+// y[v] = A x[v] for NV lines at once (NV = 1 or 2: one table load feeds all lines); T = EoTab<NI,NO,SG> in shared memory
+template <int NI, int NO, int SG, int NV>
+__device__ __forceinline__ void eo_contract(const double* __restrict__ T, const double (&x)[NV][NI], double (&y)[NV][NO]) {
+  using E = EoTab<NI, NO, SG>;
+  constexpr int HI = E::HI, OI = E::OI, HO = E::HO, LS = E::LS, LQ = E::LQ;
+  constexpr int NS2 = E::LS / 2, ND2 = E::LQ / 2;
+  double2 s[NV][NS2 > 0 ? NS2 : 1], d[NV][ND2 > 0 ? ND2 : 1];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+#pragma unroll
+    for (int m = 0; m < NS2; ++m) s[v][m] = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int m = 0; m < ND2; ++m) d[v][m] = make_double2(0.0, 0.0);
+  }
+#pragma unroll
+  for (int k = 0; k < HI; ++k) {
+    double e[NV], o[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      e[v] = x[v][k] + x[v][NI - 1 - k];
+      o[v] = x[v][k] - x[v][NI - 1 - k];
+    }
+    const double2* P = reinterpret_cast<const double2*>(T + k * LS);
+#pragma unroll
+    for (int m = 0; m < NS2; ++m) {
+      const double2 p = P[m];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        s[v][m].x = fma(p.x, e[v], s[v][m].x);
+        s[v][m].y = fma(p.y, e[v], s[v][m].y);
+      }
+    }
+    const double2* Q = reinterpret_cast<const double2*>(T + E::OFFQ + k * LQ);
+#pragma unroll
+    for (int m = 0; m < ND2; ++m) {
+      const double2 q = Q[m];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        d[v][m].x = fma(q.x, o[v], d[v][m].x);
+        d[v][m].y = fma(q.y, o[v], d[v][m].y);
+      }
+    }
+  }
+  if (OI) {  // middle input
+    const double2* P = reinterpret_cast<const double2*>(T + HI * LS);
+#pragma unroll
+    for (int m = 0; m < NS2; ++m) {
+      const double2 p = P[m];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        s[v][m].x = fma(p.x, x[v][HI], s[v][m].x);
+        s[v][m].y = fma(p.y, x[v][HI], s[v][m].y);
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+#pragma unroll
+    for (int m = 0; m < HO; ++m) {
+      const double sm = (m & 1) ? s[v][m >> 1].y : s[v][m >> 1].x;
+      const double dm = (m & 1) ? d[v][m >> 1].y : d[v][m >> 1].x;
+      y[v][m] = sm + dm;
+      y[v][NO - 1 - m] = SG > 0 ? sm - dm : dm - sm;
+    }
+    if (NO & 1) {
+      if (SG > 0) y[v][HO] = (HO & 1) ? s[v][HO >> 1].y : s[v][HO >> 1].x;
+      else y[v][HO] = (HO & 1) ? d[v][HO >> 1].y : d[v][HO >> 1].x;
+    }
+  }
+}
+
 template <int N, int M>
 struct AdvCfg {
   static constexpr int EB = ADV_T / M;   // elements per batch
   static constexpr int S = N | 1;        // element stride inside a tile row (odd: both mappings conflict-free)
-  static constexpr int SD = M | 1;       // same for the B_D tile
+  static constexpr int SD = M | 1;       // same for the D-grid tiles
   static constexpr int PV = EB * S, PD = EB * SD;
-  static constexpr int NP = N + (N & 1), MP = M + (M & 1);  // table rows padded to even (LDS.128)
-  // tables [k][o]: Dr, Ds (N x NP), Jr, Js (N x MP), Jr', Js' (M x NP)
-  static constexpr int OFF_DR = 0, OFF_DS = N * NP, OFF_JR = 2 * N * NP, OFF_JS = OFF_JR + N * MP,
-                       OFF_JRT = OFF_JS + N * MP, OFF_JST = OFF_JRT + M * NP, TAB = OFF_JST + M * NP;
-  static constexpr int OFF_ST = TAB;                   // [N][PV]    T -> ur
-  static constexpr int OFF_TF = OFF_ST + N * PV;       // [2][M][PV] y-interpolated Tx, Ty; [0] reused for Jr' JCu
+  using TD = EoTab<N, N, -1>;   // Dr, Ds
+  using TJ = EoTab<N, M, +1>;   // Jr, Js
+  using TP = EoTab<M, N, +1>;   // Jr', Js'
+  static constexpr int OFF_DR = 0, OFF_DS = TD::SIZE, OFF_JR = 2 * TD::SIZE, OFF_JS = OFF_JR + TJ::SIZE,
+                       OFF_JRT = OFF_JS + TJ::SIZE, OFF_JST = OFF_JRT + TP::SIZE, TAB = (OFF_JST + TP::SIZE + 1) & ~1;
+  static constexpr int OFF_ST = TAB;                   // [N][PV]    T (staged by cp.async) -> ur
+  static constexpr int OFF_IN = OFF_ST + N * PV;       // [6][N][PV] staged ux, uy, rx, ry, sx, sy of the batch
+  static constexpr int OFF_TF = OFF_IN + 6 * N * PV;   // [2][M][PV] y-interpolated Tx, Ty; [0] reused for Jr' JCu
   static constexpr int OFF_TU = OFF_TF + 2 * M * PV;   // [2][M][PD] y-interpolated ux, uy (N per element), then Jux, Juy (M per
                                                        // element) written in place by the row's owner thread
   static constexpr int OFF_BD = OFF_TU + 2 * M * PD;   // [M][PD]
@@ -61,265 +176,200 @@ struct AdvCfg {
   static constexpr int OCC = OCC0 < 1 ? 1 : (OCC0 > 4 ? 4 : OCC0);
 };
 
-// y[o] = sum_k T[k*LD + o] * x[k], o < NO; T in shared memory, rows 16-byte aligned (LD even): broadcast LDS.128
-template <int NI, int NO, int LD>
-__device__ __forceinline__ void adv_contract(const double* __restrict__ T, const double (&x)[NI], double (&y)[NO]) {
-  constexpr int NO2 = (NO + 1) / 2;
-  double2 acc[NO2];
-#pragma unroll
-  for (int k = 0; k < NI; ++k) {
-    const double2* row = reinterpret_cast<const double2*>(T + k * LD);
-#pragma unroll
-    for (int o = 0; o < NO2; ++o) {
-      const double2 t = row[o];
-      if (k == 0) {
-        acc[o].x = t.x * x[0];
-        acc[o].y = t.y * x[0];
-      } else {
-        acc[o].x = fma(t.x, x[k], acc[o].x);
-        acc[o].y = fma(t.y, x[k], acc[o].y);
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 0; o < NO; ++o) y[o] = (o & 1) ? acc[o >> 1].y : acc[o >> 1].x;
-}
-
-// y[o] = sum_k T[k*LD + O0 + o] * x[k], o < NO (O0 even)
-template <int NI, int O0, int NO, int LD>
-__device__ __forceinline__ void adv_contract_part(const double* __restrict__ T, const double (&x)[NI], double (&y)[NO]) {
-  constexpr int NO2 = (NO + 1) / 2;
-  double2 acc[NO2];
-#pragma unroll
-  for (int k = 0; k < NI; ++k) {
-    const double2* row = reinterpret_cast<const double2*>(T + k * LD + O0);
-#pragma unroll
-    for (int o = 0; o < NO2; ++o) {
-      const double2 t = row[o];
-      if (k == 0) {
-        acc[o].x = t.x * x[0];
-        acc[o].y = t.y * x[0];
-      } else {
-        acc[o].x = fma(t.x, x[k], acc[o].x);
-        acc[o].y = fma(t.y, x[k], acc[o].y);
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 0; o < NO; ++o) y[o] = (o & 1) ? acc[o >> 1].y : acc[o >> 1].x;
-}
-
-// outputs m in [O0, O0+NO) of one dealiasing-grid row: interpolate, multiply, and add their share of the Jr' projection
-template <int N, int M, int O0, int NO>
-__device__ __forceinline__ void adv_phase4_part(const double* sh, const double* rowF, const double* rowU, const double* rowB,
-                                                double (&pr)[N]) {
-  using C = AdvCfg<N, M>;
-  constexpr int PV = C::PV, PD = C::PD, MP = C::MP, NP = C::NP;
-  double xl[N], jt[NO], cu[NO];
-#pragma unroll
-  for (int i = 0; i < N; ++i) xl[i] = rowF[i];
-  adv_contract_part<N, O0, NO, MP>(sh + C::OFF_JR, xl, jt);
-#pragma unroll
-  for (int o = 0; o < NO; ++o) cu[o] = __dmul_rn(rowU[O0 + o], jt[o]);
-#pragma unroll
-  for (int i = 0; i < N; ++i) xl[i] = rowF[M * PV + i];
-  adv_contract_part<N, O0, NO, MP>(sh + C::OFF_JR, xl, jt);
-#pragma unroll
-  for (int o = 0; o < NO; ++o)
-    cu[o] = __dmul_rn(__dadd_rn(cu[o], __dmul_rn(rowU[M * PD + O0 + o], jt[o])), rowB[O0 + o]);
-  // pr[i] += sum_o Jr(O0+o, i) * cu[o]
-#pragma unroll
-  for (int o = 0; o < NO; ++o) {
-    const double2* row = reinterpret_cast<const double2*>(sh + C::OFF_JRT + (O0 + o) * NP);
-#pragma unroll
-    for (int i2 = 0; i2 < (N + 1) / 2; ++i2) {
-      const double2 t = row[i2];
-      pr[2 * i2] = fma(t.x, cu[o], pr[2 * i2]);
-      if (2 * i2 + 1 < N) pr[2 * i2 + 1] = fma(t.y, cu[o], pr[2 * i2 + 1]);
-    }
-  }
-}
-
-// x-interpolation of one velocity row in place: N values -> M values in the same SD-wide slot
-template <int N, int M>
-__device__ __forceinline__ void adv_interp_row_inplace(const double* sh, double* row) {
-  using C = AdvCfg<N, M>;
-  constexpr int MP = C::MP;
-  constexpr int H0 = ((M + 1) / 2 + 1) & ~1;
-  constexpr int NA = H0 < M ? H0 : M;
-  double xl[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i) xl[i] = row[i];
-  {
-    double y[NA];
-    adv_contract_part<N, 0, NA, MP>(sh + C::OFF_JR, xl, y);
-#pragma unroll
-    for (int o = 0; o < NA; ++o) row[o] = y[o];
-  }
-  if constexpr (H0 < M) {
-    double y[M - H0];
-    adv_contract_part<N, H0, M - H0, MP>(sh + C::OFF_JR, xl, y);
-#pragma unroll
-    for (int o = 0; o < M - H0; ++o) row[H0 + o] = y[o];
-  }
-}
-
 template <int N, int M>
 __global__ void __launch_bounds__(ADV_T, AdvCfg<N, M>::OCC) semb_advect_tile_kernel(const AdvTileArgs a) {
   using C = AdvCfg<N, M>;
-  constexpr int EB = C::EB, S = C::S, SD = C::SD, PV = C::PV, PD = C::PD, NP = C::NP, MP = C::MP;
+  constexpr int EB = C::EB, S = C::S, SD = C::SD, PV = C::PV, PD = C::PD;
   extern __shared__ __align__(16) double sh[];
   double* sT = sh + C::OFF_ST;
+  double* sIn = sh + C::OFF_IN;
   double* tF = sh + C::OFF_TF;
   double* tU = sh + C::OFF_TU;
   double* sBD = sh + C::OFF_BD;
   const int t = threadIdx.x;
-  // tables
-  for (int q = t; q < N * NP; q += ADV_T) {
-    const int k = q / NP, i = q - k * NP;
-    sh[C::OFF_DR + q] = i < N ? a.Dr[i * N + k] : 0.0;
-    sh[C::OFF_DS + q] = i < N ? a.Ds[i * N + k] : 0.0;
-  }
-  for (int q = t; q < N * MP; q += ADV_T) {
-    const int k = q / MP, m = q - k * MP;
-    sh[C::OFF_JR + q] = m < M ? a.Jr[m + k * M] : 0.0;
-    sh[C::OFF_JS + q] = m < M ? a.Js[m + k * M] : 0.0;
-  }
-  for (int q = t; q < M * NP; q += ADV_T) {
-    const int m = q / NP, i = q - m * NP;
-    sh[C::OFF_JRT + q] = i < N ? a.Jr[m + i * M] : 0.0;
-    sh[C::OFF_JST + q] = i < N ? a.Js[m + i * M] : 0.0;
-  }
+  // even-odd tables (a.Dr: row-major D(i,k) = Dr[i*N+k]; a.Jr: column-major J(m,i) = Jr[m + i*M])
+  C::TD::fill(sh + C::OFF_DR, t, ADV_T, [&](int i, int k) { return a.Dr[i * N + k]; });
+  C::TD::fill(sh + C::OFF_DS, t, ADV_T, [&](int i, int k) { return a.Ds[i * N + k]; });
+  C::TJ::fill(sh + C::OFF_JR, t, ADV_T, [&](int m, int i) { return a.Jr[m + i * M]; });
+  C::TJ::fill(sh + C::OFF_JS, t, ADV_T, [&](int m, int i) { return a.Js[m + i * M]; });
+  C::TP::fill(sh + C::OFF_JRT, t, ADV_T, [&](int i, int m) { return a.Jr[m + i * M]; });
+  C::TP::fill(sh + C::OFF_JST, t, ADV_T, [&](int i, int m) { return a.Js[m + i * M]; });
   // mapping C: column (eC, iC); mapping R on the V rows: (jR, eR); on the D rows: (nR, eD)
   const int eC = t / N, iC = t - eC * N, colC = eC * S + iC;
   const int jR = t / EB, eR = t - jR * EB;  // jR < N valid for phase 2, jR < M for phase 4 (same split, EB*M <= 128)
   const int nbx = (a.Ex + EB - 1) / EB;
   const int nbatch = nbx * a.ney;
+  // ---- asynchronous staging (cp.async, 8-byte granules: any strip alignment): the inputs of the NEXT pass / batch are
+  // issued as soon as the barrier that retires the last read of their buffer has passed, and land while the current
+  // pass computes; each column-owner thread copies its own column, so the global side is coalesced ----------------------
+  auto cp8 = [](double* dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+                 : "memory");
+  };
+  auto batch_of = [&](int b, int* r, int* e0, int* nbe) {
+    *r = b / nbx;
+    *e0 = (b - *r * nbx) * EB;
+    *nbe = min(EB, a.Ex - *e0);
+  };
+  auto issue_T = [&](int b, int it) {
+    int r, e0, nbe;
+    batch_of(b, &r, &e0, &nbe);
+    if (t < nbe * N) {
+      const double* src = a.T[it] + (size_t)r * N * a.pitchV + (size_t)e0 * N + t;
+#pragma unroll
+      for (int j = 0; j < N; ++j) cp8(sT + j * PV + colC, src + (size_t)j * a.pitchV);
+    }
+  };
+  auto issue_inputs = [&](int b) {
+    int r, e0, nbe;
+    batch_of(b, &r, &e0, &nbe);
+    if (t < nbe * N) {
+      const size_t g = (size_t)r * N * a.pitchV + (size_t)e0 * N + t;
+#pragma unroll
+      for (int f = 0; f < 6; ++f) {
+        const double* src = (f == 0 ? a.ux : f == 1 ? a.uy : f == 2 ? a.rx : f == 3 ? a.ry : f == 4 ? a.sx : a.sy) + g;
+#pragma unroll
+        for (int j = 0; j < N; ++j) cp8(sIn + (f * N + j) * PV + colC, src + (size_t)j * a.pitchV);
+      }
+    }
+  };
+  auto issue_BD = [&](int b) {
+    int r, e0, nbe;
+    batch_of(b, &r, &e0, &nbe);
+    for (int q = t; q < M * nbe * M; q += ADV_T) {
+      const int n = q / (nbe * M), xx = q - n * (nbe * M), e = xx / M, m = xx - e * M;
+      cp8(sBD + n * PD + e * SD + m, a.BD + (size_t)(r * M + n) * a.pitchD + (size_t)e0 * M + xx);
+    }
+  };
+  if ((int)blockIdx.x < nbatch) {
+    issue_T(blockIdx.x, 0);
+    issue_inputs(blockIdx.x);
+    issue_BD(blockIdx.x);
+  }
   for (int b = blockIdx.x; b < nbatch; b += gridDim.x) {
-    const int r = b / nbx, e0 = (b - r * nbx) * EB;
-    const int nbe = min(EB, a.Ex - e0);
+    int r, e0, nbe;
+    batch_of(b, &r, &e0, &nbe);
     const bool actC = t < nbe * N;
     const bool actR2 = jR < N && eR < nbe;
     const bool actR4 = jR < M && eR < nbe;
     const size_t gV = (size_t)r * N * a.pitchV + (size_t)e0 * N + t;  // + j*pitchV: this thread's column on mshV
-    __syncthreads();  // previous batch done with every tile (and the tables are in place)
-    // L2 prefetch of the next batch's inputs (128-byte lines): the phases below then wait on L2, not on HBM
-    if (b + (int)gridDim.x < nbatch) {
-      const int b2 = b + gridDim.x, r2 = b2 / nbx, f0 = (b2 - r2 * nbx) * EB, nb2 = min(EB, a.Ex - f0);
-      const int lv = (nb2 * N * 8 + 127) / 128 + 1, ld = (nb2 * M * 8 + 127) / 128 + 1;  // lines per row (+1: misalignment)
-      const int nV = (6 + a.nT) * N * lv, nD = M * ld;
-      for (int q = t; q < nV + nD; q += ADV_T) {
-        const char* p;
-        bool ok;  // stay inside the (padded) row
-        if (q < nV) {
-          const int f = q / (N * lv), rem = q - f * (N * lv), j = rem / lv, l = rem - j * lv;
-          const double* base = f == 0 ? a.ux : f == 1 ? a.uy : f == 2 ? a.rx : f == 3 ? a.ry : f == 4 ? a.sx : f == 5 ? a.sy
-                                                                                                             : a.T[f - 6];
-          p = (const char*)(base + (size_t)(r2 * N + j) * a.pitchV + (size_t)f0 * N) + l * 128;
-          ok = (long long)f0 * N * 8 + l * 128 < a.pitchV * 8;
-        } else {
-          const int rem = q - nV, n = rem / ld, l = rem - n * ld;
-          p = (const char*)(a.BD + (size_t)(r2 * M + n) * a.pitchD + (size_t)f0 * M) + l * 128;
-          ok = (long long)f0 * M * 8 + l * 128 < a.pitchD * 8;
-        }
-        if (ok) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-      }
-    }
-    // B_D tile of the batch: rows r*M+n, columns e0*M .. e0*M + nbe*M (coalesced), consumed in phase 4
-    for (int q = t; q < M * nbe * M; q += ADV_T) {
-      const int n = q / (nbe * M), xx = q - n * (nbe * M), e = xx / M, m = xx - e * M;
-      sBD[n * PD + e * SD + m] = a.BD[(size_t)(r * M + n) * a.pitchD + (size_t)e0 * M + xx];
-    }
+    const int bnext = b + gridDim.x;
 #pragma unroll 1
     for (int it = 0; it < a.nT; ++it) {
-      const double* __restrict__ Tg = a.T[it];
-      double us[N];
-      // ---- phase 1 (C): T column -> registers and tile; us = Ds * T -------------------------------------------------
+      const bool last = it + 1 == a.nT;
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncthreads();  // staged T (and, for the first T, the batch inputs) visible; the tables are in place;
+                        // the previous pass is done with tF
+      double us[1][N];
+      // ---- phase 1 (C): T column -> registers; us = Ds * T --------------------------------------------------------------
       if (actC) {
-        double tc[N];
+        double tc[1][N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) tc[j] = Tg[gV + (size_t)j * a.pitchV];
-#pragma unroll
-        for (int j = 0; j < N; ++j) sT[j * PV + colC] = tc[j];
-        adv_contract<N, N, NP>(sh + C::OFF_DS, tc, us);
+        for (int j = 0; j < N; ++j) tc[0][j] = sT[j * PV + colC];
+        eo_contract<N, N, -1, 1>(sh + C::OFF_DS, tc, us);
       }
       __syncthreads();
       // ---- phase 2 (R): ur = Dr * T along x, in place ---------------------------------------------------------------
       if (actR2) {
-        double xl[N], ur[N];
+        double xl[1][N], ur[1][N];
         double* row = sT + jR * PV + eR * S;
 #pragma unroll
-        for (int i = 0; i < N; ++i) xl[i] = row[i];
-        adv_contract<N, N, NP>(sh + C::OFF_DR, xl, ur);
+        for (int i = 0; i < N; ++i) xl[0][i] = row[i];
+        eo_contract<N, N, -1, 1>(sh + C::OFF_DR, xl, ur);
 #pragma unroll
-        for (int i = 0; i < N; ++i) row[i] = ur[i];
+        for (int i = 0; i < N; ++i) row[i] = ur[0][i];
       }
       __syncthreads();
-      // ---- phase 3 (C): Tx, Ty (grad.jl:30-31), y-interpolation of Tx, Ty (and ux, uy for the first T) ----------------
+      // ---- phase 3 (C): Tx, Ty (grad.jl:30-31), y-interpolation of the pair Tx, Ty (and ux, uy for the first T) -----------
       if (actC) {
-        // one field per trip (not unrolled: bounds the loads in flight and the live registers)
-        const int nf = it == 0 ? 4 : 2;
-#pragma unroll 1
-        for (int f = 0; f < nf; ++f) {
-          double xc[N], o[M];
-          if (f < 2) {
-            const double* __restrict__ ca = f == 0 ? a.rx : a.ry;
-            const double* __restrict__ cb = f == 0 ? a.sx : a.sy;
+        {
+          double xc[2][N], o[2][M];
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-              const size_t g = gV + (size_t)j * a.pitchV;
-              xc[j] = __dadd_rn(__dmul_rn(ca[g], sT[j * PV + colC]), __dmul_rn(cb[g], us[j]));
-            }
-          } else {
-            const double* __restrict__ src = f == 2 ? a.ux : a.uy;
-#pragma unroll
-            for (int j = 0; j < N; ++j) xc[j] = src[gV + (size_t)j * a.pitchV];
+          for (int j = 0; j < N; ++j) {
+            const int q = j * PV + colC;
+            const double ur = sT[q];
+            xc[0][j] = __dadd_rn(__dmul_rn(sIn[2 * N * PV + q], ur), __dmul_rn(sIn[4 * N * PV + q], us[0][j]));  // rx, sx
+            xc[1][j] = __dadd_rn(__dmul_rn(sIn[3 * N * PV + q], ur), __dmul_rn(sIn[5 * N * PV + q], us[0][j]));  // ry, sy
           }
-          adv_contract<N, M, MP>(sh + C::OFF_JS, xc, o);
-          if (f < 2) {
-            double* dst = tF + f * M * PV + colC;
+          eo_contract<N, M, +1, 2>(sh + C::OFF_JS, xc, o);
 #pragma unroll
-            for (int n = 0; n < M; ++n) dst[n * PV] = o[n];
-          } else {
-            double* dst = tU + (f - 2) * M * PD + eC * SD + iC;
+          for (int n = 0; n < M; ++n) {
+            tF[n * PV + colC] = o[0][n];
+            tF[(M + n) * PV + colC] = o[1][n];
+          }
+        }
+        if (it == 0) {
+          double xc[2][N], o[2][M];
 #pragma unroll
-            for (int n = 0; n < M; ++n) dst[n * PD] = o[n];
+          for (int j = 0; j < N; ++j) {
+            xc[0][j] = sIn[j * PV + colC];        // ux
+            xc[1][j] = sIn[(N + j) * PV + colC];  // uy
+          }
+          eo_contract<N, M, +1, 2>(sh + C::OFF_JS, xc, o);
+          double* dst = tU + eC * SD + iC;
+#pragma unroll
+          for (int n = 0; n < M; ++n) {
+            dst[n * PD] = o[0][n];
+            dst[(M + n) * PD] = o[1][n];
           }
         }
       }
       __syncthreads();
+      // sT is free (and, after the last T, the staged inputs): start the copies of the next pass
+      if (!last) {
+        issue_T(b, it + 1);
+      } else if (bnext < nbatch) {
+        issue_T(bnext, 0);
+        issue_inputs(bnext);
+      }
       // ---- phase 4 (R): x-interpolation, JCu = (Jux.*JTx + Juy.*JTy).*B_D (advect.jl:59-60), x-projection Jr' -----------
-      // done in two halves of the M outputs to bound the live registers (a double is two registers)
       if (actR4) {
-        double pr[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) pr[i] = 0.0;
-        const double* rowF = tF + jR * PV + eR * S;
+        double* rowF = tF + jR * PV + eR * S;
         double* rowU = tU + jR * PD + eR * SD;
         const double* rowB = sBD + jR * PD + eR * SD;
-        if (it == 0) {  // Jux, Juy of the batch, shared by all T's
-          adv_interp_row_inplace<N, M>(sh, rowU);
-          adv_interp_row_inplace<N, M>(sh, rowU + M * PD);
-        }
-        constexpr int H0 = ((M + 1) / 2 + 1) & ~1;  // even split point (LDS.128 alignment of the table rows)
-        adv_phase4_part<N, M, 0, (H0 < M ? H0 : M)>(sh, rowF, rowU, rowB, pr);
-        if constexpr (H0 < M) adv_phase4_part<N, M, H0, M - H0>(sh, rowF, rowU, rowB, pr);
-        double* rowO = tF + jR * PV + eR * S;
+        if (it == 0) {  // Jux, Juy of the batch, shared by all T's: N values -> M values in the same SD-wide slot
+          double xl[2][N], ju[2][M];
 #pragma unroll
-        for (int i = 0; i < N; ++i) rowO[i] = pr[i];  // only this thread touches the row
+          for (int i = 0; i < N; ++i) {
+            xl[0][i] = rowU[i];
+            xl[1][i] = rowU[M * PD + i];
+          }
+          eo_contract<N, M, +1, 2>(sh + C::OFF_JR, xl, ju);
+#pragma unroll
+          for (int m = 0; m < M; ++m) {
+            rowU[m] = ju[0][m];
+            rowU[M * PD + m] = ju[1][m];
+          }
+        }
+        double cu[1][M], pr[1][N];
+        {
+          double xl[2][N], jt[2][M];
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            xl[0][i] = rowF[i];
+            xl[1][i] = rowF[M * PV + i];
+          }
+          eo_contract<N, M, +1, 2>(sh + C::OFF_JR, xl, jt);
+#pragma unroll
+          for (int m = 0; m < M; ++m)
+            cu[0][m] = __dmul_rn(__dadd_rn(__dmul_rn(rowU[m], jt[0][m]), __dmul_rn(rowU[M * PD + m], jt[1][m])), rowB[m]);
+        }
+        eo_contract<M, N, +1, 1>(sh + C::OFF_JRT, cu, pr);
+#pragma unroll
+        for (int i = 0; i < N; ++i) rowF[i] = pr[0][i];  // only this thread touches the row
       }
       __syncthreads();
+      if (last && bnext < nbatch) issue_BD(bnext);  // the B_D tile is free
       // ---- phase 5 (C): y-projection Js', store Cu ---------------------------------------------------------------------
       if (actC) {
-        double cl[M], cu[N];
+        double cl[1][M], cu[1][N];
 #pragma unroll
-        for (int n = 0; n < M; ++n) cl[n] = tF[n * PV + colC];
-        adv_contract<M, N, NP>(sh + C::OFF_JST, cl, cu);
+        for (int n = 0; n < M; ++n) cl[0][n] = tF[n * PV + colC];
+        eo_contract<M, N, +1, 1>(sh + C::OFF_JST, cl, cu);
         double* __restrict__ og = a.out[it];
 #pragma unroll
-        for (int j = 0; j < N; ++j) og[gV + (size_t)j * a.pitchV] = cu[j];
+        for (int j = 0; j < N; ++j) og[gV + (size_t)j * a.pitchV] = cu[0][j];
       }
-      // the next T's phase 1 writes sT (last read in phase 3) and its phase 3 writes tF after two more barriers
     }
   }
 }
@@ -355,10 +405,11 @@ int launch_tile(semb_ctx* ctx, const AdvTileArgs& a) {
 #endif
 
 // returns SEMB_OK and *done = 1 if the tiled kernel ran (nT <= 4 fields T[i] -> out[i]), *done = 0 if (N, M) is not served
+// or the mesh's derivative matrices are not centro-antisymmetric (V->eo; the J's are GLL interpolants, symmetric)
 int semb_launch_advect_tile(semb_ctx* ctx, semb_mesh* V, semb_mesh* D, int nT, const double* const* T, const double* ux,
                             const double* uy, const double* dJr, const double* dJs, double* const* out, int* done) {
   *done = 0;
-  if (V->nr != V->ns || D->nr != D->ns || nT < 1 || nT > ADV_MAXT) return SEMB_OK;
+  if (V->nr != V->ns || D->nr != D->ns || nT < 1 || nT > ADV_MAXT || !V->eo) return SEMB_OK;
   AdvTileArgs a;
   for (int i = 0; i < ADV_MAXT; ++i) {
     a.T[i] = i < nT ? T[i] : nullptr;
