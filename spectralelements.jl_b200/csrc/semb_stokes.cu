@@ -137,6 +137,47 @@ __global__ void semb_hinv_mid_kernel(const double* __restrict__ g, const double*
     }
 }
 
+// One-pass gatherScatter (gatherScatter.jl:8-21) of a single-rank field with a pointwise epilogue: every node adds its
+// x partner, then the (x-summed) y partner -- the reference's (a+b)+(c+d) association, bitwise equal to the two-pass
+// gs_x + seam_y form -- and applies  mode 0: nothing | 1: (M.*g).*Bi./b0 (diver.jl:96-98) | 2: M.*g (mask.jl:14).
+struct GsFusedArgs {
+  const double* u;
+  double* out;
+  const double* Bi;
+  double b0;
+  long long pitch;
+  int nr, ns, Ex, ney, nxl, nyl, perx, pery, mode, mx0, mx1, my0, my1;
+};
+__global__ void semb_gs_fused_kernel(const GsFusedArgs a) {
+  for (int row = blockIdx.y; row < a.nyl; row += gridDim.y) {
+    const int rl = row / a.ns, j = row - rl * a.ns;
+    int yp = -1;
+    if (j == a.ns - 1) yp = rl < a.ney - 1 ? row + 1 : (a.pery ? 0 : -1);
+    else if (j == 0) yp = rl > 0 ? row - 1 : (a.pery ? a.nyl - 1 : -1);
+    const double* ur = a.u + (size_t)row * a.pitch;
+    const double* up = a.u + (size_t)(yp < 0 ? row : yp) * a.pitch;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < a.nxl; x += gridDim.x * blockDim.x) {
+      const int e = x / a.nr, i = x - e * a.nr;
+      int xp = -1;
+      if (i == a.nr - 1) xp = e < a.Ex - 1 ? x + 1 : (a.perx ? 0 : -1);
+      else if (i == 0) xp = e > 0 ? x - 1 : (a.perx ? a.nxl - 1 : -1);
+      double g = ur[x];
+      if (xp >= 0) g = __dadd_rn(g, ur[xp]);
+      if (yp >= 0) {
+        double h = up[x];
+        if (xp >= 0) h = __dadd_rn(h, up[xp]);
+        g = __dadd_rn(g, h);
+      }
+      if (a.mode) {
+        const bool z = (x == 0 && a.mx0) || (x == a.nxl - 1 && a.mx1) || (row == 0 && a.my0) || (row == a.nyl - 1 && a.my1);
+        g = __dmul_rn(z ? 0.0 : 1.0, g);
+        if (a.mode == 1) g = __ddiv_rn(__dmul_rn(g, a.Bi[(size_t)row * a.pitch + x]), a.b0);
+      }
+      a.out[(size_t)row * a.pitch + x] = g;
+    }
+  }
+}
+
 int local_launch_cfg(semb_ctx* ctx, semb_mesh* m, int ntiles, StokesLocalArgs* a, size_t* smem, int* grid) {
   const int S = m->nr | 1;
   int EB = 256 / (m->nr * m->ns);  // about one node per thread
@@ -204,6 +245,37 @@ int semb_launch_hinv_mid(semb_ctx* ctx, semb_mesh* m, const double* g, double b0
   const int gy = m->nyl > 32768 ? 32768 : m->nyl;
   semb_hinv_mid_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(g, m->arr[SEMB_BI], b0, m->pitch, m->nxl, m->nyl, mx0, mx1,
                                                              my0, my1, out);
+  SEMB_CHECK_CUDA(cudaGetLastError());
+  ctx->launches++;
+  return SEMB_OK;
+}
+
+// single-rank fused gatherScatter + epilogue (mode: 0 none, 1 (M.*g).*Bi./b0, 2 M.*g); out must not alias u
+int semb_launch_gs_fused(semb_ctx* ctx, semb_mesh* m, const double* u, double* out, int mode, double b0, int mx0, int mx1,
+                         int my0, int my1) {
+  GsFusedArgs a;
+  a.u = u;
+  a.out = out;
+  a.Bi = m->arr[SEMB_BI];
+  a.b0 = b0;
+  a.pitch = m->pitch;
+  a.nr = m->nr;
+  a.ns = m->ns;
+  a.Ex = m->Ex;
+  a.ney = m->ney;
+  a.nxl = m->nxl;
+  a.nyl = m->nyl;
+  a.perx = m->perx;
+  a.pery = m->pery;
+  a.mode = mode;
+  a.mx0 = mx0;
+  a.mx1 = mx1;
+  a.my0 = my0;
+  a.my1 = my1;
+  int gx = (m->nxl + 255) / 256;
+  if (gx > 1024) gx = 1024;
+  const int gy = m->nyl > 32768 ? 32768 : m->nyl;
+  semb_gs_fused_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(a);
   SEMB_CHECK_CUDA(cudaGetLastError());
   ctx->launches++;
   return SEMB_OK;

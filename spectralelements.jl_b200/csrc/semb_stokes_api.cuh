@@ -39,6 +39,11 @@ extern "C" int semb_approx_hlmz_inv(semb_mesh* m, const semb_field* u, double b0
   if (!m->w_t1) SEMB_TRY(semb_field_create(m, &m->w_t1));
   semb_field* t = m->w_t1;
   SEMB_REQUIRE(t != u && t != out, "approxHlmzInv: argument aliases the mesh work field");
+  if (m->ctx->nranks == 1 && !getenv("SEMB_NO_TILED_STOKES")) {
+    // single rank: two one-pass kernels (gatherScatter with the pointwise step as its epilogue), same bits
+    SEMB_TRY(semb_launch_gs_fused(m->ctx, m, u->d, t->d, 1, b0, f.mx0, f.mx1, f.my0, f.my1));        // diver.jl:95-98
+    return semb_launch_gs_fused(m->ctx, m, t->d, out->d, bc ? 2 : 0, b0, f.mx0, f.mx1, f.my0, f.my1);  // :100-101
+  }
   SEMB_TRY(semb_gather_scatter(m, u, t));                                                            // diver.jl:95
   SEMB_TRY(semb_launch_hinv_mid(m->ctx, m, t->d, b0, f.mx0, f.mx1, f.my0, f.my1, out->d));           // :96-98
   SEMB_TRY(semb_gather_scatter(m, out, t));                                                          // :100
@@ -138,16 +143,27 @@ static int stokes_interp_VP(semb_stokes* s, const double* v, double* outP) {
   return semb_launch_abu_s(c, s->dJsT, P->ns, V->ns, s->mid, P->nxl, V->nyl, P->pitch, outP, P->pitch);
 }
 
-// diver(ux,uy,mshV,Jr,Js), diver.jl:17-31
-extern "C" int semb_diver(semb_stokes* s, const semb_field* ux, const semb_field* uy, semb_field* out) {
-  SEMB_REQUIRE(s, "null Stokes handle");
-  SEMB_ENTER(s->V->ctx);
+// diver(ux,uy,mshV,Jr,Js), diver.jl:17-31, times `sign`: one register-tiled launch when (nr, nr-2) is served
+// (semb_stokes_tile.cu), else the generic chain
+static int stokes_diver(semb_stokes* s, const semb_field* ux, const semb_field* uy, semb_field* out, double sign) {
   SEMB_TRY(check_field(s->V, ux, "diver(ux)"));
   SEMB_TRY(check_field(s->V, uy, "diver(uy)"));
   SEMB_TRY(check_field(s->P, out, "diver(out)"));
   SEMB_REQUIRE(ux != s->v4 && uy != s->v4, "diver: argument aliases the work field");
-  SEMB_TRY(semb_launch_diver_local(s->V->ctx, s->V, ux->d, uy->d, s->v4->d));  // B .* (uxdx + uydy), :22-27
-  return stokes_interp_VP(s, s->v4->d, out->d);                                 // ABu(Js',Jr',Bdiv), :28
+  semb_ctx* c = s->V->ctx;
+  int done = 0;
+  if (!getenv("SEMB_NO_TILED_STOKES"))
+    SEMB_TRY(semb_launch_stokes_tile(c, s->V, s->P, 0, ux->d, uy->d, out->d, nullptr, s->dJr, s->dJs, sign, &done));
+  if (done) return SEMB_OK;
+  SEMB_TRY(semb_launch_diver_local(c, s->V, ux->d, uy->d, s->v4->d));  // B .* (uxdx + uydy), :22-27
+  SEMB_TRY(stokes_interp_VP(s, s->v4->d, out->d));                      // ABu(Js',Jr',Bdiv), :28
+  return sign == 1.0 ? SEMB_OK : semb_field_axpby(0.0, out, sign, out);
+}
+
+extern "C" int semb_diver(semb_stokes* s, const semb_field* ux, const semb_field* uy, semb_field* out) {
+  SEMB_REQUIRE(s, "null Stokes handle");
+  SEMB_ENTER(s->V->ctx);
+  return stokes_diver(s, ux, uy, out, 1.0);
 }
 
 // diverT(pr,mshV,Jr,Js), diver.jl:53-63
@@ -158,6 +174,10 @@ extern "C" int semb_diverT(semb_stokes* s, const semb_field* pr, semb_field* qx,
   SEMB_TRY(check_field(s->V, qx, "diverT(qx)"));
   SEMB_TRY(check_field(s->V, qy, "diverT(qy)"));
   SEMB_REQUIRE(qx != qy && qx != s->v4 && qy != s->v4, "diverT: outputs must not alias (each other or the work field)");
+  int done = 0;
+  if (!getenv("SEMB_NO_TILED_STOKES"))
+    SEMB_TRY(semb_launch_stokes_tile(s->V->ctx, s->V, s->P, 1, pr->d, nullptr, qx->d, qy->d, s->dJr, s->dJs, 1.0, &done));
+  if (done) return SEMB_OK;
   SEMB_TRY(stokes_interp_PV(s, pr->d, s->v4->d));                                                   // Jp, :57
   return semb_launch_gradT(s->V->ctx, s->V, s->v4->d, s->V->arr[SEMB_B], qx->d, qy->d);            // mass, gradT, :58-60
 }
@@ -172,8 +192,7 @@ extern "C" int semb_stokes_op(semb_stokes* s, const semb_field* q, semb_field* o
   SEMB_TRY(semb_diverT(s, q, s->v1, s->v2));                                  // DD'
   SEMB_TRY(semb_approx_hlmz_inv(s->V, s->v1, s->b0, s->bcx, s->v3));          // HH^-1
   SEMB_TRY(semb_approx_hlmz_inv(s->V, s->v2, s->b0, s->bcy, s->v1));
-  SEMB_TRY(semb_diver(s, s->v3, s->v1, s->p_rhs));                            // DD
-  SEMB_TRY(semb_field_axpby(0.0, s->p_rhs, -1.0, s->p_rhs));                  // return -Eq, diver.jl:88 (0*x + (-1)*y)
+  SEMB_TRY(stokes_diver(s, s->v3, s->v1, s->p_rhs, -1.0));                    // DD, and "return -Eq" (diver.jl:88)
   return semb_gather_scatter(s->P, s->p_rhs, out);                           // stokes.jl:118
 }
 

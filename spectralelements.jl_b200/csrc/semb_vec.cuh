@@ -65,3 +65,8 @@ int semb_launch_gradT(semb_ctx* ctx, semb_mesh* m, const double* u, const double
 int semb_launch_diver_local(semb_ctx* ctx, semb_mesh* m, const double* ux, const double* uy, double* out);
 int semb_launch_hinv_mid(semb_ctx* ctx, semb_mesh* m, const double* g, double b0, int mx0, int mx1, int my0, int my1,
                          double* out);
+// register-tiled Stokes element kernels (semb_stokes_tile.cu): diverT (transpose = 1) / diver (0) in one launch
+int semb_launch_stokes_tile(semb_ctx* ctx, semb_mesh* V, semb_mesh* P, int transpose, const double* in1, const double* in2,
+                            double* out1, double* out2, const double* dJr, const double* dJs, double sign, int* done);
+int semb_launch_gs_fused(semb_ctx* ctx, semb_mesh* m, const double* u, double* out, int mode, double b0, int mx0, int mx1,
+                         int my0, int my1);

@@ -25,8 +25,24 @@ def meshes(sem, ctx, nr, Ex, Ey, per, deform):
     return oV, oP, gV, gP
 
 
-@pytest.mark.parametrize("nr,Ex,Ey,per,deform,bcx,bcy", CASES)
-def test_stokes_operators(sem, ctx, nr, Ex, Ey, per, deform, bcx, bcy):
+@pytest.fixture(params=["tiled", "generic"])
+def stokes_path(request):
+    """the register-tiled element kernels + one-pass gatherScatter (default) and the generic chain of launches they
+    replace (SEMB_NO_TILED_STOKES=1: ABu kernels, gradT/diver tile kernels, gs_x + seam_y + pointwise passes)"""
+    import os
+    if request.param == "generic":
+        os.environ["SEMB_NO_TILED_STOKES"] = "1"
+    yield request.param
+    os.environ.pop("SEMB_NO_TILED_STOKES", None)
+
+
+# ragged batches of the tiled kernels: Ex not a multiple of 128 // nr
+CASES_OPS = CASES + [(9, 17, 2, (False, False), "wavy", "DDDD", "DDDD"), (5, 27, 2, (True, False), "wavy", "NNDD", "NNDD"),
+                     (13, 10, 2, (False, False), "wavy", "DDDD", "DDDD"), (4, 33, 2, (False, False), "wavy", "DDDD", "DDDD")]
+
+
+@pytest.mark.parametrize("nr,Ex,Ey,per,deform,bcx,bcy", CASES_OPS)
+def test_stokes_operators(sem, ctx, stokes_path, nr, Ex, Ey, per, deform, bcx, bcy):
     oV, oP, gV, gP = meshes(sem, ctx, nr, Ex, Ey, per, deform)
     osk = so.make_stokes(list(bcx), list(bcy), oV, oP, b0=1.5)
     gsk = sem.Stokes(bcx, bcy, gV, gP, b0=1.5)
