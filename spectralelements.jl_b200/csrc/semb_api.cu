@@ -1343,11 +1343,22 @@ static int pcg_one_iteration(semb_mesh* m) {
   sp.bc = o.bc;
   sp.M_arr = o.M_arr;
   sp.gs = true;
-  SEMB_TRY(run_operator(m, m->w_r->d, m->w_Ap->d, sp, true, m->w_p->d, o.precond, o.prec_b0));
-  if (c->nranks > 1 && !m->p2p) {
-    SEMB_TRY(semb_launch_pcg_pack_pap(c, m));
-    SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_pap), 1));
-    SEMB_TRY(semb_launch_pcg_combine_pap(c, m));
+  if (m->pcg_custom) {
+    SEMB_TRY(semb_launch_pcg_dir(c, m, m->w_r->d, m->w_p->d, o.precond, o.prec_b0));  // p = h + beta*p, pcg.jl:46-50
+    SEMB_TRY(m->pcg_custom());                                                         // w_Ap = opA(w_p), pcg.jl:51
+    SEMB_TRY(semb_launch_reduce(c, m, 0, m->w_p->d, m->w_Ap->d, p2p_args(m, m->p2p ? ++m->ep_red : 0)));  // pcg.jl:52
+    if (c->nranks > 1 && !m->p2p) {
+      SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_red), 1));
+      SEMB_TRY(semb_launch_reduce_finalize(c, m, 0));
+    }
+    SEMB_TRY(semb_launch_pcg_set_pap(c, m));
+  } else {
+    SEMB_TRY(run_operator(m, m->w_r->d, m->w_Ap->d, sp, true, m->w_p->d, o.precond, o.prec_b0));
+    if (c->nranks > 1 && !m->p2p) {
+      SEMB_TRY(semb_launch_pcg_pack_pap(c, m));
+      SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_pap), 1));
+      SEMB_TRY(semb_launch_pcg_combine_pap(c, m));
+    }
   }
   // P2P: the update kernel's last block all-gathers {t, norm(r,Inf)} over NVLink and advances the state
   SEMB_TRY(semb_launch_pcg_update(c, m, m->pcg_x->d, m->w_r->d, m->w_p->d, m->w_Ap->d, o.precond, o.prec_b0,

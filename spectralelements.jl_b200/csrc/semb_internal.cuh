@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <nccl.h>
 #include <stdint.h>
+#include <functional>
 #include <mutex>
 #include <stdio.h>
 #include <string.h>
@@ -182,6 +183,9 @@ struct semb_mesh {
   semb_field* pcg_x = nullptr;
   semb_pcg_opts pcg_opts;
   bool pcg_active = false;
+  // operator hook of the device-resident PCG: when set, an iteration is p = h + beta*p, w_Ap = pcg_custom(w_p),
+  // sum(p.*Ap.*mult) by the reduction kernel, update -- instead of the fused strip kernel (Stokes Schur operator)
+  std::function<int()> pcg_custom;
   std::vector<semb_field*> fields;     // live fields (for leak-free destroy)
   std::vector<semb_field*> host_tmp;   // cached device fields of the *_host twins
 };

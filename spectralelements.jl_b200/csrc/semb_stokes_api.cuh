@@ -12,7 +12,7 @@ struct semb_stokes {
   double *dJr = nullptr, *dJs = nullptr, *dJrT = nullptr, *dJsT = nullptr;
   double* mid = nullptr;                                      // mixed-resolution intermediate of the two-pass ABu
   semb_field *v1 = nullptr, *v2 = nullptr, *v3 = nullptr, *v4 = nullptr;  // work fields on mshV
-  semb_field *p_r = nullptr, *p_u = nullptr, *p_Au = nullptr, *p_rhs = nullptr, *p_dp = nullptr;  // on mshP
+  semb_field *p_Au = nullptr, *p_rhs = nullptr, *p_dp = nullptr;  // on mshP
 };
 
 extern "C" int semb_gradT(semb_mesh* m, const semb_field* u, semb_field* ux, semb_field* uy) {
@@ -57,7 +57,7 @@ extern "C" int semb_stokes_destroy(semb_stokes* s) {
   cudaFree(s->dJrT);
   cudaFree(s->dJsT);
   cudaFree(s->mid);
-  semb_field* fs[] = {s->v1, s->v2, s->v3, s->v4, s->p_r, s->p_u, s->p_Au, s->p_rhs, s->p_dp};
+  semb_field* fs[] = {s->v1, s->v2, s->v3, s->v4, s->p_Au, s->p_rhs, s->p_dp};
   for (semb_field* f : fs) semb_field_destroy(f);
   delete s;
   return SEMB_OK;
@@ -93,9 +93,10 @@ static int stokes_create_impl(semb_stokes* s) {
   SEMB_TRY(up(JsT, &s->dJsT));
   const size_t nmid = std::max((size_t)V->pitch * P->nyl, (size_t)P->pitch * V->nyl);
   SEMB_CHECK_CUDA(cudaMalloc(&s->mid, nmid * sizeof(double)));
+  if (!V->w_t1) SEMB_TRY(semb_field_create(V, &V->w_t1));  // work field of approxHlmzInv: no allocation while a graph is captured
   semb_field** fv[] = {&s->v1, &s->v2, &s->v3, &s->v4};
   for (semb_field** f : fv) SEMB_TRY(semb_field_create(V, f));
-  semb_field** fp[] = {&s->p_r, &s->p_u, &s->p_Au, &s->p_rhs, &s->p_dp};
+  semb_field** fp[] = {&s->p_Au, &s->p_rhs, &s->p_dp};
   for (semb_field** f : fp) SEMB_TRY(semb_field_create(P, f));
   return SEMB_OK;
 }
@@ -206,8 +207,9 @@ extern "C" int semb_stokes_rhs(semb_stokes* s, const semb_field* vx, const semb_
   return semb_gather_scatter(s->P, s->p_Au, rhs);
 }
 
-// solveStokes!, stokes.jl:143-154: pcg(rhs, opStokesLHS; mult = mshP.mult) with the loop of pcg.jl:16-60 driven from
-// the host over device vectors (the operator is a chain of ~25 launches; scalars come back per iteration)
+// solveStokes!, stokes.jl:143-154: pcg(rhs, opStokesLHS; mult = mshP.mult, opM = identity (stokes.jl:123-126)) on the
+// device-resident PCG of the pressure mesh (pcg.jl:16-60: scalars, convergence flag and iteration count live in device
+// memory; CUDA-graph replay on one rank) with the Schur operator plugged in as its operator hook
 extern "C" int semb_stokes_solve(semb_stokes* s, const semb_field* rhs, semb_field* dp, double tol, long long maxiter,
                                  long long* iters, double* resinf) {
   SEMB_REQUIRE(s, "null Stokes handle");
@@ -215,37 +217,17 @@ extern "C" int semb_stokes_solve(semb_stokes* s, const semb_field* rhs, semb_fie
   SEMB_ENTER(P->ctx);
   SEMB_TRY(check_field(P, rhs, "solveStokes(rhs)"));
   SEMB_TRY(check_field(P, dp, "solveStokes(dp)"));
-  SEMB_REQUIRE(rhs != dp, "solveStokes: dp must not alias rhs");
-  if (maxiter < 0) maxiter = (long long)P->nxl * P->ns * P->Ey;  // length(b), pcg.jl:21
-  semb_field *r = s->p_r, *u = s->p_u, *Au = s->p_Au;
-  SEMB_TRY(semb_field_fill(dp, 0.0));     // x = zero(b), pcg.jl:25
-  SEMB_TRY(semb_field_copy(r, rhs));      // ra = b - opA*x = b
-  long long k = 0;
-  double rinf = 0.0, t_prev = 0.0;
-  int rc = SEMB_OK;
-  for (;;) {
-    SEMB_TRY(semb_norm_inf(P, r, &rinf));
-    if (!(rinf > tol)) break;             // pcg.jl:36
-    if (k == maxiter) {                   // pcg.jl:39
-      rc = SEMB_NOT_CONVERGED;
-      break;
-    }
-    ++k;
-    double t = 0.0, uAu = 0.0;
-    SEMB_TRY(semb_dot_mult(P, r, r, &t));                    // pcg.jl:45 with opM = identity (stokes.jl:123-126)
-    if (k == 1)
-      SEMB_TRY(semb_field_copy(u, r));                       // pcg.jl:47
-    else
-      SEMB_TRY(semb_field_axpby(1.0, r, t / t_prev, u));     // u = hp + beta*u, pcg.jl:49
-    SEMB_TRY(semb_stokes_op(s, u, Au));                      // pcg.jl:51
-    SEMB_TRY(semb_dot_mult(P, u, Au, &uAu));                 // pcg.jl:52
-    const double a = t / uAu;
-    SEMB_TRY(semb_field_axpby(a, u, 1.0, dp));               // pcg.jl:53
-    SEMB_TRY(semb_field_axpby(-a, Au, 1.0, r));              // pcg.jl:54
-    t_prev = t;
-  }
-  if (iters) *iters = k;
-  if (resinf) *resinf = rinf;
+  SEMB_REQUIRE(rhs != dp && rhs != s->p_rhs && dp != s->p_rhs, "solveStokes: rhs / dp alias each other or a work field");
+  SEMB_TRY(ensure_tmp(P, &P->w_p));
+  SEMB_TRY(ensure_tmp(P, &P->w_Ap));
+  semb_pcg_opts o;
+  memset(&o, 0, sizeof(o));
+  o.nu = 1.0;
+  o.tol = tol;
+  o.maxiter = maxiter;
+  P->pcg_custom = [s, P]() -> int { return semb_stokes_op(s, P->w_p, P->w_Ap); };
+  const int rc = semb_pcg(P, &o, rhs, dp, iters, resinf);
+  P->pcg_custom = nullptr;
   return rc;
 }
 

@@ -995,6 +995,20 @@ int semb_launch_reduce(semb_ctx* ctx, semb_mesh* m, int which, const double* a, 
   SEMB_POST_LAUNCH(ctx);
 }
 
+// custom-operator PCG: the reduction kernel left sum(p.*Ap.*mult) (all ranks) in red[0]; hand it to the update kernel
+__global__ void semb_pcg_set_pap_kernel(SembScal* scal) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double v = scal->red[0];
+  scal->pap[0] = v;
+  scal->pap[1] = 0.0;
+  scal->pap[2] = 0.0;
+  scal->pap_total = v;
+}
+int semb_launch_pcg_set_pap(semb_ctx* ctx, semb_mesh* m) {
+  semb_pcg_set_pap_kernel<<<1, 32, 0, ctx->stream>>>(m->d_scal);
+  SEMB_POST_LAUNCH(ctx);
+}
+
 int semb_launch_reduce_finalize(semb_ctx* ctx, semb_mesh* m, int which) {
   semb_reduce_finalize_kernel<<<1, 32, 0, ctx->stream>>>(m->d_scal, which);
   SEMB_POST_LAUNCH(ctx);

@@ -70,3 +70,4 @@ int semb_launch_stokes_tile(semb_ctx* ctx, semb_mesh* V, semb_mesh* P, int trans
                             double* out1, double* out2, const double* dJr, const double* dJs, double sign, int* done);
 int semb_launch_gs_fused(semb_ctx* ctx, semb_mesh* m, const double* u, double* out, int mode, double b0, int mx0, int mx1,
                          int my0, int my1);
+int semb_launch_pcg_set_pap(semb_ctx* ctx, semb_mesh* m);
