@@ -160,6 +160,97 @@ function advect(T::Array, ux::Array, uy::Array, mshV::Mesh, mshD::Mesh, Jr, Js)
     return devget(fo, T)
 end
 
+# ---- explicit-argument forms on plain arrays (examples/p2d_explicit.jl:183-188, examples/semPS.jl:168-172) ----------
+nz(a) = length(a) == 0 ? nothing : f64(a)          # Julia's `[]` -> NULL
+ptr(a) = a === nothing ? Ptr{Float64}(C_NULL) : pointer(a)
+# laplace(u,Dr,Ds,G11,G12,G22), lapl.jl:70-81 ; laplace(u,Jr,Js,Dr,Ds,G11,G12,G22), lapl.jl:83-103 (dealiased)
+function laplace(u::Array, Jr, Js, Dr, Ds, G11, G12, G22)
+    out = similar(u, Float64)
+    (jr, js) = (nz(Jr), nz(Js))
+    (uf, dr, ds, g11, g12, g22) = (f64(u), f64(Dr), f64(Ds), f64(G11), f64(G12), f64(G22))
+    GC.@preserve jr js uf dr ds g11 g12 g22 check(ccall((:semb_laplace_host, libsemb), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Float64}, Cint,
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        context(), size(u, 1), size(u, 2), dr, size(Dr, 1), ds, size(Ds, 1), ptr(jr), jr === nothing ? 0 : size(Jr, 1),
+        ptr(js), js === nothing ? 0 : size(Js, 1), g11, g12, g22, uf, out))
+    return out
+end
+laplace(u::Array, Dr, Ds, G11, G12, G22) = laplace(u, [], [], Dr, Ds, G11, G12, G22)
+mul(a::Array, b::Array) = (out = similar(b, Float64); check(ccall((:semb_mul_host, libsemb), Cint,
+    (Ptr{Cvoid}, Csize_t, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), context(), length(b), f64(a), f64(b), out)); out)
+# lapl(u,M,Jr,Js,QQtx,QQty,Dr,Ds,G11,G12,G22,mult), lapl.jl:54-68 (the mult hook only acts in the reverse pass)
+function lapl(u::Array, M, Jr, Js, QQtx, QQty, Dr, Ds, G11, G12, G22, mult)
+    Au = ABu(QQty, QQtx, laplace(u, Jr, Js, Dr, Ds, G11, G12, G22))     # gatherScatter.jl:8-16
+    return length(M) == 0 ? Au : mul(f64(M), Au)                         # mask.jl:10-18
+end
+# mass(u,M,B,Jr,Js,QQtx,QQty,mult), mass.jl:32-50
+function mass(u::Array, M, B, Jr, Js, QQtx, QQty, mult)
+    out = similar(u, Float64)
+    (jr, js, b, uf) = (nz(Jr), nz(Js), nz(B), f64(u))
+    GC.@preserve jr js b uf check(ccall((:semb_mass_explicit_host, libsemb), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        context(), size(u, 1), size(u, 2), ptr(jr), jr === nothing ? 0 : size(Jr, 1), jr === nothing ? 0 : size(Jr, 2),
+        ptr(js), js === nothing ? 0 : size(Js, 1), js === nothing ? 0 : size(Js, 2), ptr(b), uf, out))
+    Bu = ABu(QQty, QQtx, out)
+    return length(M) == 0 ? Bu : mul(f64(M), Bu)
+end
+
+# ---- Stokes split: diver.jl / stokes.jl are not executable as shipped (stokes.jl is not even included,
+# SpectralElements.jl:53); these methods bind the reconstruction documented in include/semb.h ----------------------------
+bcstr(bc) = String(bc)          # ['D','D','N','N'] -> "DDNN"
+mutable struct StokesB200       # Stokes(bcVX,bcVY,mshV,mshD,mshP), stokes.jl:75-108, reduced to the pressure system
+    h::Ptr{Cvoid}
+    mshV::Mesh
+    mshP::Mesh
+end
+function StokesB200(bcVX, bcVY, mshV::Mesh, mshP::Mesh; b0 = 1.0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:semb_stokes_create, libsemb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cstring, Cstring, Cdouble, Ref{Ptr{Cvoid}}),
+                devmesh(mshV), devmesh(mshP), bcstr(bcVX), bcstr(bcVY), b0, h))
+    return finalizer(s -> ccall((:semb_stokes_destroy, libsemb), Cint, (Ptr{Cvoid},), s.h), StokesB200(h[], mshV, mshP))
+end
+function gradᵀ(u::Array, msh::Mesh)          # grad.jl:44-63
+    (fu, fx, fy) = (devfield(msh, u), devfield(msh), devfield(msh))
+    check(ccall((:semb_gradT, libsemb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), devmesh(msh), fu, fx, fy))
+    ccall((:semb_field_destroy, libsemb), Cint, (Ptr{Cvoid},), fu)
+    return devget(fx, u), devget(fy, u)
+end
+function diver(ux::Array, uy::Array, sks::StokesB200)      # diver.jl:17-31
+    (fx, fy, fo) = (devfield(sks.mshV, ux), devfield(sks.mshV, uy), devfield(sks.mshP))
+    check(ccall((:semb_diver, libsemb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), sks.h, fx, fy, fo))
+    for f in (fx, fy); ccall((:semb_field_destroy, libsemb), Cint, (Ptr{Cvoid},), f); end
+    return devget(fo, sks.mshP.x)
+end
+function diverᵀ(pr::Array, sks::StokesB200)                # diver.jl:53-63
+    (fp, fx, fy) = (devfield(sks.mshP, pr), devfield(sks.mshV), devfield(sks.mshV))
+    check(ccall((:semb_diverT, libsemb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), sks.h, fp, fx, fy))
+    ccall((:semb_field_destroy, libsemb), Cint, (Ptr{Cvoid},), fp)
+    return devget(fx, sks.mshV.x), devget(fy, sks.mshV.x)
+end
+function approxHlmzInv(u::Array, b0::Number, mshV::Mesh, bc)   # diver.jl:92-104
+    (fu, fo) = (devfield(mshV, u), devfield(mshV))
+    check(ccall((:semb_approx_hlmz_inv, libsemb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cstring, Ptr{Cvoid}),
+                devmesh(mshV), fu, b0, bcstr(bc), fo))
+    ccall((:semb_field_destroy, libsemb), Cint, (Ptr{Cvoid},), fu)
+    return devget(fo, u)
+end
+function opStokesLHS(q::Array, sks::StokesB200)            # stokes.jl:110-121
+    (fq, fo) = (devfield(sks.mshP, q), devfield(sks.mshP))
+    check(ccall((:semb_stokes_op, libsemb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), sks.h, fq, fo))
+    ccall((:semb_field_destroy, libsemb), Cint, (Ptr{Cvoid},), fq)
+    return devget(fo, q)
+end
+# pressureProject!, stokes.jl:159-177: vx, vy, pr are updated in place; returns the PCG iteration count
+function pressureProject!(vx::Array, vy::Array, pr::Array, sks::StokesB200; tol = 1e-8, maxiter = -1)
+    (fx, fy, fp) = (devfield(sks.mshV, vx), devfield(sks.mshV, vy), devfield(sks.mshP, pr))
+    (it, res) = (Ref{Clonglong}(0), Ref{Cdouble}(0.0))
+    check(ccall((:semb_stokes_project, libsemb), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Clonglong, Ref{Clonglong}, Ref{Cdouble}),
+                sks.h, fx, fy, fp, tol, maxiter, it, res))
+    vx .= devget(fx, vx); vy .= devget(fy, vy); pr .= devget(fp, pr)
+    return it[]
+end
+
 # ---- the fused unit and the device-resident Krylov loop ------------------------------------------------
 """opLHS as a callable struct: applying it runs the fused kernel; handing it to pcg runs the whole
 loop on the device (an arbitrary Julia closure cannot execute there)."""

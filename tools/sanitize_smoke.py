@@ -43,5 +43,25 @@ d = sem.Diffusion(list("DDDD"), mV, Tf=1.0, dt=0.1)
 d.nu = 1.0 + 0 * mV.x; d.f = 1.0 + 0 * mV.x
 sem.evolve_b(d)
 cd.free(); d.free(); mV.free(); mD.free()
+# register-tiled advection (ragged batches), Stokes element kernels, one-pass gatherScatter, explicit-argument forms
+for nr, nrd, Ex in ((9, 14, 11), (8, 12, 13), (5, 8, 17)):
+    aV, aD = sem.Mesh(nr, nr, Ex, 2, (False, False), sem.wavy, ctx=ctx), sem.Mesh(nrd, nrd, Ex, 2, (False, False), sem.wavy, ctx=ctx)
+    T = np.asfortranarray(rng.standard_normal(aV.shape))
+    sem.advect(T, 1.0 + 0.3 * aV.x, np.cos(aV.y), aV, aD)
+    aV.free(); aD.free()
+for nr, Ex in ((11, 13), (7, 19), (4, 33)):
+    sV, sP = sem.Mesh(nr, nr, Ex, 2, (False, False), sem.wavy, ctx=ctx), sem.Mesh(nr - 2, nr - 2, Ex, 2, (False, False), sem.wavy, ctx=ctx)
+    sk = sem.Stokes("DDDD", "DDNN", sV, sP, 1.0)
+    q = np.asfortranarray(rng.standard_normal(sP.shape))
+    v = np.asfortranarray(rng.standard_normal(sV.shape))
+    sem.opStokesLHS(q, sk); sem.diver(v, v, sk); sem.diverT(q, sk); sem.gradT(v, sV)
+    sem.pressureProject(sem.mask(v, sem.generateMask(list("DDDD"), sV), sV), 0 * v, 0 * q, sk, tol=1e-6, maxiter=5)
+    sk.free(); sV.free(); sP.free()
+eV = sem.Mesh(5, 5, 3, 2, (False, False), sem.wavy, ctx=ctx)
+ue = np.asfortranarray(rng.standard_normal(eV.shape))
+Dr = np.asfortranarray(eV.Dr)
+sem.laplace(ue, Dr, Dr, eV.G11, eV.G12, eV.G22)
+sem.mass(ue, [], eV.B, [], [], [], [], eV.mult)
+eV.free()
 sem.finalize()
 print("sanitize smoke done")
