@@ -324,36 +324,31 @@ def run_semb(args):
                               "gdof_steps_per_s": nV / dt4 / 1e9, "ms_per_dealiased_advect_incl_alloc": dta * 1e3}
         cdn.free(); mV.free(); mD.free()
 
-    # ---- BASELINE configs[4]: Stokes pressure-velocity split, order 10 velocity / order 8 pressure ---------------------
-    if rank == 0 and world == 1 and not args.skip_cfg5:
+    # ---- BASELINE configs[4]: Stokes pressure-velocity split, order 10 velocity / order 8 pressure, 1/2/4/8 GPUs --------
+    # (weak scaling like the headline: E5 x E5 elements per GPU, y-slabs; every rank takes part)
+    if not args.skip_cfg5:
         E5 = args.cfg5_elements
-        mV = sem.Mesh(11, 11, E5, E5, (False, False), "wavy", ctx=ctx)
-        mP = sem.Mesh(9, 9, E5, E5, (False, False), "wavy", ctx=ctx)   # pressure order nr-2 (examples/semPS.jl:31)
+        mV = sem.Mesh(11, 11, E5, E5 * world, (False, False), "wavy", ctx=ctx)
+        mP = sem.Mesh(9, 9, E5, E5 * world, (False, False), "wavy", ctx=ctx)   # pressure order nr-2 (examples/semPS.jl:31)
         sks = sem.Stokes("DDDD", "DDDD", mV, mP, 1.0)
-        nV5, nP5 = mV.shape[0] * mV.shape[1], mP.shape[0] * mP.shape[1]
+        nV5, nP5 = mV.shape[0] * mV.shape[1] * world, mP.shape[0] * mP.shape[1] * world
         q5, o5 = mP.field().fill_random(3), mP.field()
-        for _ in range(3):
-            sks.op_device(q5, o5)
-        ctx.timer_start()
-        nop = 20
-        for _ in range(nop):
-            sks.op_device(q5, o5)
-        ms5 = ctx.timer_stop() / nop
+        ms5 = time_steps(ctx, dist, lambda: sks.op_device(q5, o5), 20, 3) / 20
         vx5, vy5, pr5 = mV.field().fill_random(5), mV.field().fill_random(6), mP.field()
         sks.project_device(vx5, vy5, pr5, tol=0.0, maxiter=2)   # first-use allocations outside the timed call
-        ctx.sync()
+        barrier(dist, ctx)
         t0 = time.perf_counter()
         nit5 = 50
         sks.project_device(vx5, vy5, pr5, tol=0.0, maxiter=nit5)
         ctx.sync()
-        dt5 = time.perf_counter() - t0
+        dt5 = max_over_ranks(dist, time.perf_counter() - t0)
         extra["cfg5_stokes"] = {"workload": "Stokes split (reconstruction of diver.jl/stokes.jl): Schur operator -DD HH^-1 DD' + "
-                                            "QQ^T on the pressure mesh, %dx%d elements, velocity order 10 (%d DOF per component), "
-                                            "pressure order 8 (%d DOF), wavy box" % (E5, E5, nV5, nP5),
+                                            "QQ^T on the pressure mesh, %dx%d elements per GPU, velocity order 10 (%d DOF per "
+                                            "component), pressure order 8 (%d DOF), wavy box, %d GPU(s)" % (E5, E5, nV5, nP5, world),
                                 "ms_per_schur_apply": ms5, "velocity_gdof_per_s": nV5 / ms5 / 1e6,
                                 "pressure_pcg_iters_per_s": nit5 / dt5,
-                                "note": "pressureProject timed over %d PCG iterations incl. the right-hand side and the "
-                                        "velocity correction; host-driven loop (3 scalar read-backs per iteration)" % nit5}
+                                "note": "pressureProject timed over %d device-resident PCG iterations incl. the right-hand "
+                                        "side and the velocity correction" % nit5}
         sks.free(); mV.free(); mP.free()
 
     # ---- CPU baseline beside it (rank 0, N = 1): bounded sample of the same workload -------------------

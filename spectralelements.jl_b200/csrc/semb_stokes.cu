@@ -147,6 +147,7 @@ struct GsFusedArgs {
   double b0;
   long long pitch;
   int nr, ns, Ex, ney, nxl, nyl, perx, pery, mode, mx0, mx1, my0, my1;
+  int raw_lo, raw_hi;  // multi-rank: row 0 / nyl-1 still wait for the neighbour's row: no epilogue yet
 };
 __global__ void semb_gs_fused_kernel(const GsFusedArgs a) {
   for (int row = blockIdx.y; row < a.nyl; row += gridDim.y) {
@@ -168,13 +169,27 @@ __global__ void semb_gs_fused_kernel(const GsFusedArgs a) {
         if (xp >= 0) h = __dadd_rn(h, up[xp]);
         g = __dadd_rn(g, h);
       }
-      if (a.mode) {
+      if (a.mode && !(row == 0 && a.raw_lo) && !(row == a.nyl - 1 && a.raw_hi)) {
         const bool z = (x == 0 && a.mx0) || (x == a.nxl - 1 && a.mx1) || (row == 0 && a.my0) || (row == a.nyl - 1 && a.my1);
         g = __dmul_rn(z ? 0.0 : 1.0, g);
         if (a.mode == 1) g = __ddiv_rn(__dmul_rn(g, a.Bi[(size_t)row * a.pitch + x]), a.b0);
       }
       a.out[(size_t)row * a.pitch + x] = g;
     }
+  }
+}
+
+// the epilogue of semb_gs_fused_kernel on the slab's first / last row, once the neighbour's row has been added
+__global__ void semb_gs_rows_epilogue_kernel(const GsFusedArgs a) {
+  for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < 2 * a.nxl; id += gridDim.x * blockDim.x) {
+    const int which = id / a.nxl, x = id - which * a.nxl;
+    if (which == 0 ? !a.raw_lo : !a.raw_hi) continue;
+    const int row = which == 0 ? 0 : a.nyl - 1;
+    const size_t idx = (size_t)row * a.pitch + x;
+    const bool z = (x == 0 && a.mx0) || (x == a.nxl - 1 && a.mx1) || (row == 0 && a.my0) || (row == a.nyl - 1 && a.my1);
+    double g = __dmul_rn(z ? 0.0 : 1.0, a.out[idx]);
+    if (a.mode == 1) g = __ddiv_rn(__dmul_rn(g, a.Bi[idx]), a.b0);
+    a.out[idx] = g;
   }
 }
 
@@ -250,9 +265,11 @@ int semb_launch_hinv_mid(semb_ctx* ctx, semb_mesh* m, const double* g, double b0
   return SEMB_OK;
 }
 
-// single-rank fused gatherScatter + epilogue (mode: 0 none, 1 (M.*g).*Bi./b0, 2 M.*g); out must not alias u
+// fused gatherScatter + epilogue (mode: 0 none, 1 (M.*g).*Bi./b0, 2 M.*g); out must not alias u.
+// stage 0: the one-pass kernel over the slab (rows with a neighbour rank are left as raw local sums);
+// stage 1: the epilogue on those rows, to be launched after the halo rows have been added (multi-rank only).
 int semb_launch_gs_fused(semb_ctx* ctx, semb_mesh* m, const double* u, double* out, int mode, double b0, int mx0, int mx1,
-                         int my0, int my1) {
+                         int my0, int my1, int stage) {
   GsFusedArgs a;
   a.u = u;
   a.out = out;
@@ -266,16 +283,25 @@ int semb_launch_gs_fused(semb_ctx* ctx, semb_mesh* m, const double* u, double* o
   a.nxl = m->nxl;
   a.nyl = m->nyl;
   a.perx = m->perx;
-  a.pery = m->pery;
+  a.pery = (m->pery && ctx->nranks == 1) ? 1 : 0;  // with several ranks the periodic wrap is a halo
   a.mode = mode;
   a.mx0 = mx0;
   a.mx1 = mx1;
   a.my0 = my0;
   a.my1 = my1;
-  int gx = (m->nxl + 255) / 256;
-  if (gx > 1024) gx = 1024;
-  const int gy = m->nyl > 32768 ? 32768 : m->nyl;
-  semb_gs_fused_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(a);
+  a.raw_lo = m->halo_lo;
+  a.raw_hi = m->halo_hi;
+  if (stage == 0) {
+    int gx = (m->nxl + 255) / 256;
+    if (gx > 1024) gx = 1024;
+    const int gy = m->nyl > 32768 ? 32768 : m->nyl;
+    semb_gs_fused_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(a);
+  } else {
+    if (mode == 0 || (!a.raw_lo && !a.raw_hi)) return SEMB_OK;
+    int blocks = (2 * m->nxl + 255) / 256;
+    if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
+    semb_gs_rows_epilogue_kernel<<<blocks, 256, 0, ctx->stream>>>(a);
+  }
   SEMB_CHECK_CUDA(cudaGetLastError());
   ctx->launches++;
   return SEMB_OK;

@@ -39,10 +39,30 @@ extern "C" int semb_approx_hlmz_inv(semb_mesh* m, const semb_field* u, double b0
   if (!m->w_t1) SEMB_TRY(semb_field_create(m, &m->w_t1));
   semb_field* t = m->w_t1;
   SEMB_REQUIRE(t != u && t != out, "approxHlmzInv: argument aliases the mesh work field");
-  if (m->ctx->nranks == 1 && !getenv("SEMB_NO_TILED_STOKES")) {
-    // single rank: two one-pass kernels (gatherScatter with the pointwise step as its epilogue), same bits
-    SEMB_TRY(semb_launch_gs_fused(m->ctx, m, u->d, t->d, 1, b0, f.mx0, f.mx1, f.my0, f.my1));        // diver.jl:95-98
-    return semb_launch_gs_fused(m->ctx, m, t->d, out->d, bc ? 2 : 0, b0, f.mx0, f.mx1, f.my0, f.my1);  // :100-101
+  if (!getenv("SEMB_NO_TILED_STOKES")) {
+    // two one-pass kernels (gatherScatter with the pointwise step as its epilogue), same bits as the chain below;
+    // with neighbour ranks the slab's boundary rows are completed by the halo exchange before their epilogue
+    const int modes[2] = {1, bc ? 2 : 0};
+    const double* src[2] = {u->d, t->d};
+    double* dst[2] = {t->d, out->d};
+    for (int k = 0; k < 2; ++k) {
+      SEMB_TRY(semb_launch_gs_fused(m->ctx, m, src[k], dst[k], modes[k], b0, f.mx0, f.mx1, f.my0, f.my1, 0));  // diver.jl:95-98 | :100-101
+      if (m->halo_lo || m->halo_hi) {
+        unsigned long long eph = 0;
+        SEMB_TRY(halo_exchange(m, dst[k], 0, &eph));
+        OpArgs y;
+        fill_common(m, y);
+        if (m->p2p) {
+          y.halo_lo = mail_halo(m, m->d_mailbox, (int)(eph & 1ull), 0);
+          y.halo_hi = mail_halo(m, m->d_mailbox, (int)(eph & 1ull), 1);
+        }
+        y.out = dst[k];
+        y.nyseam = 0;  // only the received rows
+        SEMB_TRY(semb_launch_seam_y(m->ctx, y, m->halo_lo, m->halo_hi, false, p2p_args(m, eph)));
+        SEMB_TRY(semb_launch_gs_fused(m->ctx, m, src[k], dst[k], modes[k], b0, f.mx0, f.mx1, f.my0, f.my1, 1));
+      }
+    }
+    return SEMB_OK;
   }
   SEMB_TRY(semb_gather_scatter(m, u, t));                                                            // diver.jl:95
   SEMB_TRY(semb_launch_hinv_mid(m->ctx, m, t->d, b0, f.mx0, f.mx1, f.my0, f.my1, out->d));           // :96-98

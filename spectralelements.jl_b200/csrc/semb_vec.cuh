@@ -69,5 +69,5 @@ int semb_launch_hinv_mid(semb_ctx* ctx, semb_mesh* m, const double* g, double b0
 int semb_launch_stokes_tile(semb_ctx* ctx, semb_mesh* V, semb_mesh* P, int transpose, const double* in1, const double* in2,
                             double* out1, double* out2, const double* dJr, const double* dJs, double sign, int* done);
 int semb_launch_gs_fused(semb_ctx* ctx, semb_mesh* m, const double* u, double* out, int mode, double b0, int mx0, int mx1,
-                         int my0, int my1);
+                         int my0, int my1, int stage);
 int semb_launch_pcg_set_pap(semb_ctx* ctx, semb_mesh* m);
