@@ -1322,7 +1322,13 @@ extern "C" int semb_pcg_begin(semb_mesh* m, const semb_pcg_opts* o, const semb_f
   m->h_scal->nranks = c->nranks;
   m->h_scal->rank = c->rank;
   SEMB_CHECK_CUDA(cudaMemcpyAsync(m->d_scal, m->h_scal, SEMB_SCAL_HOST_BYTES, cudaMemcpyHostToDevice, c->stream));
-  SEMB_TRY(semb_launch_pcg_init(c, m, b->d, x->d, m->w_r->d, m->w_p->d, o->precond, o->prec_b0, o->tol, maxiter,
+  // diagonal preconditioner on the fused path: init / update keep h = r./B./b0 (they form it anyway for t), and the
+  // strip kernel stages h instead of r: same bits, no divisions and no B column at the head of the strip kernel's row
+  const bool keep_h = o->precond && m->fast && !m->pcg_custom && !getenv("SEMB_NO_PCG_H");
+  if (keep_h) SEMB_TRY(ensure_tmp(m, &m->w_h));
+  m->pcg_keep_h = keep_h;
+  SEMB_TRY(semb_launch_pcg_init(c, m, b->d, x->d, m->w_r->d, m->w_p->d, keep_h ? m->w_h->d : nullptr, o->precond,
+                                o->prec_b0, o->tol, maxiter,
                                 p2p_args(m, m->p2p ? ++m->ep_t : 0)));
   if (c->nranks > 1 && !m->p2p) {
     SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_t), 2));
@@ -1353,7 +1359,10 @@ static int pcg_one_iteration(semb_mesh* m) {
     }
     SEMB_TRY(semb_launch_pcg_set_pap(c, m));
   } else {
-    SEMB_TRY(run_operator(m, m->w_r->d, m->w_Ap->d, sp, true, m->w_p->d, o.precond, o.prec_b0));
+    if (m->pcg_keep_h)
+      SEMB_TRY(run_operator(m, m->w_h->d, m->w_Ap->d, sp, true, m->w_p->d, 0, o.prec_b0));
+    else
+      SEMB_TRY(run_operator(m, m->w_r->d, m->w_Ap->d, sp, true, m->w_p->d, o.precond, o.prec_b0));
     if (c->nranks > 1 && !m->p2p) {
       SEMB_TRY(semb_launch_pcg_pack_pap(c, m));
       SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_pap), 1));
@@ -1361,7 +1370,8 @@ static int pcg_one_iteration(semb_mesh* m) {
     }
   }
   // P2P: the update kernel's last block all-gathers {t, norm(r,Inf)} over NVLink and advances the state
-  SEMB_TRY(semb_launch_pcg_update(c, m, m->pcg_x->d, m->w_r->d, m->w_p->d, m->w_Ap->d, o.precond, o.prec_b0,
+  SEMB_TRY(semb_launch_pcg_update(c, m, m->pcg_x->d, m->w_r->d, m->w_p->d, m->w_Ap->d,
+                                  m->pcg_keep_h ? m->w_h->d : nullptr, o.precond, o.prec_b0,
                                   p2p_args(m, m->p2p ? ++m->ep_t : 0)));
   if (c->nranks > 1 && !m->p2p) {
     SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_t), 2));

@@ -177,12 +177,14 @@ struct semb_mesh {
   semb_field* w_r = nullptr;
   semb_field* w_p = nullptr;
   semb_field* w_Ap = nullptr;
+  semb_field* w_h = nullptr;           // h = opM(r) of the preconditioned PCG (written by init / update, staged by the strip kernel)
   semb_field* w_tmp = nullptr;
   semb_field* w_t1 = nullptr;
   semb_field* w_t2 = nullptr;
   semb_field* pcg_x = nullptr;
   semb_pcg_opts pcg_opts;
   bool pcg_active = false;
+  bool pcg_keep_h = false;             // preconditioned PCG on the fused path: h kept in w_h
   // operator hook of the device-resident PCG: when set, an iteration is p = h + beta*p, w_Ap = pcg_custom(w_p),
   // sum(p.*Ap.*mult) by the reduction kernel, update -- instead of the fused strip kernel (Stokes Schur operator)
   std::function<int()> pcg_custom;

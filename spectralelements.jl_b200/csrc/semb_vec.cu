@@ -496,7 +496,7 @@ __device__ __forceinline__ void semb_pcg_advance(SembScal* s, double tnew, doubl
 
 // x = 0, r = b, p = 0 (pcg.jl:25-33); t0, rmax0
 __global__ void __launch_bounds__(256) semb_pcg_init_kernel(const double2* __restrict__ b, double2* x, double2* r,
-                                                            double2* p, const double2* __restrict__ Bm,
+                                                            double2* p, double2* hout, const double2* __restrict__ Bm,
                                                             const double2* __restrict__ wx1d,
                                                             const double* __restrict__ wy1d, int p2, int nxl,
                                                             int nyl, int precond, double b0, double tol,
@@ -517,6 +517,7 @@ __global__ void __launch_bounds__(256) semb_pcg_init_kernel(const double2* __res
       const double2 B2 = Bm[i];
       hx = (2 * c2 < nxl) ? semb_prec(bv.x, B2.x, 1, b0) : 0.0;
       hy = (2 * c2 + 1 < nxl) ? semb_prec(bv.y, B2.y, 1, b0) : 0.0;
+      if (hout) hout[i] = make_double2(hx, hy);  // h = opM(r), kept for the strip kernel (staged instead of r)
     }
     acc += __dmul_rn(__dmul_rn(bv.x, hx), m2.x);
     acc += __dmul_rn(__dmul_rn(bv.y, hy), m2.y);
@@ -541,7 +542,7 @@ __global__ void __launch_bounds__(256) semb_pcg_init_kernel(const double2* __res
 
 // x += a*p ; r -= a*Ap (pcg.jl:53-54) with a = t / sum(p.*Ap.*mult) (pcg.jl:52); new t and norm(r,Inf)
 __global__ void __launch_bounds__(256) semb_pcg_update_kernel(double2* x, double2* r, const double2* __restrict__ p,
-                                                              const double2* __restrict__ Ap,
+                                                              const double2* __restrict__ Ap, double2* hout,
                                                               const double2* __restrict__ Bm,
                                                               const double2* __restrict__ wx1d,
                                                               const double* __restrict__ wy1d, int p2, int nxl,
@@ -573,6 +574,7 @@ __global__ void __launch_bounds__(256) semb_pcg_update_kernel(double2* x, double
       const double2 B2 = Bm[i];
       hx = (2 * c2 < nxl) ? semb_prec(rv.x, B2.x, 1, b0) : 0.0;
       hy = (2 * c2 + 1 < nxl) ? semb_prec(rv.y, B2.y, 1, b0) : 0.0;
+      if (hout) hout[i] = make_double2(hx, hy);
     }
     acc += __dmul_rn(__dmul_rn(rv.x, hx), m2.x);
     acc += __dmul_rn(__dmul_rn(rv.y, hy), m2.y);
@@ -1014,21 +1016,21 @@ int semb_launch_reduce_finalize(semb_ctx* ctx, semb_mesh* m, int which) {
   SEMB_POST_LAUNCH(ctx);
 }
 
-int semb_launch_pcg_init(semb_ctx* ctx, semb_mesh* m, const double* b, double* x, double* r, double* p,
+int semb_launch_pcg_init(semb_ctx* ctx, semb_mesh* m, const double* b, double* x, double* r, double* p, double* hout,
                          int precond, double prec_b0, double tol, long long maxiter, const P2PArgs& xa) {
   Grid2D g = grid2d(m->pitch, m->nyl, ctx->sm_count, m->npartials / 2);
   semb_pcg_init_kernel<<<g.grid, g.block, 0, ctx->stream>>>(
-      (const double2*)b, (double2*)x, (double2*)r, (double2*)p, (const double2*)m->arr[SEMB_B],
+      (const double2*)b, (double2*)x, (double2*)r, (double2*)p, (double2*)hout, (const double2*)m->arr[SEMB_B],
       (const double2*)m->d_wx1d, m->d_wy1d, (int)(m->pitch / 2), m->nxl, m->nyl, precond, prec_b0, tol, maxiter,
       m->d_partials, m->d_counters + 3, m->d_scal, xa);
   SEMB_POST_LAUNCH(ctx);
 }
 
 int semb_launch_pcg_update(semb_ctx* ctx, semb_mesh* m, double* x, double* r, const double* p, const double* Ap,
-                           int precond, double prec_b0, const P2PArgs& xa) {
+                           double* hout, int precond, double prec_b0, const P2PArgs& xa) {
   Grid2D g = grid2d(m->pitch, m->nyl, ctx->sm_count, m->npartials / 2);
   semb_pcg_update_kernel<<<g.grid, g.block, 0, ctx->stream>>>(
-      (double2*)x, (double2*)r, (const double2*)p, (const double2*)Ap, (const double2*)m->arr[SEMB_B],
+      (double2*)x, (double2*)r, (const double2*)p, (const double2*)Ap, (double2*)hout, (const double2*)m->arr[SEMB_B],
       (const double2*)m->d_wx1d, m->d_wy1d, (int)(m->pitch / 2), m->nxl, m->nyl, precond, prec_b0, m->d_partials,
       m->d_counters + 3, m->d_scal, xa);
   SEMB_POST_LAUNCH(ctx);

@@ -34,10 +34,11 @@ int semb_launch_generic_local(semb_ctx* ctx, const OpArgs& a, int nr, int ns, co
 int semb_launch_reduce(semb_ctx* ctx, semb_mesh* m, int which, const double* a, const double* b, const P2PArgs& x,
                        double ref = 0.0);
 // PCG vector kernels
-int semb_launch_pcg_init(semb_ctx* ctx, semb_mesh* m, const double* b, double* x, double* r, double* p,
+// hout (may be NULL): where h = opM(r) is kept when the diagonal preconditioner is on (the strip kernel then stages h)
+int semb_launch_pcg_init(semb_ctx* ctx, semb_mesh* m, const double* b, double* x, double* r, double* p, double* hout,
                          int precond, double prec_b0, double tol, long long maxiter, const P2PArgs& xa);
 int semb_launch_pcg_update(semb_ctx* ctx, semb_mesh* m, double* x, double* r, const double* p, const double* Ap,
-                           int precond, double prec_b0, const P2PArgs& xa);
+                           double* hout, int precond, double prec_b0, const P2PArgs& xa);
 int semb_launch_pcg_dir(semb_ctx* ctx, semb_mesh* m, const double* r, double* p, int precond, double prec_b0);
 int semb_launch_mask_dot(semb_ctx* ctx, semb_mesh* m, const OpArgs& a);
 int semb_launch_pcg_pack_pap(semb_ctx* ctx, semb_mesh* m);
