@@ -39,7 +39,7 @@ ALG_BYTES_POISSON = 40.0    # read u, G11, G12, G22; write Au
 ALG_BYTES_HELMHOLTZ = 48.0  # + B
 ALG_BYTES_PCG_ITER = 112.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one strip-kernel launch (ncu --set full), keyed by (nr, E)
-NCU_TRAFFIC_GB = {(9, 1112): 3.2096 + 0.7811}
+NCU_TRAFFIC_GB = {(9, 1112): 3.2108 + 0.7850}
 
 
 def measured_peak():
@@ -369,7 +369,7 @@ def run_semb(args):
                        "l2": "inputs (%.1f GB per apply) exceed the 126 MB L2" % (ALG_BYTES_POISSON * ndof_local / 1e9),
                        "strips_x_chunks": [plan["nstrips"], plan["nchunks"]]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_GB.get((nr, E)), "traffic_unit": "GB per launch (ncu --set full, profiles/r01_strip9_r1e.txt)",
+                         "traffic": NCU_TRAFFIC_GB.get((nr, E)), "traffic_unit": "GB per launch (ncu --set full, profiles/r01_strip9_r1k.txt)",
                          "kernel": "semb_strip_kernel<%d>" % nr,
                          "algorithmic_bytes_per_dof": ALG_BYTES_POISSON, "kernel_ms": strip_ms,
                          "kernel_share_of_step": strip_ms / ms_per_step, "peak_source": peak_src,

@@ -98,3 +98,37 @@ def test_pressure_projection(sem, ctx, nr, Ex, Ey, per, deform, bcx, bcy):
         gsk.free()
         gV.free()
         gP.free()
+
+
+def test_stokes_error_behaviour(sem, ctx):
+    """DimensionMismatch-style failures surface as SembError (no silent fallback): meshes that do not pair, fields of the
+    wrong mesh, aliasing outputs, a zero b0, a bad bc string."""
+    gV = sem.Mesh(7, 7, 3, 2, (False, False), sem.wavy, ctx=ctx)
+    gP = sem.Mesh(5, 5, 3, 2, (False, False), sem.wavy, ctx=ctx)
+    gQ = sem.Mesh(5, 5, 2, 2, (False, False), sem.wavy, ctx=ctx)   # different element count
+    try:
+        with pytest.raises(sem.SembError):
+            sem.Stokes("DDDD", "DDDD", gV, gQ)
+        with pytest.raises(sem.SembError):
+            sem.Stokes("DDDD", "DDDD", gV, gP, b0=0.0)
+        with pytest.raises(sem.SembError):
+            sem.Stokes("DDXD", "DDDD", gV, gP)
+        sks = sem.Stokes("DDDD", "DDDD", gV, gP)
+        fv, fp, fq = gV.field(), gP.field(), gQ.field()
+        lib = ctx.lib
+        assert lib.semb_diver(sks.h, fv.h, fp.h, fp.h) < 0          # uy is a pressure-mesh field
+        assert lib.semb_diverT(sks.h, fv.h, fv.h, fv.h) < 0         # pr must live on mshP
+        assert lib.semb_diverT(sks.h, fp.h, fv.h, fv.h) < 0         # outputs alias
+        assert lib.semb_stokes_op(sks.h, fp.h, fp.h) < 0            # out aliases q
+        assert lib.semb_stokes_op(sks.h, fq.h, fp.h) < 0            # field of another mesh
+        assert lib.semb_gradT(gV.h, fv.h, fv.h, fv.h) < 0
+        assert lib.semb_approx_hlmz_inv(gV.h, fv.h, 0.0, b"DDDD", gV.field().h) < 0
+        assert b"b0" in lib.semb_last_error()
+        # a well-formed call still works after the failures
+        q = so.splitmix_uniform(gP.shape, seed=3)
+        assert np.all(np.isfinite(sem.opStokesLHS(q, sks)))
+        sks.free()
+    finally:
+        gV.free()
+        gP.free()
+        gQ.free()
