@@ -3,12 +3,12 @@
 The reference has no golden vectors and cannot be executed here (Julia missing), so these fixtures pin
 the ORACLE (drift detector) and give the GPU tests committed input/output pairs.  tools/ref_dump.jl
 writes the same arrays from the real Julia reference for anyone who has it.
-    python tools/make_golden.py
+    python tests/golden/make_golden.py
 """
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
 import sem_oracle as so

@@ -22,7 +22,7 @@ def rhs_for(om, M, f):
 
 def count_close(it_g, it_o):
     """CG on these unpreconditioned systems is chaotic in rounding after ~60 iterations: the oracle's own
-    count moves by 1-3 % when its operator is perturbed by 1 ulp (tools/pcg_divergence.py).
+    count moves by 1-3 % when its operator is perturbed by 1 ulp (tests/tools/pcg_divergence.py).
     Counts must agree exactly for short solves and within that spread for long ones."""
     return it_g == it_o if it_o <= 60 else abs(it_g - it_o) <= max(3, int(0.05 * it_o))
 
@@ -54,7 +54,7 @@ def test_pcg_matches_oracle(sem, ctx, nr, E, per, deform, bc, k):
         info_o = {}
         xo = so.pcg(b, opo, mult=om.mult, tol=1e-8, info=info_o)
         # (1) the trajectory itself: norm(r,Inf) of the first 12 iterations agrees to 1e-10 (rounding differences
-        # grow roughly 10x every 5-10 iterations afterwards: tools/pcg_divergence.py)
+        # grow roughly 10x every 5-10 iterations afterwards: tests/tools/pcg_divergence.py)
         fb, fx = gm.field(b), gm.field()
         hg = gpu_history(gm, fb, fx, 12, nu=1.0, k=k, bc=bc, tol=0.0)
         ho = np.array(info_o["hist"][:13])

@@ -1,12 +1,12 @@
 """Compare a true-reference dump (tools/ref_dump.jl, run where Julia exists) with the CPU oracle, and -- when a GPU
 and libsemb.so are available -- with the CUDA path.  This is how "parity unpinned" gets pinned.
-    python tools/compare_ref_dump.py ref_dump_dir [--gpu]
+    python tests/tools/compare_ref_dump.py ref_dump_dir [--gpu]
 """
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tools")]
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests", "golden")]
 import numpy as np
 import sem_oracle as so
 from make_golden import CASES, build

@@ -1,7 +1,7 @@
 """Diagnostic: per-iteration norm(r,Inf) of the device PCG against the CPU oracle (same mesh, same rhs).
 Shows how rounding-level differences (reduction order, FMA contraction) grow along the CG trajectory."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import numpy as np
 import sem_oracle as so

@@ -1,6 +1,6 @@
 """Wall time of complete small PCG solves (launch-bound regime): CUDA-graph replay vs plain launches."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import numpy as np
 import sem_oracle as so

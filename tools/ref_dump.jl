@@ -1,7 +1,7 @@
 #!/usr/bin/env julia
 # Regenerate TRUE-reference goldens with the Julia reference (SpectralElements.jl) on a machine that
 # has Julia: writes raw little-endian Float64 column-major files matching tests/golden/*.npz keys, so
-# tools/compare_ref_dump.py can check oracle/sem_oracle.py and the CUDA path against them.
+# tests/tools/compare_ref_dump.py can check oracle/sem_oracle.py and the CUDA path against them.
 #   julia --project=/path/to/SpectralElements.jl tools/ref_dump.jl outdir
 using SpectralElements, LinearAlgebra
 wavy(x, y) = (d = @. 0.1 * sin(pi * x) * sin(pi * y); (x .+ d, y .+ d))
