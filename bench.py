@@ -435,9 +435,12 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "laplacian_gs_mask_apply_throughput", "value": val, "unit": "GDOF/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "fused Laplacian+QQ^T+mask apply (opLHS, Poisson), order %d (nr=%d), bounded sample: "
-                                   "%dx%d-element y-slab of the %dx%d headline mesh, throughput per DOF"
-                                   % (args.nr - 1, args.nr, args.elements, args.cpu_rows, args.elements, args.elements)},
+            "config": {"workload": "fused Laplacian+QQ^T+mask apply (opLHS, Poisson nu=1 k=0, bc DDDD), order %d "
+                                   "(nr=%d), %dx%d elements per GPU, wavy-deformed box, %d DOF per GPU"
+                                   % (args.nr - 1, args.nr, args.elements, args.elements,
+                                      (args.nr * args.elements) ** 2),
+                       "sample": "each step = one apply on a %dx%d-element y-slab of that mesh (%d DOF); throughput per DOF"
+                                 % (args.elements, args.cpu_rows, u.size)},
             "cpu_baseline": cpu,
             "e2e": {"value": val, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference = NumPy/OpenBLAS restatement of the Julia CPU path (oracle/); Julia is not installed"}
