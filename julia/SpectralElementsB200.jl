@@ -9,11 +9,16 @@
 # NOTE: Julia is not installed in the build container, so this file is written against the C ABI and
 # syntax-reviewed, but has NOT been executed.  tests/ drive the same ABI through Python ctypes.
 #
+# The methods below have the reference's exact signatures and REPLACE its CPU methods (that is the drop-in);
+# Julia >= 1.10 refuses method overwriting while precompiling a package, so this module opts out.
+__precompile__(false)
+
 module SpectralElementsB200
 
 using SpectralElements
 using SpectralElements: Mesh, Diffusion, ConvectionDiffusion
-import SpectralElements: ABu, lapl, hlmz, mass, gatherScatter, mask, pcg, pcg!, opLHS, solve!, grad, advect
+import SpectralElements: ABu, lapl, hlmz, mass, gatherScatter, mask, pcg, pcg!, opLHS, solve!, grad, advect,
+                         laplace, evolve!, step!, fixU!
 
 const libsemb = get(ENV, "LIBSEMB", joinpath(@__DIR__, "..", "spectralelements.jl_b200", "lib", "libsemb.so"))
 
@@ -93,6 +98,9 @@ function hlmz(u::Array, ν, k, msh::Mesh)
     return out
 end
 lapl(u::Array, ν::Array, msh::Mesh) = hlmz(u, ν, 0.0, msh)
+# the reference's "dealiased" mesh-pair forms ignore msh2 (lapl.jl:47-52, hlmz.jl:22-30, mass.jl:25-30)
+lapl(u::Array, msh1::Mesh, msh2::Mesh) = lapl(u, msh1)
+hlmz(u::Array, ν, k, msh1::Mesh, msh2::Mesh) = hlmz(u, ν, k, msh1)
 
 # mass(u,msh), mass.jl:12-22
 function mass(u::Array, msh::Mesh)
@@ -100,6 +108,8 @@ function mass(u::Array, msh::Mesh)
     check(ccall((:semb_mass_host, libsemb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), devmesh(msh), f64(u), out))
     return out
 end
+
+mass(u::Array, msh1::Mesh, msh2::Mesh) = mass(u, msh1)
 
 # gatherScatter(u,msh), gatherScatter.jl:18-21
 function gatherScatter(u, msh::Mesh)
@@ -124,7 +134,7 @@ function ABu(As::AbstractArray, Br::AbstractArray, u::AbstractArray)
     return out
 end
 
-# mask(u,M), mask.jl:10-18 needs the device layout of u: the mesh whose size matches is looked up
+# mask with the mesh at hand (padded device layout, no extra copy); the reference's 2-argument form follows below
 function mask(u::Array, M::Array, msh::Mesh)
     out = similar(u, Float64)
     Mf = length(M) == 0 ? Float64[] : f64(M)
@@ -132,6 +142,11 @@ function mask(u::Array, M::Array, msh::Mesh)
                 devmesh(msh), f64(u), length(M) == 0 ? C_NULL : pointer(Mf), out))
     return out
 end
+
+# mask(u,M), mask.jl:10-18 as the reference calls it (no mesh): M .* u on the device, copy(u) for M = []
+mask(u::Array, M::Array) = length(M) == 0 ? copy(u) : mul(f64(M), f64(u))
+# gatherScatter(u,QQtx,QQty), gatherScatter.jl:8-16: the dense form, through the device ABu
+gatherScatter(u, QQtx::AbstractArray, QQty::AbstractArray) = ABu(QQty, QQtx, u)
 
 # grad(u,msh), grad.jl:15-34 ; advect(T,ux,uy,mshV,mshD,Jr,Js), advect.jl:45-64 (Jr, Js are rebuilt by the library)
 function devfield(msh::Mesh, a::Union{Array,Nothing} = nothing)
@@ -251,6 +266,90 @@ function pressureProject!(vx::Array, vy::Array, pr::Array, sks::StokesB200; tol 
     return it[]
 end
 
+# ---- device-resident time-step drivers (SURVEY 8f-1/8f-2): u, uh[1..k], ub, ν, f, rhs (+ vx, vy) stay in HBM ----------
+# enum semb_diffusion_field_id (include/semb.h)
+const DFN_U, DFN_UB, DFN_NU, DFN_F, DFN_RHS, DFN_VX, DFN_VY, DFN_UH0 = 0, 1, 2, 3, 4, 5, 6, 8
+const DRIVERS = Dict{UInt,Ptr{Cvoid}}()
+
+# Field keeps only the mask array (mesh.jl:179-185): the 'D'/'N' flags are read back from its four outer lines
+bcflags(M) = (m = f64(M); String([m[1, 2] == 0 ? 'D' : 'N', m[end, 2] == 0 ? 'D' : 'N',
+                                  m[2, 1] == 0 ? 'D' : 'N', m[2, end] == 0 ? 'D' : 'N']))
+function dfnfield(d::Ptr{Cvoid}, which::Integer)
+    f = Ref{Ptr{Cvoid}}(C_NULL)      # borrowed handle: owned by the driver, never destroyed here
+    check(ccall((:semb_diffusion_field, libsemb), Cint, (Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}), d, which, f))
+    return f[]
+end
+dfnput(d::Ptr{Cvoid}, which::Integer, a::Array) =
+    check(ccall((:semb_field_upload, libsemb), Cint, (Ptr{Cvoid}, Ptr{Float64}), dfnfield(d, which), f64(a)))
+dfnget!(a::Array, d::Ptr{Cvoid}, which::Integer) =
+    check(ccall((:semb_field_download, libsemb), Cint, (Ptr{Cvoid}, Ptr{Float64}), dfnfield(d, which), a))
+
+"""The device twin of a `Diffusion` / `ConvectionDiffusion`, created at the first step (so at `istep == 0`) from
+the host struct's current state and cached by `objectid`."""
+function driver(eq, mshV::Mesh, mshD::Union{Mesh,Nothing} = nothing)
+    get!(DRIVERS, objectid(eq)) do
+        (fld, ts) = (eq.fld, eq.tstep)
+        k = length(fld.uh)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        if mshD === nothing          # Diffusion(bc,msh;Ti,Tf,dt,k), diffusion.jl:20-34
+            check(ccall((:semb_diffusion_create, libsemb), Cint,
+                        (Ptr{Cvoid}, Cstring, Cdouble, Cdouble, Cdouble, Cint, Ref{Ptr{Cvoid}}),
+                        devmesh(mshV), bcflags(fld.M), ts.time[1], ts.Tf[1], ts.dt[1], k, h))
+        else                         # ConvectionDiffusion(...), convectionDiffusion.jl:31-56
+            check(ccall((:semb_convdiff_create, libsemb), Cint,
+                        (Ptr{Cvoid}, Ptr{Cvoid}, Cstring, Cdouble, Cdouble, Cdouble, Cint, Ref{Ptr{Cvoid}}),
+                        devmesh(mshV), devmesh(mshD), bcflags(fld.M), ts.time[1], ts.Tf[1], ts.dt[1], k, h))
+            dfnput(h[], DFN_VX, eq.vx); dfnput(h[], DFN_VY, eq.vy)
+        end
+        dfnput(h[], DFN_U, fld.u); dfnput(h[], DFN_UB, fld.ub); dfnput(h[], DFN_NU, eq.ν); dfnput(h[], DFN_F, eq.f)
+        for i in 1:k
+            dfnput(h[], DFN_UH0 + i - 1, fld.uh[i])
+        end
+        h[]
+    end
+end
+
+# one step of either equation: updateHist! + time/BDF update on the device, the user closures on the host (only
+# what a closure other than the no-op fixU! may have changed is uploaded), makeRHS! + solve! on the device
+function devstep!(eq, d::Ptr{Cvoid}, msh::Mesh, setBC!, setForcing!, setVisc!; tol = 1e-8)
+    (fld, ts) = (eq.fld, eq.tstep)
+    (t, n) = (Ref{Cdouble}(0.0), Ref{Clonglong}(0))
+    check(ccall((:semb_diffusion_begin_step, libsemb), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Ref{Clonglong}), d, t, n))
+    # the host TimeStepper follows (time.jl:70-82), so callbacks and the loop test of simulate! read current values
+    check(ccall((:semb_diffusion_state, libsemb), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Clonglong}), d, ts.time, ts.bdfA, ts.bdfB, n))
+    ts.istep[1] = n[]
+    for (set!, a, which) in ((setBC!, fld.ub, DFN_UB), (setForcing!, eq.f, DFN_F), (setVisc!, eq.ν, DFN_NU))
+        set! === fixU! && continue
+        set!(a, msh.x, msh.y, ts.time[1])
+        dfnput(d, which, a)
+    end
+    (it, res) = (Ref{Clonglong}(0), Ref{Cdouble}(0.0))
+    rc = check(ccall((:semb_diffusion_finish_step, libsemb), Cint, (Ptr{Cvoid}, Cdouble, Ref{Clonglong}, Ref{Cdouble}),
+                     d, tol, it, res))
+    rc == 1 && println("warning: res:", res[])           # pcg.jl:39
+    SpectralElements.updateHist!(fld)                    # host copy of the history, for callbacks (mesh.jl:199-215)
+    dfnget!(fld.u, d, DFN_U)
+    return it[]
+end
+
+# evolve!(dfn,setBC!,setForcing!,setVisc!), diffusion.jl:81-106
+function evolve!(dfn::Diffusion, setBC! = fixU!, setForcing! = fixU!, setVisc! = fixU!)
+    devstep!(dfn, driver(dfn, dfn.msh), dfn.msh, setBC!, setForcing!, setVisc!)
+    return
+end
+# step!(cdn), convectionDiffusion.jl:150-157 (updateHist!, updateHist!(tstep), evolve! with the struct's closures)
+function step!(cdn::ConvectionDiffusion)
+    devstep!(cdn, driver(cdn, cdn.mshV, cdn.mshD), cdn.mshV, cdn.set∂!, cdn.setF!, cdn.setν!)
+    return
+end
+"""Release the device twin of an equation (the library frees its fields)."""
+function release!(eq)
+    d = pop!(DRIVERS, objectid(eq), C_NULL)
+    d == C_NULL || ccall((:semb_diffusion_destroy, libsemb), Cint, (Ptr{Cvoid},), d)
+    return
+end
+
 # ---- the fused unit and the device-resident Krylov loop ------------------------------------------------
 """opLHS as a callable struct: applying it runs the fused kernel; handing it to pcg runs the whole
 loop on the device (an arbitrary Julia closure cannot execute there)."""
@@ -325,6 +424,6 @@ function solve!(cdn::ConvectionDiffusion)
     return
 end
 
-export OpLHS, DiagPrecond, comm_unique_id, comm_init
+export OpLHS, DiagPrecond, StokesB200, release!, comm_unique_id, comm_init
 
 end # module

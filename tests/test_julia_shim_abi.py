@@ -161,9 +161,32 @@ def test_shim_blocks_balance():
 
 
 @pytest.mark.parametrize("name", ["ABu", "lapl", "hlmz", "mass", "gatherScatter", "mask", "pcg", "pcg!", "opLHS", "solve!",
-                                  "grad", "advect"])
+                                  "grad", "advect", "laplace", "evolve!", "step!"])
 def test_shim_defines_the_reference_methods(name):
     """The reference's signatures for the path are extended, not renamed."""
     src = open(SHIM).read()
     assert re.search(r"^import SpectralElements:.*\b%s(?![\w!])" % re.escape(name), src, flags=re.M), name
     assert re.search(r"^(?:function\s+)?%s\(" % re.escape(name), src, flags=re.M), name
+
+
+def test_pcg_opts_struct_layout_matches():
+    """`struct PcgOpts` in the shim is passed by reference as `semb_pcg_opts`: same fields, order and C types."""
+    hdr = _strip_c_comments(open(HEADER).read())
+    body = re.search(r"typedef struct semb_pcg_opts \{(.*?)\} semb_pcg_opts;", hdr, flags=re.S).group(1)
+    cfields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            name = re.search(r"(\w+)$", decl).group(1)
+            cfields.append((name, _norm_ctype(decl)))
+    src = re.sub(r"#[^\n]*", "", open(SHIM).read())
+    jbody = re.search(r"struct PcgOpts\n(.*?)\nend", src, flags=re.S).group(1)
+    jfields = [tuple(x.strip() for x in f.split("::")) for f in re.split(r"[;\n]", jbody) if f.strip()]
+    assert [n for n, _ in cfields] == [n for n, _ in jfields]
+    want = {"double": {"Cdouble"}, "int": {"Cint"}, "long long": {"Clonglong"}, "semb_field*": {"Ptr{Cvoid}"},
+            "char*": {"Ptr{UInt8}", "Cstring"}}
+    for (cn, ct), (jn, jt) in zip(cfields, jfields):
+        assert jt in want[ct], (cn, ct, jt)
+    # the positional constructor call in pcg() passes one value per field
+    ctor = re.search(r"PcgOpts\(([^\n]*)\)\)\n", src).group(1)
+    assert len(_split_top(ctor)) == len(cfields)
