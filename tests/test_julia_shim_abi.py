@@ -148,9 +148,10 @@ def test_every_ccall_matches_its_prototype():
     assert not bad, "\n".join(bad)
 
 
-def test_shim_blocks_balance():
-    """Every block opener has its `end` (a cheap guard for a file that cannot be parsed by Julia here)."""
-    src = re.sub(r"#[^\n]*", "", open(SHIM).read())
+@pytest.mark.parametrize("path", [SHIM, os.path.join(ROOT, "tools", "ref_dump.jl"), os.path.join(ROOT, "bench", "ref_cpu.jl")])
+def test_julia_blocks_balance(path):
+    """Every block opener has its `end` (a cheap guard for files that cannot be parsed by Julia here)."""
+    src = re.sub(r"#[^\n]*", "", open(path).read())
     src = re.sub(r'"""(?:.|\n)*?"""', '""', src)
     src = re.sub(r'"(?:\\.|[^"\\\n])*"', '""', src)
     src = re.sub(r"\[[^\[\]\n]*\bend\b[^\[\]\n]*\]", "[]", src)  # a[end] indexing
