@@ -325,8 +325,11 @@ static int mesh_build_plan(semb_mesh* m) {
   if (m->fast) SEMB_TRY(semb_strip_regs(m->nr, false, false, nullptr, nullptr, &occ));
   if (occ < 1) occ = 1;
   // chunks: fill the resident CTA slots.  Small meshes (fewer element rows than slots) get one chunk per
-  // element row (parallelism beats seam overhead); large ones the count in [1 wave, 4 waves] with the best
-  // wave efficiency and at least 2 element rows per chunk.
+  // element row (parallelism beats seam overhead); larger ones the count in [1 wave, 4 waves] that minimises
+  //   waves * (element rows of the longest chunk + F),   waves = ceil(CTAs / slots),
+  // i.e. the critical path in element-row times: every wave pays the rows of its longest chunk plus a pipeline
+  // fill/drain of F ~ half a row.  Measured (profiles/r01_sweep_chunks_r1l.txt): 256x256 order 8 picks 29 chunks
+  // (one full wave, 59.4 us per apply) instead of 59 (two waves of 4-5 rows, 66.5 us); 1112x1112 keeps 22.
   const int slots = c->sm_count * occ;
   const int lo = std::max(1, slots / m->nstrips), hi = std::max(lo, 4 * slots / m->nstrips);
   int best = 1;
@@ -335,13 +338,14 @@ static int mesh_build_plan(semb_mesh* m) {
   } else if (m->ney / 2 <= lo) {
     best = lo;
   } else {
-    double best_eff = -1.0;
+    double best_cost = 1e300;
     for (int nc = lo; nc <= hi && nc <= m->ney / 2; ++nc) {
       const long long ctas = (long long)nc * m->nstrips;
       const long long waves = (ctas + slots - 1) / slots;
-      const double eff = (double)ctas / (double)(waves * slots) - 1e-4 * nc;  // prefer fewer seams on ties
-      if (eff > best_eff) {
-        best_eff = eff;
+      const int rows = (m->ney + nc - 1) / nc;
+      const double cost = (double)waves * ((double)rows + 0.5);
+      if (cost <= best_cost) {  // ties: more chunks (fuller last wave, fewer CTAs carrying the extra row)
+        best_cost = cost;
         best = nc;
       }
     }
