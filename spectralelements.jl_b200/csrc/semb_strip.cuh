@@ -168,13 +168,26 @@ __device__ __forceinline__ void semb_bulk_g2s(void* dst_smem, const void* src_gm
                "l"(src_gmem), "r"(bytes), "r"(semb_smem_u32(bar))
                : "memory");
 }
+// global -> L2 bulk prefetch (no destination, no registers): rows a later plain load will hit in L2
+__device__ __forceinline__ void semb_bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void semb_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+#ifndef SEMB_LATE_B
+#define SEMB_LATE_B 1
+#endif
 
 template <int N, bool PCGM, bool MASS, bool EO>
 __global__ void __launch_bounds__(StripCfg<N>::T, StripCfg<N>::MINB)
 semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
   using C = StripCfg<N>;
   constexpr int S = C::S, PW = C::PW, PWS = C::PWS, BX = C::BX, TSZ = StripTab<N>::SIZE;
+  // where the B column of the mass term is loaded: at the top of the row (plain apply: 20 bytes of spills, latency
+  // hidden behind steps 1-2) or in step 5 after an L2 prefetch (PCG variant, which also carries the p prefetch:
+  // 184 -> 56 bytes of spills, 0.618 -> 0.590 ms per preconditioned iteration at 512x512 order 8; the plain
+  // apply measured 4 % slower in the late form, so it keeps the early one)
+  constexpr bool LATE_B = SEMB_LATE_B && PCGM;
   extern __shared__ __align__(128) double smem[];
   // [N][PW] transposition buffer, updated IN PLACE by the alternating mappings (each phase touches
   // every location from exactly one thread): u -> Dr u -> wr -> Dr^T wr
@@ -237,6 +250,9 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
       const double* src = (first_arr + q == 0) ? a.u : (first_arr + q == 1) ? a.G11 : (first_arr + q == 2) ? a.G12 : a.G22;
       semb_bulk_g2s(stage + (q * N + j) * PWS, src + (size_t)(r * N + j) * pitch + x0, row_bytes, bar);
     }
+    // general coefficients: B is read late (step 5) with plain loads; its rows travel to L2 alongside the G rows
+    if (MASS && LATE_B && first_arr == 1 && a.B && t < N)
+      semb_bulk_prefetch_l2(a.B + (size_t)(r * N + t) * pitch + x0, row_bytes);
   };
   for (int q = t; q < 4 * TSZ; q += C::T) sT[q] = (&P.tab[0][0])[q];
   if (t == 0) {
@@ -277,7 +293,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     const uint32_t parity = (uint32_t)((r - r0) & 1);
     // coefficient columns that are not staged: issued now, consumed in step 3
     double bq[N];
-    if (MASS) {  // MASS = "general coefficients": k != 0, array k, or (non-constant) array nu
+    if (MASS && !LATE_B) {  // MASS = "general coefficients": k != 0, array k, or (non-constant) array nu
 #pragma unroll
       for (int j = 0; j < N; ++j) bq[j] = (a.B && actB) ? a.B[base + j * pitch] : 0.0;
     }
@@ -289,7 +305,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
       double v = SU[j * PWS + tr];
       if (PCGM && actB) {
         const int idx = base + j * pitch;
-        if (a.precond) v = (v / (MASS ? bq[j] : a.B[idx])) / a.prec_b0;  // convectionDiffusion.jl:89
+        if (a.precond) v = (v / ((MASS && !LATE_B) ? bq[j] : a.B[idx])) / a.prec_b0;  // convectionDiffusion.jl:89
         v = __dadd_rn(v, __dmul_rn(beta, pn[j]));        // pcg.jl:49
         a.pout[idx] = v;
       }
@@ -324,7 +340,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     }
     semb_contract<N, EO>(sT + 2 * TSZ, ws, aus);  // (Ds^T ws)[m] = sum_j Ds(j,m) ws[j]
     double mt[N];  // k .* (B .* u), hlmz.jl:16 / mass.jl:17
-    if (MASS) {
+    if (MASS && !LATE_B) {
 #pragma unroll
       for (int j = 0; j < N; ++j) {
         const double kk = (a.k_arr && actB) ? a.k_arr[base + j * pitch] : a.k;
@@ -344,6 +360,17 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     }
     __syncthreads();
     // ---- step 5 (B): combine, hlmz, gather-scatter, mask, store -----------------------------------
+    if (MASS && LATE_B) {
+      // the B column is fetched here (L2 hits: prefetched with the G rows) instead of at the top of the row, where it
+      // stayed live across steps 1-3 next to u, us, ws and the p prefetch (184 bytes of spills in the PCG variant)
+#pragma unroll
+      for (int j = 0; j < N; ++j) bq[j] = (a.B && actB) ? a.B[base + j * pitch] : 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const double kk = (a.k_arr && actB) ? a.k_arr[base + j * pitch] : a.k;
+        mt[j] = __dmul_rn(kk, __dmul_rn(bq[j], u[j]));
+      }
+    }
     double v[N];
 #pragma unroll
     for (int j = 0; j < N; ++j)
