@@ -1405,7 +1405,9 @@ extern "C" int semb_pcg(semb_mesh* m, const semb_pcg_opts* o, const semb_field* 
                         double* resinf) {
   SEMB_TRY(semb_pcg_begin(m, o, b, x));
   semb_ctx* c = m->ctx;
-  const int every = o->check_every > 0 ? o->check_every : 16;
+  // polling interval of the done flag: 16 iterations when the kernels themselves stop at `done` (a late poll costs a
+  // few empty launches), 4 with a custom operator, whose kernels run in full until the host notices
+  const int every = o->check_every > 0 ? o->check_every : (m->pcg_custom ? 4 : 16);
   // The loop is launch-bound on small meshes: capture `every` iterations (4 kernels each, all scalars live in
   // device memory, so the arguments never change) into a CUDA graph and replay it between polls of the
   // device-side done flag.  Multi-rank runs keep plain launches (per-iteration epochs / NCCL calls).
