@@ -561,6 +561,9 @@ __global__ void __launch_bounds__(256) semb_pcg_update_kernel(double2* x, double
   SEMB_FOR_2D(p2, nyl) {
     const size_t i = (size_t)row * p2 + c2;
     const double2 pv = p[i], av = Ap[i];
+    // B travels with the other four loads (inside the `if (precond)` below it was issued only after they had
+    // arrived: two exposed memory latencies per trip, long-scoreboard stalls 78 %, profiles/r01_update_prec_r1n.txt)
+    const double2 B2 = precond ? Bm[i] : make_double2(1.0, 1.0);
     const double2 m2 = semb_mult2(wx1d, wy1d, c2, row);
     double2 xv = x[i], rv = r[i];
     xv.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
@@ -571,7 +574,6 @@ __global__ void __launch_bounds__(256) semb_pcg_update_kernel(double2* x, double
     r[i] = rv;
     double hx = rv.x, hy = rv.y;
     if (precond) {
-      const double2 B2 = Bm[i];
       hx = (2 * c2 < nxl) ? semb_prec(rv.x, B2.x, 1, b0) : 0.0;
       hy = (2 * c2 + 1 < nxl) ? semb_prec(rv.y, B2.y, 1, b0) : 0.0;
       if (hout) hout[i] = make_double2(hx, hy);
