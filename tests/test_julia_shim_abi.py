@@ -148,13 +148,15 @@ def test_every_ccall_matches_its_prototype():
     assert not bad, "\n".join(bad)
 
 
-@pytest.mark.parametrize("path", [SHIM, os.path.join(ROOT, "tools", "ref_dump.jl"), os.path.join(ROOT, "bench", "ref_cpu.jl")])
+@pytest.mark.parametrize("path", [SHIM, os.path.join(ROOT, "tools", "ref_dump.jl"), os.path.join(ROOT, "bench", "ref_cpu.jl"),
+                                  os.path.join(ROOT, "julia", "test", "runtests.jl")])
 def test_julia_blocks_balance(path):
     """Every block opener has its `end` (a cheap guard for files that cannot be parsed by Julia here)."""
     src = re.sub(r"#[^\n]*", "", open(path).read())
     src = re.sub(r'"""(?:.|\n)*?"""', '""', src)
     src = re.sub(r'"(?:\\.|[^"\\\n])*"', '""', src)
     src = re.sub(r"\[[^\[\]\n]*\bend\b[^\[\]\n]*\]", "[]", src)  # a[end] indexing
+    src = re.sub(r"\[[^\[\]\n]*\bfor\b[^\[\]\n]*\]", "[]", src)  # comprehensions
     opens = len(re.findall(r"(?<![\w.:])(?:function|if|for|while|let|try|begin|do|struct|module|quote|macro)\b(?!\s*=)", src))
     opens -= len(re.findall(r"\bmutable\s+struct\b", src)) * 0
     ends = len(re.findall(r"(?<![\w.:])end\b", src))
