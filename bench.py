@@ -403,11 +403,49 @@ def cpu_reference(nr, E, sample_rows, reps):
         thr = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
     except Exception:
         thr = os.cpu_count()
-    return {"value": u.size / dt / 1e9, "unit": "GDOF/s", "cores": thr, "kind": "port",
+    c_port = None
+    try:  # second restatement (oracle/sem_oracle.c, plain C loops per element): a compiled figure beside the NumPy one
+        c_port = cpu_reference_c(nr, E, min(sample_rows, 64))
+    except Exception as e:  # checker-side extra: never lets the bench fail
+        c_port = {"unavailable": str(e)[:120]}
+    return {"value": u.size / dt / 1e9, "unit": "GDOF/s", "cores": thr, "kind": "port", "c_port": c_port,
             "sample": "oracle/sem_oracle.py opLHS (NumPy/OpenBLAS restatement; Julia not installed) on a %dx%d-element "
                       "y-slab of the headline mesh (%d DOF), %d applies, %.2f s each; index-form QQ^T (dense QQ^T "
                       "does not fit); host cpu_count=%s" % (E, sample_rows, u.size, reps, dt, os.cpu_count()),
             "seconds_per_apply_sample": dt}
+
+
+def cpu_reference_c(nr, E, rows, reps=3):
+    """The same fused opLHS on an E x rows-element slab through oracle/_build/libsem_oracle_c.so (built by
+    __graft_entry__.build(); single thread unless the toolchain had OpenMP)."""
+    lib_path = os.path.join(ROOT, "oracle", "_build", "libsem_oracle_c.so")
+    if not os.path.exists(lib_path):
+        raise FileNotFoundError("oracle/_build/libsem_oracle_c.so not built")
+    import numpy as np
+    lib = C.CDLL(lib_path)
+    dp = C.POINTER(C.c_double)
+    lib.so_mesh_create.restype = C.c_void_p
+    lib.so_mesh_create.argtypes = [C.c_int] * 7
+    lib.so_mesh_free.argtypes = [C.c_void_p]
+    lib.so_generate_mask.argtypes = [C.c_void_p, C.c_char_p, dp]
+    lib.so_oplhs.argtypes = [C.c_void_p, dp, dp, C.c_double, dp, C.c_double, dp, dp]
+    lib.so_oplhs.restype = None
+    h = lib.so_mesh_create(nr, nr, E, rows, 0, 0, 2)   # 2 = wavy
+    try:
+        n = nr * E * nr * rows
+        u = np.random.default_rng(0x5EED).uniform(-1.0, 1.0, n)
+        out, M = np.zeros(n), np.zeros(n)
+        P = lambda a: a.ctypes.data_as(dp)
+        lib.so_generate_mask(h, b"DDDD", P(M))
+        lib.so_oplhs(h, P(u), None, 1.0, None, 0.0, P(M), P(out))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            lib.so_oplhs(h, P(u), None, 1.0, None, 0.0, P(M), P(out))
+        dt = (time.perf_counter() - t0) / reps
+    finally:
+        lib.so_mesh_free(h)
+    return {"value": n / dt / 1e9, "unit": "GDOF/s", "cores": 1,
+            "sample": "oracle/sem_oracle.c opLHS on a %dx%d-element slab (%d DOF), %d applies, %.2f s each" % (E, rows, n, reps, dt)}
 
 
 def run_reference(args):
