@@ -194,3 +194,35 @@ def test_pcg_opts_struct_layout_matches():
     # the positional constructor call in pcg() passes one value per field
     ctor = re.search(r"PcgOpts\(([^\n]*)\)\)\n", src).group(1)
     assert len(_split_top(ctor)) == len(cfields)
+
+
+def _c_enum(name):
+    hdr = _strip_c_comments(open(HEADER).read())
+    body = re.search(r"enum %s \{(.*?)\}" % name, hdr, flags=re.S).group(1)
+    vals, nxt = {}, 0
+    for item in body.split(","):
+        item = item.strip()
+        if not item:
+            continue
+        if "=" in item:
+            k, v = [x.strip() for x in item.split("=")]
+            nxt = int(v)
+        else:
+            k = item
+        vals[k] = nxt
+        nxt += 1
+    return vals
+
+
+def test_shim_enum_constants_match_the_header():
+    """Integer selectors hard-coded in the shim (mesh arrays for semb_mesh_set, driver fields) equal the C enums."""
+    src = open(SHIM).read()
+    ma = _c_enum("semb_mesh_array")
+    pairs = re.search(r"for \(which, a\) in \(\((\d+), msh\.rx\), \((\d+), msh\.ry\), \((\d+), msh\.sx\), \((\d+), msh\.sy\)\)", src)
+    assert [int(g) for g in pairs.groups()] == [ma["SEMB_RX"], ma["SEMB_RY"], ma["SEMB_SX"], ma["SEMB_SY"]]
+    df = _c_enum("semb_diffusion_field_id")
+    names = re.search(r"const (DFN_\w+(?:, DFN_\w+)*) = ([\d, ]+)\n", src)
+    got = dict(zip([n.strip() for n in names.group(1).split(",")], [int(v) for v in names.group(2).split(",")]))
+    want = {"DFN_U": df["SEMB_DFN_U"], "DFN_UB": df["SEMB_DFN_UB"], "DFN_NU": df["SEMB_DFN_NU"], "DFN_F": df["SEMB_DFN_F"],
+            "DFN_RHS": df["SEMB_DFN_RHS"], "DFN_VX": df["SEMB_DFN_VX"], "DFN_VY": df["SEMB_DFN_VY"], "DFN_UH0": df["SEMB_DFN_UH0"]}
+    assert got == want
