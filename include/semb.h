@@ -79,6 +79,10 @@ int semb_free_pinned(void* p);
 /* ---- multi-GPU plumbing (new; the reference is single-process) ------------------ */
 /* Contiguous y-slab owned by `rank`: element rows [ey0, ey0+ney). No GPU needed. */
 int semb_partition(int Ey, int nranks, int rank, int* ey0, int* ney);
+/* Chunk count of the strip-kernel launch plan (grid = strips x chunks) for a slab of `ney` element rows on `slots`
+ * resident CTA slots: minimises waves x (element rows of the longest chunk + 1/2).  No reference counterpart (the
+ * reference has no launch geometry); exported so the host logic is testable without a GPU. */
+int semb_plan_chunks(int nstrips, int ney, int slots, int* nchunks);
 /* Neighbour ranks of a slab (periodic wrap included); rank_lo/rank_hi = -1 when absent. No GPU needed. */
 int semb_halo_plan(int nranks, int rank, int pery, int* halo_lo, int* halo_hi, int* rank_lo, int* rank_hi);
 /* rank 0: fill a 128-byte ncclUniqueId; the host language broadcasts it (torch.distributed / MPI). */

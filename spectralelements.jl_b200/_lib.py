@@ -50,6 +50,7 @@ _SIGS = {
     "semb_alloc_pinned": ([C.c_size_t, C.POINTER(vp)], C.c_int),
     "semb_free_pinned": ([vp], C.c_int),
     "semb_partition": ([C.c_int, C.c_int, C.c_int, c_int_p, c_int_p], C.c_int),
+    "semb_plan_chunks": ([C.c_int, C.c_int, C.c_int, c_int_p], C.c_int),
     "semb_halo_plan": ([C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p], C.c_int),
     "semb_comm_unique_id": ([C.c_char_p], C.c_int),
     "semb_comm_init": ([vp, C.c_int, C.c_int, C.c_char_p], C.c_int),

@@ -324,32 +324,12 @@ static int mesh_build_plan(semb_mesh* m) {
   int occ = 1;
   if (m->fast) SEMB_TRY(semb_strip_regs(m->nr, false, false, nullptr, nullptr, &occ));
   if (occ < 1) occ = 1;
-  // chunks: fill the resident CTA slots.  Small meshes (fewer element rows than slots) get one chunk per
-  // element row (parallelism beats seam overhead); larger ones the count in [1 wave, 4 waves] that minimises
-  //   waves * (element rows of the longest chunk + F),   waves = ceil(CTAs / slots),
-  // i.e. the critical path in element-row times: every wave pays the rows of its longest chunk plus a pipeline
-  // fill/drain of F ~ half a row.  Measured (profiles/r01_sweep_chunks_r1l.txt): 256x256 order 8 picks 29 chunks
-  // (one full wave, 59.4 us per apply) instead of 59 (two waves of 4-5 rows, 66.5 us); 1112x1112 keeps 22.
+  // chunks: fill the resident CTA slots; the rule (waves x (rows of the longest chunk + 1/2), measured on chunk sweeps:
+  // 256x256 order 8 takes 29 chunks = one full wave, 59.4 us per apply, instead of 59 = two waves of 4-5 rows, 66.5 us;
+  // 1112x1112 keeps 22) lives in semb_plan_chunks (semb_host.cpp) so that it is testable without a GPU
   const int slots = c->sm_count * occ;
-  const int lo = std::max(1, slots / m->nstrips), hi = std::max(lo, 4 * slots / m->nstrips);
   int best = 1;
-  if (m->ney <= lo) {
-    best = m->ney;
-  } else if (m->ney / 2 <= lo) {
-    best = lo;
-  } else {
-    double best_cost = 1e300;
-    for (int nc = lo; nc <= hi && nc <= m->ney / 2; ++nc) {
-      const long long ctas = (long long)nc * m->nstrips;
-      const long long waves = (ctas + slots - 1) / slots;
-      const int rows = (m->ney + nc - 1) / nc;
-      const double cost = (double)waves * ((double)rows + 0.5);
-      if (cost <= best_cost) {  // ties: more chunks (fuller last wave, fewer CTAs carrying the extra row)
-        best_cost = cost;
-        best = nc;
-      }
-    }
-  }
+  SEMB_TRY(semb_plan_chunks(m->nstrips, m->ney, slots, &best));
   if (best > m->ney) best = m->ney;
   if ((long long)best * m->nstrips > SEMB_NPARTIALS) best = SEMB_NPARTIALS / m->nstrips;
   if (best < 1) best = 1;

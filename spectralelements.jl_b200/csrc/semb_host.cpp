@@ -2,6 +2,7 @@
 // derivative / interpolation matrices, the 1-D SEM grid, BDF/EXT coefficients, slab partition.
 // They restate (reference /root/reference/src): FastGaussQuadrature.gausslobatto as called at
 // mesh.jl:70-71; derivMat.jl:9-35; interp.jl:10-35; semmesh.jl:9-27; time.jl:31-53.
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -167,6 +168,43 @@ extern "C" int semb_partition(int Ey, int nranks, int rank, int* ey0, int* ney) 
   const long long lo = (long long)rank * Ey / nranks, hi = (long long)(rank + 1) * Ey / nranks;
   if (ey0) *ey0 = (int)lo;
   if (ney) *ney = (int)(hi - lo);
+  return SEMB_OK;
+}
+
+// Chunk count of the strip-kernel launch plan (grid = strips x chunks): small slabs (no more element rows than one wave
+// of CTA slots has room for) get one chunk per element row; larger ones the count in [1 wave, 4 waves], with at least two
+// element rows per chunk, that minimises
+//     waves * (element rows of the longest chunk + 1/2),   waves = ceil(strips * chunks / slots),
+// i.e. the critical path in element-row times: every wave pays the rows of its longest chunk plus a pipeline fill/drain
+// of about half a row.  Ties go to the larger count (fuller last wave).  Calibrated on chunk sweeps over eight mesh shapes
+// (profiles/r01_sweep_chunks_r1l.txt).  Host logic only: mesh_build_plan (semb_api.cu) calls it, tests call it directly.
+extern "C" int semb_plan_chunks(int nstrips, int ney, int slots, int* nchunks) {
+  if (nstrips < 1 || ney < 1 || slots < 1 || !nchunks) {
+    semb_set_error("semb_plan_chunks: need nstrips, ney, slots >= 1 (got %d, %d, %d)", nstrips, ney, slots);
+    return SEMB_EINVAL;
+  }
+  const int lo = std::max(1, slots / nstrips), hi = std::max(lo, 4 * slots / nstrips);
+  int best = 1;
+  if (ney <= lo) {
+    best = ney;
+  } else if (ney / 2 <= lo) {
+    best = lo;
+  } else {
+    double best_cost = 1e300;
+    for (int nc = lo; nc <= hi && nc <= ney / 2; ++nc) {
+      const long long ctas = (long long)nc * nstrips;
+      const long long waves = (ctas + slots - 1) / slots;
+      const int rows = (ney + nc - 1) / nc;
+      const double cost = (double)waves * ((double)rows + 0.5);
+      if (cost <= best_cost) {
+        best_cost = cost;
+        best = nc;
+      }
+    }
+  }
+  if (best > ney) best = ney;
+  if (best < 1) best = 1;
+  *nchunks = best;
   return SEMB_OK;
 }
 

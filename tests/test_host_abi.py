@@ -93,3 +93,38 @@ def test_bench_reference_arm_runs_on_cpu():
                         "--warmup", "0", "--elements", "64", "--cpu-rows", "8"], capture_output=True, text=True, timeout=300)
     line = json.loads(p.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def test_plan_chunks_rule(sem):
+    """Launch-plan host logic (semb_plan_chunks, used by mesh_build_plan): the counts the chunk sweeps on the B200 found
+    best (profiles/r01_sweep_chunks_r1l.txt, 296 CTA slots = 148 SMs x 2), and the invariants of any plan."""
+    import ctypes as C
+    lib = sem._lib.load()
+
+    def pick(nstrips, ney, slots=296):
+        n = C.c_int()
+        assert lib.semb_plan_chunks(nstrips, ney, slots, C.byref(n)) == 0
+        return n.value
+
+    measured = {  # (strips, element rows) -> best measured chunk count
+        (40, 1112): 22,   # order 8, 1112x1112 (headline): 736 us; 7/14/29/36/44 chunks: 784-795 us
+        (19, 512): 31,    # order 8, 512x512 (cfg4)
+        (10, 256): 29,    # order 8, 256x256 (cfg2): 59.4 us vs 66.5 us at 59 chunks
+        (12, 256): 24,    # order 10, 256x256 (cfg5 velocity mesh): 84.5 us vs 92.8 us at 74
+        (56, 776): 21,    # order 12, 776x776 (cfg3)
+        (40, 139): 7,     # 1/8 strong-scaling slab of the headline mesh: 113.4 us vs 118.3 us at 22
+        (5, 128): 59,
+        (3, 64): 64,      # fewer rows than slots per strip: one chunk per element row
+    }
+    for (nstrips, ney), want in measured.items():
+        assert pick(nstrips, ney) == want, (nstrips, ney)
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        nstrips, ney, slots = int(rng.integers(1, 200)), int(rng.integers(1, 5000)), int(rng.integers(1, 9)) * 148
+        nc = pick(nstrips, ney, slots)
+        assert 1 <= nc <= ney
+        lo = max(1, slots // nstrips)
+        if ney > 2 * lo:  # large slab: at least one wave's worth of CTAs, at most four, >= 2 element rows per chunk
+            assert lo <= nc <= max(lo, 4 * slots // nstrips) and nc <= ney // 2
+    assert lib.semb_plan_chunks(0, 10, 296, C.byref(C.c_int())) < 0   # bad arguments are errors, not crashes
+    assert b"semb_plan_chunks" in lib.semb_last_error()
