@@ -277,3 +277,44 @@ def test_explicit_argument_forms_match_the_mesh_forms():
            for q in (md, me)]
     assert np.max(np.abs(dea[0] - dea[1])) < 1e-11 * np.max(np.abs(dea[0]))
     assert np.max(np.abs(dea[0] - so.laplace(ub, mb.Dr, mb.Ds, mb.G11, mb.G12, mb.G22))) > 1e-3
+
+
+def test_time_steppers_track_the_examples_analytic_solutions():
+    """The two time-dependent examples carry closed-form solutions (their callbacks print the error against them):
+    examples/d2d.jl:13-16 (forced heat equation, u = sin 2pi x sin 2pi y cos 2pi t) and examples/cd2d.jl:11-16
+    (travelling wave u = sin pi(x - t) sin pi y, zero viscosity, periodic in x, dealiased advection 8 -> 12).  The
+    oracle's BDF3/EXT3 drivers are run with the examples' own meshes and steps; the error stays at the level of the
+    third-order time discretisation and shrinks by about 2^3 per halving of dt."""
+    kx = ky = kt = 2.0
+
+    def ut(x, y, t):
+        return np.sin(kx * np.pi * x) * np.sin(ky * np.pi * y) * np.cos(kt * np.pi * t)
+
+    def forcing(x, y, t):  # d2d.jl:29-31
+        return ut(x, y, t) * ((kx ** 2 + ky ** 2) * np.pi ** 2) \
+            - np.sin(kx * np.pi * x) * np.sin(ky * np.pi * y) * np.sin(kt * np.pi * t) * (kt * np.pi)
+
+    msh = so.make_mesh(8, 8, 5, 5)  # d2d.jl:62-65
+    errs = []
+    for dt, steps in ((0.01, 20), (0.005, 40)):
+        d = so.Diffusion(list("DDDD"), msh, Ti=0.0, Tf=1.0, dt=dt)
+        so.diffusion_simulate(d, setIC=ut, setBC=lambda x, y, t: 0.0 * x, setForcing=forcing,
+                              setVisc=lambda x, y, t: 1.0 + 0.0 * x, max_steps=steps)
+        assert d.istep == steps and abs(d.time[0] - 0.2) < 1e-12
+        errs.append(float(np.max(np.abs(d.u - ut(msh.x, msh.y, d.time[0])))))
+    assert errs[0] < 5e-3 and errs[1] < errs[0] / 3.0, errs
+
+    def wave(x, y, t):  # cd2d.jl:11-16 with ux = 1, uy = 0
+        return np.sin(np.pi * (x - t)) * np.sin(np.pi * y)
+
+    mV = so.make_mesh(8, 8, 5, 5, (True, False))   # cd2d.jl:54-60
+    mD = so.make_mesh(12, 12, 5, 5, (True, False))
+    errs = []
+    for dt, steps in ((5e-3, 20), (2.5e-3, 40)):
+        c = so.ConvectionDiffusion(list("NNDD"), mV, mD, 1.0 + 0.0 * mV.x, 0.0 * mV.x, Ti=0.0, Tf=1.0, dt=dt)
+        c.u = np.asfortranarray(wave(mV.x, mV.y, 0.0))
+        for _ in range(steps):
+            so.convdiff_step(c)   # set0!/set∂!/setF!/setν! of the example leave ub = f = nu = 0
+        assert c.istep == steps
+        errs.append(float(np.max(np.abs(c.u - wave(mV.x, mV.y, c.time[0])))))
+    assert errs[0] < 1e-3 and errs[1] < errs[0] / 3.0, errs
