@@ -449,3 +449,86 @@ long long so_pcg(const so_mesh* m, const double* b, const double* nu_arr, double
   free(r); free(h); free(u); free(Au);
   return it;
 }
+
+/* ---- explicit dealiased convection --------------------------------------------------------------- */
+/* grad(u,msh), grad.jl:15-34: ux = rx.*ur + sx.*us, uy = ry.*ur + sy.*us */
+void so_grad(const so_mesh* m, const double* u, double* ux, double* uy) {
+  const size_t n = (size_t)m->nxl * m->nyl;
+  double *ur = dalloc(n), *us = dalloc(n);
+  deriv(m, u, 0, 0, ur);
+  deriv(m, u, 1, 0, us);
+  for (size_t q = 0; q < n; ++q) {
+    ux[q] = m->rx[q] * ur[q] + m->sx[q] * us[q]; /* grad.jl:30 */
+    uy[q] = m->ry[q] * ur[q] + m->sy[q] * us[q]; /* grad.jl:31 */
+  }
+  free(ur);
+  free(us);
+}
+
+/* one element's tile through J (no x ni, column-major) along r and s: out (no_r x no_s) = Jr * tile * Js', i.e. the
+ * element block of ABu(Js,Jr,.) (ABu.jl:14-33: Br = Jr first, then As = Js); T != 0 applies the transposes */
+static void tile_interp(const double* Jr, int mr, int nr_, const double* Js, int ms, int ns_, int T, const double* in,
+                        size_t ldin, double* out, size_t ldout, double* tmp) {
+  const int ir = T ? mr : nr_, or_ = T ? nr_ : mr, is = T ? ms : ns_, os = T ? ns_ : ms;
+  for (int j = 0; j < is; ++j)
+    for (int i = 0; i < or_; ++i) {
+      double s = 0.0;
+      for (int k = 0; k < ir; ++k) s += (T ? Jr[k + i * mr] : Jr[i + k * mr]) * in[(size_t)j * ldin + k];
+      tmp[(size_t)j * or_ + i] = s;
+    }
+  for (int j = 0; j < os; ++j)
+    for (int i = 0; i < or_; ++i) {
+      double s = 0.0;
+      for (int k = 0; k < is; ++k) s += tmp[(size_t)k * or_ + i] * (T ? Js[k + j * ms] : Js[j + k * ms]);
+      out[(size_t)j * ldout + i] = s;
+    }
+}
+
+/* advect(T,ux,uy,mshV,mshD,Jr,Js), advect.jl:45-64 with Jr = interpMat(mshD.zr,mshV.zr) (advect.jl:72-73): gradient on
+ * mshV, interpolation of Tx, Ty, ux, uy to the dealiasing mesh, pointwise product with mshD.B, projection back with the
+ * transposes.  mD == NULL: the un-dealiased form advect(T,ux,uy,msh), advect.jl:27-43.  Element by element. */
+int so_advect(const so_mesh* V, const so_mesh* D, const double* T, const double* ux, const double* uy, double* out) {
+  const size_t n = (size_t)V->nxl * V->nyl;
+  double *Tx = dalloc(n), *Ty = dalloc(n);
+  so_grad(V, T, Tx, Ty);
+  if (!D) {
+    for (size_t q = 0; q < n; ++q) out[q] = (ux[q] * Tx[q] + uy[q] * Ty[q]) * V->B[q]; /* advect.jl:36-37 */
+    free(Tx);
+    free(Ty);
+    return 0;
+  }
+  if (D->Ex != V->Ex || D->Ey != V->Ey) {
+    free(Tx);
+    free(Ty);
+    return -1;
+  }
+  const int nr = V->nr, ns = V->ns, mr = D->nr, ms = D->ns;
+  double *Jr = dalloc((size_t)mr * nr), *Js = dalloc((size_t)ms * ns);
+  so_interpmat(mr, D->zr, nr, V->zr, Jr);
+  so_interpmat(ms, D->zs, ns, V->zs, Js);
+#pragma omp parallel for schedule(static)
+  for (int ey = 0; ey < V->Ey; ++ey) {
+    const size_t td = (size_t)mr * ms;
+    double* w = (double*)malloc(sizeof(double) * (5 * td + (size_t)mr * (ns > ms ? ns : ms)));
+    double *jtx = w, *jty = w + td, *jux = w + 2 * td, *juy = w + 3 * td, *jc = w + 4 * td, *tmp = w + 5 * td;
+    for (int ex = 0; ex < V->Ex; ++ex) {
+      const size_t oV = (size_t)(ey * ns) * V->nxl + (size_t)ex * nr, oD = (size_t)(ey * ms) * D->nxl + (size_t)ex * mr;
+      tile_interp(Jr, mr, nr, Js, ms, ns, 0, Tx + oV, V->nxl, jtx, mr, tmp); /* advect.jl:54-57 */
+      tile_interp(Jr, mr, nr, Js, ms, ns, 0, Ty + oV, V->nxl, jty, mr, tmp);
+      tile_interp(Jr, mr, nr, Js, ms, ns, 0, ux + oV, V->nxl, jux, mr, tmp);
+      tile_interp(Jr, mr, nr, Js, ms, ns, 0, uy + oV, V->nxl, juy, mr, tmp);
+      for (int j = 0; j < ms; ++j)
+        for (int i = 0; i < mr; ++i) {
+          const size_t q = (size_t)j * mr + i;
+          jc[q] = (jux[q] * jtx[q] + juy[q] * jty[q]) * D->B[oD + (size_t)j * D->nxl + i]; /* advect.jl:59-60 */
+        }
+      tile_interp(Jr, mr, nr, Js, ms, ns, 1, jc, mr, out + oV, V->nxl, tmp); /* advect.jl:61: ABu(Js',Jr',JCu) */
+    }
+    free(w);
+  }
+  free(Jr);
+  free(Js);
+  free(Tx);
+  free(Ty);
+  return 0;
+}

@@ -165,3 +165,35 @@ def test_abu_rectangular_and_setup_helpers(co):
     J = np.zeros((14, 9), order="F")
     co.so_interpmat(14, P(np.ascontiguousarray(zo)), 9, P(np.ascontiguousarray(zi)), P(J))
     assert relerr(J, so.interpMat(zo, zi)) < 1e-13
+
+
+@pytest.mark.parametrize("nr,nrd,Ex,Ey,per,deform", [(8, 12, 3, 4, (True, False), "fixU"), (9, 14, 3, 3, (False, False), "wavy"),
+                                                     (5, 7, 4, 2, (False, True), "annulus")])
+def test_grad_and_dealiased_advect_agree(co, nr, nrd, Ex, Ey, per, deform):
+    """grad.jl:15-34 and advect.jl:27-64 (the explicit convection term of cd2d): element-tile loops in C against the
+    ABu-structured NumPy form, with and without the dealiasing mesh."""
+    co.so_grad.argtypes = [C.c_void_p, dp, dp, dp]
+    co.so_grad.restype = None
+    co.so_advect.argtypes = [C.c_void_p, C.c_void_p, dp, dp, dp, dp]
+    co.so_advect.restype = C.c_int
+    kind, fn = DEFORM[deform]
+    oV, oD = so.make_mesh(nr, nr, Ex, Ey, per, fn), so.make_mesh(nrd, nrd, Ex, Ey, per, fn)
+    hV = co.so_mesh_create(nr, nr, Ex, Ey, int(per[0]), int(per[1]), kind)
+    hD = co.so_mesh_create(nrd, nrd, Ex, Ey, int(per[0]), int(per[1]), kind)
+    try:
+        shape = oV.x.shape
+        T = np.asfortranarray(np.sin(1.3 * oV.x) * np.cos(0.7 * oV.y) + 0.2 * oV.x * oV.y)
+        vx = np.asfortranarray(1.0 + 0.3 * oV.y)
+        vy = np.asfortranarray(-0.5 + 0.2 * oV.x ** 2)
+        gx, gy, out = (np.zeros(shape, order="F") for _ in range(3))
+        co.so_grad(hV, P(T), P(gx), P(gy))
+        ox, oy = so.grad(T, oV)
+        scale = max(np.max(np.abs(ox)), np.max(np.abs(oy)))
+        assert np.max(np.abs(gx - ox)) / scale < 1e-12 and np.max(np.abs(gy - oy)) / scale < 1e-12
+        assert co.so_advect(hV, None, P(T), P(vx), P(vy), P(out)) == 0
+        assert relerr(out, so.advect(T, vx, vy, oV)) < 1e-12
+        assert co.so_advect(hV, hD, P(T), P(vx), P(vy), P(out)) == 0
+        assert relerr(out, so.advect(T, vx, vy, oV, oD)) < 1e-12
+    finally:
+        co.so_mesh_free(hV)
+        co.so_mesh_free(hD)
