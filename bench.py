@@ -38,8 +38,36 @@ sys.path.insert(0, ROOT)
 ALG_BYTES_POISSON = 40.0    # read u, G11, G12, G22; write Au
 ALG_BYTES_HELMHOLTZ = 48.0  # + B
 ALG_BYTES_PCG_ITER = 112.0
-# dram__bytes_read.sum + dram__bytes_write.sum of one strip-kernel launch (ncu --set full), keyed by (nr, E)
-NCU_TRAFFIC_GB = {(9, 1112): 3.2108 + 0.7850}
+
+
+def ncu_traffic(nr, ncta):
+    """dram__bytes_read.sum + dram__bytes_write.sum (GB per launch) of the strip kernel, read from the NEWEST ncu summary
+    under profiles/ (tools/ncu_summary.py output, `--set full`) taken for the same launch geometry: kernel
+    semb_strip_kernel<nr, 0, 0, *> with launch__grid_size == ncta.  None when no such profile is committed."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_strip%d_*.txt" % nr))):
+        try:
+            blocks = open(path).read().split("=" * 100)
+        except OSError:
+            continue
+        for blk in blocks:
+            if not re.search(r"semb_strip_kernel<%d, 0, 0, [01]>" % nr, blk):
+                continue
+            g = re.search(r"launch__grid_size\s+(\d+)", blk)
+            if not g or int(g.group(1)) != ncta:
+                continue
+            tot = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                mm = re.search(re.escape(key) + r"\s+(\w+)\s+([0-9.]+)", blk)
+                if not mm:
+                    tot = None
+                    break
+                tot += float(mm.group(2)) * {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9}[mm.group(1)]
+            if tot:
+                best = (tot, os.path.relpath(path, ROOT))   # later files (sorted by name: rNN_..._tag) win
+    return best
 
 
 def measured_peak():
@@ -182,6 +210,107 @@ def time_steps(ctx, dist, fn, steps, warmup, flush=False):
     return max_over_ranks(dist, ms)
 
 
+def poisson_rhs(msh, bc):
+    """rhs = gatherScatter(mask(B .* 1))  (diffusion.jl:55,62-63), built on the device"""
+    b, rhs = msh.field().fill(1.0), msh.field()
+    msh.mass_device(b, rhs)
+    msh.mask_bc_device(rhs, bc, b)
+    msh.gs_device(b, rhs)
+    b.free()
+    return rhs
+
+
+def time_apply_and_pcg(ctx, dist, msh, steps, warmup, bc="DDDD", pcg_iters=100):
+    """(ms per fused Poisson apply, ms per PCG iteration) on `msh`, device-resident, max over ranks."""
+    u, out = msh.field().fill_random(0x5EED), msh.field()
+    fn = lambda: msh.oplhs_device(u, out, nu=1.0, k=0.0, bc=bc)
+    ms_apply = time_steps(ctx, dist, fn, steps, warmup) / steps
+    rhs, x = poisson_rhs(msh, bc), msh.field()
+    msh.pcg_begin(rhs, x, nu=1.0, k=0.0, bc=bc, tol=0.0, maxiter=10 ** 9)
+    msh.pcg_iterate(max(warmup, 3))
+    barrier(dist, ctx)
+    ctx.timer_start()
+    msh.pcg_iterate(pcg_iters)
+    ms_pcg = max_over_ranks(dist, ctx.timer_stop()) / pcg_iters
+    barrier(dist, ctx)
+    for f in (u, out, rhs, x):
+        f.free()
+    return ms_apply, ms_pcg
+
+
+def strong_block(sem, ctx, dist, world, rank, local, steps, peak):
+    """Strong scaling of the FIXED ~1e8-DOF meshes north_star / BASELINE configs[2] name: the whole mesh on ONE GPU (a
+    second, communicator-less context on this rank's own GPU; mean over the ranks' GPUs) against the same mesh split
+    into `world` y-slabs.  efficiency_vs_n1 = t(1 GPU) / (world * t(world GPUs)), measured inside this run."""
+    import torch
+    out = {}
+    for tag, nr, E in (("order8_1112", 9, 1112), ("cfg3_order12_776", 13, 776)):
+        solo = sem.Context(local)
+        m1 = sem.Mesh(nr, nr, E, E, (False, False), "wavy", ctx=solo)
+        a1, p1 = time_apply_and_pcg(solo, None, m1, steps, 3)
+        m1.free()
+        solo.close()
+        t = torch.tensor([a1, p1], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        a1, p1 = (t / world).tolist()
+        mN = sem.Mesh(nr, nr, E, E, (False, False), "wavy", ctx=ctx)   # Ey = E globally: split over the ranks
+        aN, pN = time_apply_and_pcg(ctx, dist, mN, steps, 3)
+        plan, tail = mN.plan(), mN.fused_tail()
+        mN.peer_status()
+        mN.free()
+        ndof = (nr * E) ** 2
+        out[tag] = {"workload": "fixed mesh: order %d, %dx%d elements, %d DOF, split into %d y-slabs" % (nr - 1, E, E, ndof, world),
+                    "apply_ms_1gpu": a1, "apply_ms": aN, "apply_gdof_per_s": ndof / aN / 1e6,
+                    "apply_efficiency_vs_n1": a1 / (world * aN),
+                    "pcg_ms_per_iter_1gpu": p1, "pcg_ms_per_iter": pN, "pcg_iters_per_s": 1e3 / pN,
+                    "pcg_efficiency_vs_n1": p1 / (world * pN),
+                    "apply_hbm_frac_per_gpu": ALG_BYTES_POISSON * ndof / world / (aN * 1e-3) / 1e9 / peak,
+                    "strips_x_chunks": [plan["nstrips"], plan["nchunks"]], "fused_tail": tail}
+    return out
+
+
+def parity_block(sem, ctx, world, rank):
+    """Correctness of the multi-rank path INSIDE the bench run (the driver's test box has one GPU): a small mesh cut
+    into `world` slabs against the single-domain CPU oracle -- opLHS < 1e-12 relative, gatherScatter bit-exact,
+    PCG iteration count and solution.  The oracle is the checker here, never the thing timed."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import sem_oracle as so
+    worst, fails = 0.0, []
+    for nr, Ex, Ey, per, bc in ((9, 40, 2 * world, (False, False), "DDDD"), (6, 70, world + 1, (True, True), "NNNN")):
+        om = so.make_mesh(nr, nr, Ex, Ey, per, so.wavy)
+        e0, ne = sem.partition(Ey, world, rank)
+        loc = lambda a: np.asfortranarray(a[:, e0 * nr:(e0 + ne) * nr])
+        gm = sem.Mesh.from_arrays(nr, nr, Ex, Ey, per, om.Dr, om.Ds, loc(om.G11), loc(om.G12), loc(om.G22), loc(om.B), ctx=ctx)
+        u = so.splitmix_uniform(om.x.shape, seed=21)
+        M = so.generateMask(list(bc), om).astype(np.float64)
+        if not np.array_equal(sem.gatherScatter(loc(u), gm), loc(so.gatherScatter(u, om))):
+            fails.append("gatherScatter not bit-exact (nr=%d)" % nr)
+        ref = so.opLHS(u, 1.0, 0.7, M, om)
+        e = float(np.max(np.abs(sem.OpLHS(gm, 1.0, 0.7, bc=bc)(loc(u)) - loc(ref))) / np.max(np.abs(ref)))
+        worst = max(worst, e)
+        if e > 1e-12:
+            fails.append("opLHS %.2e (nr=%d)" % (e, nr))
+        b = so.gatherScatter(so.mask(so.mass(np.sin(np.pi * om.x) * np.sin(np.pi * om.y), om), M), om)
+        io, ig = {}, {}
+        opo = lambda v: so.opLHS(v, 1.0, 0.7, M, om)
+        xo = so.pcg(b, opo, mult=om.mult, tol=1e-12, info=io)
+        xg = sem.pcg(loc(b), sem.OpLHS(gm, 1.0, 0.7, bc=bc), tol=1e-12, info=ig)
+        ex = float(np.max(np.abs(xg - loc(xo))) / np.max(np.abs(xo)))
+        if ex > 1e-10 or abs(ig["iters"] - io["iters"]) > max(2, int(0.02 * io["iters"])):
+            fails.append("pcg err %.2e iters %d vs %d (nr=%d)" % (ex, ig["iters"], io["iters"], nr))
+        try:
+            gm.peer_status()
+        except Exception as ex2:
+            fails.append(str(ex2)[:80])
+        tail = gm.fused_tail()
+        gm.free()
+    v = ctx.allreduce_max([worst, float(len(fails))])
+    return {"world": world, "ok": v[1] == 0.0, "max_rel": float(v[0]), "fused_tail": tail,
+            "checks": "opLHS slab vs single-domain oracle < 1e-12, gatherScatter bit-exact, PCG count (+-2 %) and solution < 1e-10; "
+                      "2 meshes (two strips; periodic x and y, three strips)", "fails_rank0": fails}
+
+
 def run_semb(args):
     import numpy as np
     import spectralelements_jl_b200 as sem
@@ -190,6 +319,10 @@ def run_semb(args):
     ctx = sem.init(local)
     if world > 1:
         ctx.comm_init_torch()
+    peak, peak_src = measured_peak()
+    parity = None
+    if world > 1 and not args.skip_parity:
+        parity = parity_block(sem, ctx, world, rank)
     nr, E = args.nr, args.elements
     Ey_global = E * world if args.scaling == "weak" else E
     msh = sem.Mesh(nr, nr, E, Ey_global, (False, False), "wavy", ctx=ctx)
@@ -197,7 +330,6 @@ def run_semb(args):
     ndof_global = msh.shape[0] * nr * Ey_global
     u, out = msh.field().fill_random(0x5EED), msh.field()
     bc = "DDDD"
-    peak, peak_src = measured_peak()
 
     # ---- headline: fused Laplacian + QQ^T + mask apply, inputs resident in HBM ---------------------
     apply_fn = lambda: msh.oplhs_device(u, out, nu=1.0, k=0.0, bc=bc)
@@ -228,25 +360,44 @@ def run_semb(args):
     achieved = ALG_BYTES_POISSON * ndof_local / (strip_ms * 1e-3) / 1e9
 
     extra = {}
+    # ---- sustained: the same apply back to back for >= 300 steps (power-limited regime), its own clocks record ----
+    if not args.skip_sustained:
+        ns = max(args.sustained_steps, 300)
+        s2 = ClockSampler(local)
+        s2.start()
+        for _ in range(50):
+            apply_fn()
+        barrier(dist, ctx)
+        time.sleep(0.2)
+        s2.mark_begin()
+        ctx.timer_start()
+        for _ in range(ns):
+            apply_fn()
+        sms = ctx.timer_stop()
+        s2.mark_end()
+        barrier(dist, ctx)
+        sms = max_over_ranks(dist, sms) / ns
+        extra["sustained"] = {"steps": ns, "ms_per_step": sms, "gdof_per_s": ndof_global / (sms * 1e-3) / 1e9,
+                              "whole_apply_frac": ALG_BYTES_POISSON * ndof_local / (sms * 1e-3) / 1e9 / peak,
+                              "clocks": s2.stop(),
+                              "note": "the headline `value` is a %d-step burst; this is the same apply run %d times back to back" % (args.steps, ns)}
+
     # ---- PCG iterations/s on the same mesh (device-resident loop) -------------------------------------
     if not args.skip_pcg:
-        b, x, rhs = msh.field().fill(1.0), msh.field(), msh.field()
-        msh.mass_device(b, rhs)           # B .* f, f = 1          (diffusion.jl:55)
-        msh.mask_bc_device(rhs, bc, b)    # mask(rhs, M)            (diffusion.jl:62)
-        msh.gs_device(b, rhs)             # gatherScatter(rhs, msh) (diffusion.jl:63)
+        rhs, x = poisson_rhs(msh, bc), msh.field()
         msh.pcg_begin(rhs, x, nu=1.0, k=0.0, bc=bc, tol=0.0, maxiter=10 ** 9)
-        pcg_fn = lambda: msh.pcg_iterate(1)
-        for _ in range(args.warmup):
-            pcg_fn()
+        msh.pcg_iterate(args.warmup)
         nit = max(min(args.steps, 100), 10)
         barrier(dist, ctx)
+        lp0 = ctx.launch_count()
         ctx.timer_start()
         msh.pcg_iterate(nit)
         pms = max_over_ranks(dist, ctx.timer_stop()) / nit
         barrier(dist, ctx)
         extra["pcg"] = {"iters_per_s": 1e3 / pms, "ms_per_iter": pms, "gdof_iter_per_s": ndof_global / (pms * 1e-3) / 1e9,
-                        "hbm_frac_112B": ALG_BYTES_PCG_ITER * ndof_local / (pms * 1e-3) / 1e9 / peak}
-        for f in (b, x, rhs):
+                        "hbm_frac_112B": ALG_BYTES_PCG_ITER * ndof_local / (pms * 1e-3) / 1e9 / peak,
+                        "launches_per_iter": (ctx.launch_count() - lp0) / nit}
+        for f in (x, rhs):
             f.free()
 
     # ---- end to end through the host-buffer C-ABI twin (pinned host memory) --------------------------
@@ -290,6 +441,24 @@ def run_semb(args):
                                    "hbm_frac_48B": ALG_BYTES_HELMHOLTZ * n2 / (ms2 * 1e-3) / 1e9 / peak,
                                    "l2": "flushed before every apply (256 MB memset, cost subtracted)"}
         m2.free()
+
+    # ---- BASELINE configs[2] on ONE GPU: order 12 (nr = 13), 776x776 elements, 1.018e8 DOF: apply + Poisson PCG --------
+    if world == 1 and not args.skip_cfg3:
+        m3 = sem.Mesh(13, 13, 776, 776, (False, False), "wavy", ctx=ctx)
+        n3 = m3.shape[0] * m3.shape[1]
+        a3, p3 = time_apply_and_pcg(ctx, None, m3, min(args.steps, 100), 3)
+        pl3 = m3.plan()
+        m3.free()
+        extra["cfg3_order12"] = {"workload": "Poisson opLHS + PCG, order 12, 776x776 elements, wavy box, %d DOF, 1 GPU" % n3,
+                                 "apply_ms": a3, "apply_gdof_per_s": n3 / a3 / 1e6,
+                                 "apply_hbm_frac_40B": ALG_BYTES_POISSON * n3 / (a3 * 1e-3) / 1e9 / peak,
+                                 "pcg_ms_per_iter": p3, "pcg_iters_per_s": 1e3 / p3,
+                                 "pcg_hbm_frac_112B": ALG_BYTES_PCG_ITER * n3 / (p3 * 1e-3) / 1e9 / peak,
+                                 "strips_x_chunks": [pl3["nstrips"], pl3["nchunks"]]}
+
+    # ---- strong scaling of the fixed 1e8-DOF meshes (order 8 1112^2; cfg3 = order 12 776^2) over the ranks -------------
+    if world > 1 and not args.skip_strong:
+        extra["strong"] = strong_block(sem, ctx, dist, world, rank, local, min(args.steps, 200), peak)
 
     # ---- BASELINE configs[3]: convection-diffusion implicit stepping, order 8, 512x512 elements (cd2d) ------------
     if rank == 0 and world == 1 and not args.skip_cfg4:
@@ -356,7 +525,17 @@ def run_semb(args):
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = cpu_reference(nr, E, sample_rows=min(args.cpu_rows, E), reps=5)
 
-    plan = msh.plan()
+    plan, tail = msh.plan(), msh.fused_tail()
+    if world > 1:
+        msh.peer_status()   # raises if any kernel of this run gave up waiting for a peer
+    if world == 1:
+        transport = "1 rank, no exchange"
+    elif tail:
+        transport = ("%d ranks; boundary rows stored into the neighbours' memory over NVLink (CUDA IPC peer memory) from inside "
+                     "the strip kernel, per-strip epoch flags; PCG scalars all-gathered the same way (no NCCL call per apply)" % world)
+    else:
+        transport = "%d ranks; NCCL send/recv halo exchange + ncclAllGather of the PCG scalars" % world
+    traffic = ncu_traffic(nr, plan["nstrips"] * plan["ngroups"]) if world == 1 else None
     if rank == 0:
         line = {
             "metric": "laplacian_gs_mask_apply_throughput", "value": value, "unit": "GDOF/s", "n_gpus": world,
@@ -365,16 +544,19 @@ def run_semb(args):
             "config": {"workload": "fused Laplacian+QQ^T+mask apply (opLHS, Poisson nu=1 k=0, bc DDDD), order %d "
                                    "(nr=%d), %dx%d elements per GPU, wavy-deformed box, %d DOF per GPU"
                                    % (nr - 1, nr, E, msh.ney, ndof_local),
-                       "global_dofs": ndof_global, "partition": "y-slabs, %d rank(s), NCCL halo exchange" % world,
+                       "global_dofs": ndof_global, "partition": "y-slabs: " + transport,
                        "l2": "inputs (%.1f GB per apply) exceed the 126 MB L2" % (ALG_BYTES_POISSON * ndof_local / 1e9),
-                       "strips_x_chunks": [plan["nstrips"], plan["nchunks"]]},
+                       "strips_x_chunks": [plan["nstrips"], plan["nchunks"]], "launches_per_apply": launches / args.steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_GB.get((nr, E)), "traffic_unit": "GB per launch (ncu --set full, profiles/r01_strip9_r1k.txt)",
+                         "traffic": traffic[0] if traffic else None,
+                         "traffic_unit": ("GB per launch (ncu --set full, %s)" % traffic[1]) if traffic else
+                                         "GB per launch; null: no ncu --set full summary of this launch geometry under profiles/",
                          "kernel": "semb_strip_kernel<%d>" % nr,
                          "algorithmic_bytes_per_dof": ALG_BYTES_POISSON, "kernel_ms": strip_ms,
                          "kernel_share_of_step": strip_ms / ms_per_step, "peak_source": peak_src,
-                         "whole_apply_frac": ALG_BYTES_POISSON * ndof_local / (ms_per_step * 1e-3) / 1e9 / peak},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "cpu_baseline": cpu, "extra": extra,
+                         "whole_apply_frac": ALG_BYTES_POISSON * ndof_local / (ms_per_step * 1e-3) / 1e9 / peak,
+                         "sustained_whole_apply_frac": extra.get("sustained", {}).get("whole_apply_frac")},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "cpu_baseline": cpu, "parity": parity, "extra": extra,
         }
         print(json.dumps(line))
     msh.free()
@@ -501,6 +683,11 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-cfg4", action="store_true")
     ap.add_argument("--skip-cfg5", action="store_true")
+    ap.add_argument("--skip-cfg3", action="store_true")
+    ap.add_argument("--skip-strong", action="store_true")
+    ap.add_argument("--skip-parity", action="store_true")
+    ap.add_argument("--skip-sustained", action="store_true")
+    ap.add_argument("--sustained-steps", type=int, default=400)
     ap.add_argument("--cfg5-elements", type=int, default=256)
     ap.add_argument("--cfg4-elements", type=int, default=512)
     args = ap.parse_args()

@@ -318,6 +318,17 @@ int semb_strip_kernel_info(int N, int pcg, int massterm, int* regs, int* smem, i
 int semb_mesh_plan(semb_mesh* mesh, int* nstrips, int* nchunks, int* nxseam, int* nyseam, int* fast);
 /* override the number of y chunks (tests exercise every seam configuration with it) */
 int semb_mesh_set_chunks(semb_mesh* mesh, int nchunks);
+/* 1 when the interface sums, the halo exchange and the PCG reduction run inside the strip kernel (one launch per
+   apply: single rank, or peer memory between ranks), 0 when the separate seam kernels / NCCL path is used */
+int semb_mesh_fused_tail(semb_mesh* mesh, int* on);
+/* timing instrumentation of the fused tail (builds with -DSEMB_TAIL_TIMING only; SEMB_EINVAL otherwise) */
+int semb_mesh_debug_read(semb_mesh* mesh, long long* host, int ncta);
+/* CTA rows (grid.y) of the strip kernel; a CTA row marches through one chunk, or two at a rank boundary */
+int semb_mesh_groups(semb_mesh* mesh, int* ngroups);
+/* Multi-GPU health: SEMB_OK, or SEMB_ENCCL once any kernel of this mesh gave up waiting for a peer rank (bounded
+   waits on peer memory, SEMB_PEER_TIMEOUT_MS, default 20 s).  The reference is single-process (no counterpart);
+   SURVEY 5 asks that a lost peer surfaces as a status code instead of a hang. */
+int semb_mesh_peer_status(semb_mesh* mesh);
 
 #ifdef __cplusplus
 }

@@ -379,10 +379,24 @@ class Mesh:
     def plan(self):
         v = [C.c_int() for _ in range(5)]
         check(self.lib.semb_mesh_plan(self.h, *[C.byref(a) for a in v]))
-        return dict(zip(("nstrips", "nchunks", "nxseam", "nyseam", "fast"), [a.value for a in v]))
+        d = dict(zip(("nstrips", "nchunks", "nxseam", "nyseam", "fast"), [a.value for a in v]))
+        g = C.c_int()
+        check(self.lib.semb_mesh_groups(self.h, C.byref(g)))
+        d["ngroups"] = g.value   # CTA rows of the strip kernel (a CTA row marches through 1 or 2 chunks)
+        return d
 
     def set_chunks(self, n: int):
         check(self.lib.semb_mesh_set_chunks(self.h, int(n)))
+
+    def fused_tail(self) -> bool:
+        """True when one apply is ONE kernel launch (interface sums / halo exchange / PCG reduction in the strip kernel)"""
+        v = C.c_int()
+        check(self.lib.semb_mesh_fused_tail(self.h, C.byref(v)))
+        return bool(v.value)
+
+    def peer_status(self):
+        """raises SembError (SEMB_ENCCL) once a kernel of this mesh timed out waiting for a peer rank"""
+        check(self.lib.semb_mesh_peer_status(self.h))
 
     # device-resident operators ------------------------------------------------------------------
     def lapl_device(self, u: DeviceField, out: DeviceField):

@@ -132,6 +132,10 @@ _SIGS = {
     "semb_strip_kernel_info": ([C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p], C.c_int),
     "semb_mesh_plan": ([vp] + [c_int_p] * 5, C.c_int),
     "semb_mesh_set_chunks": ([vp, C.c_int], C.c_int),
+    "semb_mesh_fused_tail": ([vp, c_int_p], C.c_int),
+    "semb_mesh_groups": ([vp, c_int_p], C.c_int),
+    "semb_mesh_debug_read": ([vp, c_ll_p, C.c_int], C.c_int),
+    "semb_mesh_peer_status": ([vp], C.c_int),
 }
 
 _lib = None

@@ -304,10 +304,122 @@ static int download_pitched(semb_mesh* m, const double* src, double* host) {
   return SEMB_OK;
 }
 
+// layout of a mesh's mailbox allocation (exported through CUDA IPC):
+//   [SembScal][stand-alone halo rows: 2 parities x 2 sides x pitch][fused-tail rows: 2 x 2 x pitch][segment flags: 2 sides x nstrips]
+static size_t mail_scal_bytes() { return (sizeof(SembScal) + 255) / 256 * 256; }
+static size_t mail_bytes(semb_mesh* m) {
+  return mail_scal_bytes() + 8 * (size_t)m->pitch * sizeof(double) + 2 * (size_t)m->nstrips * sizeof(unsigned long long);
+}
+static double* mail_tail_rows(semb_mesh* m, void* mailbox) {
+  return (double*)((char*)mailbox + mail_scal_bytes()) + 4 * (size_t)m->pitch;
+}
+static unsigned long long* mail_tail_flags(semb_mesh* m, void* mailbox) {
+  return (unsigned long long*)(mail_tail_rows(m, mailbox) + 4 * (size_t)m->pitch);
+}
+
+// Chunk tables of the strip kernel for `groups` CTA rows: chunk offsets, y-seam flags, seam lists, and the tables
+// of the fused tail (semb_tail.cuh).  With a neighbour rank above, the slab's last element row becomes a chunk of
+// its own that the top CTA row marches through FIRST, and the two edge CTA rows are scheduled first, so that both
+// boundary rows are on their way to the neighbours while the rest of the slab is computed.
+static int mesh_set_groups(semb_mesh* m, int groups) {
+  semb_ctx* c = m->ctx;
+  const int N = m->ns, P = c->nranks;
+  const bool wrap_local = m->pery && P == 1;
+  if (groups > m->ney) groups = m->ney;
+  if (groups < 1) groups = 1;
+  std::vector<int> g0(groups + 1);
+  for (int k = 0; k <= groups; ++k) g0[k] = (int)((long long)k * m->ney / groups);
+  const bool split = m->tail && m->halo_hi && g0[groups] - g0[groups - 1] >= 2 && !getenv("SEMB_NO_EDGE_FIRST");
+  m->ngroups = groups;
+  m->nchunks = groups + (split ? 1 : 0);
+  m->h_chunk_r0.assign(g0.begin(), g0.end());
+  if (split) m->h_chunk_r0.insert(m->h_chunk_r0.end() - 1, m->ney - 1);
+  std::vector<int> grp(2 * (size_t)groups, -1);
+  {
+    std::vector<int> order(groups);  // CTA row -> group: the top group first when it feeds a neighbour
+    for (int g = 0; g < groups; ++g) order[g] = g;
+    if (m->tail && m->halo_hi && groups > 1) {
+      order.pop_back();
+      order.insert(order.begin(), groups - 1);
+    }
+    for (int by = 0; by < groups; ++by) {
+      const int g = order[by];
+      if (split && g == groups - 1) {
+        grp[2 * by] = groups;  // the one-row chunk [ney-1, ney)
+        grp[2 * by + 1] = groups - 1;
+      } else {
+        grp[2 * by] = g;
+      }
+    }
+  }
+  // y seam flags per element row
+  m->h_ystart.assign(m->ney + 1, 0);
+  for (int k = 1; k < m->nchunks; ++k) m->h_ystart[m->h_chunk_r0[k]] = 1;
+  m->h_ystart[0] = (m->halo_lo || wrap_local) ? 1 : 0;
+  m->h_ystart[m->ney] = (m->halo_hi || wrap_local) ? 1 : 0;
+  std::vector<int> ys;
+  for (int k = 1; k < m->nchunks; ++k) {
+    ys.push_back(m->h_chunk_r0[k] * N - 1);
+    ys.push_back(m->h_chunk_r0[k] * N);
+  }
+  if (wrap_local) {
+    ys.push_back(m->nyl - 1);
+    ys.push_back(0);
+  }
+  m->nyseam = (int)ys.size() / 2;
+  // all y interfaces (stand-alone gatherScatter), appended after the chunk seams
+  for (int r = 1; r < m->ney; ++r) {
+    ys.push_back(r * N - 1);
+    ys.push_back(r * N);
+  }
+  if (wrap_local) {
+    ys.push_back(m->nyl - 1);
+    ys.push_back(0);
+  }
+  SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(m->d_chunk_r0);
+  cudaFree(m->d_yseam);
+  cudaFree(m->d_ystart);
+  cudaFree(m->d_grp);
+  cudaFree(m->d_tcnt);
+  cudaFree(m->d_tpart);
+  m->d_chunk_r0 = nullptr, m->d_yseam = nullptr, m->d_ystart = nullptr, m->d_grp = nullptr, m->d_tcnt = nullptr,
+  m->d_tpart = nullptr;
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_chunk_r0, (m->nchunks + 1) * sizeof(int)));
+  SEMB_CHECK_CUDA(cudaMemcpy(m->d_chunk_r0, m->h_chunk_r0.data(), (m->nchunks + 1) * sizeof(int),
+                             cudaMemcpyHostToDevice));
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_ystart, m->ney + 1));
+  SEMB_CHECK_CUDA(cudaMemcpy(m->d_ystart, m->h_ystart.data(), m->ney + 1, cudaMemcpyHostToDevice));
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_yseam, std::max<size_t>(ys.size(), 2) * sizeof(int)));
+  if (!ys.empty())
+    SEMB_CHECK_CUDA(cudaMemcpy(m->d_yseam, ys.data(), ys.size() * sizeof(int), cudaMemcpyHostToDevice));
+  // micro-tasks (32 lines each) of an x seam per chunk, as a prefix, appended to the group table
+  for (int k = 0, acc = 0; k <= m->nchunks; ++k) {
+    grp.push_back(acc);
+    if (k < m->nchunks) acc += ((m->h_chunk_r0[k + 1] - m->h_chunk_r0[k]) * N + 31) / 32;
+  }
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_grp, grp.size() * sizeof(int)));
+  SEMB_CHECK_CUDA(cudaMemcpy(m->d_grp, grp.data(), grp.size() * sizeof(int), cudaMemcpyHostToDevice));
+  m->xmic_total = grp.back();
+  const SembTailLayout L(m->nstrips, m->nchunks, m->nstrips - 1 + m->perx, m->xmic_total);
+  m->ntcnt = L.ntasks() + 1;
+  m->ntpart = m->nstrips * m->ngroups + L.nparts();
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_tcnt, (size_t)m->ntcnt * sizeof(unsigned)));
+  SEMB_CHECK_CUDA(cudaMemset(m->d_tcnt, 0, (size_t)m->ntcnt * sizeof(unsigned)));
+#ifdef SEMB_TAIL_TIMING
+  if (!m->d_dbg) {
+    SEMB_CHECK_CUDA(cudaMalloc(&m->d_dbg, 8 * (size_t)SEMB_NPARTIALS * sizeof(long long)));
+    SEMB_CHECK_CUDA(cudaMemset(m->d_dbg, 0, 8 * (size_t)SEMB_NPARTIALS * sizeof(long long)));
+  }
+#endif
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_tpart, (size_t)m->ntpart * sizeof(double)));
+  SEMB_CHECK_CUDA(cudaMemset(m->d_tpart, 0, (size_t)m->ntpart * sizeof(double)));
+  return SEMB_OK;
+}
+
 // Launch plan of the fused operator: strips x chunks, seam lists, halo neighbours.
 static int mesh_build_plan(semb_mesh* m) {
   semb_ctx* c = m->ctx;
-  const int N = m->ns;  // y-direction points per element
   m->fast = (m->nr == m->ns && m->nr >= 2 && m->nr <= SEMB_MAXN);
   m->bx = m->fast ? semb_strip_bx(m->nr) : 32;
   // derivative matrices on symmetric nodes are centro-antisymmetric: the even-odd kernel variant applies
@@ -321,31 +433,11 @@ static int mesh_build_plan(semb_mesh* m) {
       if (widest <= m->bx) break;
     }
   }
-  int occ = 1;
-  if (m->fast) SEMB_TRY(semb_strip_regs(m->nr, false, false, nullptr, nullptr, &occ));
-  if (occ < 1) occ = 1;
-  // chunks: fill the resident CTA slots; the rule (waves x (rows of the longest chunk + 1/2), measured on chunk sweeps:
-  // 256x256 order 8 takes 29 chunks = one full wave, 59.4 us per apply, instead of 59 = two waves of 4-5 rows, 66.5 us;
-  // 1112x1112 keeps 22) lives in semb_plan_chunks (semb_host.cpp) so that it is testable without a GPU
-  const int slots = c->sm_count * occ;
-  int best = 1;
-  SEMB_TRY(semb_plan_chunks(m->nstrips, m->ney, slots, &best));
-  if (best > m->ney) best = m->ney;
-  if ((long long)best * m->nstrips > SEMB_NPARTIALS) best = SEMB_NPARTIALS / m->nstrips;
-  if (best < 1) best = 1;
-  m->nchunks = best;
-  m->h_chunk_r0.resize(m->nchunks + 1);
-  for (int k = 0; k <= m->nchunks; ++k) m->h_chunk_r0[k] = (int)((long long)k * m->ney / m->nchunks);
   // halo neighbours
   const int P = c->nranks, rk = c->rank;
   SEMB_TRY(semb_halo_plan(P, rk, m->pery, &m->halo_lo, &m->halo_hi, &m->rank_lo, &m->rank_hi));
-  const bool wrap_local = m->pery && P == 1;
-  // y seam flags per element row
-  m->h_ystart.assign(m->ney + 1, 0);
-  for (int k = 1; k < m->nchunks; ++k) m->h_ystart[m->h_chunk_r0[k]] = 1;
-  m->h_ystart[0] = (m->halo_lo || wrap_local) ? 1 : 0;
-  m->h_ystart[m->ney] = (m->halo_hi || wrap_local) ? 1 : 0;
-  std::vector<int> xs, ys;
+  // x seams (strip boundaries + the periodic wrap): column pairs
+  std::vector<int> xs;
   for (int s = 1; s < m->nstrips; ++s) {
     const int e = m->fast ? semb_strip_e0(s, m->nstrips, m->Ex, m->nr) : s * m->bx;
     xs.push_back(e * m->nr - 1);
@@ -355,55 +447,24 @@ static int mesh_build_plan(semb_mesh* m) {
     xs.push_back(m->nxl - 1);
     xs.push_back(0);
   }
-  for (int k = 1; k < m->nchunks; ++k) {
-    ys.push_back(m->h_chunk_r0[k] * N - 1);
-    ys.push_back(m->h_chunk_r0[k] * N);
-  }
-  if (wrap_local) {
-    ys.push_back(m->nyl - 1);
-    ys.push_back(0);
-  }
   m->nxseam = (int)xs.size() / 2;
-  m->nyseam = (int)ys.size() / 2;
-  // all y interfaces (stand-alone gatherScatter), appended after the chunk seams
-  std::vector<int> yall;
-  for (int r = 1; r < m->ney; ++r) {
-    yall.push_back(r * N - 1);
-    yall.push_back(r * N);
-  }
-  if (wrap_local) {
-    yall.push_back(m->nyl - 1);
-    yall.push_back(0);
-  }
-  const size_t nys = ys.size();
-  ys.insert(ys.end(), yall.begin(), yall.end());
-  SEMB_CHECK_CUDA(cudaMalloc(&m->d_chunk_r0, (m->nchunks + 1) * sizeof(int)));
-  SEMB_CHECK_CUDA(cudaMemcpy(m->d_chunk_r0, m->h_chunk_r0.data(), (m->nchunks + 1) * sizeof(int),
-                             cudaMemcpyHostToDevice));
-  SEMB_CHECK_CUDA(cudaMalloc(&m->d_ystart, m->ney + 1));
-  SEMB_CHECK_CUDA(cudaMemcpy(m->d_ystart, m->h_ystart.data(), m->ney + 1, cudaMemcpyHostToDevice));
   SEMB_CHECK_CUDA(cudaMalloc(&m->d_xseam, std::max<size_t>(xs.size(), 2) * sizeof(int)));
   if (!xs.empty())
     SEMB_CHECK_CUDA(cudaMemcpy(m->d_xseam, xs.data(), xs.size() * sizeof(int), cudaMemcpyHostToDevice));
-  SEMB_CHECK_CUDA(cudaMalloc(&m->d_yseam, std::max<size_t>(ys.size(), 2) * sizeof(int)));
-  if (!ys.empty())
-    SEMB_CHECK_CUDA(cudaMemcpy(m->d_yseam, ys.data(), ys.size() * sizeof(int), cudaMemcpyHostToDevice));
-  (void)nys;
   SEMB_CHECK_CUDA(cudaMalloc(&m->d_halo_lo, (size_t)m->pitch * sizeof(double)));
   SEMB_CHECK_CUDA(cudaMalloc(&m->d_halo_hi, (size_t)m->pitch * sizeof(double)));
   m->npartials = SEMB_NPARTIALS;
   SEMB_CHECK_CUDA(cudaMalloc(&m->d_partials, 3 * (size_t)m->npartials * sizeof(double)));
   SEMB_CHECK_CUDA(cudaMalloc(&m->d_counters, 8 * sizeof(unsigned)));
   SEMB_CHECK_CUDA(cudaMemset(m->d_counters, 0, 8 * sizeof(unsigned)));
-  // Mailbox = [SembScal][halo rows: 2 parities x 2 sides x pitch].  With more than one rank it is exported
-  // through CUDA IPC so that the neighbours' kernels can store into it over NVLink (P2P mode).
-  const size_t scal_bytes = (sizeof(SembScal) + 255) / 256 * 256;
-  const size_t mail_bytes = scal_bytes + 4 * (size_t)m->pitch * sizeof(double);
-  SEMB_CHECK_CUDA(cudaMalloc(&m->d_mailbox, mail_bytes));
-  SEMB_CHECK_CUDA(cudaMemset(m->d_mailbox, 0, mail_bytes));
+  // Mailbox (layout above).  With more than one rank it is exported through CUDA IPC so that the neighbours'
+  // kernels can store into it over NVLink (P2P mode).
+  SEMB_CHECK_CUDA(cudaMalloc(&m->d_mailbox, mail_bytes(m)));
+  SEMB_CHECK_CUDA(cudaMemset(m->d_mailbox, 0, mail_bytes(m)));
   m->d_scal = (SembScal*)m->d_mailbox;
-  m->d_mail_halo = (double*)((char*)m->d_mailbox + scal_bytes);
+  m->d_mail_halo = (double*)((char*)m->d_mailbox + mail_scal_bytes());
   m->p2p = false;
+  m->peer_mailbox[rk] = m->d_mailbox;
   if (P > 1 && m->fast && !getenv("SEMB_NO_P2P")) {
     // exchange the IPC handles with the communicator itself, then map every peer's mailbox
     cudaIpcMemHandle_t mine;
@@ -421,10 +482,7 @@ static int mesh_build_plan(semb_mesh* m) {
     SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(d_h);
     for (int r = 0; r < P && ok; ++r) {
-      if (r == rk) {
-        m->peer_mailbox[r] = m->d_mailbox;
-        continue;
-      }
+      if (r == rk) continue;
       e = cudaIpcOpenMemHandle(&m->peer_mailbox[r], all[r], cudaIpcMemLazyEnablePeerAccess);
       if (e != cudaSuccess) {
         cudaGetLastError();
@@ -448,6 +506,32 @@ static int mesh_build_plan(semb_mesh* m) {
   m->h_scal->rank = rk;
   m->h_scal->done = 1;
   SEMB_CHECK_CUDA(cudaMemcpy(m->d_scal, m->h_scal, SEMB_SCAL_HOST_BYTES, cudaMemcpyHostToDevice));
+  {  // persistent part: the peer table and the bound of every wait on a peer
+    SembScal* peers[SEMB_MAX_RANKS] = {nullptr};
+    for (int r = 0; r < P; ++r) peers[r] = (SembScal*)m->peer_mailbox[r];
+    SEMB_CHECK_CUDA(cudaMemcpy((char*)m->d_scal + offsetof(SembScal, peers), peers, sizeof(peers), cudaMemcpyHostToDevice));
+    double ms = 20000.0;
+    if (const char* e = getenv("SEMB_PEER_TIMEOUT_MS")) ms = atof(e);
+    cudaDeviceProp prop;
+    SEMB_CHECK_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    const long long ticks = ms > 0 ? (long long)(ms * (double)prop.clockRate) : 0;  // clockRate is in kHz = ticks per ms
+    SEMB_CHECK_CUDA(cudaMemcpy((char*)m->d_scal + offsetof(SembScal, spin_limit), &ticks, sizeof(ticks), cudaMemcpyHostToDevice));
+  }
+  // interface completion inside the strip kernel (one launch per apply): single rank, or peer memory between ranks
+  m->tail = m->fast && (P == 1 || m->p2p) && !getenv("SEMB_NO_TAIL");
+  int occ = 1;
+  if (m->fast) SEMB_TRY(semb_strip_regs(m->nr, false, false, nullptr, nullptr, &occ));
+  if (occ < 1) occ = 1;
+  // chunks: fill the resident CTA slots; the rule (waves x (rows of the longest chunk + 1/2), measured on chunk sweeps:
+  // 256x256 order 8 takes 29 chunks = one full wave, 59.4 us per apply, instead of 59 = two waves of 4-5 rows, 66.5 us;
+  // 1112x1112 keeps 22) lives in semb_plan_chunks (semb_host.cpp) so that it is testable without a GPU
+  const int slots = c->sm_count * occ;
+  int best = 1;
+  SEMB_TRY(semb_plan_chunks(m->nstrips, m->ney, slots, &best));
+  if (best > m->ney) best = m->ney;
+  if ((long long)(best + 1) * m->nstrips > SEMB_NPARTIALS) best = SEMB_NPARTIALS / m->nstrips - 1;
+  if (best < 1) best = 1;
+  SEMB_TRY(mesh_set_groups(m, best));
   if (P > 1) SEMB_TRY(semb_comm_barrier(c));  // every mailbox is mapped and initialised before anyone pushes
   return SEMB_OK;
 }
@@ -673,6 +757,10 @@ extern "C" int semb_mesh_destroy(semb_mesh* m) {
   cudaFree(m->d_wy1d);
   cudaFree(m->d_chunk_r0);
   cudaFree(m->d_ystart);
+  cudaFree(m->d_grp);
+  cudaFree(m->d_tcnt);
+  cudaFree(m->d_tpart);
+  cudaFree(m->d_dbg);
   cudaFree(m->d_xseam);
   cudaFree(m->d_yseam);
   cudaFree(m->d_halo_lo);
@@ -716,50 +804,35 @@ extern "C" int semb_mesh_plan(semb_mesh* m, int* nstrips, int* nchunks, int* nxs
   return SEMB_OK;
 }
 
-// test / tuning hook: override the number of y chunks of the strip kernel
-extern "C" int semb_mesh_set_chunks(semb_mesh* m, int nchunks) {
-  SEMB_REQUIRE(m && nchunks >= 1 && nchunks <= m->ney, "semb_mesh_set_chunks: 1 <= nchunks <= ney");
-  SEMB_REQUIRE((long long)nchunks * m->nstrips <= SEMB_NPARTIALS, "semb_mesh_set_chunks: too many CTAs");
+// -DSEMB_TAIL_TIMING builds: 8 values per CTA of the last fused-tail launch (globaltimer ns: start, rows done / announced
+// per chunk, tail prologue done, tasks done; [7] = micro-tasks this CTA ran).  SEMB_EINVAL in a normal build.
+extern "C" int semb_mesh_debug_read(semb_mesh* m, long long* host, int ncta) {
+  SEMB_REQUIRE(m && host && ncta >= 1 && ncta <= SEMB_NPARTIALS, "semb_mesh_debug_read: bad argument");
+  SEMB_REQUIRE(m->d_dbg, "semb_mesh_debug_read: library was not built with -DSEMB_TAIL_TIMING (or no fused apply ran yet)");
   SEMB_ENTER(m->ctx);
   SEMB_CHECK_CUDA(cudaStreamSynchronize(m->ctx->stream));
-  const int N = m->ns;
-  m->nchunks = nchunks;
-  m->h_chunk_r0.resize(nchunks + 1);
-  for (int k = 0; k <= nchunks; ++k) m->h_chunk_r0[k] = (int)((long long)k * m->ney / nchunks);
-  const unsigned char b0 = m->h_ystart[0], b1 = m->h_ystart[m->ney];
-  m->h_ystart.assign(m->ney + 1, 0);
-  m->h_ystart[0] = b0;
-  m->h_ystart[m->ney] = b1;
-  for (int k = 1; k < nchunks; ++k) m->h_ystart[m->h_chunk_r0[k]] = 1;
-  std::vector<int> ys;
-  for (int k = 1; k < nchunks; ++k) {
-    ys.push_back(m->h_chunk_r0[k] * N - 1);
-    ys.push_back(m->h_chunk_r0[k] * N);
-  }
-  const bool wrap_local = m->pery && m->ctx->nranks == 1;
-  if (wrap_local) {
-    ys.push_back(m->nyl - 1);
-    ys.push_back(0);
-  }
-  m->nyseam = (int)ys.size() / 2;
-  for (int r = 1; r < m->ney; ++r) {
-    ys.push_back(r * N - 1);
-    ys.push_back(r * N);
-  }
-  if (wrap_local) {
-    ys.push_back(m->nyl - 1);
-    ys.push_back(0);
-  }
-  cudaFree(m->d_chunk_r0);
-  cudaFree(m->d_yseam);
-  SEMB_CHECK_CUDA(cudaMalloc(&m->d_chunk_r0, (nchunks + 1) * sizeof(int)));
-  SEMB_CHECK_CUDA(cudaMemcpy(m->d_chunk_r0, m->h_chunk_r0.data(), (nchunks + 1) * sizeof(int),
-                             cudaMemcpyHostToDevice));
-  SEMB_CHECK_CUDA(cudaMemcpy(m->d_ystart, m->h_ystart.data(), m->ney + 1, cudaMemcpyHostToDevice));
-  SEMB_CHECK_CUDA(cudaMalloc(&m->d_yseam, std::max<size_t>(ys.size(), 2) * sizeof(int)));
-  if (!ys.empty())
-    SEMB_CHECK_CUDA(cudaMemcpy(m->d_yseam, ys.data(), ys.size() * sizeof(int), cudaMemcpyHostToDevice));
+  SEMB_CHECK_CUDA(cudaMemcpy(host, m->d_dbg, 8 * (size_t)ncta * sizeof(long long), cudaMemcpyDeviceToHost));
   return SEMB_OK;
+}
+
+extern "C" int semb_mesh_groups(semb_mesh* m, int* ngroups) {
+  SEMB_REQUIRE(m && ngroups, "semb_mesh_groups: null argument");
+  *ngroups = m->ngroups;
+  return SEMB_OK;
+}
+
+extern "C" int semb_mesh_fused_tail(semb_mesh* m, int* on) {
+  SEMB_REQUIRE(m && on, "semb_mesh_fused_tail: null argument");
+  *on = m->tail ? 1 : 0;
+  return SEMB_OK;
+}
+
+// test / tuning hook: override the number of y chunks (CTA rows) of the strip kernel
+extern "C" int semb_mesh_set_chunks(semb_mesh* m, int nchunks) {
+  SEMB_REQUIRE(m && nchunks >= 1 && nchunks <= m->ney, "semb_mesh_set_chunks: 1 <= nchunks <= ney");
+  SEMB_REQUIRE((long long)(nchunks + 1) * m->nstrips <= SEMB_NPARTIALS, "semb_mesh_set_chunks: too many CTAs");
+  SEMB_ENTER(m->ctx);
+  return mesh_set_groups(m, nchunks);
 }
 
 extern "C" int semb_mesh_get(semb_mesh* m, int which, double* host) {
@@ -904,21 +977,18 @@ static int check_field(semb_mesh* m, const semb_field* f, const char* what, bool
   return SEMB_OK;
 }
 
-static P2PArgs p2p_args(semb_mesh* m, unsigned long long epoch, unsigned long long epoch_b = 0) {
+static P2PArgs p2p_args(semb_mesh* m, unsigned long long epoch = 0) {
   P2PArgs x;
   x.on = m->p2p ? 1 : 0;
   x.nranks = m->ctx->nranks;
   x.rank = m->ctx->rank;
   x.epoch = epoch;
-  x.epoch_b = epoch_b;
-  for (int r = 0; r < x.nranks; ++r) x.peer[r] = (SembScal*)m->peer_mailbox[r];
   return x;
 }
 
 // local / peer halo rows inside a mailbox: [parity][side][pitch], side 0 = row from below, 1 = from above
 static double* mail_halo(semb_mesh* m, void* mailbox, int parity, int side) {
-  const size_t scal_bytes = (sizeof(SembScal) + 255) / 256 * 256;
-  return (double*)((char*)mailbox + scal_bytes) + (size_t)(2 * parity + side) * m->pitch;
+  return (double*)((char*)mailbox + mail_scal_bytes()) + (size_t)(2 * parity + side) * m->pitch;
 }
 
 // Exchange the slab's boundary rows with the neighbour ranks.  P2P mode: one small kernel stores the rows
@@ -991,6 +1061,8 @@ static void fill_common(semb_mesh* m, OpArgs& a) {
   a.scal = m->d_scal;
   a.halo_lo = m->d_halo_lo;
   a.halo_hi = m->d_halo_hi;
+  a.wx1d = m->d_wx1d;
+  a.wy1d = m->d_wy1d;
 }
 
 // out = [mask(gs(]  nu .* laplace(u) + k .* B .* u  [))]   -- the one place operators are composed
@@ -1026,6 +1098,32 @@ static int run_operator(semb_mesh* m, const double* u, double* out, const OpSpec
   a.mx1 = f.mx1;
   a.my0 = f.my0;
   a.my1 = f.my1;
+  if (m->fast && m->tail && sp.gs) {
+    // ONE launch: the strip kernel's CTAs finish the interfaces, exchange the halo rows through peer memory and
+    // (PCG) reduce + all-gather sum(p.*Ap.*mult) themselves (semb_tail.cuh)
+    a.tail = 1;
+    a.grp = m->d_grp;
+    a.xmic = m->d_grp + 2 * m->ngroups;
+    a.xmic_total = m->xmic_total;
+    a.tcnt = m->d_tcnt;
+    a.tpart = m->d_tpart;
+    a.nxs = m->nstrips - 1 + m->perx;
+    a.ywrap = (m->pery && c->nranks == 1) ? 1 : 0;
+    a.has_lo = m->halo_lo;
+    a.has_hi = m->halo_hi;
+    if (m->halo_lo) {
+      a.peer_rows_lo = mail_tail_rows(m, m->peer_mailbox[m->rank_lo]);
+      a.peer_flags_lo = mail_tail_flags(m, m->peer_mailbox[m->rank_lo]);
+    }
+    if (m->halo_hi) {
+      a.peer_rows_hi = mail_tail_rows(m, m->peer_mailbox[m->rank_hi]);
+      a.peer_flags_hi = mail_tail_flags(m, m->peer_mailbox[m->rank_hi]);
+    }
+    a.my_rows = mail_tail_rows(m, m->d_mailbox);
+    a.my_flags = mail_tail_flags(m, m->d_mailbox);
+    a.dbg = m->d_dbg;
+    return semb_launch_strip(c, a, m->hDr.data(), m->hDs.data(), m->nstrips, m->ngroups, pcg, massterm, m->eo);
+  }
   if (m->fast) {
     a.partials = m->d_partials;
     a.counters = m->d_counters + 0;
@@ -1043,7 +1141,7 @@ static int run_operator(semb_mesh* m, const double* u, double* out, const OpSpec
     a.partials = m->d_partials + 2 * (size_t)m->npartials;
     a.counters = m->d_counters + 2;
     // P2P + PCG: the y-seam kernel's last block also all-gathers sum(p.*Ap.*mult) over NVLink
-    SEMB_TRY(semb_launch_seam_y(c, a, m->halo_lo, m->halo_hi, true, p2p_args(m, eph, (m->p2p && pcg) ? ++m->ep_pap : 0)));
+    SEMB_TRY(semb_launch_seam_y(c, a, m->halo_lo, m->halo_hi, true, p2p_args(m, eph)));
     return SEMB_OK;
   }
   // generic path (nr != ns, or outside 2..17): separate passes, same arithmetic per node
@@ -1213,7 +1311,18 @@ static int gather_scalars(semb_mesh* m, double* xchg, int per_rank) {
 static int read_scal(semb_mesh* m) {
   SEMB_CHECK_CUDA(cudaMemcpyAsync(m->h_scal, m->d_scal, sizeof(SembScal), cudaMemcpyDeviceToHost, m->ctx->stream));
   SEMB_CHECK_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  if (m->h_scal->err) {  // a kernel gave up waiting for a peer (semb_wait_epoch): results since then are undefined
+    semb_set_error("peer exchange timed out on rank %d of %d (a neighbour rank is lost or has diverged); "
+                   "SEMB_PEER_TIMEOUT_MS sets the bound", m->ctx->rank, m->ctx->nranks);
+    return SEMB_ENCCL;
+  }
   return SEMB_OK;
+}
+
+extern "C" int semb_mesh_peer_status(semb_mesh* m) {
+  SEMB_REQUIRE(m, "null mesh");
+  SEMB_ENTER(m->ctx);
+  return read_scal(m);
 }
 
 static int reduce_common(semb_mesh* m, int which, const semb_field* a, const semb_field* b, double* result,
@@ -1221,7 +1330,7 @@ static int reduce_common(semb_mesh* m, int which, const semb_field* a, const sem
   semb_ctx* c = m->ctx;
   SEMB_ENTER(c);
   SEMB_REQUIRE(result, "reduction: null result");
-  SEMB_TRY(semb_launch_reduce(c, m, which, a->d, b ? b->d : nullptr, p2p_args(m, m->p2p ? ++m->ep_red : 0), ref));
+  SEMB_TRY(semb_launch_reduce(c, m, which, a->d, b ? b->d : nullptr, p2p_args(m), ref));
   if (c->nranks > 1 && !m->p2p) {
     SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_red), 1));
     SEMB_TRY(semb_launch_reduce_finalize(c, m, which));
@@ -1279,6 +1388,11 @@ extern "C" int semb_pcg_begin(semb_mesh* m, const semb_pcg_opts* o, const semb_f
   SEMB_TRY(ensure_tmp(m, &m->w_r));
   SEMB_TRY(ensure_tmp(m, &m->w_p));
   SEMB_TRY(ensure_tmp(m, &m->w_Ap));
+  if (!m->fast) {  // the generic operator's work fields: never allocated while a CUDA graph is being captured
+    SEMB_TRY(ensure_tmp(m, &m->w_tmp));
+    SEMB_TRY(ensure_tmp(m, &m->w_t1));
+    SEMB_TRY(ensure_tmp(m, &m->w_t2));
+  }
   m->pcg_opts = *o;
   m->pcg_x = x;
   if (o->nu_arr) {
@@ -1313,7 +1427,7 @@ extern "C" int semb_pcg_begin(semb_mesh* m, const semb_pcg_opts* o, const semb_f
   m->pcg_keep_h = keep_h;
   SEMB_TRY(semb_launch_pcg_init(c, m, b->d, x->d, m->w_r->d, m->w_p->d, keep_h ? m->w_h->d : nullptr, o->precond,
                                 o->prec_b0, o->tol, maxiter,
-                                p2p_args(m, m->p2p ? ++m->ep_t : 0)));
+                                p2p_args(m)));
   if (c->nranks > 1 && !m->p2p) {
     SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_t), 2));
     SEMB_TRY(semb_launch_pcg_finalize(c, m, 1));
@@ -1336,7 +1450,7 @@ static int pcg_one_iteration(semb_mesh* m) {
   if (m->pcg_custom) {
     SEMB_TRY(semb_launch_pcg_dir(c, m, m->w_r->d, m->w_p->d, o.precond, o.prec_b0));  // p = h + beta*p, pcg.jl:46-50
     SEMB_TRY(m->pcg_custom());                                                         // w_Ap = opA(w_p), pcg.jl:51
-    SEMB_TRY(semb_launch_reduce(c, m, 0, m->w_p->d, m->w_Ap->d, p2p_args(m, m->p2p ? ++m->ep_red : 0)));  // pcg.jl:52
+    SEMB_TRY(semb_launch_reduce(c, m, 0, m->w_p->d, m->w_Ap->d, p2p_args(m)));  // pcg.jl:52
     if (c->nranks > 1 && !m->p2p) {
       SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_red), 1));
       SEMB_TRY(semb_launch_reduce_finalize(c, m, 0));
@@ -1356,7 +1470,7 @@ static int pcg_one_iteration(semb_mesh* m) {
   // P2P: the update kernel's last block all-gathers {t, norm(r,Inf)} over NVLink and advances the state
   SEMB_TRY(semb_launch_pcg_update(c, m, m->pcg_x->d, m->w_r->d, m->w_p->d, m->w_Ap->d,
                                   m->pcg_keep_h ? m->w_h->d : nullptr, o.precond, o.prec_b0,
-                                  p2p_args(m, m->p2p ? ++m->ep_t : 0)));
+                                  p2p_args(m)));
   if (c->nranks > 1 && !m->p2p) {
     SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_t), 2));
     SEMB_TRY(semb_launch_pcg_finalize(c, m, 0));
@@ -1390,11 +1504,13 @@ extern "C" int semb_pcg(semb_mesh* m, const semb_pcg_opts* o, const semb_field* 
   const int every = o->check_every > 0 ? o->check_every : (m->pcg_custom ? 4 : 16);
   // The loop is launch-bound on small meshes: capture `every` iterations (4 kernels each, all scalars live in
   // device memory, so the arguments never change) into a CUDA graph and replay it between polls of the
-  // device-side done flag.  Multi-rank runs keep plain launches (per-iteration epochs / NCCL calls).
+  // device-side done flag.
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   long long per_graph = 0;
-  const bool use_graph = c->nranks == 1 && every >= 2 && !getenv("SEMB_NO_GRAPH");
+  // Several ranks: only when every exchange of an iteration is a peer-memory one whose epoch lives in device memory
+  // (fused tail + in-kernel all-gathers), i.e. nothing host-side changes from one iteration to the next.
+  const bool use_graph = (c->nranks == 1 || (m->p2p && m->tail && !m->pcg_custom)) && every >= 2 && !getenv("SEMB_NO_GRAPH");
   int rc = SEMB_OK;
   for (;;) {
     rc = read_scal(m);

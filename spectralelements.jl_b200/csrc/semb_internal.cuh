@@ -96,14 +96,20 @@ struct SembScal {
   double box_pap[2][SEMB_MAX_RANKS];
   double box_t[2][2 * SEMB_MAX_RANKS];
   double box_red[2][2 * SEMB_MAX_RANKS];
+  // ---- persistent device-side state (never overwritten by the host after mesh creation) ------------------
+  // Epochs of the peer-memory exchanges live HERE, not in kernel arguments, so that a batch of PCG iterations
+  // can be replayed as a CUDA graph on several ranks: [0] fused-tail halo, [1] pap, [2] {t, rmax}, [3] reductions
+  unsigned long long ep_dev[4];
+  SembScal* peers[SEMB_MAX_RANKS];  // peers[r] = rank r's mailbox as mapped into THIS process (r == rank: local)
+  long long spin_limit;             // clock64 ticks a kernel may wait for a peer before it gives up (0 = forever)
+  int err;                          // 1 once a peer wait timed out (surfaced as SEMB_ENCCL by the host)
 };
 
-// Peer pointers handed to the kernels that exchange data through mapped peer memory (CUDA IPC).
+// Switch + halo epoch handed to the kernels that exchange data through mapped peer memory (CUDA IPC); the peer
+// pointers themselves and the epochs of the scalar all-gathers live in device memory (SembScal::peers, ep_dev).
 struct P2PArgs {
   int on = 0, nranks = 1, rank = 0;
-  unsigned long long epoch = 0;    // epoch of the exchange this kernel takes part in
-  unsigned long long epoch_b = 0;  // second exchange in the same kernel (y-seam kernel: halo = epoch, pap = epoch_b)
-  SembScal* peer[SEMB_MAX_RANKS] = {nullptr};  // peer[r] = rank r's mailbox (r == rank: the local one)
+  unsigned long long epoch = 0;    // epoch of the stand-alone halo exchange this kernel consumes (host-side counter)
 };
 
 struct semb_ctx {
@@ -166,7 +172,15 @@ struct semb_mesh {
   void* d_mailbox = nullptr;
   double* d_mail_halo = nullptr;       // local halo rows inside the mailbox
   void* peer_mailbox[SEMB_MAX_RANKS] = {nullptr};
-  unsigned long long ep_halo = 0, ep_pap = 0, ep_t = 0, ep_red = 0;
+  unsigned long long ep_halo = 0;      // epoch of the stand-alone halo exchange (host-side; the others live in SembScal::ep_dev)
+  // fused tail (semb_tail.cuh)
+  bool tail = false;                   // interface completion fused into the strip kernel
+  int ngroups = 0;                     // grid.y of the strip kernel (CTA rows); a CTA row marches through 1 or 2 chunks
+  int* d_grp = nullptr;                // 2*ngroups chunk ids
+  unsigned* d_tcnt = nullptr;
+  double* d_tpart = nullptr;
+  int ntcnt = 0, ntpart = 0, xmic_total = 0;
+  long long* d_dbg = nullptr;          // -DSEMB_TAIL_TIMING builds only
   // reductions
   int npartials = 0;
   double* d_partials = nullptr;        // 3 * npartials doubles
@@ -228,6 +242,54 @@ struct OpArgs {
   double* partials = nullptr;
   unsigned* counters = nullptr;
   int pcg = 0;         // 1: PCG mode (read scal, fuse p update and dot)
+  // ---- fused tail (semb_tail.cuh): interface sums, halo exchange and the PCG dot finished INSIDE the strip kernel
+  int tail = 0;                  // 1: seams are completed by the last CTA to arrive at each of them (no seam kernels)
+  const int* grp = nullptr;      // 2 ints per blockIdx.y: the chunks that CTA row marches through, in order (-1: none)
+  const int* xmic = nullptr;     // nchunks+1 prefix of ceil(lines of chunk / 32): micro-tasks of an x seam
+  int xmic_total = 0;            // = xmic[nchunks]
+  unsigned* tcnt = nullptr;      // arrival counters [x tasks][y tasks][corner tasks][final ticket]
+  double* tpart = nullptr;       // PCG partial sums [CTA][x tasks][y tasks][corner tasks]
+  int nxs = 0;                   // x seams (strip boundaries + the periodic wrap)
+  int ywrap = 0;                 // periodic y closed inside this rank: boundary nchunks == boundary 0
+  int has_lo = 0, has_hi = 0;    // neighbour ranks below / above
+  double* peer_rows_lo = nullptr;              // neighbour-below's tail rows  [parity][side][pitch] (we write side 1)
+  double* peer_rows_hi = nullptr;              // neighbour-above's tail rows  (we write side 0)
+  unsigned long long* peer_flags_lo = nullptr; // neighbour-below's segment flags [side][nstrips] (we write side 1)
+  unsigned long long* peer_flags_hi = nullptr;
+  const double* my_rows = nullptr;             // rows the neighbours wrote into OUR mailbox
+  const unsigned long long* my_flags = nullptr;
+  const double* wx1d = nullptr;  // mult(x,y) = wx1d[x] * wy1d[y] (factors 1 or 1/2)
+  const double* wy1d = nullptr;
+  long long* dbg = nullptr;      // -DSEMB_TAIL_TIMING builds: 8 globaltimer stamps per CTA (tools/tail_timing.py)
+};
+
+#ifdef SEMB_TAIL_TIMING
+__device__ __forceinline__ void semb_stamp(const OpArgs& a, int i) {
+  if (a.dbg && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    a.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + i] = t;
+  }
+}
+#else
+#define semb_stamp(a, i) ((void)0)
+#endif
+
+// Layout of the arrival counters / PCG partial slots of the fused tail (host: mesh_set_groups; device: semb_tail.cuh)
+struct SembTailLayout {
+  int nX, nY, nC;  // task counts: nxs*nchunks, (nchunks+1)*nstrips, (nchunks+1)*nxs
+  int pX, pY;      // partial slots (one per MICRO-task of 32 items): nxs * xmic, nY * 8
+  __host__ __device__ SembTailLayout(int nstrips, int nchunks, int nxs, int xmic)
+      : nX(nxs * nchunks), nY((nchunks + 1) * nstrips), nC((nchunks + 1) * nxs), pX(nxs * xmic), pY(nY * 8) {}
+  __host__ __device__ int offX() const { return 0; }
+  __host__ __device__ int offY() const { return nX; }
+  __host__ __device__ int offC() const { return nX + nY; }
+  __host__ __device__ int ntasks() const { return nX + nY + nC; }
+  __host__ __device__ int final_ticket() const { return nX + nY + nC; }
+  __host__ __device__ int partX() const { return 0; }
+  __host__ __device__ int partY() const { return pX; }
+  __host__ __device__ int partC() const { return pX + pY; }
+  __host__ __device__ int nparts() const { return pX + pY + nC; }
 };
 
 // launchers implemented in the .cu files

@@ -87,52 +87,70 @@ __device__ __forceinline__ void semb_st_release_sys(unsigned long long* p, unsig
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// Wait until a peer-written epoch flag reaches `ep`.  Bounded: after SembScal::spin_limit clock ticks the kernel
+// gives up, records it in SembScal::err (the host turns that into SEMB_ENCCL) and goes on with whatever is there --
+// a lost or diverged peer must not hang every other rank inside a kernel.
+__device__ __forceinline__ void semb_wait_epoch(const unsigned long long* flag, unsigned long long ep, SembScal* me) {
+  if (semb_ld_acquire_sys(flag) >= ep) return;
+  const long long lim = me->spin_limit, t0 = clock64();
+  while (semb_ld_acquire_sys(flag) < ep) {
+    if (lim > 0 && clock64() - t0 > lim) {
+      atomicExch(&me->err, 1);
+      return;
+    }
+  }
+}
+
 // All-gather of up to two doubles per rank through peer memory, executed by ONE block per rank (all of
 // its threads must call): thread r stores this rank's values into rank r's mailbox (NVLink st.global),
 // releases a flag, then waits for rank r's values to arrive in the local mailbox.  Afterwards thread 0
 // combines in rank order (v0: sum, v1: max) => bitwise identical results on every rank.  This is the
 // collective fused into the producing kernel: no NCCL launch.  kind: 0 = pap, 1 = {t, rmax}, 2 = reductions.
-__device__ __forceinline__ void semb_p2p_allgather(const P2PArgs& x, SembScal* me, int kind, double v0, double v1,
-                                                   double* sum0, double* max1, int tid) {
-  const int par = (int)(x.epoch & 1ull);
-  if (tid < x.nranks) {
-    SembScal* dst = x.peer[tid];
+// The epoch is a device-side counter (SembScal::ep_dev[1 + kind]) advanced here, so the calling kernel's
+// arguments never change between iterations (CUDA-graph replay on several ranks).
+__device__ __forceinline__ void semb_p2p_allgather(SembScal* me, int kind, double v0, double v1, double* sum0,
+                                                   double* max1, int tid) {
+  const int nranks = me->nranks, rank = me->rank;
+  const unsigned long long ep = me->ep_dev[1 + kind] + 1ull;
+  const int par = (int)(ep & 1ull);
+  if (tid < nranks) {
+    SembScal* dst = me->peers[tid];
     unsigned long long* fdst;
     const unsigned long long* fsrc;
     if (kind == 0) {
-      dst->box_pap[par][x.rank] = v0;
-      fdst = &dst->flag_pap[x.rank];
+      dst->box_pap[par][rank] = v0;
+      fdst = &dst->flag_pap[rank];
       fsrc = &me->flag_pap[tid];
     } else if (kind == 1) {
-      dst->box_t[par][2 * x.rank] = v0;
-      dst->box_t[par][2 * x.rank + 1] = v1;
-      fdst = &dst->flag_t[x.rank];
+      dst->box_t[par][2 * rank] = v0;
+      dst->box_t[par][2 * rank + 1] = v1;
+      fdst = &dst->flag_t[rank];
       fsrc = &me->flag_t[tid];
     } else {
-      dst->box_red[par][2 * x.rank] = v0;
-      dst->box_red[par][2 * x.rank + 1] = v1;
-      fdst = &dst->flag_red[x.rank];
+      dst->box_red[par][2 * rank] = v0;
+      dst->box_red[par][2 * rank + 1] = v1;
+      fdst = &dst->flag_red[rank];
       fsrc = &me->flag_red[tid];
     }
     __threadfence_system();
-    semb_st_release_sys(fdst, x.epoch);
-    while (semb_ld_acquire_sys(fsrc) < x.epoch) {
-    }
+    semb_st_release_sys(fdst, ep);
+    semb_wait_epoch(fsrc, ep, me);
   }
-  __syncthreads();
+  __syncthreads();  // (every reader of ep_dev is past its load: thread 0 may advance it)
   if (tid == 0) {
     double s = 0.0, m = 0.0;
-    for (int r = 0; r < x.nranks; ++r) {
+    for (int r = 0; r < nranks; ++r) {
       if (kind == 0) {
-        s += me->box_pap[par][r];
+        s += ((volatile double*)me->box_pap[par])[r];
       } else {
-        const double* b = (kind == 1) ? me->box_t[par] : me->box_red[par];
+        const volatile double* b = (kind == 1) ? me->box_t[par] : me->box_red[par];
         s += b[2 * r];
         m = fmax(m, b[2 * r + 1]);
       }
     }
     *sum0 = s;
     if (max1) *max1 = m;
+    me->ep_dev[1 + kind] = ep;
   }
 }
 

@@ -25,6 +25,7 @@
 // (a+b)+(c+d) association bit for bit.
 #pragma once
 #include "semb_reduce.cuh"
+#include "semb_tail.cuh"
 
 // Contraction tables.  Four N x N matrices are applied per element row: A1 = Ds (y-lines of u),
 // A2 = Dr (x-lines of u), A3 = Ds^T (y-lines of ws), A4 = Dr^T (x-lines of wr).  Each is shipped to the
@@ -168,6 +169,30 @@ __device__ __forceinline__ void semb_bulk_g2s(void* dst_smem, const void* src_gm
                "l"(src_gmem), "r"(bytes), "r"(semb_smem_u32(bar))
                : "memory");
 }
+// L2 residency hints.  The coefficient / input rows are read exactly once (evict_first: they should not displace
+// anything), while the raw interface values a CTA leaves for the fused tail are re-read by another CTA up to a chunk
+// later (evict_last: without it they come back from DRAM as scattered 32-byte sectors at the very end of the kernel)
+__device__ __forceinline__ uint64_t semb_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t semb_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void semb_bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                                   uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          semb_smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(semb_smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void semb_st_keep(double* p, double v) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(semb_policy_evict_last()) : "memory");
+}
 // global -> L2 bulk prefetch (no destination, no registers): rows a later plain load will hit in L2
 __device__ __forceinline__ void semb_bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
@@ -218,7 +243,6 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
   const bool actB = eB < nbe;                   // (eB < BX is implied: nbe <= BX)
   const bool inB = t < BX * N;                  // threads BX*N..T-1 own no column (T need not divide by N)
   const bool actA = (jA < N) && (eA < nbe);
-  const int r0 = a.chunk_r0[a.chunk0 + blockIdx.y], r1 = a.chunk_r0[a.chunk0 + blockIdx.y + 1];
   const int pitch = (int)a.pitch;
   const int x0 = e0 * N;
   const int xg = x0 + t;
@@ -232,8 +256,14 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
   const bool mzero = (xg == 0 && a.mx0) || (xg == a.nxl - 1 && a.mx1);  // Dirichlet column
   // mult = 1 ./ gatherScatter(ones) (mesh.jl:94-96) is structural: 1/(cx*cy)
   const double wx = (xl || xr || xs) ? 0.5 : 1.0;
-  const bool seam_bot = a.ystart[r0] != 0;  // chunk's first line belongs to a y seam
-  const bool seam_top = a.ystart[r1] != 0;
+  // Fused tail (semb_tail.cuh): this CTA row marches through one or two chunks (the one-row chunk of a rank
+  // boundary first), announces each finished chunk and afterwards runs the interface tasks it arrived last at.
+  const bool tail = a.tail != 0;
+  __shared__ SembTailTask s_task[16];
+  // epoch of this apply's halo exchange: a device-side counter (graph-replayable) that only the grid's very last
+  // CTA advances, so it is re-read at the few places that need it instead of living in registers
+  auto cur_ep = [&]() { return *(volatile unsigned long long*)&a.scal->ep_dev[0] + 1ull; };
+  if (tail && t < 16) s_task[t].n = 0, s_task[t].target = 0;
 
   // ---- bulk-copy producer (warp 0): one row = nbe*N doubles (rounded up to 16 bytes; the pad double
   // lies inside the padded row pitch), N rows per array, completion counted on an mbarrier ------------
@@ -245,10 +275,17 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
       semb_mbar_expect_tx(bar, row_bytes * (uint32_t)(narr * N));
     }
     __syncwarp();
+#ifndef SEMB_NO_L2_HINTS
+    const uint64_t pol = semb_policy_evict_first();
+#endif
     for (int c = t; c < narr * N; c += 32) {
       const int q = c / N, j = c - q * N;
       const double* src = (first_arr + q == 0) ? a.u : (first_arr + q == 1) ? a.G11 : (first_arr + q == 2) ? a.G12 : a.G22;
+#ifndef SEMB_NO_L2_HINTS
+      semb_bulk_g2s_hint(stage + (q * N + j) * PWS, src + (size_t)(r * N + j) * pitch + x0, row_bytes, bar, pol);
+#else
       semb_bulk_g2s(stage + (q * N + j) * PWS, src + (size_t)(r * N + j) * pitch + x0, row_bytes, bar);
+#endif
     }
     // general coefficients: B is read late (step 5) with plain loads; its rows travel to L2 alongside the G rows
     if (MASS && LATE_B && first_arr == 1 && a.B && t < N)
@@ -261,10 +298,6 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (t < 32 && r0 < r1) {
-    issue_rows(r0, 0, 1, SU, &bars[0]);
-    issue_rows(r0, 1, 3, SG, &bars[1]);
-  }
 
   double carry = 0.0, carry_u = 0.0;
   double acc = 0.0;  // PCG: sum p*Ap*mult over the nodes this thread finalises
@@ -274,6 +307,34 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
 #pragma unroll
     for (int j = 0; j < N; ++j) pn[j] = actB ? a.pold[b + j * pitch] : 0.0;
   };
+  semb_stamp(a, 0);
+  uint32_t phase = 0;  // both mbarriers complete one phase per element row, across chunks
+  // (chunk ids are re-read where needed rather than kept in registers: the PCG variants have none to spare)
+  auto chunk_of = [&](int sub) { return tail ? a.grp[2 * blockIdx.y + sub] : a.chunk0 + (int)blockIdx.y; };
+  for (int sub = 0; sub < 2; ++sub) {
+  if (sub == 1 && !(tail && a.grp[2 * blockIdx.y + 1] >= 0)) break;
+  const int r0 = a.chunk_r0[chunk_of(sub)], r1 = a.chunk_r0[chunk_of(sub) + 1];
+  const bool seam_bot = a.ystart[r0] != 0;  // chunk's first line belongs to a y seam
+  const bool seam_top = a.ystart[r1] != 0;
+  // rank boundary: the raw boundary line also goes straight into the neighbour's mailbox (NVLink stores from the
+  // registers that hold it), rows [parity][side][pitch]: our first line is the lower neighbour's "row from above"
+  // (side 1), our last line the upper neighbour's "row from below" (side 0)
+  auto push_row = [&](bool lo, double val) {
+    const int par = (int)(cur_ep() & 1ull);
+    double* row = lo ? a.peer_rows_lo + (size_t)(2 * par + 1) * pitch : a.peer_rows_hi + (size_t)(2 * par) * pitch;
+    row[xg] = val;
+    __threadfence_system();
+  };
+  auto publish = [&](int which) {  // one epoch flag per strip segment and side, in the neighbour's mailbox
+    const unsigned long long ep = cur_ep();
+    if (which & 1) semb_st_release_sys(&a.peer_flags_lo[1 * gridDim.x + blockIdx.x], ep);
+    if (which & 2) semb_st_release_sys(&a.peer_flags_hi[0 * gridDim.x + blockIdx.x], ep);
+  };
+  if (t < 32 && r0 < r1) {  // (every read of the staging buffers by the previous chunk is behind a CTA barrier)
+    issue_rows(r0, 0, 1, SU, &bars[0]);
+    issue_rows(r0, 1, 3, SG, &bars[1]);
+  }
+  if (tail) semb_tail_prepare(a, (int)blockIdx.x, (int)gridDim.x, chunk_of(sub), r0, r1, s_task + 8 * sub);
   if (PCGM && r0 < r1) issue_p(r0);
 
   // inactive threads read through clamped indices (no selects in the inner loops); they never store
@@ -288,9 +349,16 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     return lap;
   };
 
-  for (int r = r0; r < r1; ++r) {
+  for (int r = r0; r < r1; ++r, ++phase) {
     const int base = r * N * pitch + xg;
-    const uint32_t parity = (uint32_t)((r - r0) & 1);
+    const uint32_t parity = phase & 1u;
+    // the slab's first line was pushed in iteration r = 0: publish it now (block-uniform; once per bottom-edge CTA);
+    // its last line is pushed in the last iteration of its chunk and published right after the loop
+    if (tail && a.has_lo && r == 1 && r0 == 0) {
+      __syncthreads();
+      if (t == 0) publish(1);
+    }
+    const bool plo = tail && a.has_lo && r == 0, phi = tail && a.has_hi && r == a.ney - 1;
     // coefficient columns that are not staged: issued now, consumed in step 3
     double bq[N];
     if (MASS && !LATE_B) {  // MASS = "general coefficients": k != 0, array k, or (non-constant) array nu
@@ -398,7 +466,9 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     if (xs) {
       // strip seam column: raw values for every line; the x-seam kernel forms x pairs, then y pairs
 #pragma unroll
-      for (int j = 0; j < N; ++j) a.out[base + j * pitch] = v[j];
+      for (int j = 0; j < N; ++j) semb_st_keep(&a.out[base + j * pitch], v[j]);
+      if (plo) push_row(true, v[0]);
+      if (phi) push_row(false, v[N - 1]);
       continue;
     }
     // final value (+ mask, mask.jl:14) and the PCG dot contribution (pcg.jl:52) of one node;
@@ -412,8 +482,10 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     };
     // line 0
     if (r == r0) {
-      if (seam_bot) a.out[base] = v[0];
-      else finish(base, v[0], u[0], r == 0 && a.my0, 1.0);
+      if (seam_bot) {
+        semb_st_keep(&a.out[base], v[0]);
+        if (plo) push_row(true, v[0]);
+      } else finish(base, v[0], u[0], r == 0 && a.my0, 1.0);
     } else {
       const double s = __dadd_rn(carry, v[0]);  // y pair (after the x pairs)
       finish(base, s, u[0], false, 0.5);
@@ -424,14 +496,31 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     // line N-1
     if (r == r1 - 1) {
       const int idx = base + (N - 1) * pitch;
-      if (seam_top) a.out[idx] = v[N - 1];
-      else finish(idx, v[N - 1], u[N - 1], r == a.ney - 1 && a.my1, 1.0);
+      if (seam_top) {
+        semb_st_keep(&a.out[idx], v[N - 1]);
+        if (phi) push_row(false, v[N - 1]);
+      } else finish(idx, v[N - 1], u[N - 1], r == a.ney - 1 && a.my1, 1.0);
     } else {
       carry = v[N - 1];
       if (PCGM) carry_u = u[N - 1];
     }
   }
 
+    if (tail) {  // chunk finished: fence this thread's stores, announce, note the tasks this CTA now owns
+      semb_stamp(a, 1 + 2 * sub);
+      __threadfence();
+      __syncthreads();
+      if (t == 0) publish(((a.has_lo && r0 == 0 && r1 == 1) ? 1 : 0) | ((a.has_hi && r1 == a.ney) ? 2 : 0));
+      semb_tail_announce(a, s_task + 8 * sub);
+      semb_stamp(a, 2 + 2 * sub);
+    }
+  }  // sub
+
+  if (tail) {
+    __syncthreads();
+    semb_strip_tail(a, s_task, (int)blockIdx.x, (int)gridDim.x, (a.has_lo || a.has_hi) ? cur_ep() : 0ull, acc, red);
+    return;
+  }
   if (PCGM) {
     const int nblocks = gridDim.x * gridDim.y;
     const int bid = blockIdx.y * gridDim.x + blockIdx.x;

@@ -78,10 +78,8 @@ __global__ void __launch_bounds__(256) semb_seam_y_kernel(const OpArgs a, int nh
     // P2P halo: the neighbours' boundary rows arrive in the local mailbox over NVLink (semb_halo_push_kernel
     // on the neighbour); wait for this apply's epoch before touching them
     if (threadIdx.x == 0) {
-      if (nhalo_lo) while (semb_ld_acquire_sys(&a.scal->flag_halo[0]) < x.epoch) {
-        }
-      if (nhalo_hi) while (semb_ld_acquire_sys(&a.scal->flag_halo[1]) < x.epoch) {
-        }
+      if (nhalo_lo) semb_wait_epoch(&a.scal->flag_halo[0], x.epoch, a.scal);
+      if (nhalo_hi) semb_wait_epoch(&a.scal->flag_halo[1], x.epoch, a.scal);
     }
     __syncthreads();
   }
@@ -118,9 +116,7 @@ __global__ void __launch_bounds__(256) semb_seam_y_kernel(const OpArgs a, int nh
         // sum(p .* Ap .* mult) over all ranks, fused here: this kernel is the last contributor
         const double mine = __dadd_rn(__dadd_rn(a.scal->pap[0], a.scal->pap[1]), sh_tot[0]);
         double tot;
-        P2PArgs xb = x;
-        xb.epoch = x.epoch_b;
-        semb_p2p_allgather(xb, a.scal, 0, mine, 0.0, &tot, nullptr, threadIdx.x);
+        semb_p2p_allgather(a.scal, 0, mine, 0.0, &tot, nullptr, threadIdx.x);
         if (threadIdx.x == 0) a.scal->pap_total = tot;
       }
     }
@@ -454,7 +450,7 @@ __global__ void __launch_bounds__(256) semb_reduce_kernel(int which, const doubl
     const double v = (which == 0) ? sh_tot[0] : sh_tot[1];
     if (x.on) {
       double s0, m1;
-      semb_p2p_allgather(x, scal, 2, which == 0 ? v : 0.0, which == 0 ? 0.0 : v, &s0, &m1, SEMB_TID);
+      semb_p2p_allgather(scal, 2, which == 0 ? v : 0.0, which == 0 ? 0.0 : v, &s0, &m1, SEMB_TID);
       if (SEMB_TID == 0) scal->red[which] = (which == 0) ? s0 : m1;
     } else if (SEMB_TID == 0) {
       scal->red[which] = v;
@@ -535,7 +531,7 @@ __global__ void __launch_bounds__(256) semb_pcg_init_kernel(const double2* __res
       scal->xchg_t[2 * scal->rank] = tot;
       scal->xchg_t[2 * scal->rank + 1] = tmx;
     }
-    if (xp.on) semb_p2p_allgather(xp, scal, 1, tot, tmx, &tot, &tmx, SEMB_TID);
+    if (xp.on) semb_p2p_allgather(scal, 1, tot, tmx, &tot, &tmx, SEMB_TID);
     if (SEMB_TID == 0 && (scal->nranks == 1 || xp.on)) semb_pcg_advance(scal, tot, tmx, true);
   }
 }
@@ -592,7 +588,7 @@ __global__ void __launch_bounds__(256) semb_pcg_update_kernel(double2* x, double
       scal->xchg_t[2 * scal->rank] = tot;
       scal->xchg_t[2 * scal->rank + 1] = tmx;
     }
-    if (xp.on) semb_p2p_allgather(xp, scal, 1, tot, tmx, &tot, &tmx, SEMB_TID);  // fused all-gather over NVLink
+    if (xp.on) semb_p2p_allgather(scal, 1, tot, tmx, &tot, &tmx, SEMB_TID);  // fused all-gather over NVLink
     if (SEMB_TID == 0 && (scal->nranks == 1 || xp.on)) semb_pcg_advance(scal, tot, tmx, false);
   }
 }

@@ -101,6 +101,38 @@ def test_fused_oplhs(sem, ctx, nr, Ex, Ey, per, deform):
         gm.free()
 
 
+@pytest.mark.parametrize("nr,Ex,Ey,per,deform", [CASES[0], CASES[3], CASES[7], CASES[8], CASES[9], CASES[10],
+                                                 (2, 300, 4, (True, True), "box")])
+def test_fused_tail_equals_seam_kernels(sem, ctx, monkeypatch, nr, Ex, Ey, per, deform):
+    """One apply is ONE launch by default: the strip kernel's own CTAs finish the strip / chunk interfaces
+    (semb_tail.cuh).  The separate seam kernels remain (SEMB_NO_TAIL=1, the NCCL fallback and the pipelined host
+    twin use them): both must give the same BITS for every chunking (2-term interface sums, gatherScatter.jl:13)."""
+    om, gt = make_pair(sem, ctx, nr, Ex, Ey, per, deform)
+    monkeypatch.setenv("SEMB_NO_TAIL", "1")
+    _, gs = make_pair(sem, ctx, nr, Ex, Ey, per, deform)
+    monkeypatch.delenv("SEMB_NO_TAIL")
+    try:
+        assert gt.fused_tail() and not gs.fused_tail()
+        u = so.splitmix_uniform(gt.shape, seed=17)
+        M = so.generateMask(list("DNDN"), om).astype(np.float64)
+        for nch in sorted({1, 2, 3, Ey}):
+            if nch > Ey:
+                continue
+            gt.set_chunks(nch)
+            gs.set_chunks(nch)
+            for kw in (dict(bc="DDDD"), dict(bc="NNNN"), dict(M=M)):
+                a, b = sem.OpLHS(gt, 1.0, 0.3, **kw)(u), sem.OpLHS(gs, 1.0, 0.3, **kw)(u)
+                assert np.array_equal(a, b), (nch, kw.keys())
+            fu, fo = gt.field(u), gt.field()
+            l0 = ctx.launch_count()
+            gt.oplhs_device(fu, fo, nu=1.0, k=0.0, bc="DDDD")
+            assert ctx.launch_count() - l0 == 1
+            fu.free(); fo.free()
+    finally:
+        gt.free()
+        gs.free()
+
+
 def test_fused_is_deterministic(sem, ctx):
     om, gm = make_pair(sem, ctx, 9, 40, 8, (False, False), "wavy")
     try:

@@ -77,6 +77,53 @@ def test_pcg_matches_oracle(sem, ctx, nr, E, per, deform, bc, k):
         gm.free()
 
 
+@pytest.mark.parametrize("nr,ns,E", [(5, 7, 4), (20, 20, 2)])
+def test_pcg_on_a_fresh_generic_mesh(sem, ctx, nr, ns, E):
+    """nr != ns / nr > 17 take the generic kernels, whose work fields used to be allocated lazily INSIDE the CUDA-graph
+    capture of the first PCG batch (cudaMalloc while capturing: the solve failed on a mesh that had not run a plain
+    apply before).  semb_pcg_begin allocates them now."""
+    om = so.make_mesh(nr, ns, E, E, (False, False), so.wavy)
+    gm = sem.Mesh.from_arrays(nr, ns, E, E, (False, False), om.Dr, om.Ds, om.G11, om.G12, om.G22, om.B, ctx=ctx)
+    try:
+        assert gm.plan()["fast"] == 0
+        M = so.generateMask(list("DDDD"), om).astype(np.float64)
+        b = rhs_for(om, M, np.ones(gm.shape))
+        io, ig = {}, {}
+        xo = so.pcg(b, lambda v: so.opLHS(v, 1.0, 0.0, M, om), mult=om.mult, tol=1e-8, info=io)
+        xg = sem.pcg(b, sem.OpLHS(gm, 1.0, 0.0, bc="DDDD"), mult=gm.mult, tol=1e-8, info=ig)   # first call on this mesh
+        assert ig["converged"] and count_close(ig["iters"], io["iters"]), (ig, io["iters"])
+        assert relerr(xg, xo) < 1e-6
+    finally:
+        gm.free()
+
+
+def test_pcg_fused_tail_equals_seam_kernels(sem, ctx, monkeypatch):
+    """The PCG dot sum(p.*Ap.*mult) is reduced in a fixed slot order in both forms, but the slots differ (per task vs per
+    kernel): iterates agree to rounding, iteration counts exactly on a short solve."""
+    om = so.make_mesh(9, 9, 40, 6, (True, False), so.wavy)
+    mk = lambda: sem.Mesh.from_arrays(9, 9, 40, 6, (True, False), om.Dr, om.Ds, om.G11, om.G12, om.G22, om.B, ctx=ctx)
+    gt = mk()
+    monkeypatch.setenv("SEMB_NO_TAIL", "1")
+    gs = mk()
+    monkeypatch.delenv("SEMB_NO_TAIL")
+    try:
+        M = so.generateMask(list("DDDD"), om).astype(np.float64)
+        b = rhs_for(om, M, np.sin(np.pi * om.x) * np.sin(np.pi * om.y))
+        for nch in (None, 3):
+            if nch:
+                gt.set_chunks(nch); gs.set_chunks(nch)
+            it, is_ = {}, {}
+            xt = sem.pcg(b, sem.OpLHS(gt, 1.0, 0.0, bc="DDDD"), mult=gt.mult, tol=1e-9, maxiter=40, info=it)
+            xs = sem.pcg(b, sem.OpLHS(gs, 1.0, 0.0, bc="DDDD"), mult=gs.mult, tol=1e-9, maxiter=40, info=is_)
+            assert it["iters"] == is_["iters"]
+            assert relerr(xt, xs) < 1e-11
+            x2 = sem.pcg(b, sem.OpLHS(gt, 1.0, 0.0, bc="DDDD"), mult=gt.mult, tol=1e-9, maxiter=40)
+            assert np.array_equal(x2, xt)   # deterministic whichever CTA ran which task
+    finally:
+        gt.free()
+        gs.free()
+
+
 def test_pcg_short_solve_exact_count(sem, ctx):
     """Manufactured u* = sin(pi x) sin(pi y) on the box: ~36 iterations, below the rounding-divergence
     horizon => identical iteration count, solution within 1e-10."""
