@@ -297,7 +297,7 @@ def parity_block(sem, ctx, world, rank):
         xo = so.pcg(b, opo, mult=om.mult, tol=1e-12, info=io)
         xg = sem.pcg(loc(b), sem.OpLHS(gm, 1.0, 0.7, bc=bc), tol=1e-12, info=ig)
         ex = float(np.max(np.abs(xg - loc(xo))) / np.max(np.abs(xo)))
-        if ex > 1e-10 or abs(ig["iters"] - io["iters"]) > max(2, int(0.02 * io["iters"])):
+        if ex > 1e-10 or abs(ig["iters"] - io["iters"]) > max(3, int(0.02 * io["iters"])):
             fails.append("pcg err %.2e iters %d vs %d (nr=%d)" % (ex, ig["iters"], io["iters"], nr))
         try:
             gm.peer_status()
@@ -306,8 +306,8 @@ def parity_block(sem, ctx, world, rank):
         tail = gm.fused_tail()
         gm.free()
     v = ctx.allreduce_max([worst, float(len(fails))])
-    return {"world": world, "ok": v[1] == 0.0, "max_rel": float(v[0]), "fused_tail": tail,
-            "checks": "opLHS slab vs single-domain oracle < 1e-12, gatherScatter bit-exact, PCG count (+-2 %) and solution < 1e-10; "
+    return {"world": world, "ok": bool(v[1] == 0.0), "max_rel": float(v[0]), "fused_tail": tail,
+            "checks": "opLHS slab vs single-domain oracle < 1e-12, gatherScatter bit-exact, PCG count (+-2 %, min 3) and solution < 1e-10; "
                       "2 meshes (two strips; periodic x and y, three strips)", "fails_rank0": fails}
 
 
@@ -558,7 +558,7 @@ def run_semb(args):
                          "sustained_whole_apply_frac": extra.get("sustained", {}).get("whole_apply_frac")},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "cpu_baseline": cpu, "parity": parity, "extra": extra,
         }
-        print(json.dumps(line))
+        print(json.dumps(line, default=lambda o: o.item() if hasattr(o, "item") else str(o)))
     msh.free()
     if dist is not None:
         dist.destroy_process_group()
@@ -590,7 +590,8 @@ def cpu_reference(nr, E, sample_rows, reps):
         c_port = cpu_reference_c(nr, E, min(sample_rows, 64))
     except Exception as e:  # checker-side extra: never lets the bench fail
         c_port = {"unavailable": str(e)[:120]}
-    return {"value": u.size / dt / 1e9, "unit": "GDOF/s", "cores": thr, "kind": "port", "c_port": c_port,
+    best = u.size / dt / 1e9
+    return {"value": best, "unit": "GDOF/s", "cores": thr, "kind": "port", "c_port": c_port,
             "sample": "oracle/sem_oracle.py opLHS (NumPy/OpenBLAS restatement; Julia not installed) on a %dx%d-element "
                       "y-slab of the headline mesh (%d DOF), %d applies, %.2f s each; index-form QQ^T (dense QQ^T "
                       "does not fit); host cpu_count=%s" % (E, sample_rows, u.size, reps, dt, os.cpu_count()),
@@ -612,6 +613,11 @@ def cpu_reference_c(nr, E, rows, reps=3):
     lib.so_generate_mask.argtypes = [C.c_void_p, C.c_char_p, dp]
     lib.so_oplhs.argtypes = [C.c_void_p, dp, dp, C.c_double, dp, C.c_double, dp, dp]
     lib.so_oplhs.restype = None
+    try:
+        lib.so_num_threads.restype = C.c_int
+        nthr = int(lib.so_num_threads())
+    except AttributeError:
+        nthr = 1
     h = lib.so_mesh_create(nr, nr, E, rows, 0, 0, 2)   # 2 = wavy
     try:
         n = nr * E * nr * rows
@@ -626,12 +632,15 @@ def cpu_reference_c(nr, E, rows, reps=3):
         dt = (time.perf_counter() - t0) / reps
     finally:
         lib.so_mesh_free(h)
-    return {"value": n / dt / 1e9, "unit": "GDOF/s", "cores": 1,
-            "sample": "oracle/sem_oracle.c opLHS on a %dx%d-element slab (%d DOF), %d applies, %.2f s each" % (E, rows, n, reps, dt)}
+    return {"value": n / dt / 1e9, "unit": "GDOF/s", "cores": nthr,
+            "sample": "oracle/sem_oracle.c opLHS (plain C loops per element, OpenMP over elements: %d thread(s)) on a %dx%d-element "
+                      "slab (%d DOF), %d applies, %.3f s each" % (nthr, E, rows, n, reps, dt)}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (restated, oracle/) on the host cores, rank 0 only."""
+    """--impl reference: the reference's CPU path (restated, oracle/) on the host cores, rank 0 only.  Two restatements
+    exist -- NumPy/OpenBLAS (line-faithful to the Julia code, all host threads) and plain C loops per element (one
+    thread); the line reports the FASTER of the two, so that the GPU/CPU ratio is not flattered by the slower one."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     args.cpu_rows = min(args.cpu_rows, args.elements)
@@ -651,6 +660,16 @@ def run_reference(args):
         so.opLHS(u, 1.0, 0.0, M, om)
     dt = (time.perf_counter() - t0) / steps
     val = u.size / dt / 1e9
+    sample_dofs, which = u.size, "numpy"
+    cpu["numpy_value"] = val
+    c_port = cpu.get("c_port") or {}
+    if isinstance(c_port.get("value"), float) and c_port["value"] > val:   # the compiled restatement is faster: report it
+        rows_c = min(args.cpu_rows, 64)
+        sample_dofs = (args.nr * args.elements) * (args.nr * rows_c)
+        val, dt, which = c_port["value"], sample_dofs / c_port["value"] / 1e9, "c"
+        cpu["cores"] = c_port.get("cores", 1)
+        cpu["sample"] = c_port["sample"] + " (faster than the NumPy/OpenBLAS restatement: %.4f GDOF/s on %s threads)" % (
+            cpu["numpy_value"], cpu.get("cores"))
     cpu["value"] = val
     line = {"impl": "reference", "metric": "laplacian_gs_mask_apply_throughput", "value": val, "unit": "GDOF/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -659,11 +678,13 @@ def run_reference(args):
                                    "(nr=%d), %dx%d elements per GPU, wavy-deformed box, %d DOF per GPU"
                                    % (args.nr - 1, args.nr, args.elements, args.elements,
                                       (args.nr * args.elements) ** 2),
-                       "sample": "each step = one apply on a %dx%d-element y-slab of that mesh (%d DOF); throughput per DOF"
-                                 % (args.elements, args.cpu_rows, u.size)},
+                       "sample": "each step = one apply on a y-slab of that mesh (%d DOF, %s restatement); throughput per DOF, "
+                                 "so comparable with the GPU arm although config and steps are a bounded sample"
+                                 % (sample_dofs, which)},
             "cpu_baseline": cpu,
             "e2e": {"value": val, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "reference = NumPy/OpenBLAS restatement of the Julia CPU path (oracle/); Julia is not installed"}
+            "note": "reference = CPU restatement of the Julia path (oracle/: NumPy/OpenBLAS and plain C; the faster is reported); "
+                    "Julia is not installed"}
     print(json.dumps(line))
 
 

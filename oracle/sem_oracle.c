@@ -16,6 +16,18 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* threads the element loops run on (1 without OpenMP): bench.py reports it as cpu_baseline.cores */
+int so_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
 
 #define SO_PI 3.14159265358979323846
 

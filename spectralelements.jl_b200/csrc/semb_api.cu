@@ -305,16 +305,14 @@ static int download_pitched(semb_mesh* m, const double* src, double* host) {
 }
 
 // layout of a mesh's mailbox allocation (exported through CUDA IPC):
-//   [SembScal][stand-alone halo rows: 2 parities x 2 sides x pitch][fused-tail rows: 2 x 2 x pitch][segment flags: 2 sides x nstrips]
+//   [SembScal][stand-alone halo rows: 2 parities x 2 sides x pitch doubles]
+//   [fused-tail rows: 2 parities x 2 sides x pitch 16-byte flag-in-data entries (semb_ll_store)]
 static size_t mail_scal_bytes() { return (sizeof(SembScal) + 255) / 256 * 256; }
 static size_t mail_bytes(semb_mesh* m) {
-  return mail_scal_bytes() + 8 * (size_t)m->pitch * sizeof(double) + 2 * (size_t)m->nstrips * sizeof(unsigned long long);
+  return mail_scal_bytes() + 4 * (size_t)m->pitch * sizeof(double) + 4 * (size_t)m->pitch * sizeof(uint4);
 }
-static double* mail_tail_rows(semb_mesh* m, void* mailbox) {
-  return (double*)((char*)mailbox + mail_scal_bytes()) + 4 * (size_t)m->pitch;
-}
-static unsigned long long* mail_tail_flags(semb_mesh* m, void* mailbox) {
-  return (unsigned long long*)(mail_tail_rows(m, mailbox) + 4 * (size_t)m->pitch);
+static uint4* mail_tail_rows(semb_mesh* m, void* mailbox) {
+  return (uint4*)((char*)mailbox + mail_scal_bytes() + 4 * (size_t)m->pitch * sizeof(double));
 }
 
 // Chunk tables of the strip kernel for `groups` CTA rows: chunk offsets, y-seam flags, seam lists, and the tables
@@ -328,7 +326,8 @@ static int mesh_set_groups(semb_mesh* m, int groups) {
   if (groups > m->ney) groups = m->ney;
   if (groups < 1) groups = 1;
   std::vector<int> g0(groups + 1);
-  for (int k = 0; k <= groups; ++k) g0[k] = (int)((long long)k * m->ney / groups);
+  // (rounded up: the LAST group is the short one -- with a neighbour above it is the CTA row with the extra edge chunk)
+  for (int k = 0; k <= groups; ++k) g0[k] = (int)(((long long)k * m->ney + groups - 1) / groups);
   const bool split = m->tail && m->halo_hi && g0[groups] - g0[groups - 1] >= 2 && !getenv("SEMB_NO_EDGE_FIRST");
   m->ngroups = groups;
   m->nchunks = groups + (split ? 1 : 0);
@@ -1111,16 +1110,15 @@ static int run_operator(semb_mesh* m, const double* u, double* out, const OpSpec
     a.ywrap = (m->pery && c->nranks == 1) ? 1 : 0;
     a.has_lo = m->halo_lo;
     a.has_hi = m->halo_hi;
+    a.ep_host = m->ep_tail_host;
+    if (!pcg && (m->halo_lo || m->halo_hi)) ++m->ep_tail_host;  // (PCG-mode applies count on the device: graph replay)
     if (m->halo_lo) {
       a.peer_rows_lo = mail_tail_rows(m, m->peer_mailbox[m->rank_lo]);
-      a.peer_flags_lo = mail_tail_flags(m, m->peer_mailbox[m->rank_lo]);
     }
     if (m->halo_hi) {
       a.peer_rows_hi = mail_tail_rows(m, m->peer_mailbox[m->rank_hi]);
-      a.peer_flags_hi = mail_tail_flags(m, m->peer_mailbox[m->rank_hi]);
     }
     a.my_rows = mail_tail_rows(m, m->d_mailbox);
-    a.my_flags = mail_tail_flags(m, m->d_mailbox);
     a.dbg = m->d_dbg;
     return semb_launch_strip(c, a, m->hDr.data(), m->hDs.data(), m->nstrips, m->ngroups, pcg, massterm, m->eo);
   }

@@ -172,6 +172,7 @@ struct semb_mesh {
   void* d_mailbox = nullptr;
   double* d_mail_halo = nullptr;       // local halo rows inside the mailbox
   void* peer_mailbox[SEMB_MAX_RANKS] = {nullptr};
+  unsigned long long ep_tail_host = 0; // fused-tail applies outside PCG issued so far (the PCG-mode count lives in ep_dev[0])
   unsigned long long ep_halo = 0;      // epoch of the stand-alone halo exchange (host-side; the others live in SembScal::ep_dev)
   // fused tail (semb_tail.cuh)
   bool tail = false;                   // interface completion fused into the strip kernel
@@ -252,12 +253,11 @@ struct OpArgs {
   int nxs = 0;                   // x seams (strip boundaries + the periodic wrap)
   int ywrap = 0;                 // periodic y closed inside this rank: boundary nchunks == boundary 0
   int has_lo = 0, has_hi = 0;    // neighbour ranks below / above
-  double* peer_rows_lo = nullptr;              // neighbour-below's tail rows  [parity][side][pitch] (we write side 1)
-  double* peer_rows_hi = nullptr;              // neighbour-above's tail rows  (we write side 0)
-  unsigned long long* peer_flags_lo = nullptr; // neighbour-below's segment flags [side][nstrips] (we write side 1)
-  unsigned long long* peer_flags_hi = nullptr;
-  const double* my_rows = nullptr;             // rows the neighbours wrote into OUR mailbox
-  const unsigned long long* my_flags = nullptr;
+  unsigned long long ep_host = 0;  // halo exchanges of non-PCG applies issued so far (host-side part of the epoch)
+  // boundary rows travel as 16-byte {lo32, tag, hi32, tag} entries (flag-in-data: no fence, no separate flag)
+  uint4* peer_rows_lo = nullptr;   // neighbour-below's tail rows  [parity][side][pitch] (we write side 1)
+  uint4* peer_rows_hi = nullptr;   // neighbour-above's tail rows  (we write side 0)
+  const uint4* my_rows = nullptr;  // rows the neighbours wrote into OUR mailbox
   const double* wx1d = nullptr;  // mult(x,y) = wx1d[x] * wy1d[y] (factors 1 or 1/2)
   const double* wy1d = nullptr;
   long long* dbg = nullptr;      // -DSEMB_TAIL_TIMING builds: 8 globaltimer stamps per CTA (tools/tail_timing.py)

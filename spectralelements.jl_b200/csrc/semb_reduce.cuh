@@ -101,6 +101,33 @@ __device__ __forceinline__ void semb_wait_epoch(const unsigned long long* flag, 
   }
 }
 
+// Flag-in-data exchange of a double through peer memory (the idea of NCCL's LL protocol): the value travels as one
+// 16-byte store {lo32, tag, hi32, tag}; each 8-byte half is self-validating (8-byte stores are never torn), so the
+// consumer needs neither a fence on the producer side nor a separate flag -- it re-reads the entry until both tags
+// carry this exchange's epoch.  The tag of epoch e differs from that of e-2 (the previous use of the same buffer)
+// and is never 0 (the initial contents).
+__device__ __forceinline__ unsigned semb_ll_tag(unsigned long long ep) { return (unsigned)(ep & 0x7fffffffull) | 0x80000000u; }
+__device__ __forceinline__ void semb_ll_store(uint4* dst, double v, unsigned tag) {
+  asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"((unsigned)__double2loint(v)), "r"(tag),
+               "r"((unsigned)__double2hiint(v)), "r"(tag)
+               : "memory");
+}
+// Bounded like semb_wait_epoch: after SembScal::spin_limit ticks it records SembScal::err and returns what is there.
+__device__ __forceinline__ double semb_ll_load(const uint4* src, unsigned tag, SembScal* me) {
+  unsigned a, b, c, d;
+  long long t0 = 0;
+  for (int spin = 0;; ++spin) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(src) : "memory");
+    if (b == tag && d == tag) break;
+    if (spin == 0) t0 = clock64();
+    else if ((spin & 63) == 0 && me->spin_limit > 0 && clock64() - t0 > me->spin_limit) {
+      atomicExch(&me->err, 1);
+      break;
+    }
+  }
+  return __hiloint2double((int)c, (int)a);
+}
+
 // All-gather of up to two doubles per rank through peer memory, executed by ONE block per rank (all of
 // its threads must call): thread r stores this rank's values into rank r's mailbox (NVLink st.global),
 // releases a flag, then waits for rank r's values to arrive in the local mailbox.  Afterwards thread 0

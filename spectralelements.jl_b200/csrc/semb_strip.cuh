@@ -256,13 +256,17 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
   const bool mzero = (xg == 0 && a.mx0) || (xg == a.nxl - 1 && a.mx1);  // Dirichlet column
   // mult = 1 ./ gatherScatter(ones) (mesh.jl:94-96) is structural: 1/(cx*cy)
   const double wx = (xl || xr || xs) ? 0.5 : 1.0;
-  // Fused tail (semb_tail.cuh): this CTA row marches through one or two chunks (the one-row chunk of a rank
-  // boundary first), announces each finished chunk and afterwards runs the interface tasks it arrived last at.
+  // Fused tail (semb_tail.cuh): this CTA row marches through one chunk -- or two: with a neighbour rank above, the
+  // slab's LAST element row is a chunk of its own that the top CTA row computes FIRST (so that the boundary line is on
+  // its way over NVLink for the whole kernel), followed without a pipeline bubble by the rows of its main chunk.
+  // Afterwards the CTA announces its chunk(s) and runs the interface tasks it arrived last at.
   const bool tail = a.tail != 0;
   __shared__ SembTailTask s_task[16];
-  // epoch of this apply's halo exchange: a device-side counter (graph-replayable) that only the grid's very last
-  // CTA advances, so it is re-read at the few places that need it instead of living in registers
-  auto cur_ep = [&]() { return *(volatile unsigned long long*)&a.scal->ep_dev[0] + 1ull; };
+  const bool two = tail && a.grp[2 * blockIdx.y + 1] >= 0;   // edge row first, then the main chunk
+  // epoch of this apply's halo exchange = applies issued by the host + PCG-mode applies completed on the device (the
+  // latter count lives in device memory so that a captured batch of PCG iterations replays with unchanged arguments;
+  // only the grid's very last CTA of a PCG-mode launch advances it)
+  auto cur_ep = [&]() { return a.ep_host + *(volatile unsigned long long*)&a.scal->ep_dev[0] + 1ull; };
   if (tail && t < 16) s_task[t].n = 0, s_task[t].target = 0;
 
   // ---- bulk-copy producer (warp 0): one row = nbe*N doubles (rounded up to 16 bytes; the pad double
@@ -308,34 +312,28 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     for (int j = 0; j < N; ++j) pn[j] = actB ? a.pold[b + j * pitch] : 0.0;
   };
   semb_stamp(a, 0);
-  uint32_t phase = 0;  // both mbarriers complete one phase per element row, across chunks
-  // (chunk ids are re-read where needed rather than kept in registers: the PCG variants have none to spare)
-  auto chunk_of = [&](int sub) { return tail ? a.grp[2 * blockIdx.y + sub] : a.chunk0 + (int)blockIdx.y; };
-  for (int sub = 0; sub < 2; ++sub) {
-  if (sub == 1 && !(tail && a.grp[2 * blockIdx.y + 1] >= 0)) break;
-  const int r0 = a.chunk_r0[chunk_of(sub)], r1 = a.chunk_r0[chunk_of(sub) + 1];
-  const bool seam_bot = a.ystart[r0] != 0;  // chunk's first line belongs to a y seam
-  const bool seam_top = a.ystart[r1] != 0;
-  // rank boundary: the raw boundary line also goes straight into the neighbour's mailbox (NVLink stores from the
-  // registers that hold it), rows [parity][side][pitch]: our first line is the lower neighbour's "row from above"
-  // (side 1), our last line the upper neighbour's "row from below" (side 0)
+  const int cm = tail ? a.grp[2 * blockIdx.y + (two ? 1 : 0)] : a.chunk0 + (int)blockIdx.y;  // the (main) chunk
+  const int r0 = a.chunk_r0[cm], r1 = a.chunk_r0[cm + 1];
+  const int nrows = (r1 - r0) + (two ? 1 : 0);
+  auto row_of = [&](int i) { return two ? (i == 0 ? a.ney - 1 : r0 + i - 1) : r0 + i; };
+  const bool seam_bot_m = a.ystart[r0] != 0;  // main chunk's first / last line belongs to a y seam
+  const bool seam_top_m = a.ystart[r1] != 0;
+  // rank boundary: the raw boundary line also goes straight into the neighbour's mailbox over NVLink, from the
+  // registers that hold it, as flag-in-data entries (semb_ll_store: no fence, no flag, nobody stalls); rows
+  // [parity][side][pitch]: our first line is the lower neighbour's "row from above" (side 1), our last line the upper
+  // neighbour's "row from below" (side 0)
   auto push_row = [&](bool lo, double val) {
-    const int par = (int)(cur_ep() & 1ull);
-    double* row = lo ? a.peer_rows_lo + (size_t)(2 * par + 1) * pitch : a.peer_rows_hi + (size_t)(2 * par) * pitch;
-    row[xg] = val;
-    __threadfence_system();
-  };
-  auto publish = [&](int which) {  // one epoch flag per strip segment and side, in the neighbour's mailbox
     const unsigned long long ep = cur_ep();
-    if (which & 1) semb_st_release_sys(&a.peer_flags_lo[1 * gridDim.x + blockIdx.x], ep);
-    if (which & 2) semb_st_release_sys(&a.peer_flags_hi[0 * gridDim.x + blockIdx.x], ep);
+    const int par = (int)(ep & 1ull);
+    uint4* row = lo ? a.peer_rows_lo + (size_t)(2 * par + 1) * pitch : a.peer_rows_hi + (size_t)(2 * par) * pitch;
+    semb_ll_store(row + xg, val, semb_ll_tag(ep));
   };
-  if (t < 32 && r0 < r1) {  // (every read of the staging buffers by the previous chunk is behind a CTA barrier)
-    issue_rows(r0, 0, 1, SU, &bars[0]);
-    issue_rows(r0, 1, 3, SG, &bars[1]);
+  if (t < 32 && nrows > 0) {
+    issue_rows(row_of(0), 0, 1, SU, &bars[0]);
+    issue_rows(row_of(0), 1, 3, SG, &bars[1]);
   }
-  if (tail) semb_tail_prepare(a, (int)blockIdx.x, (int)gridDim.x, chunk_of(sub), r0, r1, s_task + 8 * sub);
-  if (PCGM && r0 < r1) issue_p(r0);
+  if (tail) semb_tail_prepare(a, (int)blockIdx.x, (int)gridDim.x, cm, two ? a.grp[2 * blockIdx.y] : -1, s_task);
+  if (PCGM && nrows > 0) issue_p(row_of(0));
 
   // inactive threads read through clamped indices (no selects in the inner loops); they never store
   const int tr = inB ? t : 0;  // (the staging buffers are only written by the async proxy, between barriers)
@@ -349,15 +347,13 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     return lap;
   };
 
-  for (int r = r0; r < r1; ++r, ++phase) {
+  for (int i = 0; i < nrows; ++i) {
+    const int r = row_of(i);
     const int base = r * N * pitch + xg;
-    const uint32_t parity = phase & 1u;
-    // the slab's first line was pushed in iteration r = 0: publish it now (block-uniform; once per bottom-edge CTA);
-    // its last line is pushed in the last iteration of its chunk and published right after the loop
-    if (tail && a.has_lo && r == 1 && r0 == 0) {
-      __syncthreads();
-      if (t == 0) publish(1);
-    }
+    const uint32_t parity = (uint32_t)(i & 1);  // both mbarriers complete one phase per element row
+    const bool edge = two && i == 0;            // the one-row chunk [ney-1, ney): y seams on both sides
+    const bool first = edge || r == r0, last = edge || r == r1 - 1;   // first / last row of its chunk
+    const bool seam_bot = edge || seam_bot_m, seam_top = edge || seam_top_m;
     const bool plo = tail && a.has_lo && r == 0, phi = tail && a.has_hi && r == a.ney - 1;
     // coefficient columns that are not staged: issued now, consumed in step 3
     double bq[N];
@@ -380,11 +376,11 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
       u[j] = v;
       if (inB) S1[j * PW + colB] = v;
     }
-    if (PCGM && r + 1 < r1) issue_p(r + 1);
+    if (PCGM && i + 1 < nrows) issue_p(row_of(i + 1));
     double us[N];  // us = Ds * u along y: us[j] = sum_k Ds(j,k) u[k]
     semb_contract<N, EO>(sT + 0 * TSZ, u, us);
     __syncthreads();
-    if (t < 32 && r + 1 < r1) issue_rows(r + 1, 0, 1, SU, &bars[0]);  // u stage is free: prefetch row r+1
+    if (t < 32 && i + 1 < nrows) issue_rows(row_of(i + 1), 0, 1, SU, &bars[0]);  // u stage is free: prefetch the next row
     // ---- step 2 (A): ur = Dr * u along x -------------------------------------------------------------
     if (actA) {
       double c[N], o[N];  // ur[m] = sum_i Dr(m,i) u[i]
@@ -416,7 +412,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
       }
     }
     __syncthreads();
-    if (t < 32 && r + 1 < r1) issue_rows(r + 1, 1, 3, SG, &bars[1]);  // G stage is free: prefetch row r+1
+    if (t < 32 && i + 1 < nrows) issue_rows(row_of(i + 1), 1, 3, SG, &bars[1]);  // G stage is free: prefetch the next row
     // ---- step 4 (A): Dr^T contraction ---------------------------------------------------------------
     if (actA) {
       double c[N], o[N];  // (Dr^T wr)[m] = sum_i Dr(i,m) wr[i]
@@ -481,7 +477,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
       if (PCGM) acc += __dmul_rn(__dmul_rn(pval, o), wx * wy);
     };
     // line 0
-    if (r == r0) {
+    if (first) {
       if (seam_bot) {
         semb_st_keep(&a.out[base], v[0]);
         if (plo) push_row(true, v[0]);
@@ -494,7 +490,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
 #pragma unroll
     for (int j = 1; j < N - 1; ++j) finish(base + j * pitch, v[j], u[j], false, 1.0);
     // line N-1
-    if (r == r1 - 1) {
+    if (last) {
       const int idx = base + (N - 1) * pitch;
       if (seam_top) {
         semb_st_keep(&a.out[idx], v[N - 1]);
@@ -506,17 +502,12 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     }
   }
 
-    if (tail) {  // chunk finished: fence this thread's stores, announce, note the tasks this CTA now owns
-      semb_stamp(a, 1 + 2 * sub);
-      __threadfence();
-      __syncthreads();
-      if (t == 0) publish(((a.has_lo && r0 == 0 && r1 == 1) ? 1 : 0) | ((a.has_hi && r1 == a.ney) ? 2 : 0));
-      semb_tail_announce(a, s_task + 8 * sub);
-      semb_stamp(a, 2 + 2 * sub);
-    }
-  }  // sub
-
-  if (tail) {
+  if (tail) {  // rows finished: fence this thread's stores, announce the chunk(s), run the tasks this CTA now owns
+    semb_stamp(a, 1);
+    __threadfence();
+    __syncthreads();
+    semb_tail_announce(a, s_task);
+    semb_stamp(a, 2);
     __syncthreads();
     semb_strip_tail(a, s_task, (int)blockIdx.x, (int)gridDim.x, (a.has_lo || a.has_hi) ? cur_ep() : 0ull, acc, red);
     return;

@@ -43,11 +43,15 @@ struct SembTailTask {
   int target;  // arrivals it takes
 };
 
-// Threads 0..7 of the CTA describe the eight interfaces of chunk ck of strip s (slot = interface kind) in s_task[0..7].
-static __device__ __noinline__ void semb_tail_prepare(const OpArgs& a, int s, int nstrips, int ck, int r0, int r1,
+// Threads 0..7 of the CTA describe the eight interfaces (slot & 7 = interface kind) of its main chunk cm in
+// s_task[0..7], threads 8..15 those of its edge chunk ce (-1: none) in s_task[8..15].
+static __device__ __noinline__ void semb_tail_prepare(const OpArgs& a, int s, int nstrips, int cm, int ce,
                                                       SembTailTask* s_task) {
-  const int t = threadIdx.x;
-  if (t >= 8) return;
+  if (threadIdx.x >= 16) return;
+  const int t = threadIdx.x & 7;
+  const int ck = threadIdx.x < 8 ? cm : ce;
+  if (ck < 0) return;
+  const int r0 = a.chunk_r0[ck], r1 = a.chunk_r0[ck + 1];
   const int nxs = a.nxs, nch = a.nchunks, N = a.N;
   const SembTailLayout L(nstrips, nch, nxs, a.xmic_total);
   const int ls = s > 0 ? s - 1 : (a.perx ? nxs - 1 : -1);            // x seam on the left / right of this strip
@@ -100,14 +104,14 @@ static __device__ __noinline__ void semb_tail_prepare(const OpArgs& a, int s, in
     T.pbase = L.partC() + id;
     T.cnt = L.offC() + id, T.target = hal ? 2 : 4;
   }
-  s_task[t] = T;
+  s_task[threadIdx.x] = T;
 }
 
 // Called by ALL threads of the CTA right after it has finished the chunk (its stores fenced and a CTA barrier passed):
-// threads 0..7 each announce one interface and keep the task only if this CTA arrived last.
+// threads 0..15 each announce one interface and keep the task only if this CTA arrived last.
 __device__ __forceinline__ void semb_tail_announce(const OpArgs& a, SembTailTask* s_task) {
   const int t = threadIdx.x;
-  if (t < 8) {
+  if (t < 16) {
     const int target = s_task[t].target;
     if (target > 0) {
       unsigned* cnt = a.tcnt + s_task[t].cnt;
@@ -144,7 +148,8 @@ struct SembTailItem {
 // micro-task's own slot => the grid total does not depend on which CTA or warp ran it.
 template <int U>
 __device__ __forceinline__ void semb_tail_run(const OpArgs& a, const SembTailTask* s_task, const int* s_pre, int total,
-                                              int ncta, const double* rem_lo, const double* rem_hi, bool pcg) {
+                                              int ncorner, int ncta, const uint4* rem_lo, const uint4* rem_hi, unsigned tag,
+                                              bool pcg) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, N = a.N;
   const size_t pitch = (size_t)a.pitch;
   for (int mt0 = warp; mt0 < total; mt0 += U * nwarps) {
@@ -158,6 +163,16 @@ __device__ __forceinline__ void semb_tail_run(const OpArgs& a, const SembTailTas
       I.x0 = I.x1 = I.y0 = I.y1 = I.y2 = 0;
       pslot[u] = -1;
       if (mt >= total) continue;
+      if (mt == total - 1 && ncorner) {
+        // the CTA's corner tasks (up to eight, one item each) share the last micro-task: lane c <-> task slot 4..7, 12..15
+        pslot[u] = -2;  // (per-lane partial slots, see below)
+        const int q = 4 + (lane & 3) + 8 * (lane >> 2);
+        if (lane >= 8 || s_task[q].n == 0) continue;
+        const SembTailTask T = s_task[q];
+        I.x0 = T.x0, I.x1 = T.x1, I.y0 = I.y1 = T.ya, I.y2 = T.yb, I.four = true, I.rem2 = (T.flags & 4) != 0;
+        I.valid = true;
+        continue;
+      }
       int q = 0;
       while (s_pre[q + 1] <= mt) ++q;
       const SembTailTask T = s_task[q];
@@ -177,24 +192,20 @@ __device__ __forceinline__ void semb_tail_run(const OpArgs& a, const SembTailTas
         if (x >= T.x1) continue;
         I.x0 = I.x1 = x, I.y0 = T.ya, I.y1 = T.yb, I.rem1 = (T.flags & 4) != 0;
         I.valid = true;
-      } else {  // C: the corner, one item
-        if (lane != 0) continue;
-        I.x0 = T.x0, I.x1 = T.x1, I.y0 = I.y1 = T.ya, I.y2 = T.yb, I.four = true, I.rem2 = (T.flags & 4) != 0;
-        I.valid = true;
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {  // ---- every load of every item
       SembTailItem& I = it[u];
       if (!I.valid) continue;
-      const double* rem = (I.y0 == 0) ? rem_lo : rem_hi;  // (only read when rem1 / rem2)
+      const uint4* rem = (I.y0 == 0) ? rem_lo : rem_hi;  // (only read when rem1 / rem2)
       const size_t i0 = (size_t)I.y0 * pitch + I.x0, i1 = (size_t)I.y1 * pitch + I.x1;
       const size_t i2 = (size_t)I.y2 * pitch + I.x0, i3 = (size_t)I.y2 * pitch + I.x1;
       I.v[0] = __ldcg(&a.out[i0]);
-      I.v[1] = I.rem1 ? __ldcg(&rem[I.x1]) : __ldcg(&a.out[i1]);
-      if (I.four) {
-        I.v[2] = I.rem2 ? __ldcg(&rem[I.x0]) : __ldcg(&a.out[i2]);
-        I.v[3] = I.rem2 ? __ldcg(&rem[I.x1]) : __ldcg(&a.out[i3]);
+      if (!I.rem1) I.v[1] = __ldcg(&a.out[i1]);
+      if (I.four && !I.rem2) {
+        I.v[2] = __ldcg(&a.out[i2]);
+        I.v[3] = __ldcg(&a.out[i3]);
       }
       if (pcg) {
         I.p[0] = __ldcg(&a.pout[i0]);
@@ -203,6 +214,17 @@ __device__ __forceinline__ void semb_tail_run(const OpArgs& a, const SembTailTas
           I.p[2] = __ldcg(&a.pout[i2]);
           I.p[3] = __ldcg(&a.pout[i3]);
         }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {  // ---- the neighbour rank's values (flag-in-data: re-read until this epoch's tag is there)
+      SembTailItem& I = it[u];
+      if (!I.valid || !(I.rem1 || I.rem2)) continue;
+      const uint4* rem = (I.y0 == 0) ? rem_lo : rem_hi;
+      if (I.rem1) I.v[1] = semb_ll_load(&rem[I.x1], tag, a.scal);
+      if (I.rem2) {
+        I.v[2] = semb_ll_load(&rem[I.x0], tag, a.scal);
+        I.v[3] = semb_ll_load(&rem[I.x1], tag, a.scal);
       }
     }
 #pragma unroll
@@ -230,6 +252,8 @@ __device__ __forceinline__ void semb_tail_run(const OpArgs& a, const SembTailTas
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
         if (lane == 0) a.tpart[ncta + pslot[u]] = acc;
+      } else if (pcg && pslot[u] == -2 && I.valid) {  // packed corners: one slot per corner task
+        a.tpart[ncta + s_task[4 + (lane & 3) + 8 * (lane >> 2)].pbase] = acc;
       }
     }
   }
@@ -243,27 +267,17 @@ static __device__ __noinline__ void semb_strip_tail(const OpArgs& a, const SembT
   const int ncta = gridDim.x * gridDim.y;
   const int par = (int)(ep & 1ull);
   const bool pcg = a.pcg != 0;
-  const double* rem_lo = a.my_rows + (size_t)(2 * par + 0) * pitch;  // neighbour rows in OUR mailbox (side 0: from below)
-  const double* rem_hi = a.my_rows + (size_t)(2 * par + 1) * pitch;
+  const uint4* rem_lo = a.my_rows + (size_t)(2 * par + 0) * pitch;  // neighbour rows in OUR mailbox (side 0: from below)
+  const uint4* rem_hi = a.my_rows + (size_t)(2 * par + 1) * pitch;
+  const unsigned tag = semb_ll_tag(ep);
   __shared__ int s_pre[17];  // prefix of the micro-task counts of the 16 task slots
-  __shared__ int s_fin;
+  __shared__ int s_fin, s_ncorner;
   __shared__ double s_tot;
   if (tid < 16) {
     const SembTailTask T = s_task[tid];
-    if (T.n > 0 && (T.flags & 4)) {
-      // rank boundary: the neighbour's segment(s) must have arrived (bounded wait; the rows were pushed at the very
-      // start of the neighbour's kernel, so this normally falls through)
-      const int side = (T.ya == 0) ? 0 : 1;
-      if ((tid & 7) < 4) {
-        semb_wait_epoch(&a.my_flags[side * nstrips + s], ep, a.scal);
-      } else {  // corner: the segments of the strips left and right of the x seam
-        const int sL = (T.x1 == 0) ? nstrips - 1 : (((tid & 1) ? s : s - 1)), sR = (T.x1 == 0) ? 0 : sL + 1;
-        semb_wait_epoch(&a.my_flags[side * nstrips + sL], ep, a.scal);
-        semb_wait_epoch(&a.my_flags[side * nstrips + sR], ep, a.scal);
-      }
-    }
-    __syncwarp(0xffffu);  // (the waits above may have split the half-warp)
-    int v = T.n;
+    const bool corner = (tid & 7) >= 4;
+    const unsigned cmask = __ballot_sync(0xffffu, corner && T.n > 0);
+    int v = corner ? 0 : T.n;  // (the corner tasks are packed into one micro-task after all the others)
 #pragma unroll
     for (int o = 1; o < 16; o <<= 1) {
       const int w = __shfl_up_sync(0xffffu, v, o, 16);
@@ -271,22 +285,24 @@ static __device__ __noinline__ void semb_strip_tail(const OpArgs& a, const SembT
     }
     s_pre[tid + 1] = v;
     if (tid == 0) s_pre[0] = 0;
+    if (tid == 15) s_ncorner = cmask ? 1 : 0;
   }
   __syncthreads();
   semb_stamp(a, 5);
-  const int total = s_pre[16];
-  if (pcg) semb_tail_run<2>(a, s_task, s_pre, total, ncta, rem_lo, rem_hi, true);
-  else semb_tail_run<4>(a, s_task, s_pre, total, ncta, rem_lo, rem_hi, false);
+  const int ncorner = s_ncorner, total = s_pre[16] + ncorner;
+  if (pcg) semb_tail_run<3>(a, s_task, s_pre, total, ncorner, ncta, rem_lo, rem_hi, tag, true);
+  else semb_tail_run<5>(a, s_task, s_pre, total, ncorner, ncta, rem_lo, rem_hi, tag, false);
   __syncthreads();
   semb_stamp(a, 6);
 #ifdef SEMB_TAIL_TIMING
   if (a.dbg && tid == 0) a.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 7] = total;
 #endif
-  // ---- grid-wide finish: PCG reduction (+ all-gather over the ranks), epoch of the halo exchange -----------
+  // ---- grid-wide finish (PCG mode only): reduction of sum(p .* Ap .* mult) (+ all-gather over the ranks) and the
+  // device-side part of the halo epoch
+  if (!pcg) return;
   const bool halo = a.has_lo || a.has_hi;
-  if (!pcg && !halo) return;
   const int bid = blockIdx.y * gridDim.x + blockIdx.x;
-  if (pcg) {
+  {
     const double bs = semb_block_sum(cta_acc, red, tid, nt);
     if (tid == 0) a.tpart[bid] = bs;
   }
@@ -303,18 +319,17 @@ static __device__ __noinline__ void semb_strip_tail(const OpArgs& a, const SembT
   }
   __syncthreads();
   if (!s_fin) return;
-  if (pcg) {
+  {
     const int ntot = ncta + L.nparts();
-    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;  // fixed order: independent of who ran what
-    int i = tid;
-    for (; i + 3 * nt < ntot; i += 4 * nt) {
-      v0 += __ldcg(&a.tpart[i]);
-      v1 += __ldcg(&a.tpart[i + nt]);
-      v2 += __ldcg(&a.tpart[i + 2 * nt]);
-      v3 += __ldcg(&a.tpart[i + 3 * nt]);
+    double v[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // fixed order: independent of who ran what
+    for (int i = tid; i < ntot; i += 8 * nt) {
+      double w[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) w[k] = (i + k * nt < ntot) ? __ldcg(&a.tpart[i + k * nt]) : 0.0;  // 8 loads in flight
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += w[k];
     }
-    for (; i < ntot; i += nt) v0 += __ldcg(&a.tpart[i]);
-    double tot = semb_block_sum((v0 + v1) + (v2 + v3), red, tid, nt);
+    double tot = semb_block_sum(((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])), red, tid, nt);
     if (tid == 0) s_tot = tot;
     __syncthreads();
     tot = s_tot;
@@ -329,5 +344,5 @@ static __device__ __noinline__ void semb_strip_tail(const OpArgs& a, const SembT
       if (tid == 0) a.scal->pap_total = all;
     }
   }
-  if (halo && tid == 0) a.scal->ep_dev[0] = ep;
+  if (halo && tid == 0) a.scal->ep_dev[0] = ep - a.ep_host;  // = PCG-mode applies completed (see cur_ep)
 }

@@ -22,9 +22,9 @@ def rhs_for(om, M, f):
 
 def count_close(it_g, it_o):
     """CG on these unpreconditioned systems is chaotic in rounding after ~60 iterations: the oracle's own
-    count moves by 1-3 % when its operator is perturbed by 1 ulp (tests/tools/pcg_divergence.py).
-    Counts must agree exactly for short solves and within that spread for long ones."""
-    return it_g == it_o if it_o <= 60 else abs(it_g - it_o) <= max(3, int(0.05 * it_o))
+    count moves by 1-1.5 % when its operator is perturbed by 1 ulp (tests/tools/pcg_divergence.py).
+    Counts must agree exactly for short solves and within that spread (2 %, at least 3 iterations: the oracle itself moves 284 -> 287) for long ones."""
+    return it_g == it_o if it_o <= 60 else abs(it_g - it_o) <= max(3, int(0.02 * it_o))
 
 
 def gpu_history(gm, fb, fx, n, **kw):
