@@ -67,8 +67,9 @@ function devmesh(msh::Mesh)
                      Ref{Ptr{Cvoid}}),
                     context(), msh.nr, msh.ns, msh.Ex, msh.Ey, msh.ifperiodic[1], msh.ifperiodic[2],
                     msh.Dr, msh.Ds, msh.G11, msh.G12, msh.G22, msh.B, h))
-        # metric terms for grad / advect (enum semb_mesh_array: RX = 4, RY = 5, SX = 6, SY = 7)
-        for (which, a) in ((4, msh.rx), (5, msh.ry), (6, msh.sx), (7, msh.sy))
+        # metric terms for grad / advect / the Stokes split (enum semb_mesh_array: JAC = 2, JACI = 3, RX = 4, RY = 5,
+        # SX = 6, SY = 7, BI = 9; approxHlmzInv and the Stokes operators need Bi)
+        for (which, a) in ((2, msh.Jac), (3, msh.Jaci), (4, msh.rx), (5, msh.ry), (6, msh.sx), (7, msh.sy), (9, msh.Bi))
             check(ccall((:semb_mesh_set, libsemb), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h[], which, a))
         end
         h[]
@@ -138,8 +139,8 @@ end
 function mask(u::Array, M::Array, msh::Mesh)
     out = similar(u, Float64)
     Mf = length(M) == 0 ? Float64[] : f64(M)
-    check(ccall((:semb_mask_host, libsemb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                devmesh(msh), f64(u), length(M) == 0 ? C_NULL : pointer(Mf), out))
+    GC.@preserve Mf check(ccall((:semb_mask_host, libsemb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                                devmesh(msh), f64(u), length(M) == 0 ? Ptr{Float64}(C_NULL) : pointer(Mf), out))
     return out
 end
 
@@ -311,7 +312,7 @@ end
 
 # one step of either equation: updateHist! + time/BDF update on the device, the user closures on the host (only
 # what a closure other than the no-op fixU! may have changed is uploaded), makeRHS! + solve! on the device
-function devstep!(eq, d::Ptr{Cvoid}, msh::Mesh, setBC!, setForcing!, setVisc!; tol = 1e-8)
+function devstep!(eq, d::Ptr{Cvoid}, msh::Mesh, setBC!, setForcing!, setVisc!; tol = 1e-8, sync_velocity = true)
     (fld, ts) = (eq.fld, eq.tstep)
     (t, n) = (Ref{Cdouble}(0.0), Ref{Clonglong}(0))
     check(ccall((:semb_diffusion_begin_step, libsemb), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Ref{Clonglong}), d, t, n))
@@ -323,6 +324,12 @@ function devstep!(eq, d::Ptr{Cvoid}, msh::Mesh, setBC!, setForcing!, setVisc!; t
         set! === fixU! && continue
         set!(a, msh.x, msh.y, ts.time[1])
         dfnput(d, which, a)
+    end
+    # makeRHS! reads cdn.vx, cdn.vy every step (convectionDiffusion.jl:100-105): a user may have changed them between
+    # steps, so the device copies follow the host arrays (2 uploads per step; `sync_velocity = false` skips them when
+    # the advecting field is known to be constant)
+    if hasproperty(eq, :vx) && sync_velocity
+        dfnput(d, DFN_VX, eq.vx); dfnput(d, DFN_VY, eq.vy)
     end
     (it, res) = (Ref{Clonglong}(0), Ref{Cdouble}(0.0))
     rc = check(ccall((:semb_diffusion_finish_step, libsemb), Cint, (Ptr{Cvoid}, Cdouble, Ref{Clonglong}, Ref{Cdouble}),
@@ -389,8 +396,13 @@ struct DiagPrecond
     b0::Float64
 end
 
-# pcg(b,opA;opM,mult,ifv,tol,maxiter), pcg.jl:16-60 -- device-resident
+# pcg(b,opA;opM,mult,ifv,tol,maxiter), pcg.jl:16-60 -- device-resident.
+# mult: the device loop weights its inner products with the mesh's own msh.mult, what every caller in the reference passes
+# (diffusion.jl:71, examples/p2d.jl:60).  DEVIATION from the bare default: pcg.jl:18 defaults mult to ones(size(b)); here
+# `nothing` means msh.mult, and any other array is an error instead of being silently dropped.
 function pcg(b, opA::OpLHS; opM = nothing, mult = nothing, ifv = false, tol = 1e-8, maxiter = length(b))
+    (mult === nothing || mult == opA.msh.mult) ||
+        throw(ArgumentError("pcg: mult must be msh.mult (or nothing = msh.mult); the device loop has no other weighting"))
     x = zeros(Float64, size(b))
     (pν, sν, kν) = coef(opA.ν); (pk, sk, kk) = coef(opA.k)
     prec = opM isa DiagPrecond

@@ -735,13 +735,20 @@ class DiagPrecond:
 def pcg(b, opA, opM=None, mult=None, ifv=False, tol=1e-8, maxiter=None, info: Optional[dict] = None):
     """pcg(b,opA;opM,mult,ifv,tol,maxiter), pcg.jl:16-60 -- whole loop on the device.
 
-    opA must be an OpLHS (see its docstring); opM None/identity or DiagPrecond; mult must be the
-    mesh's own (msh.mult) or None.  Returns x; `info` receives iters/resinf/converged."""
+    opA must be an OpLHS (see its docstring); opM None/identity or DiagPrecond.  Returns x; `info` receives
+    iters/resinf/converged.
+    mult: the device loop weights its inner products with the mesh's own multiplicity msh.mult (structural 1, 1/2, 1/4)
+    -- what every caller in the reference passes (diffusion.jl:71, examples/p2d.jl:60).  DEVIATION from the bare default:
+    pcg.jl:18 defaults mult to ones(size(b)); here mult=None means msh.mult, and any other array is rejected instead of
+    being silently dropped."""
     if not isinstance(opA, OpLHS):
         raise TypeError("pcg: opA must be an OpLHS (device operator); host closures cannot run on the GPU and "
                         "this package has no CPU fallback")
     msh = opA.msh
     b = as_f64(b, msh.shape)
+    if mult is not None and not np.array_equal(np.asarray(mult, dtype=np.float64), msh.mult):
+        raise ValueError("pcg: mult must be the mesh's own msh.mult (or None, which means msh.mult); the device loop has no "
+                         "other weighting (pcg.jl:18's ones(size(b)) default is not reproduced)")
     nua, nus = _split_coef(opA.nu, msh.shape)
     ka, ks = _split_coef(opA.k, msh.shape)
     Mf = None if opA.M is None or np.size(opA.M) == 0 else as_f64(opA.M, msh.shape)

@@ -7,7 +7,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsemb.so")
+# SEMB_LIB: an experimental variant built with `build.py --tag` (A/B tools only; the product library is lib/libsemb.so)
+LIB_PATH = os.environ.get("SEMB_LIB") or os.path.join(HERE, "lib", "libsemb.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)

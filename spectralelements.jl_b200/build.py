@@ -46,7 +46,13 @@ def _run(cmd):
     return p.stdout + p.stderr
 
 
-def build(force: bool = False, jobs: int | None = None, verbose: bool = False, lib: str = LIB) -> str:
+def build(force: bool = False, jobs: int | None = None, verbose: bool = False, tag: str = "") -> str:
+    """tag: build an experimental variant (SEMB_EXTRA_FLAGS=...) beside the product library, into lib/libsemb_<tag>.so
+    with its own object directory; load it with SEMB_LIB=<path> (tools/ A/B scripts)."""
+    global BUILD, LIB
+    if tag:
+        BUILD = os.path.join(HERE, "_build_" + tag)
+        LIB = os.path.join(LIBDIR, "libsemb_%s.so" % tag)
     os.makedirs(BUILD, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(BUILD, "stamp")
@@ -83,5 +89,6 @@ if __name__ == "__main__":
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--jobs", type=int, default=None)
     ap.add_argument("-v", "--verbose", action="store_true")
+    ap.add_argument("--tag", default="", help="experimental variant: lib/libsemb_<tag>.so (use with SEMB_EXTRA_FLAGS)")
     a = ap.parse_args()
-    print(build(a.force, a.jobs, a.verbose))
+    print(build(a.force, a.jobs, a.verbose, a.tag))

@@ -1603,11 +1603,22 @@ static int advect_work_free(AdvectWork* w) {
   return SEMB_OK;
 }
 
+static int advect_work_fill(AdvectWork* w, semb_mesh* V, semb_mesh* D);
 static int advect_work_create(semb_mesh* V, semb_mesh* D, AdvectWork** out) {
   SEMB_REQUIRE(V->arr[SEMB_RX] && V->arr[SEMB_B], "advect: mshV has no metric terms / B");
   AdvectWork* w = new AdvectWork();
   w->V = V;
   w->D = D;
+  const int rc = advect_work_fill(w, V, D);  // any failure below releases the struct and what it already holds
+  if (rc < 0) {
+    advect_work_free(w);
+    return rc;
+  }
+  *out = w;
+  return SEMB_OK;
+}
+
+static int advect_work_fill(AdvectWork* w, semb_mesh* V, semb_mesh* D) {
   if (D) {
     SEMB_REQUIRE(D->ctx == V->ctx && D->Ex == V->Ex && D->Ey == V->Ey && D->ney == V->ney && D->perx == V->perx &&
                      D->pery == V->pery,
@@ -1641,7 +1652,6 @@ static int advect_work_create(semb_mesh* V, semb_mesh* D, AdvectWork** out) {
     SEMB_TRY(up(JrT, &w->dJrT));
     SEMB_TRY(up(JsT, &w->dJsT));
   }
-  *out = w;
   return SEMB_OK;
 }
 

@@ -18,7 +18,13 @@
 #ifndef SEMB_T9
 #define SEMB_T9 256
 #endif
-constexpr int semb_strip_threads(int n) { return (n >= 12 && n <= 14) ? 192 : (n == 9 ? SEMB_T9 : 256); }
+#ifndef SEMB_T12
+#define SEMB_T12 192
+#endif
+#ifndef SEMB_T15
+#define SEMB_T15 256
+#endif
+constexpr int semb_strip_threads(int n) { return (n >= 12 && n <= 14) ? SEMB_T12 : (n >= 15 ? SEMB_T15 : (n == 9 ? SEMB_T9 : 256)); }
 // elements per strip: as many as fit the CTA, with BX*N even so that every staged row is a multiple of 16 bytes
 constexpr int semb_strip_bx(int n) {
   return ((semb_strip_threads(n) / n) * n) % 2 == 0 ? semb_strip_threads(n) / n : semb_strip_threads(n) / n - 1;

@@ -218,8 +218,10 @@ def test_shim_enum_constants_match_the_header():
     """Integer selectors hard-coded in the shim (mesh arrays for semb_mesh_set, driver fields) equal the C enums."""
     src = open(SHIM).read()
     ma = _c_enum("semb_mesh_array")
-    pairs = re.search(r"for \(which, a\) in \(\((\d+), msh\.rx\), \((\d+), msh\.ry\), \((\d+), msh\.sx\), \((\d+), msh\.sy\)\)", src)
-    assert [int(g) for g in pairs.groups()] == [ma["SEMB_RX"], ma["SEMB_RY"], ma["SEMB_SX"], ma["SEMB_SY"]]
+    pairs = re.search(r"for \(which, a\) in \(\((\d+), msh\.Jac\), \((\d+), msh\.Jaci\), \((\d+), msh\.rx\), \((\d+), msh\.ry\), "
+                      r"\((\d+), msh\.sx\), \((\d+), msh\.sy\), \((\d+), msh\.Bi\)\)", src)
+    assert [int(g) for g in pairs.groups()] == [ma["SEMB_JAC"], ma["SEMB_JACI"], ma["SEMB_RX"], ma["SEMB_RY"], ma["SEMB_SX"],
+                                                ma["SEMB_SY"], ma["SEMB_BI"]]   # (Bi: the Stokes split needs it)
     df = _c_enum("semb_diffusion_field_id")
     names = re.search(r"const (DFN_\w+(?:, DFN_\w+)*) = ([\d, ]+)\n", src)
     got = dict(zip([n.strip() for n in names.group(1).split(",")], [int(v) for v in names.group(2).split(",")]))

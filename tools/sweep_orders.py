@@ -8,7 +8,10 @@ import spectralelements_jl_b200 as sem
 ctx = sem.init(0)
 target = float(sys.argv[1]) if len(sys.argv) > 1 else 5e7
 orders = [int(a) for a in sys.argv[2:]] or [3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17]
-peak = 6533.8
+try:
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    peak = 6650.0
 for nr in orders:
     E = max(2, int(round(target ** 0.5 / nr)))
     msh = sem.Mesh(nr, nr, E, E, (False, False), "wavy", ctx=ctx)
