@@ -190,7 +190,7 @@ typedef struct semb_pcg_opts {
   const semb_field* k_arr;  /* array coefficient, examples/poissonNonlin.jl:84,87 */
   const char* bc;           /* "DDDD"-style flags or NULL */
   const semb_field* M_arr;  /* explicit mask array or NULL */
-  int precond;              /* 0 = identity, 1 = u ./ B ./ prec_b0 */
+  int precond;              /* 0 = identity, 1 = u ./ B ./ prec_b0, 2 = the mesh's FDM preconditioner (semb_fdm_create) */
   double prec_b0;
   double tol;               /* absolute, on norm(r,Inf); pcg.jl:20 default 1e-8 */
   long long maxiter;        /* <0 => length(b) */
@@ -203,6 +203,22 @@ int semb_pcg(semb_mesh* m, const semb_pcg_opts* opts, const semb_field* b, semb_
 int semb_pcg_begin(semb_mesh* m, const semb_pcg_opts* opts, const semb_field* b, semb_field* x);
 int semb_pcg_iterate(semb_mesh* m, int n);
 int semb_pcg_status(semb_mesh* m, long long* iters, double* resinf, int* done);
+
+/* ---- FDM Laplacian / Helmholtz preconditioner -----------------------------------------------------
+ * The reference holds it as commented-out sketches: lapl_fdm(b,Bi,Sx,Sy,Sxi,Syi,Di) (lapl.jl:105-119) and its set-up from
+ * eigen(Ax,Bx), eigen(Ay,By) (examples/p2d_explicit.jl:109-141).  Built here in the form in which it works as the opM of
+ * pcg (pcg.jl:37): the same tensor solve on every element extended by one node into its neighbours, combined
+ * symmetrically with counting weights (the CPU checker restates it as fdm_schwarz; 5-8x fewer iterations).
+ * One per mesh: semb_fdm_create registers it, semb_pcg_opts.precond = 2 uses it, semb_fdm_apply is h = opM(r). */
+typedef struct semb_fdm semb_fdm;
+int semb_fdm_create(semb_mesh* m, const char bc[4], double nu, double k, semb_fdm** out);
+int semb_fdm_destroy(semb_mesh* m);
+int semb_fdm_apply(semb_mesh* m, const semb_field* r, semb_field* out);
+int semb_fdm_apply_host(semb_mesh* m, const double* r, double* out);
+/* 1-D reference decomposition behind it (host only, no GPU): A S = B S diag(lam), S' B S = I for A = D' diag(w) D,
+ * B = diag(w) extended by one node into neighbours of equal size; kinds: 0 neighbour, 1 Dirichlet, 2 free boundary.
+ * S: (n+2) x (n+2) column-major, lam: n+2 (+inf padding). */
+int semb_fdm_tables(int n, const double* D, const double* w, int left_kind, int right_kind, double* S, double* lam);
 
 /* ---- implicit diffusion driver, device resident (the caller that defines the fused unit) ---- */
 /* Diffusion(bc,msh;Ti,Tf,dt,k), diffusion.jl:20-34, with its Field (mesh.jl:179-195: u, uh[1..k], ub, M) and

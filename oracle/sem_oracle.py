@@ -525,6 +525,194 @@ def pcg(b, opA, opM=lambda x: x, mult=None, ifv=False, tol=1e-8, maxiter=None, i
 
 
 # ----------------------------------------------------------------------------
+# Fast-diagonalisation (FDM) Laplacian preconditioner -- SURVEY 8f-3.  The reference holds it only as commented-out
+# sketches: the element-wise solve `lapl_fdm(b,Bi,Sx,Sy,Sxi,Syi,Di)` (lapl.jl:105-119) and its construction from the
+# generalised eigenproblems eigen(Ax,Bx), eigen(Ay,By) of the 1-D stiffness / mass matrices
+# (examples/p2d_explicit.jl:109-141).  Both are restated literally below; `fdm_schwarz` is the form in which they
+# work as the opM of pcg (pcg.jl:37): the same per-element tensor solve on subdomains EXTENDED BY ONE NODE into the
+# neighbouring elements, combined symmetrically with counting weights (additive Schwarz).  The sketch as written --
+# element Neumann problems, no overlap, no restriction -- raises the iteration count (tests/tools/fdm_prototype.py).
+# ----------------------------------------------------------------------------
+def lapl_fdm(b, Bi, Sx, Sy, Sxi, Syi, Di):
+    """lapl.jl:112-119, literally: u = b.*Bi; u = ABu(Syi,Sxi,u); u = u.*Di; u = ABu(Sy,Sx,u)"""
+    u = b * Bi
+    u = ABu(Syi, Sxi, u)
+    u = u * Di
+    return ABu(Sy, Sx, u)
+
+
+def fdm_setup_reference(msh: Mesh):
+    """examples/p2d_explicit.jl:112-141 for an undeformed box mesh (the sketch takes rx, sy, Jac from node [1]):
+    returns (Bi, Sx, Sy, Sxi, Syi, Di) such that lapl_fdm(b, ...) applies the element-wise inverse of the Laplacian
+    with natural boundary conditions, the null mode cut off where |1/lambda| > 1e8 (:132-134)."""
+    import scipy.linalg as sl
+    rx, sy = msh.rx[0, 0], msh.sy[0, 0]
+    Bx, By = np.diag(msh.wr / rx), np.diag(msh.ws / sy)       # :115-116 (By uses sy: the sketch's `rx` there is a typo)
+    Dx, Dy = rx * msh.Dr, sy * msh.Ds                          # :117-118
+    Ax, Ay = Dx.T @ Bx @ Dx, Dy.T @ By @ Dy                    # :119-120
+    Lx, Sx = sl.eigh(Ax, Bx)                                   # :127-128
+    Ly, Sy = sl.eigh(Ay, By)
+    Lfdm = Lx[:, None] + Ly[None, :]                           # :131
+    with np.errstate(divide="ignore"):
+        Lfdmi = 1.0 / Lfdm
+    Lfdmi[np.abs(Lfdmi) > 1e8] = 0.0                           # :132-134
+    Iex, Iey = np.eye(msh.Ex), np.eye(msh.Ey)
+    Sxk, Syk = np.kron(Iex, Sx), np.kron(Iey, Sy)              # :135-136
+    Sxi, Syi = np.kron(Iex, np.linalg.inv(Sx)), np.kron(Iey, np.linalg.inv(Sy))
+    Di = np.kron(np.ones((msh.Ex, msh.Ey)), Lfdmi)             # :137
+    # Bi of the sketch is 1 ./ B of the whole mesh; in tensor form B = Bx (x) By per element
+    Bi = 1.0 / np.kron(np.ones((msh.Ex, msh.Ey)), np.outer(np.diag(Bx), np.diag(By)))
+    return _F(Bi), Sxk, Syk, Sxi, Syi, _F(Di)
+
+
+def _fdm_1d_extended(D, w, h, hL, hR, left, right):
+    """Generalised eigen-decomposition of the 1-D stiffness / mass pair of one element (half-length h, reference
+    matrices A = D' diag(w) D / h, B = h diag(w)) extended by ONE node into each neighbour (half-lengths hL, hR).
+    left/right: 'N' neighbour element (extension node = its first node off the interface, zero beyond it),
+                'D' Dirichlet boundary (the boundary node itself is removed), 'F' free boundary (no extension).
+    Returns S ((n+2) x (n+2), rows = [left ext, own 0..n-1, right ext], S' B S = I on the active nodes, zero rows for
+    inactive ones) and lam (n+2, inf for the padding modes)."""
+    import scipy.linalg as sl
+    n = D.shape[0]
+    A0 = D.T @ np.diag(w) @ D
+    A = np.zeros((n + 2, n + 2))
+    B = np.zeros(n + 2)
+    A[1:n + 1, 1:n + 1] += A0 / h
+    B[1:n + 1] += h * w
+    active = np.ones(n + 2, dtype=bool)
+    if left == "N":   # neighbour's nodes (n-2, n-1) sit on extended indices (0, 1)
+        A[0:2, 0:2] += A0[n - 2:, n - 2:] / hL
+        B[0:2] += hL * w[n - 2:]
+    else:
+        active[0] = False
+        if left == "D":
+            active[1] = False
+    if right == "N":  # neighbour's nodes (0, 1) sit on extended indices (n, n+1)
+        A[n:n + 2, n:n + 2] += A0[:2, :2] / hR
+        B[n:n + 2] += hR * w[:2]
+    else:
+        active[n + 1] = False
+        if right == "D":
+            active[n] = False
+    idx = np.nonzero(active)[0]
+    lam_a, S_a = sl.eigh(A[np.ix_(idx, idx)], np.diag(B[idx]))
+    S = np.zeros((n + 2, n + 2))
+    lam = np.full(n + 2, np.inf)
+    S[np.ix_(idx, np.arange(idx.size))] = S_a
+    lam[:idx.size] = lam_a
+    return S, lam
+
+
+def fdm_schwarz(msh: Mesh, bc, nu=1.0, k=0.0, uniform_neighbours=True):
+    """opM(r) = mask(gs(sum_e R_e' W_e A_e^-1 W_e R_e r)): additive Schwarz with the tensor-product FDM solve of
+    lapl_fdm (lapl.jl:112-119) on every element extended by one node (lapl_fdm's S, Si = S', Di = 1/(nu*(lx+ly)+k)),
+    element half-lengths from the element-averaged metric, counting weights W = 1/sqrt(number of subdomains holding the
+    node) on both sides (symmetric, as pcg needs).  r must be continuous (pcg's residual is).
+    uniform_neighbours: the extension of an element is taken with the element's OWN half-length (the form libsemb
+    builds: the 1-D eigenvectors then depend on the element only through the scaling S/sqrt(h), lambda/h^2, i.e. three
+    reference decompositions per direction -- first / interior / last element -- instead of one per element); False uses
+    the neighbours' true half-lengths.  Either way opM is symmetric positive definite."""
+    nr, ns, Ex, Ey = msh.nr, msh.ns, msh.Ex, msh.Ey
+    px, py = msh.ifperiodic
+    bc = list(bc)
+
+    def elavg(a):
+        return a.reshape(nr, Ex, ns, Ey, order="F").mean(axis=(0, 2))
+
+    # element half-lengths along r and s (p2d_explicit.jl:112-113 reads 1/rx, 1/sy at node [1], which only holds for an
+    # axis-aligned box): |dx/dr| = Jac*sqrt(sx^2+sy^2), |dx/ds| = Jac*sqrt(rx^2+ry^2), written with the arrays every
+    # Mesh carries -- Jac = B ./ (wr*ws'), G22 = B.*(sx^2+sy^2), G11 = B.*(rx^2+ry^2) (mesh.jl:117-123) -- and averaged
+    # over the element
+    Jw = msh.B / _F(np.outer(np.kron(np.ones(Ex), msh.wr), np.kron(np.ones(Ey), msh.ws)))
+    hx, hy = elavg(Jw * np.sqrt(msh.G22 / msh.B)), elavg(Jw * np.sqrt(msh.G11 / msh.B))
+
+    def side(e, E, per, lo, bcl, bch):
+        if lo:
+            if e > 0 or per:
+                return "N", (e - 1) % E
+            return ("D" if bcl == "D" else "F"), e
+        if e < E - 1 or per:
+            return "N", (e + 1) % E
+        return ("D" if bch == "D" else "F"), e
+
+    M = generateMask(bc, msh).astype(np.float64)
+    # counting weights: how many extended subdomains hold each (global) node -- obtained by applying R' R to ones
+    nxl, nyl = nr * Ex, ns * Ey
+
+    def gather(v, ex, ey):
+        """(nr+2) x (ns+2) extended tile of the continuous field v (zeros where there is no extension)."""
+        t = np.zeros((nr + 2, ns + 2))
+        xs = [None] * (nr + 2)
+        ys = [None] * (ns + 2)
+        for i in range(nr):
+            xs[i + 1] = ex * nr + i
+        for j in range(ns):
+            ys[j + 1] = ey * ns + j
+        kl, el = side(ex, Ex, px, True, bc[0], bc[1])
+        kr, er = side(ex, Ex, px, False, bc[0], bc[1])
+        if kl == "N":
+            xs[0] = el * nr + nr - 2
+        if kr == "N":
+            xs[nr + 1] = er * nr + 1
+        kb, eb = side(ey, Ey, py, True, bc[2], bc[3])
+        kt, et = side(ey, Ey, py, False, bc[2], bc[3])
+        if kb == "N":
+            ys[0] = eb * ns + ns - 2
+        if kt == "N":
+            ys[ns + 1] = et * ns + 1
+        ix = [i for i in range(nr + 2) if xs[i] is not None]
+        iy = [j for j in range(ns + 2) if ys[j] is not None]
+        gx = [xs[i] for i in ix]
+        gy = [ys[j] for j in iy]
+        t[np.ix_(ix, iy)] = v[np.ix_(gx, gy)]
+        return t, (ix, iy, gx, gy), (kl, kr, kb, kt, el, er, eb, et)
+
+    def scatter_add(z, t, maps):
+        ix, iy, gx, gy = maps
+        z[np.ix_(gx, gy)] += t[np.ix_(ix, iy)]
+
+    ones = np.ones((nxl, nyl))
+    cnt = np.zeros((nxl, nyl))
+    for ex in range(Ex):
+        for ey in range(Ey):
+            t, maps, _ = gather(ones, ex, ey)
+            scatter_add(cnt, t, maps)
+    cnt = gatherScatter(cnt, msh)               # per global node, on every copy
+    W = 1.0 / np.sqrt(np.maximum(cnt, 1.0))
+    cache = {}
+
+    def eig1(D, w, h, hL, hR, kl, kr):
+        key = (D.shape[0], round(h, 14), round(hL, 14), round(hR, 14), kl, kr, id(D))
+        if key not in cache:
+            cache[key] = _fdm_1d_extended(D, w, h, hL, hR, kl, kr)
+        return cache[key]
+
+    def opM(r):
+        rw = W * r
+        z = np.zeros((nxl, nyl))
+        for ex in range(Ex):
+            for ey in range(Ey):
+                t, maps, (kl, kr, kb, kt, el, er, eb, et) = gather(rw, ex, ey)
+                if uniform_neighbours:
+                    Sx, lx = eig1(msh.Dr, msh.wr, 1.0, 1.0, 1.0, kl, kr)
+                    Sy, ly = eig1(msh.Ds, msh.ws, 1.0, 1.0, 1.0, kb, kt)
+                    Sx, lx = Sx / math.sqrt(hx[ex, ey]), lx / hx[ex, ey] ** 2
+                    Sy, ly = Sy / math.sqrt(hy[ex, ey]), ly / hy[ex, ey] ** 2
+                else:
+                    Sx, lx = eig1(msh.Dr, msh.wr, hx[ex, ey], hx[el, ey], hx[er, ey], kl, kr)
+                    Sy, ly = eig1(msh.Ds, msh.ws, hy[ex, ey], hy[ex, eb], hy[ex, et], kb, kt)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    Di = 1.0 / (nu * (lx[:, None] + ly[None, :]) + k)
+                Di[~np.isfinite(Di)] = 0.0
+                Di[np.abs(Di) > 1e8] = 0.0       # p2d_explicit.jl:132-134 (the null mode of an all-free subdomain)
+                u = Sx @ ((Sx.T @ t @ Sy) * Di) @ Sy.T   # lapl_fdm with Si = S' (S' B S = I): lapl.jl:114-116
+                scatter_add(z, u, maps)
+        return mask(W * gatherScatter(z, msh), M)
+
+    return opM
+
+
+# ----------------------------------------------------------------------------
 # time.jl:31-53  (bdfExtK) -- host scalar work, needed for bdfB[1] in opLHS
 # ----------------------------------------------------------------------------
 def bdfExtK(t, k=3):

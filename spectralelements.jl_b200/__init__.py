@@ -483,7 +483,7 @@ def _pcg_opts(nu, k, bc, M, precond, prec_b0, tol, maxiter, check_every):
     keep.append(b)
     o.bc = b
     o.M_arr = M.h if isinstance(M, DeviceField) else None
-    o.precond = 1 if precond else 0
+    o.precond = int(precond) if not isinstance(precond, bool) else (1 if precond else 0)   # 2 = the mesh's FdmPrecond
     o.prec_b0 = float(prec_b0)
     o.tol = float(tol)
     o.maxiter = int(maxiter)
@@ -732,10 +732,49 @@ class DiagPrecond:
         self.msh, self.b0 = msh, float(b0)
 
 
+class FdmPrecond:
+    """opM = the fast-diagonalisation (FDM) Laplacian / Helmholtz preconditioner: the reference's
+    lapl_fdm(b,Bi,Sx,Sy,Sxi,Syi,Di) (lapl.jl:105-119, set-up examples/p2d_explicit.jl:109-141) applied on every element
+    extended by one node into its neighbours and combined symmetrically (additive Schwarz) -- the form in which it is a
+    working preconditioner of pcg.  nu, k: the constant coefficients of the operator it approximates (nu*lapl + k*mass);
+    bc: the operator's Dirichlet/Neumann flags.  Callable: h = opM(r) for a continuous r."""
+
+    def __init__(self, msh: Mesh, bc=None, nu: float = 1.0, k: float = 0.0):
+        self.msh, self.bc, self.nu, self.k = msh, bc, float(nu), float(k)
+        h = C.c_void_p()
+        check(msh.lib.semb_fdm_create(msh.h, _bc_bytes(bc), self.nu, self.k, C.byref(h)))
+        msh._fdm = self   # one per mesh: a later FdmPrecond on the same mesh replaces this one
+
+    def _current(self):
+        if getattr(self.msh, "_fdm", None) is not self:
+            raise ValueError("FdmPrecond: another FdmPrecond has since been created on this mesh (one per mesh)")
+
+    def __call__(self, r):
+        self._current()
+        r = as_f64(r, self.msh.shape)
+        out = np.zeros(self.msh.shape, order="F")
+        check(self.msh.lib.semb_fdm_apply_host(self.msh.h, dptr(r), dptr(out)))
+        return out
+
+    def apply_device(self, r: DeviceField, out: DeviceField):
+        self._current()
+        check(self.msh.lib.semb_fdm_apply(self.msh.h, r.h, out.h))
+
+
+def fdm_tables(D, w, left: str, right: str):
+    """(S, lam) of the extended 1-D reference decomposition (host only); kinds 'N' neighbour, 'D' Dirichlet, 'F' free"""
+    kinds = {"N": 0, "D": 1, "F": 2}
+    D, w = as_f64(D), np.ascontiguousarray(w, dtype=np.float64)
+    n = w.size
+    S, lam = np.zeros((n + 2, n + 2), order="F"), np.zeros(n + 2)
+    check(_lib.load().semb_fdm_tables(n, dptr(D), dptr(w), kinds[left], kinds[right], dptr(S), dptr(lam)))
+    return S, lam
+
+
 def pcg(b, opA, opM=None, mult=None, ifv=False, tol=1e-8, maxiter=None, info: Optional[dict] = None):
     """pcg(b,opA;opM,mult,ifv,tol,maxiter), pcg.jl:16-60 -- whole loop on the device.
 
-    opA must be an OpLHS (see its docstring); opM None/identity or DiagPrecond.  Returns x; `info` receives
+    opA must be an OpLHS (see its docstring); opM None/identity, DiagPrecond or FdmPrecond.  Returns x; `info` receives
     iters/resinf/converged.
     mult: the device loop weights its inner products with the mesh's own multiplicity msh.mult (structural 1, 1/2, 1/4)
     -- what every caller in the reference passes (diffusion.jl:71, examples/p2d.jl:60).  DEVIATION from the bare default:
@@ -758,8 +797,13 @@ def pcg(b, opA, opM=None, mult=None, ifv=False, tol=1e-8, maxiter=None, info: Op
     o.bc = bcb
     if isinstance(opM, DiagPrecond):
         o.precond, o.prec_b0 = 1, opM.b0
+    elif isinstance(opM, FdmPrecond):
+        if opM.msh is not msh:
+            raise ValueError("pcg: the FdmPrecond belongs to another mesh")
+        opM._current()
+        o.precond, o.prec_b0 = 2, 1.0
     elif opM is not None and not getattr(opM, "_semb_identity", False):
-        raise TypeError("pcg: opM must be None (identity, diffusion.jl:47-49) or DiagPrecond")
+        raise TypeError("pcg: opM must be None (identity, diffusion.jl:47-49), DiagPrecond or FdmPrecond")
     o.tol = float(tol)
     o.maxiter = -1 if maxiter is None else int(maxiter)
     o.check_every = 0

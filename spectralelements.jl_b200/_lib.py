@@ -133,6 +133,11 @@ _SIGS = {
     "semb_strip_kernel_info": ([C.c_int, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p], C.c_int),
     "semb_mesh_plan": ([vp] + [c_int_p] * 5, C.c_int),
     "semb_mesh_set_chunks": ([vp, C.c_int], C.c_int),
+    "semb_fdm_create": ([vp, C.c_char_p, C.c_double, C.c_double, C.POINTER(vp)], C.c_int),
+    "semb_fdm_destroy": ([vp], C.c_int),
+    "semb_fdm_apply": ([vp, vp, vp], C.c_int),
+    "semb_fdm_apply_host": ([vp, c_double_p, c_double_p], C.c_int),
+    "semb_fdm_tables": ([C.c_int, c_double_p, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p], C.c_int),
     "semb_mesh_fused_tail": ([vp, c_int_p], C.c_int),
     "semb_mesh_groups": ([vp, c_int_p], C.c_int),
     "semb_mesh_debug_read": ([vp, c_ll_p, C.c_int], C.c_int),

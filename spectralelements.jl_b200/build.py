@@ -61,7 +61,7 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = False, t
         return LIB
     tasks = []
     objs = []
-    for name in ("semb_api.cu", "semb_vec.cu", "semb_advect_tile.cu", "semb_stokes.cu", "semb_stokes_tile.cu"):
+    for name in ("semb_api.cu", "semb_vec.cu", "semb_advect_tile.cu", "semb_stokes.cu", "semb_stokes_tile.cu", "semb_fdm.cu"):
         o = os.path.join(BUILD, name.replace(".cu", ".o"))
         objs.append(o)
         tasks.append([NVCC] + ARCH + COMMON + ["-c", os.path.join(CSRC, name), "-o", o])

@@ -748,6 +748,8 @@ extern "C" int semb_mesh_destroy(semb_mesh* m) {
   cudaStreamSynchronize(m->ctx->stream);
   std::vector<semb_field*> fs = m->fields;
   for (semb_field* f : fs) semb_field_destroy(f);
+  semb_fdm_free_impl(m->fdm);
+  m->fdm = nullptr;
   for (int i = 0; i < SEMB_MESH_ARRAY_COUNT; ++i)
     if (m->arr[i]) cudaFree(m->arr[i]);
   cudaFree(m->dDr);
@@ -1380,7 +1382,11 @@ extern "C" int semb_pcg_begin(semb_mesh* m, const semb_pcg_opts* o, const semb_f
   SEMB_TRY(check_field(m, o->k_arr, "pcg(k)", true));
   SEMB_TRY(check_field(m, o->M_arr, "pcg(M)", true));
   SEMB_REQUIRE(b != x, "pcg: x must not alias b");
-  SEMB_REQUIRE(!o->precond || m->arr[SEMB_B], "pcg: diagonal preconditioner needs B");
+  SEMB_REQUIRE(o->precond >= 0 && o->precond <= 2, "pcg: precond must be 0 (identity), 1 (diagonal) or 2 (FDM)");
+  SEMB_REQUIRE(o->precond != 1 || m->arr[SEMB_B], "pcg: diagonal preconditioner needs B");
+  SEMB_REQUIRE(o->precond != 2 || (m->fdm && m->fast && !m->pcg_custom),
+               "pcg: precond = 2 needs an FDM preconditioner on this mesh (semb_fdm_create) and the fused operator path");
+  SEMB_REQUIRE(o->precond != 2 || c->nranks == 1, "pcg: the FDM preconditioner runs on one rank (its tile exchange between slabs is not built)");
   MaskFlags f;
   SEMB_TRY(parse_bc(m, o->bc, &f));
   SEMB_TRY(ensure_tmp(m, &m->w_r));
@@ -1420,7 +1426,7 @@ extern "C" int semb_pcg_begin(semb_mesh* m, const semb_pcg_opts* o, const semb_f
   SEMB_CHECK_CUDA(cudaMemcpyAsync(m->d_scal, m->h_scal, SEMB_SCAL_HOST_BYTES, cudaMemcpyHostToDevice, c->stream));
   // diagonal preconditioner on the fused path: init / update keep h = r./B./b0 (they form it anyway for t), and the
   // strip kernel stages h instead of r: same bits, no divisions and no B column at the head of the strip kernel's row
-  const bool keep_h = o->precond && m->fast && !m->pcg_custom && !getenv("SEMB_NO_PCG_H");
+  const bool keep_h = o->precond && m->fast && !m->pcg_custom && (o->precond == 2 || !getenv("SEMB_NO_PCG_H"));
   if (keep_h) SEMB_TRY(ensure_tmp(m, &m->w_h));
   m->pcg_keep_h = keep_h;
   SEMB_TRY(semb_launch_pcg_init(c, m, b->d, x->d, m->w_r->d, m->w_p->d, keep_h ? m->w_h->d : nullptr, o->precond,
@@ -1430,6 +1436,7 @@ extern "C" int semb_pcg_begin(semb_mesh* m, const semb_pcg_opts* o, const semb_f
     SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_t), 2));
     SEMB_TRY(semb_launch_pcg_finalize(c, m, 1));
   }
+  if (o->precond == 2) SEMB_TRY(semb_fdm_apply_impl(m->fdm, m->w_r->d, m->w_h->d, 2));  // h = opM(r), t, state (pcg.jl:37,45)
   m->pcg_active = true;
   return SEMB_OK;
 }
@@ -1473,6 +1480,7 @@ static int pcg_one_iteration(semb_mesh* m) {
     SEMB_TRY(gather_scalars(m, SEMB_SCAL_PTR(m, xchg_t), 2));
     SEMB_TRY(semb_launch_pcg_finalize(c, m, 0));
   }
+  if (o.precond == 2) SEMB_TRY(semb_fdm_apply_impl(m->fdm, m->w_r->d, m->w_h->d, 1));  // h = opM(r), t, state
   return SEMB_OK;
 }
 
@@ -2148,6 +2156,60 @@ extern "C" int semb_abu_host(semb_ctx* c, const double* As, int ma, int na, cons
   cudaFree(dA);
   cudaFree(dB);
   return rc;
+}
+
+// ---- FDM preconditioner (lapl.jl:105-119, examples/p2d_explicit.jl:109-141; kernels in semb_fdm.cu) ------
+extern "C" int semb_fdm_create(semb_mesh* m, const char bc[4], double nu, double k, semb_fdm** out) {
+  SEMB_REQUIRE(m && out, "semb_fdm_create: null argument");
+  *out = nullptr;
+  SEMB_ENTER(m->ctx);
+  SEMB_REQUIRE(m->nr == m->ns && m->nr >= 3 && m->nr <= SEMB_MAXN, "fdm: needs nr == ns in 3..%d", SEMB_MAXN);
+  SEMB_REQUIRE(m->arr[SEMB_B] && m->arr[SEMB_G11] && m->arr[SEMB_G22], "fdm: mesh needs B, G11, G22");
+  SEMB_REQUIRE(!(m->perx && m->Ex < 2) && !(m->pery && m->Ey < 2), "fdm: a periodic direction needs at least 2 elements");
+  SEMB_REQUIRE(m->ctx->nranks == 1, "fdm: the preconditioner runs on one rank (its tile exchange between slabs is not built)");
+  SEMB_REQUIRE(nu > 0.0 && k >= 0.0, "fdm: needs nu > 0, k >= 0");
+  MaskFlags f;
+  SEMB_TRY(parse_bc(m, bc, &f));
+  const int gy0 = (bc && bc[2] == 'D' && !m->pery) ? 1 : 0, gy1 = (bc && bc[3] == 'D' && !m->pery) ? 1 : 0;
+  semb_fdm_free_impl(m->fdm);  // one per mesh: the new one replaces it
+  m->fdm = nullptr;
+  semb_fdm* h = nullptr;
+  const int rc = semb_fdm_create_impl(m, nu, k, f.mx0, f.mx1, f.my0, f.my1, gy0, gy1, &h);
+  if (rc < 0) {
+    semb_fdm_free_impl(h);
+    return rc;
+  }
+  m->fdm = h;
+  *out = h;
+  return SEMB_OK;
+}
+
+extern "C" int semb_fdm_destroy(semb_mesh* m) {
+  SEMB_REQUIRE(m, "null mesh");
+  SEMB_ENTER(m->ctx);
+  SEMB_CHECK_CUDA(cudaStreamSynchronize(m->ctx->stream));
+  semb_fdm_free_impl(m->fdm);
+  m->fdm = nullptr;
+  return SEMB_OK;
+}
+
+extern "C" int semb_fdm_apply(semb_mesh* m, const semb_field* r, semb_field* out) {
+  SEMB_REQUIRE(m && m->fdm, "semb_fdm_apply: no FDM preconditioner on this mesh (semb_fdm_create)");
+  SEMB_ENTER(m->ctx);
+  SEMB_TRY(check_field(m, r, "fdm(r)"));
+  SEMB_TRY(check_field(m, out, "fdm(out)"));
+  SEMB_REQUIRE(r != out, "fdm: out must not alias r");
+  return semb_fdm_apply_impl(m->fdm, r->d, out->d, 0);
+}
+
+extern "C" int semb_fdm_apply_host(semb_mesh* m, const double* r, double* out) {
+  SEMB_REQUIRE(m && r && out, "fdm_host: null argument");
+  TmpFields t(m);
+  semb_field *fr, *fo;
+  SEMB_TRY(t.make(r, &fr));
+  SEMB_TRY(t.make(nullptr, &fo));
+  SEMB_TRY(semb_fdm_apply(m, fr, fo));
+  return semb_field_download(fo, out);
 }
 
 #include "semb_stokes_api.cuh"

@@ -225,3 +225,100 @@ extern "C" int semb_halo_plan(int nranks, int rank, int pery, int* halo_lo, int*
   if (rank_hi) *rank_hi = hi ? (rank + 1) % nranks : -1;
   return SEMB_OK;
 }
+
+// ---- FDM preconditioner set-up (examples/p2d_explicit.jl:109-141, lapl.jl:105-119) ----------------------
+// Generalised eigen-decomposition A S = B S diag(lam), S' B S = I, of the 1-D stiffness / mass pair of ONE reference
+// element (half-length 1: A = D' diag(w) D, B = diag(w)) extended by one node into each neighbour of the same size.
+// kinds (left, right): 0 = neighbour element (extension node = its first node off the interface, zero beyond it),
+// 1 = Dirichlet boundary (the boundary node itself is removed), 2 = free boundary (no extension).
+// S is (n+2) x (n+2) column-major with rows [left ext, own 0..n-1, right ext] (zero rows for removed nodes), lam has
+// n+2 entries (+inf for the padding modes).  An element of half-length h uses S/sqrt(h), lam/h^2.
+// B is diagonal, so the pair reduces to the symmetric problem B^-1/2 A B^-1/2 = Q diag(lam) Q', S = B^-1/2 Q, which the
+// cyclic Jacobi method solves to machine precision at these sizes (<= 19).
+extern "C" int semb_fdm_tables(int n, const double* D, const double* w, int left, int right, double* S, double* lam) {
+  if (!D || !w || !S || !lam || n < 3 || n > 62 || left < 0 || left > 2 || right < 0 || right > 2) {
+    semb_set_error("semb_fdm_tables: bad argument (3 <= n <= 62, kinds 0..2)");
+    return SEMB_EINVAL;
+  }
+  const int m = n + 2;
+  std::vector<double> A0((size_t)n * n, 0.0), A((size_t)m * m, 0.0), B(m, 0.0);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < n; ++k) s += D[k + (size_t)i * n] * w[k] * D[k + (size_t)j * n];  // (D' diag(w) D)(i,j)
+      A0[i + (size_t)j * n] = s;
+    }
+  auto Aat = [&](int i, int j) -> double& { return A[i + (size_t)j * m]; };
+  for (int i = 0; i < n; ++i) {
+    B[i + 1] += w[i];
+    for (int j = 0; j < n; ++j) Aat(i + 1, j + 1) += A0[i + (size_t)j * n];
+  }
+  std::vector<int> active(m, 1);
+  if (left == 0) {  // neighbour's nodes (n-2, n-1) sit on extended indices (0, 1)
+    for (int i = 0; i < 2; ++i) {
+      B[i] += w[n - 2 + i];
+      for (int j = 0; j < 2; ++j) Aat(i, j) += A0[(n - 2 + i) + (size_t)(n - 2 + j) * n];
+    }
+  } else {
+    active[0] = 0;
+    if (left == 1) active[1] = 0;
+  }
+  if (right == 0) {  // neighbour's nodes (0, 1) sit on extended indices (n, n+1)
+    for (int i = 0; i < 2; ++i) {
+      B[n + i] += w[i];
+      for (int j = 0; j < 2; ++j) Aat(n + i, n + j) += A0[i + (size_t)j * n];
+    }
+  } else {
+    active[m - 1] = 0;
+    if (right == 1) active[n] = 0;
+  }
+  std::vector<int> idx;
+  for (int i = 0; i < m; ++i)
+    if (active[i]) idx.push_back(i);
+  const int p = (int)idx.size();
+  std::vector<double> C((size_t)p * p), Q((size_t)p * p, 0.0);
+  for (int i = 0; i < p; ++i) {
+    Q[i + (size_t)i * p] = 1.0;
+    for (int j = 0; j < p; ++j) C[i + (size_t)j * p] = Aat(idx[i], idx[j]) / std::sqrt(B[idx[i]] * B[idx[j]]);
+  }
+  for (int sweep = 0; sweep < 100; ++sweep) {  // cyclic Jacobi
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < p; ++i)
+      for (int j = 0; j < p; ++j) (i == j ? diag : off) += C[i + (size_t)j * p] * C[i + (size_t)j * p];
+    if (off <= 1e-30 * diag) break;
+    for (int a = 0; a < p - 1; ++a)
+      for (int b = a + 1; b < p; ++b) {
+        const double apq = C[a + (size_t)b * p];
+        if (apq == 0.0) continue;
+        const double theta = (C[b + (size_t)b * p] - C[a + (size_t)a * p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < p; ++k) {  // columns a, b
+          const double ka = C[k + (size_t)a * p], kb = C[k + (size_t)b * p];
+          C[k + (size_t)a * p] = c * ka - s * kb;
+          C[k + (size_t)b * p] = s * ka + c * kb;
+        }
+        for (int k = 0; k < p; ++k) {  // rows a, b
+          const double ak = C[a + (size_t)k * p], bk = C[b + (size_t)k * p];
+          C[a + (size_t)k * p] = c * ak - s * bk;
+          C[b + (size_t)k * p] = s * ak + c * bk;
+        }
+        for (int k = 0; k < p; ++k) {
+          const double ka = Q[k + (size_t)a * p], kb = Q[k + (size_t)b * p];
+          Q[k + (size_t)a * p] = c * ka - s * kb;
+          Q[k + (size_t)b * p] = s * ka + c * kb;
+        }
+      }
+  }
+  std::vector<int> order(p);  // ascending eigenvalues (as LAPACK's eigh): deterministic layout
+  for (int i = 0; i < p; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int x, int y) { return C[x + (size_t)x * p] < C[y + (size_t)y * p]; });
+  for (int q = 0; q < m * m; ++q) S[q] = 0.0;
+  for (int q = 0; q < m; ++q) lam[q] = INFINITY;
+  for (int c = 0; c < p; ++c) {
+    const int o = order[c];
+    lam[c] = C[o + (size_t)o * p];
+    for (int i = 0; i < p; ++i) S[idx[i] + (size_t)c * m] = Q[i + (size_t)o * p] / std::sqrt(B[idx[i]]);
+  }
+  return SEMB_OK;
+}

@@ -209,6 +209,7 @@ struct semb_mesh {
   // operator hook of the device-resident PCG: when set, an iteration is p = h + beta*p, w_Ap = pcg_custom(w_p),
   // sum(p.*Ap.*mult) by the reduction kernel, update -- instead of the fused strip kernel (Stokes Schur operator)
   std::function<int()> pcg_custom;
+  struct semb_fdm* fdm = nullptr;      // FDM preconditioner registered on this mesh (semb_fdm_create), used by precond = 2
   std::vector<semb_field*> fields;     // live fields (for leak-free destroy)
   std::vector<semb_field*> host_tmp;   // cached device fields of the *_host twins
 };
@@ -297,6 +298,13 @@ struct SembTailLayout {
   __host__ __device__ int partC() const { return pX + pY; }
   __host__ __device__ int nparts() const { return pX + pY + nC; }
 };
+
+// FDM preconditioner (semb_fdm.cu)
+struct semb_fdm;
+int semb_fdm_create_impl(semb_mesh* m, double nu, double k, int mx0, int mx1, int my0, int my1, int gy0, int gy1,
+                         semb_fdm** out);
+int semb_fdm_free_impl(semb_fdm* f);
+int semb_fdm_apply_impl(semb_fdm* f, const double* r, double* out, int pcg);
 
 // launchers implemented in the .cu files
 int semb_launch_strip(semb_ctx* ctx, const OpArgs& a, const double* hDr, const double* hDs, int nstrips,

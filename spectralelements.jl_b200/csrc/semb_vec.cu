@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(256) semb_pcg_init_kernel(const double2* __res
     r[i] = bv;
     const double2 m2 = semb_mult2(wx1d, wy1d, c2, row);
     double hx = bv.x, hy = bv.y;
-    if (precond) {
+    if (precond == 1) {
       const double2 B2 = Bm[i];
       hx = (2 * c2 < nxl) ? semb_prec(bv.x, B2.x, 1, b0) : 0.0;
       hy = (2 * c2 + 1 < nxl) ? semb_prec(bv.y, B2.y, 1, b0) : 0.0;
@@ -530,6 +530,10 @@ __global__ void __launch_bounds__(256) semb_pcg_init_kernel(const double2* __res
       scal->maxiter = maxiter;
       scal->xchg_t[2 * scal->rank] = tot;
       scal->xchg_t[2 * scal->rank + 1] = tmx;
+    }
+    if (precond == 2) {  // opM is a kernel of its own (FDM): it forms t = sum(r.*h.*mult) and advances the state
+      if (SEMB_TID == 0) scal->red[2] = tmx;
+      return;
     }
     if (xp.on) semb_p2p_allgather(scal, 1, tot, tmx, &tot, &tmx, SEMB_TID);
     if (SEMB_TID == 0 && (scal->nranks == 1 || xp.on)) semb_pcg_advance(scal, tot, tmx, true);
@@ -559,7 +563,7 @@ __global__ void __launch_bounds__(256) semb_pcg_update_kernel(double2* x, double
     const double2 pv = p[i], av = Ap[i];
     // B travels with the other four loads (inside the `if (precond)` below it was issued only after they had
     // arrived: two exposed memory latencies per trip, long-scoreboard stalls 78 %, profiles/r01_update_prec_r1n.txt)
-    const double2 B2 = precond ? Bm[i] : make_double2(1.0, 1.0);
+    const double2 B2 = precond == 1 ? Bm[i] : make_double2(1.0, 1.0);
     const double2 m2 = semb_mult2(wx1d, wy1d, c2, row);
     double2 xv = x[i], rv = r[i];
     xv.x = __dadd_rn(xv.x, __dmul_rn(alpha, pv.x));
@@ -569,7 +573,7 @@ __global__ void __launch_bounds__(256) semb_pcg_update_kernel(double2* x, double
     x[i] = xv;
     r[i] = rv;
     double hx = rv.x, hy = rv.y;
-    if (precond) {
+    if (precond == 1) {
       hx = (2 * c2 < nxl) ? semb_prec(rv.x, B2.x, 1, b0) : 0.0;
       hy = (2 * c2 + 1 < nxl) ? semb_prec(rv.y, B2.y, 1, b0) : 0.0;
       if (hout) hout[i] = make_double2(hx, hy);
@@ -587,6 +591,10 @@ __global__ void __launch_bounds__(256) semb_pcg_update_kernel(double2* x, double
     if (SEMB_TID == 0) {
       scal->xchg_t[2 * scal->rank] = tot;
       scal->xchg_t[2 * scal->rank + 1] = tmx;
+    }
+    if (precond == 2) {  // FDM: the preconditioner kernel that follows forms t and advances the state
+      if (SEMB_TID == 0) scal->red[2] = tmx;
+      return;
     }
     if (xp.on) semb_p2p_allgather(scal, 1, tot, tmx, &tot, &tmx, SEMB_TID);  // fused all-gather over NVLink
     if (SEMB_TID == 0 && (scal->nranks == 1 || xp.on)) semb_pcg_advance(scal, tot, tmx, false);
