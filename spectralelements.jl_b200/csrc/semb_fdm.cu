@@ -13,13 +13,10 @@
 // and three reference decompositions per direction (first / interior / last element) serve the whole mesh
 // (semb_fdm_tables, semb_host.cpp).  5-8x fewer PCG iterations than no preconditioner on the BASELINE meshes.
 //
-// Two kernels per application:
-//   semb_fdm_solve_kernel<N>   one CTA = a batch of x-consecutive elements of one element row: gathers the (N+2)^2 tiles of
-//                              W.*r, applies the four contractions out of registers (the strip kernel's two thread<->line
-//                              mappings), writes the tiles to a tile-major ("fat") buffer
-//   semb_fdm_combine_kernel    per node: sums the (up to four) tile entries that land on it and on its duplicates in the
-//                              fixed (x pairs, then y pairs) association of gatherScatter.jl:13, applies W and the mask,
-//                              and -- inside pcg -- accumulates sum(r .* h .* mult) (pcg.jl:45) deterministically
+// One kernel per application (semb_fdm_kernel<N>): gathers the (N+2)^2 tiles of W.*r, applies the four contractions out of
+// registers (the strip kernel's two thread<->line mappings), sums the tile entries that land on a node and on its
+// duplicates -- x overlaps, x pairs, y overlaps, y pairs, the association of gatherScatter.jl:13 -- applies W and the mask
+// and, inside pcg, accumulates sum(r .* h .* mult) (pcg.jl:45) deterministically.  16 bytes per node of HBM traffic.
 #include "semb_reduce.cuh"
 #include "semb_vec.cuh"
 
@@ -28,7 +25,6 @@ namespace {
 struct FdmArgs {
   const double* r;      // residual (continuous)
   double* out;          // h = opM(r)
-  double* fat;          // tile buffer: row (ey*N2 + jj) * fpitch + ex*N2 + ii
   const double* tab;    // [dir 2][class 4][N2*N2 + N2]: S (column-major: S[ii + c*N2]) then lambda
   const double* hx;     // [ney][Ex] element half-lengths
   const double* hy;
@@ -36,7 +32,7 @@ struct FdmArgs {
   const double* wy;
   const double* mult_x; // mult(x,y) = mult_x[x] * mult_y[y]  (PCG reduction)
   const double* mult_y;
-  long long pitch, fpitch;
+  long long pitch;
   int N, Ex, Ey, ey0, ney, nxl, nyl, perx, pery;
   int mx0, mx1, my0, my1;
   double nu, k;
@@ -52,193 +48,397 @@ __device__ __forceinline__ int fdm_class(int e, int E, int per) {
   return (e == 0 ? 1 : 0) | (e == E - 1 ? 2 : 0);
 }
 
+// ---- contraction tables -------------------------------------------------------------------------------------------------
+// One slot per (direction, element class): [eo flag][lambda (N2)][F][G] with F the nodes -> modes matrix (rows = node,
+// padded to an even length so that a row is read with LDS.128) and G the modes -> nodes matrix (rows = mode).
+// The extended 1-D operator of an element with the same kind of neighbour on both sides is symmetric under the
+// reflection i <-> N2-1-i, so its eigenvectors are even or odd: with the even modes first, y = S'x and x = S y split
+// into two half-size products on e_k = x_k + x_{N2-1-k}, o_k = x_k - x_{N2-1-k} (half the FMAs and table loads) -- the
+// even-odd trick of the strip kernel, here for a symmetric eigenbasis.  Boundary classes use the full products.
+template <int N2>
+struct FdmTab {
+  static constexpr int NP = (N2 + 1) & ~1;
+  static constexpr int H = N2 / 2, ODD = N2 & 1, NE = H + ODD, NO = H;
+  static constexpr int NEP = (NE + 1) & ~1, NOP = (NO + 1) & ~1;
+  static constexpr int OFF_LAM = 1, OFF_F = (1 + N2 + 1) & ~1, OFF_G = OFF_F + N2 * NP;
+  static constexpr int SIZE = OFF_G + N2 * NP;
+  // S: (N2 x N2) column-major (S[i + m*N2]), lam[N2]; returns the slot (host)
+  static void fill(const double* S, const double* lam, double* slot) {
+    for (int q = 0; q < SIZE; ++q) slot[q] = 0.0;
+    // parity of every mode (padding modes: zero vectors, lambda = inf, count as even)
+    int par[N2];
+    bool eo = true;
+    for (int m = 0; m < N2; ++m) {
+      double se = 0.0, so = 0.0, nn = 0.0;
+      for (int i = 0; i < N2; ++i) {
+        const double a = S[i + (size_t)m * N2], b = S[(N2 - 1 - i) + (size_t)m * N2];
+        se += (a - b) * (a - b);
+        so += (a + b) * (a + b);
+        nn += a * a;
+      }
+      if (se <= 1e-20 * nn) par[m] = 0;
+      else if (so <= 1e-20 * nn) par[m] = 1;
+      else eo = false, par[m] = 0;
+    }
+    int ne = 0, no = 0;
+    for (int m = 0; m < N2; ++m) (par[m] ? no : ne)++;
+    if (ne != NE || no != NO) eo = false;
+    if (!eo) {
+      slot[0] = 0.0;
+      for (int m = 0; m < N2; ++m) slot[OFF_LAM + m] = lam[m];
+      for (int i = 0; i < N2; ++i)
+        for (int m = 0; m < N2; ++m) {
+          slot[OFF_F + i * NP + m] = S[i + (size_t)m * N2];
+          slot[OFF_G + m * NP + i] = S[i + (size_t)m * N2];
+        }
+      return;
+    }
+    slot[0] = 1.0;
+    int order[N2], c = 0;  // even modes first, then the odd ones (each group in ascending eigenvalue order)
+    for (int m = 0; m < N2; ++m)
+      if (!par[m]) order[c++] = m;
+    for (int m = 0; m < N2; ++m)
+      if (par[m]) order[c++] = m;
+    for (int m = 0; m < N2; ++m) slot[OFF_LAM + m] = lam[order[m]];
+    double* FE = slot + OFF_F;            // [k < NE][m < NE]: S(k, even m)   (k = H is the middle node when N2 is odd)
+    double* FO = FE + NE * NEP;           // [k < H][m < NO]:  S(k, odd m)
+    double* GE = slot + OFF_G;            // [m < NE][i < NE]: S(i, even m)
+    double* GO = GE + NE * NEP;           // [m < NO][i < H]:  S(i, odd m)
+    for (int k = 0; k < NE; ++k)
+      for (int m = 0; m < NE; ++m) {
+        FE[k * NEP + m] = S[k + (size_t)order[m] * N2];
+        GE[m * NEP + k] = S[k + (size_t)order[m] * N2];
+      }
+    for (int k = 0; k < H; ++k)
+      for (int m = 0; m < NO; ++m) {
+        FO[k * NOP + m] = S[k + (size_t)order[NE + m] * N2];
+        GO[m * NOP + k] = S[k + (size_t)order[NE + m] * N2];
+      }
+  }
+};
+
+// y = S' x (nodes -> modes) out of registers; slot = FdmTab layout in shared memory
+template <int N2, bool EO>
+__device__ __forceinline__ void fdm_fwd(const double* __restrict__ slot, const double (&x)[N2], double (&y)[N2]) {
+  using TB = FdmTab<N2>;
+  if constexpr (!EO) {
+    const double* F = slot + TB::OFF_F;
+#pragma unroll
+    for (int m = 0; m < N2; ++m) y[m] = 0.0;
+#pragma unroll
+    for (int k = 0; k < N2; ++k) {
+#pragma unroll
+      for (int m = 0; m < N2; ++m) y[m] = fma(F[k * TB::NP + m], x[k], y[m]);
+    }
+  } else {
+    constexpr int H = TB::H, NE = TB::NE, NO = TB::NO;
+    const double* FE = slot + TB::OFF_F;
+    const double* FO = FE + NE * TB::NEP;
+#pragma unroll
+    for (int m = 0; m < N2; ++m) y[m] = 0.0;
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      const double e = x[k] + x[N2 - 1 - k], o = x[k] - x[N2 - 1 - k];
+#pragma unroll
+      for (int m = 0; m < NE; ++m) y[m] = fma(FE[k * TB::NEP + m], e, y[m]);
+#pragma unroll
+      for (int m = 0; m < NO; ++m) y[NE + m] = fma(FO[k * TB::NOP + m], o, y[NE + m]);
+    }
+    if (TB::ODD) {
+#pragma unroll
+      for (int m = 0; m < NE; ++m) y[m] = fma(FE[H * TB::NEP + m], x[H], y[m]);
+    }
+  }
+}
+
+// x = S y (modes -> nodes)
+template <int N2, bool EO>
+__device__ __forceinline__ void fdm_bwd(const double* __restrict__ slot, const double (&y)[N2], double (&x)[N2]) {
+  using TB = FdmTab<N2>;
+  if constexpr (!EO) {
+    const double* G = slot + TB::OFF_G;
+#pragma unroll
+    for (int i = 0; i < N2; ++i) x[i] = 0.0;
+#pragma unroll
+    for (int m = 0; m < N2; ++m) {
+#pragma unroll
+      for (int i = 0; i < N2; ++i) x[i] = fma(G[m * TB::NP + i], y[m], x[i]);
+    }
+  } else {
+    constexpr int H = TB::H, NE = TB::NE, NO = TB::NO;
+    const double* GE = slot + TB::OFF_G;
+    const double* GO = GE + NE * TB::NEP;
+    double sv[NE], dv[H > 0 ? H : 1];
+#pragma unroll
+    for (int i = 0; i < NE; ++i) sv[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < H; ++i) dv[i] = 0.0;
+#pragma unroll
+    for (int m = 0; m < NE; ++m) {
+#pragma unroll
+      for (int i = 0; i < NE; ++i) sv[i] = fma(GE[m * TB::NEP + i], y[m], sv[i]);
+    }
+#pragma unroll
+    for (int m = 0; m < NO; ++m) {
+#pragma unroll
+      for (int i = 0; i < H; ++i) dv[i] = fma(GO[m * TB::NOP + i], y[NE + m], dv[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      x[i] = sv[i] + dv[i];
+      x[N2 - 1 - i] = sv[i] - dv[i];
+    }
+    if (TB::ODD) x[H] = sv[H];
+  }
+}
+
 template <int N>
 struct FdmCfg {
   static constexpr int N2 = N + 2;
   static constexpr int T = 256;
-  static constexpr int BX = T / N2;        // elements per CTA
+  static constexpr int BX = T / N2;        // tiles per CTA: BX - 2 output elements + one halo tile on either side
   static constexpr int S = N2 | 1;         // element stride in the tile buffer (odd: conflict-free in both mappings)
-  static constexpr int PW = BX * S;        // row pitch of the tile buffer
-  static constexpr int TSZ = N2 * N2 + N2; // one table: S then lambda
-  static constexpr int SMEM = (N2 * PW + 5 * TSZ) * 8;
+  static constexpr int PW = BX * S;        // row pitch of a tile buffer
+  static constexpr int TSZ = FdmTab<N2>::SIZE;
+  static constexpr int SMEM = (2 * N2 * PW + 4 * TSZ) * 8;   // two tile buffers, 3 x tables + the y table in use
+  static constexpr int MAXB = (227 * 1024) / (SMEM + 1024);
+  static constexpr int MINB = MAXB >= 3 ? 3 : (MAXB >= 2 ? 2 : 1);
 };
 
+__device__ __forceinline__ void fdm_cp_async8(double* dst_smem, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void fdm_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void fdm_cp_async_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// One launch per application.  A CTA owns a strip of up to BX-2 x-consecutive elements plus one halo element on either
+// side, and MARCHES through a chunk of element rows plus one halo row below and above (the halo tiles are computed twice,
+// by the two CTAs that need them: no exchange between CTAs, no second pass over the field).  Per element row:
+//   P1 (thread <-> tile column)   the (N+2) x (N+2) tiles of W.*r -- prefetched one element row ahead with cp.async into
+//                                 the other tile buffer -- Sy' along y out of registers, back into the buffer in place
+//   P2 (thread <-> tile row)      Sx' along x, Di, Sx back along x, in place
+//   P3 (thread <-> tile column)   Sy back along y; the columns next to an element interface go back to the buffer
+//   P4 (same threads)             x sums (tile overlaps, then the x pair of gatherScatter.jl:13), y sums against the three
+//                                 rows carried in registers from the previous element row (overlaps, then the y pair),
+//                                 W, mask, store; inside pcg the sum(r.*h.*mult) partial (pcg.jl:45)
+// Every sum has two terms (three for N = 3), in a fixed order: the result does not depend on the launch geometry.
 template <int N>
-__global__ void __launch_bounds__(256) semb_fdm_solve_kernel(const FdmArgs a) {
+__global__ void __launch_bounds__(256, FdmCfg<N>::MINB) semb_fdm_kernel(const FdmArgs a) {
   using C = FdmCfg<N>;
+  using TB = FdmTab<C::N2>;
   constexpr int N2 = C::N2, BX = C::BX, S = C::S, PW = C::PW, TSZ = C::TSZ;
   extern __shared__ __align__(16) double sm[];
-  double* S1 = sm;                 // [N2][PW] tiles
-  double* sTx = S1 + N2 * PW;      // [4][TSZ] x tables, all classes
-  double* sTy = sTx + 4 * TSZ;     // [TSZ] y table of this element row
+  double* sTx = sm;                // [3][TSZ] x tables: slot = class (class 3, a single element, only occurs alone: slot 0)
+  double* sTy = sTx + 3 * TSZ;     // [TSZ] y table of the current element row's class
+  double* bufs = sTy + TSZ;        // [2][N2][PW] tile buffers
+  __shared__ double red[32];
+  __shared__ double sh_tot[2];
   if (a.pcg && a.scal->done) return;
   const int t = threadIdx.x;
-  const int ey = blockIdx.y, eyg = a.ey0 + ey;
-  const int e0 = blockIdx.x * BX;
-  const int nbe = min(BX, a.Ex - e0);
-  const int cy = fdm_class(eyg, a.Ey, a.pery);
-  for (int q = t; q < 4 * TSZ; q += C::T) sTx[q] = a.tab[q];
-  for (int q = t; q < TSZ; q += C::T) sTy[q] = a.tab[4 * TSZ + cy * TSZ + q];
-  // ---- mapping B: thread <-> (element eB, tile column iB): load the column of W.*r ---------------------------------
+  // strip: output elements [o0, o1), tile slot e <-> element o0 - 1 + e
+  const int o0 = (int)(((long long)blockIdx.x * a.Ex) / gridDim.x), o1 = (int)(((long long)(blockIdx.x + 1) * a.Ex) / gridDim.x);
+  const int nout = o1 - o0;
+  // chunk: output element rows [r0, r1), tile rows r0-1 .. r1
+  const int r0 = (int)(((long long)blockIdx.y * a.ney) / gridDim.y), r1 = (int)(((long long)(blockIdx.y + 1) * a.ney) / gridDim.y);
+  const bool wrapy = a.pery && a.ney == a.Ey;
+  {
+    const int sl1 = (a.Ex == 1 && !a.perx) ? 3 : 0;  // slot 0 holds class 0, or class 3 when that is the only one
+    for (int q = t; q < 3 * TSZ; q += C::T) {
+      const int sl = q / TSZ;
+      sTx[q] = a.tab[(size_t)(sl == 0 ? sl1 : sl) * TSZ + (q - sl * TSZ)];
+    }
+  }
+  // ---- mapping B: thread <-> (tile slot eB, tile column iB) --------------------------------------------------------
   const int eB = t / N2, iB = t - eB * N2;
-  const bool actB = eB < nbe;
-  const int ex = e0 + eB;
-  double col[N2];
-  {
-    // tile column -> global column: [left neighbour's node N-2, own 0..N-1, right neighbour's node 1]
-    int x = -1;
-    if (actB) {
-      if (iB == 0) x = (ex > 0 || a.perx) ? ((ex + a.Ex - 1) % a.Ex) * N + N - 2 : -1;
-      else if (iB == N + 1) x = (ex < a.Ex - 1 || a.perx) ? ((ex + 1) % a.Ex) * N + 1 : -1;
-      else x = ex * N + iB - 1;
-    }
-    const double wxv = x >= 0 ? a.wx[x] : 0.0;
-#pragma unroll
-    for (int jj = 0; jj < N2; ++jj) {
-      int y;  // tile row -> local row (this rank's slab; the periodic wrap is local on one rank)
-      if (jj == 0) y = (ey > 0) ? (ey - 1) * N + N - 2 : ((a.pery && a.ney == a.Ey) ? (a.ney - 1) * N + N - 2 : -1);
-      else if (jj == N + 1) y = (ey < a.ney - 1) ? (ey + 1) * N + 1 : ((a.pery && a.ney == a.Ey) ? 1 : -1);
-      else y = ey * N + jj - 1;
-      col[jj] = (x >= 0 && y >= 0) ? __dmul_rn(__dmul_rn(wxv, a.wy[y]), a.r[(size_t)y * a.pitch + x]) : 0.0;
-    }
+  const bool inB = t < BX * N2;
+  int exB = o0 - 1 + eB;
+  const bool validB = inB && eB < nout + 2 && (a.perx || (exB >= 0 && exB < a.Ex));
+  exB = (exB + a.Ex) % a.Ex;
+  const bool hasL = exB > 0 || a.perx, hasR = exB < a.Ex - 1 || a.perx;
+  int xB = -1;  // tile column -> global column: [left neighbour's node N-2, own 0..N-1, right neighbour's node 1]
+  if (validB) {
+    if (iB == 0) xB = hasL ? ((exB + a.Ex - 1) % a.Ex) * N + N - 2 : -1;
+    else if (iB == N + 1) xB = hasR ? ((exB + 1) % a.Ex) * N + 1 : -1;
+    else xB = exB * N + iB - 1;
   }
-  __syncthreads();  // tables are in shared memory
-  // t1 = Sy' * col (along y): t1[c] = sum_jj Sy[jj][c] col[jj]
-  {
-    double o[N2];
+  const double wxB = xB >= 0 ? a.wx[xB] : 0.0;
+  const bool outB = validB && eB >= 1 && eB <= nout && iB >= 1 && iB <= N;   // this thread finishes node column xB
+  const int colB = eB * S + iB;
+  const bool mzx = outB && ((xB == 0 && a.mx0) || (xB == a.nxl - 1 && a.mx1));
+  const double mxB = (a.pcg && outB) ? a.mult_x[xB] : 0.0;
+  // ---- mapping A: thread <-> (tile row jA, tile slot eA) -------------------------------------------------------------
+  const int jA = t / BX, eA = t - jA * BX;
+  int exA = o0 - 1 + eA;
+  const bool validA = jA < N2 && eA < nout + 2 && (a.perx || (exA >= 0 && exA < a.Ex));
+  exA = (exA + a.Ex) % a.Ex;
+  const int clsA = fdm_class(exA, a.Ex, a.perx);
+  const double* Tx = sTx + (clsA == 3 ? 0 : clsA) * TSZ;
+  const int colA = jA * PW + eA * S;
+
+  // local row of tile row jj of element row ey (-1: no such row)
+  auto row_of = [&](int ey, int jj) {
+    if (jj == 0) return (ey > 0) ? (ey - 1) * N + N - 2 : (wrapy ? (a.ney - 1) * N + N - 2 : -1);
+    if (jj == N + 1) return (ey < a.ney - 1) ? (ey + 1) * N + 1 : (wrapy ? 1 : -1);
+    return ey * N + jj - 1;
+  };
+  auto prefetch = [&](int ey, double* buf) {
+    if (inB) {
 #pragma unroll
-    for (int c = 0; c < N2; ++c) o[c] = 0.0;
-#pragma unroll
-    for (int jj = 0; jj < N2; ++jj) {
-#pragma unroll
-      for (int c = 0; c < N2; ++c) o[c] = fma(sTy[jj + c * N2], col[jj], o[c]);
+      for (int jj = 0; jj < N2; ++jj) {
+        const int y = row_of(ey, jj);
+        double* dst = buf + jj * PW + colB;
+        if (xB >= 0 && y >= 0) fdm_cp_async8(dst, a.r + (size_t)y * a.pitch + xB);
+        else *dst = 0.0;
+      }
     }
-    if (t < BX * N2) {
-#pragma unroll
-      for (int c = 0; c < N2; ++c) S1[c * PW + eB * S + iB] = o[c];
+    fdm_cp_async_commit();
+  };
+  // tile rows of this CTA: q = 0 .. nq-1 <-> rr = ra + q (halo rows outside a non-periodic slab do not exist)
+  const int ra = (r0 > 0 || wrapy) ? r0 - 1 : r0, rb = (r1 < a.ney || wrapy) ? r1 : r1 - 1;
+  const int nq = rb - ra + 1;
+  prefetch((ra + a.ney) % a.ney, bufs);
+  int cy_loaded = -1;
+  double pend0 = 0.0, pend1 = 0.0, prevN1 = 0.0;
+  double acc = 0.0;
+
+  for (int q = 0; q < nq; ++q) {
+    const int rr = ra + q;
+    const int ey = (rr + a.ney) % a.ney, eyg = a.ey0 + ey;
+    double* S1 = bufs + (q & 1) * (N2 * PW);
+    const int cy = fdm_class(eyg, a.Ey, a.pery);
+    if (cy != cy_loaded) {  // (block-uniform; at most three times per CTA)
+      __syncthreads();
+      for (int i = t; i < TSZ; i += C::T) sTy[i] = a.tab[(size_t)(4 + cy) * TSZ + i];
+      cy_loaded = cy;
+      __syncthreads();
     }
-  }
-  __syncthreads();
-  // ---- mapping A: thread <-> (row jA = y-mode, element eA): Sx' along x, scale by Di, Sx back ---------------------------
-  {
-    const int jA = t / BX, eA = t - jA * BX;
-    if (jA < N2 && eA < nbe) {
-      const int exA = e0 + eA;
-      const double* Tx = sTx + fdm_class(exA, a.Ex, a.perx) * TSZ;
-      const double hx = a.hx[(size_t)ey * a.Ex + exA], hy = a.hy[(size_t)ey * a.Ex + exA];
-      const double ly = sTy[N2 * N2 + jA] / (hy * hy);
+    const bool eoy = sTy[0] != 0.0;
+    double hx = 1.0, hy = 1.0;
+    if (validA) hx = a.hx[(size_t)ey * a.Ex + exA], hy = a.hy[(size_t)ey * a.Ex + exA];
+    // ---- P1: W .* r, Sy' along y ------------------------------------------------------------------------------------
+    fdm_cp_async_wait();
+    {
+      double col[N2], o[N2];
+#pragma unroll
+      for (int jj = 0; jj < N2; ++jj) {
+        const int y = row_of(ey, jj);
+        const double wv = (y >= 0) ? __dmul_rn(wxB, a.wy[y]) : 0.0;
+        col[jj] = inB ? __dmul_rn(wv, S1[jj * PW + colB]) : 0.0;
+      }
+      if (eoy) fdm_fwd<N2, true>(sTy, col, o);
+      else fdm_fwd<N2, false>(sTy, col, o);
+      if (inB) {
+#pragma unroll
+        for (int c = 0; c < N2; ++c) S1[c * PW + colB] = o[c];
+      }
+    }
+    __syncthreads();
+    // the other buffer is free (its last readers were the P4 of the previous element row): next element row's tiles
+    if (q + 1 < nq) prefetch((rr + 1 + a.ney) % a.ney, bufs + ((q + 1) & 1) * (N2 * PW));
+    // ---- P2: Sx' along x, Di, Sx back ----------------------------------------------------------------------------------
+    if (validA) {
+      const bool eox = Tx[0] != 0.0;
+      const double ly = sTy[TB::OFF_LAM + jA] / (hy * hy);
       double c[N2], o[N2];
 #pragma unroll
-      for (int i = 0; i < N2; ++i) c[i] = S1[jA * PW + eA * S + i];
-#pragma unroll
-      for (int m = 0; m < N2; ++m) o[m] = 0.0;
-#pragma unroll
-      for (int i = 0; i < N2; ++i) {
-#pragma unroll
-        for (int m = 0; m < N2; ++m) o[m] = fma(Tx[i + m * N2], c[i], o[m]);
-      }
+      for (int i = 0; i < N2; ++i) c[i] = S1[colA + i];
+      if (eox) fdm_fwd<N2, true>(Tx, c, o);
+      else fdm_fwd<N2, false>(Tx, c, o);
       // Di = 1/(nu*(lx+ly)+k) (p2d_explicit.jl:131-134), times the 1/(hx*hy) of the two S/sqrt(h) pairs
-      const double sc = 1.0 / (hx * hy);
+      const double sc = 1.0 / (hx * hy), ihx2 = 1.0 / (hx * hx);
 #pragma unroll
       for (int m = 0; m < N2; ++m) {
-        const double lam = a.nu * (Tx[N2 * N2 + m] / (hx * hx) + ly) + a.k;
+        const double lam = a.nu * (Tx[TB::OFF_LAM + m] * ihx2 + ly) + a.k;
         double d = 1.0 / lam;
         if (!(fabs(d) <= 1e8)) d = 0.0;  // null mode of an all-free subdomain; padding modes (lambda = inf) give 0 anyway
         o[m] *= d * sc;
       }
+      if (eox) fdm_bwd<N2, true>(Tx, o, c);
+      else fdm_bwd<N2, false>(Tx, o, c);
 #pragma unroll
-      for (int i = 0; i < N2; ++i) c[i] = 0.0;
-#pragma unroll
-      for (int m = 0; m < N2; ++m) {
-#pragma unroll
-        for (int i = 0; i < N2; ++i) c[i] = fma(Tx[i + m * N2], o[m], c[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < N2; ++i) S1[jA * PW + eA * S + i] = c[i];
+      for (int i = 0; i < N2; ++i) S1[colA + i] = c[i];
     }
-  }
-  __syncthreads();
-  // ---- mapping B: Sy back along y, store the tile column -----------------------------------------------------------
-  if (actB) {
-    double c[N2], o[N2];
+    __syncthreads();
+    // ---- P3: Sy back along y; interface columns go back to the buffer ------------------------------------------------
+    double g[N2];
+    {
+      double c[N2];
 #pragma unroll
-    for (int m = 0; m < N2; ++m) c[m] = S1[m * PW + eB * S + iB];
+      for (int m = 0; m < N2; ++m) c[m] = inB ? S1[m * PW + colB] : 0.0;
+      if (eoy) fdm_bwd<N2, true>(sTy, c, g);
+      else fdm_bwd<N2, false>(sTy, c, g);
+      if (inB && (iB <= 1 || iB >= N)) {
 #pragma unroll
-    for (int jj = 0; jj < N2; ++jj) o[jj] = 0.0;
-#pragma unroll
-    for (int m = 0; m < N2; ++m) {
-#pragma unroll
-      for (int jj = 0; jj < N2; ++jj) o[jj] = fma(sTy[jj + m * N2], c[m], o[jj]);
-    }
-    double* dst = a.fat + (size_t)(ey * N2) * a.fpitch + (size_t)ex * N2 + iB;
-#pragma unroll
-    for (int jj = 0; jj < N2; ++jj) dst[(size_t)jj * a.fpitch] = o[jj];
-  }
-}
-
-// value the tiles leave on the LOCAL copy (ex,i,ey,j) of a node: own tile entry + the extension entries of the
-// neighbouring tiles that land on it (fixed order of additions)
-__device__ __forceinline__ double fdm_zloc(const FdmArgs& a, int ex, int i, int ey, int j) {
-  const int N = a.N, N2 = N + 2;
-  auto fat = [&](int fx, int ii, int fy, int jj) {
-    return a.fat[(size_t)(fy * N2 + jj) * a.fpitch + (size_t)fx * N2 + ii];
-  };
-  const bool wrapy = a.pery && a.ney == a.Ey;
-  const bool hasL = ex > 0 || a.perx, hasR = ex < a.Ex - 1 || a.perx;
-  const bool hasB = ey > 0 || wrapy, hasT = ey < a.ney - 1 || wrapy;
-  const int exL = (ex + a.Ex - 1) % a.Ex, exR = (ex + 1) % a.Ex;
-  const int eyB = (ey + a.ney - 1) % a.ney, eyT = (ey + 1) % a.ney;
-  const bool l = i == 1 && hasL, r = i == N - 2 && hasR, b = j == 1 && hasB, tt = j == N - 2 && hasT;
-  double z = fat(ex, i + 1, ey, j + 1);
-  if (l) z = __dadd_rn(z, fat(exL, N + 1, ey, j + 1));
-  if (r) z = __dadd_rn(z, fat(exR, 0, ey, j + 1));
-  if (b) z = __dadd_rn(z, fat(ex, i + 1, eyB, N + 1));
-  if (tt) z = __dadd_rn(z, fat(ex, i + 1, eyT, 0));
-  if (l && b) z = __dadd_rn(z, fat(exL, N + 1, eyB, N + 1));
-  if (r && b) z = __dadd_rn(z, fat(exR, 0, eyB, N + 1));
-  if (l && tt) z = __dadd_rn(z, fat(exL, N + 1, eyT, 0));
-  if (r && tt) z = __dadd_rn(z, fat(exR, 0, eyT, 0));
-  return z;
-}
-
-__global__ void __launch_bounds__(256) semb_fdm_combine_kernel(const FdmArgs a) {
-  __shared__ double red[32];
-  __shared__ double sh_tot[2];
-  if (a.pcg && a.scal->done) return;
-  const int N = a.N;
-  const bool wrapy = a.pery && a.ney == a.Ey;
-  double acc = 0.0;
-  for (int row = blockIdx.y * blockDim.y + threadIdx.y; row < a.nyl; row += gridDim.y * blockDim.y) {
-    const int ey = row / N, j = row - ey * N;
-    // partner copy in y (gatherScatter.jl:13: duplicates of a node on an element interface)
-    int eyp = -1, jp = 0;
-    if (j == N - 1 && (ey < a.ney - 1 || wrapy)) eyp = (ey + 1) % a.ney, jp = 0;
-    else if (j == 0 && (ey > 0 || wrapy)) eyp = (ey + a.ney - 1) % a.ney, jp = N - 1;
-    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < a.nxl; x += gridDim.x * blockDim.x) {
-      const int ex = x / N, i = x - ex * N;
-      int exp_ = -1, ip = 0;
-      if (i == N - 1 && (ex < a.Ex - 1 || a.perx)) exp_ = (ex + 1) % a.Ex, ip = 0;
-      else if (i == 0 && (ex > 0 || a.perx)) exp_ = (ex + a.Ex - 1) % a.Ex, ip = N - 1;
-      double g = fdm_zloc(a, ex, i, ey, j);
-      if (exp_ >= 0) g = __dadd_rn(g, fdm_zloc(a, exp_, ip, ey, j));      // x pair first ...
-      if (eyp >= 0) {
-        double h = fdm_zloc(a, ex, i, eyp, jp);
-        if (exp_ >= 0) h = __dadd_rn(h, fdm_zloc(a, exp_, ip, eyp, jp));
-        g = __dadd_rn(g, h);                                             // ... then the y pair of the x pairs
+        for (int jj = 0; jj < N2; ++jj) S1[jj * PW + colB] = g[jj];
       }
-      const bool z = (x == 0 && a.mx0) || (x == a.nxl - 1 && a.mx1) || (row == 0 && a.my0) || (row == a.nyl - 1 && a.my1);
-      const double h = __dmul_rn(z ? 0.0 : 1.0, __dmul_rn(__dmul_rn(a.wx[x], a.wy[row]), g));
-      const size_t idx = (size_t)row * a.pitch + x;
+    }
+    __syncthreads();
+    // ---- P4: sums over the tiles that hold a node, W, mask, store ---------------------------------------------------
+    if (!outB) continue;
+    {
+      // x: the neighbour tiles' extension columns (left, then right), then the x pair
+      const int i = iB - 1;
+      if (i == 1 && hasL) {
+#pragma unroll
+        for (int jj = 0; jj < N2; ++jj) g[jj] = __dadd_rn(g[jj], S1[jj * PW + (eB - 1) * S + N + 1]);
+      }
+      if (i == N - 2 && hasR) {
+#pragma unroll
+        for (int jj = 0; jj < N2; ++jj) g[jj] = __dadd_rn(g[jj], S1[jj * PW + (eB + 1) * S]);
+      }
+      if (i == 0 && hasL) {
+#pragma unroll
+        for (int jj = 0; jj < N2; ++jj) g[jj] = __dadd_rn(g[jj], S1[jj * PW + (eB - 1) * S + N]);
+      }
+      if (i == N - 1 && hasR) {
+#pragma unroll
+        for (int jj = 0; jj < N2; ++jj) g[jj] = __dadd_rn(g[jj], S1[jj * PW + (eB + 1) * S + 1]);
+      }
+    }
+    auto write = [&](int row, double gv) {
+      const bool z = mzx || (row == 0 && a.my0) || (row == a.nyl - 1 && a.my1);
+      const double h = __dmul_rn(z ? 0.0 : 1.0, __dmul_rn(__dmul_rn(wxB, a.wy[row]), gv));
+      const size_t idx = (size_t)row * a.pitch + xB;
       a.out[idx] = h;
-      if (a.pcg) acc += __dmul_rn(__dmul_rn(a.r[idx], h), a.mult_x[x] * a.mult_y[row]);  // pcg.jl:45
+      if (a.pcg) acc += __dmul_rn(__dmul_rn(a.r[idx], h), mxB * a.mult_y[row]);  // pcg.jl:45
+    };
+    if (rr < r0) {  // halo row below the chunk: only what the next element row needs of it
+      pend0 = g[N - 1], pend1 = g[N], prevN1 = g[N + 1];
+      continue;
+    }
+    const bool hb = ey > 0 || wrapy, ht = ey < a.ney - 1 || wrapy;
+    const int ep = (ey + a.ney - 1) % a.ney;  // element row of the previous tile row
+    if (rr >= r1) {  // halo row above the chunk: finishes the last two lines of the chunk
+      write(ep * N + N - 2, __dadd_rn(pend0, g[0]));
+      write(ep * N + N - 1, __dadd_rn(pend1, g[1]));
+      continue;
+    }
+    const double val1 = hb ? __dadd_rn(g[2], prevN1) : g[2];  // line 1: own tile + the tile below's extension row
+    if (hb) {
+      const double s = __dadd_rn(pend1, g[1]);                // y pair (after the x pairs)
+      if (rr > r0) {
+        write(ep * N + N - 2, __dadd_rn(pend0, g[0]));        // line N-2 below: its tile + this tile's extension row
+        write(ep * N + N - 1, s);
+      }
+      write(ey * N, s);
+    } else {
+      write(ey * N, g[1]);
+    }
+#pragma unroll
+    for (int j = 1; j <= N - 3; ++j) write(ey * N + j, j == 1 ? val1 : g[j + 1]);
+    pend0 = (N == 3) ? val1 : g[N - 1], pend1 = g[N], prevN1 = g[N + 1];
+    if (!ht) {
+      write(ey * N + N - 2, pend0);
+      write(ey * N + N - 1, pend1);
     }
   }
+
   if (a.pcg) {
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
     const int bid = blockIdx.y * gridDim.x + blockIdx.x, nb = gridDim.x * gridDim.y;
-    const double bs = semb_block_sum(acc, red, tid, nt);
-    if (semb_last_block_uniform(bs, 0.0, a.partials, nullptr, a.counter, nb, bid, red, tid, nt, sh_tot)) {
-      if (tid == 0) {
+    const double bs = semb_block_sum(acc, red, t, C::T);
+    if (semb_last_block_uniform(bs, 0.0, a.partials, nullptr, a.counter, nb, bid, red, t, C::T, sh_tot)) {
+      if (t == 0) {
         // t = sum(r .* h .* mult); norm(r,Inf) was left in red[2] by the init / update kernel: advance the PCG state
         SembScal* s = a.scal;
         const double tnew = sh_tot[0], rmax = s->red[2];
@@ -282,20 +482,57 @@ __global__ void semb_fdm_lengths_kernel(const double* __restrict__ B, const doub
   }
 }
 
+// Launch geometry: strips of at most BX-2 output elements; the number of chunks minimises (waves of CTAs) x (element
+// rows a CTA marches through, its two halo rows included)
 template <int N>
-int launch_solve(semb_ctx* ctx, const FdmArgs& a) {
+int launch_fdm(semb_ctx* ctx, const FdmArgs& a, int npartials) {
   using C = FdmCfg<N>;
-  auto kern = semb_fdm_solve_kernel<N>;
+  auto kern = semb_fdm_kernel<N>;
   static bool attr_done[64] = {false};
+  static int occ[64] = {0};
   const int dev = ctx->device & 63;
   if (!attr_done[dev]) {
     SEMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    SEMB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[dev], kern, 256, C::SMEM));
+    if (occ[dev] < 1) occ[dev] = 1;
     attr_done[dev] = true;
   }
-  kern<<<dim3((a.Ex + C::BX - 1) / C::BX, a.ney), 256, C::SMEM, ctx->stream>>>(a);
+  const int nstrips = (a.Ex + C::BX - 3) / (C::BX - 2);
+  const long long slots = (long long)occ[dev] * ctx->sm_count;
+  int best = 1;
+  long long best_cost = -1;
+  for (int nch = 1; nch <= a.ney && (long long)nch * nstrips <= npartials; ++nch) {
+    const long long waves = ((long long)nstrips * nch + slots - 1) / slots;
+    const long long cost = waves * ((a.ney + nch - 1) / nch + 2);
+    if (best_cost < 0 || cost < best_cost) best_cost = cost, best = nch;
+  }
+  kern<<<dim3(nstrips, best), 256, C::SMEM, ctx->stream>>>(a);
   SEMB_CHECK_CUDA(cudaGetLastError());
   ctx->launches++;
   return SEMB_OK;
+}
+
+int fdm_slot_size(int N) {
+  switch (N) {
+#define SEMB_CASE(n) \
+  case n:            \
+    return FdmTab<n + 2>::SIZE;
+    SEMB_CASE(3) SEMB_CASE(4) SEMB_CASE(5) SEMB_CASE(6) SEMB_CASE(7) SEMB_CASE(8) SEMB_CASE(9) SEMB_CASE(10) SEMB_CASE(11)
+    SEMB_CASE(12) SEMB_CASE(13) SEMB_CASE(14) SEMB_CASE(15) SEMB_CASE(16) SEMB_CASE(17)
+#undef SEMB_CASE
+  }
+  return 0;
+}
+void fdm_slot_fill(int N, const double* S, const double* lam, double* slot) {
+  switch (N) {
+#define SEMB_CASE(n)                       \
+  case n:                                  \
+    FdmTab<n + 2>::fill(S, lam, slot);     \
+    break;
+    SEMB_CASE(3) SEMB_CASE(4) SEMB_CASE(5) SEMB_CASE(6) SEMB_CASE(7) SEMB_CASE(8) SEMB_CASE(9) SEMB_CASE(10) SEMB_CASE(11)
+    SEMB_CASE(12) SEMB_CASE(13) SEMB_CASE(14) SEMB_CASE(15) SEMB_CASE(16) SEMB_CASE(17)
+#undef SEMB_CASE
+  }
 }
 
 }  // namespace
@@ -304,8 +541,7 @@ struct semb_fdm {
   semb_mesh* m = nullptr;
   double nu = 1.0, k = 0.0;
   int mx0 = 0, mx1 = 0, my0 = 0, my1 = 0;
-  double *d_hx = nullptr, *d_hy = nullptr, *d_tab = nullptr, *d_fat = nullptr, *d_wx = nullptr, *d_wy = nullptr;
-  long long fpitch = 0;
+  double *d_hx = nullptr, *d_hy = nullptr, *d_tab = nullptr, *d_wx = nullptr, *d_wy = nullptr;
 };
 
 int semb_fdm_free_impl(semb_fdm* f) {
@@ -313,7 +549,6 @@ int semb_fdm_free_impl(semb_fdm* f) {
   cudaFree(f->d_hx);
   cudaFree(f->d_hy);
   cudaFree(f->d_tab);
-  cudaFree(f->d_fat);
   cudaFree(f->d_wx);
   cudaFree(f->d_wy);
   delete f;
@@ -325,7 +560,7 @@ int semb_fdm_free_impl(semb_fdm* f) {
 int semb_fdm_create_impl(semb_mesh* m, double nu, double k, int mx0, int mx1, int my0, int my1, int gy0, int gy1,
                          semb_fdm** out) {
   semb_ctx* c = m->ctx;
-  const int N = m->nr, N2 = N + 2, TSZ = N2 * N2 + N2;
+  const int N = m->nr, N2 = N + 2;
   semb_fdm* f = new semb_fdm();
   *out = f;
   f->m = m;
@@ -333,14 +568,16 @@ int semb_fdm_create_impl(semb_mesh* m, double nu, double k, int mx0, int mx1, in
   f->k = k;
   f->mx0 = mx0, f->mx1 = mx1, f->my0 = my0, f->my1 = my1;
   // reference decompositions: classes 0 interior, 1 first, 2 last, 3 single; kinds 0 neighbour, 1 Dirichlet, 2 free
-  std::vector<double> tab((size_t)2 * 4 * TSZ, 0.0);
+  const int TSZ = fdm_slot_size(N);
+  SEMB_REQUIRE(TSZ > 0, "fdm: no kernel for nr = %d (3..17)", N);
+  std::vector<double> tab((size_t)2 * 4 * TSZ, 0.0), Sm((size_t)N2 * N2), lam(N2);
   for (int dir = 0; dir < 2; ++dir) {
     const std::vector<double>& D = dir == 0 ? m->hDr : m->hDs;
     const std::vector<double>& w = dir == 0 ? m->hwr : m->hws;
     const int klo = dir == 0 ? (mx0 ? 1 : 2) : (gy0 ? 1 : 2), khi = dir == 0 ? (mx1 ? 1 : 2) : (gy1 ? 1 : 2);
     for (int cls = 0; cls < 4; ++cls) {
-      double* T = tab.data() + ((size_t)dir * 4 + cls) * TSZ;
-      SEMB_TRY(semb_fdm_tables(N, D.data(), w.data(), (cls & 1) ? klo : 0, (cls & 2) ? khi : 0, T, T + N2 * N2));
+      SEMB_TRY(semb_fdm_tables(N, D.data(), w.data(), (cls & 1) ? klo : 0, (cls & 2) ? khi : 0, Sm.data(), lam.data()));
+      fdm_slot_fill(N, Sm.data(), lam.data(), tab.data() + ((size_t)dir * 4 + cls) * TSZ);
     }
   }
   SEMB_CHECK_CUDA(cudaMalloc(&f->d_tab, tab.size() * sizeof(double)));
@@ -378,8 +615,6 @@ int semb_fdm_create_impl(semb_mesh* m, double nu, double k, int mx0, int mx1, in
   cudaFree(d_ws);
   SEMB_CHECK_CUDA(e);
   c->launches++;
-  f->fpitch = ((long long)m->Ex * N2 + 15) / 16 * 16;
-  SEMB_CHECK_CUDA(cudaMalloc(&f->d_fat, (size_t)f->fpitch * m->ney * N2 * sizeof(double)));
   return SEMB_OK;
 }
 
@@ -390,7 +625,6 @@ int semb_fdm_apply_impl(semb_fdm* f, const double* r, double* out, int pcg) {
   FdmArgs a;
   a.r = r;
   a.out = out;
-  a.fat = f->d_fat;
   a.tab = f->d_tab;
   a.hx = f->d_hx;
   a.hy = f->d_hy;
@@ -399,7 +633,6 @@ int semb_fdm_apply_impl(semb_fdm* f, const double* r, double* out, int pcg) {
   a.mult_x = m->d_wx1d;
   a.mult_y = m->d_wy1d;
   a.pitch = m->pitch;
-  a.fpitch = f->fpitch;
   a.N = m->nr;
   a.Ex = m->Ex;
   a.Ey = m->Ey;
@@ -419,7 +652,7 @@ int semb_fdm_apply_impl(semb_fdm* f, const double* r, double* out, int pcg) {
   switch (m->nr) {
 #define SEMB_CASE(n) \
   case n:            \
-    SEMB_TRY(launch_solve<n>(c, a)); \
+    SEMB_TRY(launch_fdm<n>(c, a, m->npartials)); \
     break;
     SEMB_CASE(3) SEMB_CASE(4) SEMB_CASE(5) SEMB_CASE(6) SEMB_CASE(7) SEMB_CASE(8) SEMB_CASE(9) SEMB_CASE(10) SEMB_CASE(11)
     SEMB_CASE(12) SEMB_CASE(13) SEMB_CASE(14) SEMB_CASE(15) SEMB_CASE(16) SEMB_CASE(17)
@@ -428,18 +661,5 @@ int semb_fdm_apply_impl(semb_fdm* f, const double* r, double* out, int pcg) {
       semb_set_error("fdm: no kernel for nr = %d (3..17)", m->nr);
       return SEMB_EINVAL;
   }
-  int bx = 32;
-  while (bx < 256 && bx < m->nxl) bx <<= 1;
-  const int by = 256 / bx;
-  int gx = (m->nxl + bx - 1) / bx;
-  if (gx > 64) gx = 64;
-  int gy = (m->nyl + by - 1) / by;
-  const int cap = m->npartials / gx;
-  if (gy > cap) gy = cap;
-  if (gy > c->sm_count * 16) gy = c->sm_count * 16;
-  if (gy < 1) gy = 1;
-  semb_fdm_combine_kernel<<<dim3(gx, gy), dim3(bx, by), 0, c->stream>>>(a);
-  SEMB_CHECK_CUDA(cudaGetLastError());
-  c->launches++;
   return SEMB_OK;
 }
