@@ -238,6 +238,58 @@ def time_apply_and_pcg(ctx, dist, msh, steps, warmup, bc="DDDD", pcg_iters=100):
     return ms_apply, ms_pcg
 
 
+ALG_BYTES_FDM = 16.0  # read r, write h (the tiles never leave the SM)
+
+
+def fdm_block(sem, ctx, m3, n3, peak):
+    """FDM preconditioner on BASELINE configs[2]'s order: cost of one application and of a preconditioned
+    PCG iteration on the 1e8-DOF mesh, and the Poisson solve (f = 1, DDDD, tol 1e-8 * norm(b,Inf)) of an order-12
+    128x128-element mesh with and without it -- iterations and wall time of the whole device-resident solve."""
+    import ctypes as C
+    u, out, x = m3.field().fill_random(1), m3.field(), m3.field()
+    sem.FdmPrecond(m3, "DDDD", 1.0, 0.0)
+    for _ in range(3):
+        m3._fdm.apply_device(u, out)
+    ctx.sync()
+    ctx.timer_start()
+    for _ in range(30):
+        m3._fdm.apply_device(u, out)
+    fms = ctx.timer_stop() / 30
+    m3.pcg_begin(u, x, nu=1.0, k=0.0, bc="DDDD", tol=0.0, maxiter=10 ** 9, precond=2)
+    m3.pcg_iterate(3)
+    ctx.sync()
+    ctx.timer_start()
+    m3.pcg_iterate(30)
+    pms = ctx.timer_stop() / 30
+    for f in (u, out, x):
+        f.free()
+    ms = sem.Mesh(13, 13, 128, 128, (False, False), "wavy", ctx=ctx)
+    b, rhs, xs = ms.field().fill(1.0), ms.field(), ms.field()
+    ms.mass_device(b, rhs)
+    ms.mask_bc_device(rhs, "DDDD", b)
+    ms.gs_device(b, rhs)
+    tol = 1e-8 * ms.norm_inf(rhs)
+    sem.FdmPrecond(ms, "DDDD", 1.0, 0.0)
+    res = {}
+    for name, precond in (("none", 0), ("fdm", 2)):
+        o, keep = sem._pcg_opts(1.0, 0.0, "DDDD", None, precond, 1.0, tol, 200000, 0)
+        it, rn = C.c_longlong(), C.c_double()
+        ctx.sync()
+        t0 = time.perf_counter()
+        sem._lib.check(ctx.lib.semb_pcg(ms.h, C.byref(o), rhs.h, xs.h, C.byref(it), C.byref(rn)))
+        ctx.sync()
+        res[name] = (int(it.value), time.perf_counter() - t0)
+    nsolve = ms.shape[0] * ms.shape[1]
+    ms.free()
+    return {"ms_per_application": fms, "hbm_frac_16B": ALG_BYTES_FDM * n3 / (fms * 1e-3) / 1e9 / peak,
+            "pcg_ms_per_iter": pms,
+            "solve": {"workload": "Poisson solve, order 12, 128x128 elements (%d DOF), wavy box, f = 1, DDDD, tol 1e-8*norm(b,Inf)" % nsolve,
+                      "iters_none": res["none"][0], "seconds_none": res["none"][1],
+                      "iters_fdm": res["fdm"][0], "seconds_fdm": res["fdm"][1],
+                      "speedup": res["none"][1] / res["fdm"][1]},
+            "note": "overlapping Schwarz with the reference's lapl_fdm tensor solve per element (lapl.jl:105-119), one launch per application"}
+
+
 def strong_block(sem, ctx, dist, world, rank, local, steps, peak):
     """Strong scaling of the FIXED ~1e8-DOF meshes north_star / BASELINE configs[2] name: the whole mesh on ONE GPU (a
     second, communicator-less context on this rank's own GPU; mean over the ranks' GPUs) against the same mesh split
@@ -448,6 +500,9 @@ def run_semb(args):
         n3 = m3.shape[0] * m3.shape[1]
         a3, p3 = time_apply_and_pcg(ctx, None, m3, min(args.steps, 100), 3)
         pl3 = m3.plan()
+        fdm3 = None
+        if not args.skip_fdm:
+            fdm3 = fdm_block(sem, ctx, m3, n3, peak)
         m3.free()
         extra["cfg3_order12"] = {"workload": "Poisson opLHS + PCG, order 12, 776x776 elements, wavy box, %d DOF, 1 GPU" % n3,
                                  "apply_ms": a3, "apply_gdof_per_s": n3 / a3 / 1e6,
@@ -455,6 +510,8 @@ def run_semb(args):
                                  "pcg_ms_per_iter": p3, "pcg_iters_per_s": 1e3 / p3,
                                  "pcg_hbm_frac_112B": ALG_BYTES_PCG_ITER * n3 / (p3 * 1e-3) / 1e9 / peak,
                                  "strips_x_chunks": [pl3["nstrips"], pl3["nchunks"]]}
+        if fdm3:
+            extra["cfg3_order12"]["fdm_preconditioner"] = fdm3
 
     # ---- strong scaling of the fixed 1e8-DOF meshes (order 8 1112^2; cfg3 = order 12 776^2) over the ranks -------------
     if world > 1 and not args.skip_strong:
@@ -705,6 +762,7 @@ def main():
     ap.add_argument("--skip-cfg4", action="store_true")
     ap.add_argument("--skip-cfg5", action="store_true")
     ap.add_argument("--skip-cfg3", action="store_true")
+    ap.add_argument("--skip-fdm", action="store_true")
     ap.add_argument("--skip-strong", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--skip-sustained", action="store_true")

@@ -1386,7 +1386,7 @@ extern "C" int semb_pcg_begin(semb_mesh* m, const semb_pcg_opts* o, const semb_f
   SEMB_REQUIRE(o->precond != 1 || m->arr[SEMB_B], "pcg: diagonal preconditioner needs B");
   SEMB_REQUIRE(o->precond != 2 || (m->fdm && m->fast && !m->pcg_custom),
                "pcg: precond = 2 needs an FDM preconditioner on this mesh (semb_fdm_create) and the fused operator path");
-  SEMB_REQUIRE(o->precond != 2 || c->nranks == 1, "pcg: the FDM preconditioner runs on one rank (its tile exchange between slabs is not built)");
+  SEMB_REQUIRE(o->precond != 2 || c->nranks == 1 || m->p2p, "pcg: on several ranks the FDM preconditioner needs the peer-memory transport");
   MaskFlags f;
   SEMB_TRY(parse_bc(m, o->bc, &f));
   SEMB_TRY(ensure_tmp(m, &m->w_r));
@@ -2166,7 +2166,6 @@ extern "C" int semb_fdm_create(semb_mesh* m, const char bc[4], double nu, double
   SEMB_REQUIRE(m->nr == m->ns && m->nr >= 3 && m->nr <= SEMB_MAXN, "fdm: needs nr == ns in 3..%d", SEMB_MAXN);
   SEMB_REQUIRE(m->arr[SEMB_B] && m->arr[SEMB_G11] && m->arr[SEMB_G22], "fdm: mesh needs B, G11, G22");
   SEMB_REQUIRE(!(m->perx && m->Ex < 2) && !(m->pery && m->Ey < 2), "fdm: a periodic direction needs at least 2 elements");
-  SEMB_REQUIRE(m->ctx->nranks == 1, "fdm: the preconditioner runs on one rank (its tile exchange between slabs is not built)");
   SEMB_REQUIRE(nu > 0.0 && k >= 0.0, "fdm: needs nu > 0, k >= 0");
   MaskFlags f;
   SEMB_TRY(parse_bc(m, bc, &f));

@@ -26,8 +26,8 @@ struct FdmArgs {
   const double* r;      // residual (continuous)
   double* out;          // h = opM(r)
   const double* tab;    // [dir 2][class 4][N2*N2 + N2]: S (column-major: S[ii + c*N2]) then lambda
-  const double* hx;     // [ney][Ex] element half-lengths
-  const double* hy;
+  const double* el;     // [3][nel]: 1/hx^2, 1/hy^2, 1/(hx*hy) of the elements (hx, hy: half-lengths)
+  long long nel;
   const double* wx;     // W = wx[x] * wy[y]
   const double* wy;
   const double* mult_x; // mult(x,y) = mult_x[x] * mult_y[y]  (PCG reduction)
@@ -40,6 +40,17 @@ struct FdmArgs {
   double* partials;
   unsigned* counter;
   int pcg;      // 1: inside pcg (early exit on done; reduction + advance), 2: same, first call (pcg.jl:25-33 state)
+  // ---- several ranks (y-slabs): the N rows of r next to a slab boundary that the neighbour's halo tiles need travel
+  // through peer memory as flag-in-data entries (semb_ll_store), pushed by the first CTA row at kernel start
+  int has_lo, has_hi;
+  const uint4* ghost;   // local ghost rows [parity][side][N][pitch]; side 0: rows Y = -N-2, -N..-2 below the slab,
+                        // side 1: rows Y = nyl+1..nyl+N-1, nyl+N+1 above it (Y = -1 and Y = nyl are the shared lines)
+  uint4* peer_lo;       // the lower neighbour's ghost rows (we fill its side 1), the upper neighbour's (its side 0)
+  uint4* peer_hi;
+  const double* el_lo;  // [3][Ex] scalings of the neighbours' adjoining element rows
+  const double* el_hi;
+  unsigned long long ep_host;   // epoch = ep_host (stand-alone applications) + *ep_dev (applications inside pcg) + 1
+  unsigned long long* ep_dev;
 };
 
 // class of an element in a direction: 0 interior (neighbours on both sides), 1 first, 2 last, 3 single
@@ -205,29 +216,41 @@ struct FdmCfg {
   static constexpr int MINB = MAXB >= 3 ? 3 : (MAXB >= 2 ? 2 : 1);
 };
 
-__device__ __forceinline__ void fdm_cp_async8(double* dst_smem, const double* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
-               : "memory");
+__device__ __forceinline__ void fdm_cp_async8(uint32_t dst_smem, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 __device__ __forceinline__ void fdm_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void fdm_cp_async_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// 1/x without the special-case branch of the IEEE division: MUFU.RCP64H and two Newton steps (<= 1 ulp); x = 0, +-inf
+// and NaN come out as NaN, which the caller's |d| <= 1e8 test turns into 0 like the reference's cut-off
+__device__ __forceinline__ double fdm_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
 
 // One launch per application.  A CTA owns a strip of up to BX-2 x-consecutive elements plus one halo element on either
 // side, and MARCHES through a chunk of element rows plus one halo row below and above (the halo tiles are computed twice,
 // by the two CTAs that need them: no exchange between CTAs, no second pass over the field).  Per element row:
-//   P1 (thread <-> tile column)   the (N+2) x (N+2) tiles of W.*r -- prefetched one element row ahead with cp.async into
+//   P1 (thread <-> tile column)   the (N+2) x (N+2) tiles of r -- prefetched one element row ahead with cp.async into
 //                                 the other tile buffer -- Sy' along y out of registers, back into the buffer in place
 //   P2 (thread <-> tile row)      Sx' along x, Di, Sx back along x, in place
 //   P3 (thread <-> tile column)   Sy back along y; the columns next to an element interface go back to the buffer
 //   P4 (same threads)             x sums (tile overlaps, then the x pair of gatherScatter.jl:13), y sums against the three
 //                                 rows carried in registers from the previous element row (overlaps, then the y pair),
-//                                 W, mask, store; inside pcg the sum(r.*h.*mult) partial (pcg.jl:45)
-// Every sum has two terms (three for N = 3), in a fixed order: the result does not depend on the launch geometry.
+//                                 mask, store; inside pcg the sum(r.*h.*mult) partial (pcg.jl:45)
+// The counting weights W are folded into the rows of the eigenvector tables (N >= 4: the weight of a tile node only
+// depends on the class of the element; N = 3 multiplies explicitly).  Every sum has two terms (three for N = 3), in a
+// fixed order: the result does not depend on the launch geometry.
 template <int N>
 __global__ void __launch_bounds__(256, FdmCfg<N>::MINB) semb_fdm_kernel(const FdmArgs a) {
   using C = FdmCfg<N>;
   using TB = FdmTab<C::N2>;
   constexpr int N2 = C::N2, BX = C::BX, S = C::S, PW = C::PW, TSZ = C::TSZ;
+  constexpr bool FOLDW = N >= 4;
   extern __shared__ __align__(16) double sm[];
   double* sTx = sm;                // [3][TSZ] x tables: slot = class (class 3, a single element, only occurs alone: slot 0)
   double* sTy = sTx + 3 * TSZ;     // [TSZ] y table of the current element row's class
@@ -236,12 +259,35 @@ __global__ void __launch_bounds__(256, FdmCfg<N>::MINB) semb_fdm_kernel(const Fd
   __shared__ double sh_tot[2];
   if (a.pcg && a.scal->done) return;
   const int t = threadIdx.x;
+  const size_t pitch = (size_t)a.pitch;
   // strip: output elements [o0, o1), tile slot e <-> element o0 - 1 + e
   const int o0 = (int)(((long long)blockIdx.x * a.Ex) / gridDim.x), o1 = (int)(((long long)(blockIdx.x + 1) * a.Ex) / gridDim.x);
   const int nout = o1 - o0;
   // chunk: output element rows [r0, r1), tile rows r0-1 .. r1
   const int r0 = (int)(((long long)blockIdx.y * a.ney) / gridDim.y), r1 = (int)(((long long)(blockIdx.y + 1) * a.ney) / gridDim.y);
   const bool wrapy = a.pery && a.ney == a.Ey;
+  const bool lo_any = wrapy || a.has_lo, hi_any = wrapy || a.has_hi;   // an element row below / above the slab exists
+  const bool ranks = a.has_lo || a.has_hi;
+  // (re-read where it is needed instead of kept in registers: *ep_dev only moves when the last CTA is done)
+  auto cur_epoch = [&]() { return a.ep_host + *(volatile unsigned long long*)a.ep_dev + 1ull; };
+  if (ranks && blockIdx.y == 0) {
+    const unsigned long long epoch = cur_epoch();
+    const int par = (int)(epoch & 1ull);
+    const unsigned tag = semb_ll_tag(epoch);
+    // the rows the neighbours' halo tiles read, for this strip's columns, straight into their memory over NVLink
+    const int xs0 = o0 * N, ncols = nout * N;
+    for (int i = t; i < N * ncols; i += C::T) {
+      const int sl = i / ncols, x = xs0 + i - sl * ncols;
+      if (a.has_lo) {
+        const int row = (sl < N - 1) ? 1 + sl : N + 1;
+        semb_ll_store(a.peer_lo + ((size_t)(2 * par + 1) * N + sl) * pitch + x, a.r[(size_t)row * pitch + x], tag);
+      }
+      if (a.has_hi) {
+        const int row = (sl == 0) ? a.nyl - N - 2 : a.nyl - N - 1 + sl;
+        semb_ll_store(a.peer_hi + ((size_t)(2 * par) * N + sl) * pitch + x, a.r[(size_t)row * pitch + x], tag);
+      }
+    }
+  }
   {
     const int sl1 = (a.Ex == 1 && !a.perx) ? 3 : 0;  // slot 0 holds class 0, or class 3 when that is the only one
     for (int q = t; q < 3 * TSZ; q += C::T) {
@@ -262,11 +308,22 @@ __global__ void __launch_bounds__(256, FdmCfg<N>::MINB) semb_fdm_kernel(const Fd
     else if (iB == N + 1) xB = hasR ? ((exB + 1) % a.Ex) * N + 1 : -1;
     else xB = exB * N + iB - 1;
   }
-  const double wxB = xB >= 0 ? a.wx[xB] : 0.0;
+  const double wxB = (!FOLDW && xB >= 0) ? a.wx[xB] : 0.0;
   const bool outB = validB && eB >= 1 && eB <= nout && iB >= 1 && iB <= N;   // this thread finishes node column xB
   const int colB = eB * S + iB;
   const bool mzx = outB && ((xB == 0 && a.mx0) || (xB == a.nxl - 1 && a.mx1));
-  const double mxB = (a.pcg && outB) ? a.mult_x[xB] : 0.0;
+  const double mxB = (a.pcg && outB) ? a.mult_x[xB] : 0.0, mxBh = mxB * 0.5;
+  // the tile column whose entries land on this node column as well (overlap with / x pair of the neighbour element)
+  int srcCol = -1;
+  if (outB) {
+    const int i = iB - 1;
+    if (i == 1 && hasL) srcCol = (eB - 1) * S + N + 1;
+    else if (i == N - 2 && hasR) srcCol = (eB + 1) * S;
+    else if (i == 0 && hasL) srcCol = (eB - 1) * S + N;
+    else if (i == N - 1 && hasR) srcCol = (eB + 1) * S + 1;
+  }
+  const bool src3 = N == 3 && outB && iB == 2 && hasL && hasR;  // N = 3: node 1 lies in both neighbours' extensions
+  const ptrdiff_t rd = a.r - a.out;
   // ---- mapping A: thread <-> (tile row jA, tile slot eA) -------------------------------------------------------------
   const int jA = t / BX, eA = t - jA * BX;
   int exA = o0 - 1 + eA;
@@ -276,37 +333,80 @@ __global__ void __launch_bounds__(256, FdmCfg<N>::MINB) semb_fdm_kernel(const Fd
   const double* Tx = sTx + (clsA == 3 ? 0 : clsA) * TSZ;
   const int colA = jA * PW + eA * S;
 
-  // local row of tile row jj of element row ey (-1: no such row)
-  auto row_of = [&](int ey, int jj) {
-    if (jj == 0) return (ey > 0) ? (ey - 1) * N + N - 2 : (wrapy ? (a.ney - 1) * N + N - 2 : -1);
-    if (jj == N + 1) return (ey < a.ney - 1) ? (ey + 1) * N + 1 : (wrapy ? 1 : -1);
-    return ey * N + jj - 1;
+  // one tile entry from outside the rows [N, nyl-N): local row, periodic image, neighbour rank's row (ghost) or nothing
+  auto fetch_edge = [&](int Y, double* dst) {
+    const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst);
+    if (Y >= 0 && Y < a.nyl) fdm_cp_async8(d32, a.r + (size_t)Y * pitch + xB);
+    else if (wrapy) fdm_cp_async8(d32, a.r + (size_t)((Y + a.nyl) % a.nyl) * pitch + xB);
+    else if (Y < 0 && a.has_lo) {
+      if (Y == -1) fdm_cp_async8(d32, a.r + xB);   // the shared line: the neighbour's last row = our row 0
+      else {
+        const unsigned long long epoch = cur_epoch();
+        *dst = semb_ll_load(a.ghost + ((size_t)(2 * (int)(epoch & 1ull)) * N + (Y == -N - 2 ? 0 : Y + N + 1)) * pitch + xB,
+                            semb_ll_tag(epoch), a.scal);
+      }
+    } else if (Y >= a.nyl && a.has_hi) {
+      const int d = Y - a.nyl;
+      if (d == 0) fdm_cp_async8(d32, a.r + (size_t)(a.nyl - 1) * pitch + xB);
+      else {
+        const unsigned long long epoch = cur_epoch();
+        *dst = semb_ll_load(a.ghost + ((size_t)(2 * (int)(epoch & 1ull) + 1) * N + (d == N + 1 ? N - 1 : d - 1)) * pitch + xB,
+                            semb_ll_tag(epoch), a.scal);
+      }
+    } else *dst = 0.0;
   };
-  auto prefetch = [&](int ey, double* buf) {
+  // an element row's tile columns: rows rr*N + {-2, 0..N-1, N+1} of this thread's global column
+  auto prefetch = [&](int rr, double* buf) {
     if (inB) {
+      double* dst = buf + colB;
+      if (xB < 0) {
 #pragma unroll
-      for (int jj = 0; jj < N2; ++jj) {
-        const int y = row_of(ey, jj);
-        double* dst = buf + jj * PW + colB;
-        if (xB >= 0 && y >= 0) fdm_cp_async8(dst, a.r + (size_t)y * a.pitch + xB);
-        else *dst = 0.0;
+        for (int jj = 0; jj < N2; ++jj) dst[jj * PW] = 0.0;
+      } else if (rr >= 1 && rr <= a.ney - 2) {
+        const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst);
+        const double* p = a.r + ((size_t)rr * N) * pitch + xB;
+        fdm_cp_async8(d32, p - 2 * pitch);
+#pragma unroll
+        for (int jj = 1; jj <= N; ++jj) {
+          fdm_cp_async8(d32 + jj * PW * 8, p);
+          p += pitch;
+        }
+        fdm_cp_async8(d32 + (N + 1) * PW * 8, p + pitch);
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < N2; ++jj) fetch_edge(rr * N + (jj == 0 ? -2 : (jj == N + 1 ? N + 1 : jj - 1)), dst + jj * PW);
       }
     }
     fdm_cp_async_commit();
   };
   // tile rows of this CTA: q = 0 .. nq-1 <-> rr = ra + q (halo rows outside a non-periodic slab do not exist)
-  const int ra = (r0 > 0 || wrapy) ? r0 - 1 : r0, rb = (r1 < a.ney || wrapy) ? r1 : r1 - 1;
+  const int ra = (r0 > 0 || lo_any) ? r0 - 1 : r0, rb = (r1 < a.ney || hi_any) ? r1 : r1 - 1;
   const int nq = rb - ra + 1;
-  prefetch((ra + a.ney) % a.ney, bufs);
+  prefetch(ra, bufs);
+  double el_n[3] = {1.0, 1.0, 0.0};
+  auto load_el = [&](int rr) {
+    if (validA) {
+      const double* pe;
+      long long st = a.nel;
+      if (rr >= 0 && rr < a.ney) pe = a.el + (size_t)rr * a.Ex + exA;
+      else if (wrapy) pe = a.el + (size_t)((rr + a.ney) % a.ney) * a.Ex + exA;
+      else pe = (rr < 0 ? a.el_lo : a.el_hi) + exA, st = a.Ex;
+      asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(el_n[0]) : "l"(pe));
+      asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(el_n[1]) : "l"(pe + st));
+      asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(el_n[2]) : "l"(pe + 2 * st));
+    }
+  };
+  load_el(ra);
+  __syncthreads();
+  const bool eox = Tx[0] != 0.0;
   int cy_loaded = -1;
   double pend0 = 0.0, pend1 = 0.0, prevN1 = 0.0;
   double acc = 0.0;
 
   for (int q = 0; q < nq; ++q) {
     const int rr = ra + q;
-    const int ey = (rr + a.ney) % a.ney, eyg = a.ey0 + ey;
     double* S1 = bufs + (q & 1) * (N2 * PW);
-    const int cy = fdm_class(eyg, a.Ey, a.pery);
+    const int cy = fdm_class((a.ey0 + rr + a.Ey) % a.Ey, a.Ey, a.pery);
     if (cy != cy_loaded) {  // (block-uniform; at most three times per CTA)
       __syncthreads();
       for (int i = t; i < TSZ; i += C::T) sTy[i] = a.tab[(size_t)(4 + cy) * TSZ + i];
@@ -314,44 +414,44 @@ __global__ void __launch_bounds__(256, FdmCfg<N>::MINB) semb_fdm_kernel(const Fd
       __syncthreads();
     }
     const bool eoy = sTy[0] != 0.0;
-    double hx = 1.0, hy = 1.0;
-    if (validA) hx = a.hx[(size_t)ey * a.Ex + exA], hy = a.hy[(size_t)ey * a.Ex + exA];
-    // ---- P1: W .* r, Sy' along y ------------------------------------------------------------------------------------
+    // element scalings 1/hx^2, 1/hy^2, 1/(hx*hy): loaded one element row ahead (volatile asm: the loads stay here)
+    const double ihx2 = el_n[0], ihy2 = el_n[1], sc = el_n[2];
+    if (q + 1 < nq) load_el(rr + 1);
+    // ---- P1: (W .*) r, Sy' along y ----------------------------------------------------------------------------------
     fdm_cp_async_wait();
-    {
+    if (inB) {
       double col[N2], o[N2];
 #pragma unroll
-      for (int jj = 0; jj < N2; ++jj) {
-        const int y = row_of(ey, jj);
-        const double wv = (y >= 0) ? __dmul_rn(wxB, a.wy[y]) : 0.0;
-        col[jj] = inB ? __dmul_rn(wv, S1[jj * PW + colB]) : 0.0;
+      for (int jj = 0; jj < N2; ++jj) col[jj] = S1[jj * PW + colB];
+      if (!FOLDW) {
+#pragma unroll
+        for (int jj = 0; jj < N2; ++jj) {
+          int y = rr * N + (jj == 0 ? -2 : (jj == N + 1 ? N + 1 : jj - 1));   // (N = 3: single rank only)
+          if (wrapy) y = (y + a.nyl) % a.nyl;
+          col[jj] = (y >= 0 && y < a.nyl) ? __dmul_rn(__dmul_rn(wxB, a.wy[y]), col[jj]) : 0.0;
+        }
       }
       if (eoy) fdm_fwd<N2, true>(sTy, col, o);
       else fdm_fwd<N2, false>(sTy, col, o);
-      if (inB) {
 #pragma unroll
-        for (int c = 0; c < N2; ++c) S1[c * PW + colB] = o[c];
-      }
+      for (int c = 0; c < N2; ++c) S1[c * PW + colB] = o[c];
     }
     __syncthreads();
     // the other buffer is free (its last readers were the P4 of the previous element row): next element row's tiles
-    if (q + 1 < nq) prefetch((rr + 1 + a.ney) % a.ney, bufs + ((q + 1) & 1) * (N2 * PW));
+    if (q + 1 < nq) prefetch(rr + 1, bufs + ((q + 1) & 1) * (N2 * PW));
     // ---- P2: Sx' along x, Di, Sx back ----------------------------------------------------------------------------------
     if (validA) {
-      const bool eox = Tx[0] != 0.0;
-      const double ly = sTy[TB::OFF_LAM + jA] / (hy * hy);
+      const double ly = sTy[TB::OFF_LAM + jA] * ihy2;
       double c[N2], o[N2];
 #pragma unroll
       for (int i = 0; i < N2; ++i) c[i] = S1[colA + i];
       if (eox) fdm_fwd<N2, true>(Tx, c, o);
       else fdm_fwd<N2, false>(Tx, c, o);
       // Di = 1/(nu*(lx+ly)+k) (p2d_explicit.jl:131-134), times the 1/(hx*hy) of the two S/sqrt(h) pairs
-      const double sc = 1.0 / (hx * hy), ihx2 = 1.0 / (hx * hx);
 #pragma unroll
       for (int m = 0; m < N2; ++m) {
-        const double lam = a.nu * (Tx[TB::OFF_LAM + m] * ihx2 + ly) + a.k;
-        double d = 1.0 / lam;
-        if (!(fabs(d) <= 1e8)) d = 0.0;  // null mode of an all-free subdomain; padding modes (lambda = inf) give 0 anyway
+        double d = fdm_rcp(fma(a.nu, fma(Tx[TB::OFF_LAM + m], ihx2, ly), a.k));
+        if (!(fabs(d) <= 1e8)) d = 0.0;  // null mode of an all-free subdomain; padding modes (lambda = inf) give 0 too
         o[m] *= d * sc;
       }
       if (eox) fdm_bwd<N2, true>(Tx, o, c);
@@ -362,75 +462,69 @@ __global__ void __launch_bounds__(256, FdmCfg<N>::MINB) semb_fdm_kernel(const Fd
     __syncthreads();
     // ---- P3: Sy back along y; interface columns go back to the buffer ------------------------------------------------
     double g[N2];
-    {
+    if (inB) {
       double c[N2];
 #pragma unroll
-      for (int m = 0; m < N2; ++m) c[m] = inB ? S1[m * PW + colB] : 0.0;
+      for (int m = 0; m < N2; ++m) c[m] = S1[m * PW + colB];
       if (eoy) fdm_bwd<N2, true>(sTy, c, g);
       else fdm_bwd<N2, false>(sTy, c, g);
-      if (inB && (iB <= 1 || iB >= N)) {
+      if (iB <= 1 || iB >= N) {
 #pragma unroll
         for (int jj = 0; jj < N2; ++jj) S1[jj * PW + colB] = g[jj];
       }
     }
     __syncthreads();
-    // ---- P4: sums over the tiles that hold a node, W, mask, store ---------------------------------------------------
+    // ---- P4: sums over the tiles that hold a node, mask, store ------------------------------------------------------
     if (!outB) continue;
-    {
-      // x: the neighbour tiles' extension columns (left, then right), then the x pair
-      const int i = iB - 1;
-      if (i == 1 && hasL) {
+    if (srcCol >= 0) {  // x: the neighbour tile's extension column, or the x pair
 #pragma unroll
-        for (int jj = 0; jj < N2; ++jj) g[jj] = __dadd_rn(g[jj], S1[jj * PW + (eB - 1) * S + N + 1]);
-      }
-      if (i == N - 2 && hasR) {
-#pragma unroll
-        for (int jj = 0; jj < N2; ++jj) g[jj] = __dadd_rn(g[jj], S1[jj * PW + (eB + 1) * S]);
-      }
-      if (i == 0 && hasL) {
-#pragma unroll
-        for (int jj = 0; jj < N2; ++jj) g[jj] = __dadd_rn(g[jj], S1[jj * PW + (eB - 1) * S + N]);
-      }
-      if (i == N - 1 && hasR) {
-#pragma unroll
-        for (int jj = 0; jj < N2; ++jj) g[jj] = __dadd_rn(g[jj], S1[jj * PW + (eB + 1) * S + 1]);
-      }
+      for (int jj = 0; jj < N2; ++jj) g[jj] = __dadd_rn(g[jj], S1[jj * PW + srcCol]);
     }
-    auto write = [&](int row, double gv) {
-      const bool z = mzx || (row == 0 && a.my0) || (row == a.nyl - 1 && a.my1);
-      const double h = __dmul_rn(z ? 0.0 : 1.0, __dmul_rn(__dmul_rn(wxB, a.wy[row]), gv));
-      const size_t idx = (size_t)row * a.pitch + xB;
-      a.out[idx] = h;
-      if (a.pcg) acc += __dmul_rn(__dmul_rn(a.r[idx], h), mxB * a.mult_y[row]);  // pcg.jl:45
+    if (N == 3 && src3) {
+#pragma unroll
+      for (int jj = 0; jj < N2; ++jj) g[jj] = __dadd_rn(g[jj], S1[jj * PW + (eB + 1) * S]);
+    }
+    // h = mask .* (W .*) sum, and the pcg.jl:45 partial; my = the node's mult along y (structural: 1 or 1/2)
+    auto write = [&](double* po, int row, double gv, bool zrow, bool half) {
+      double h = gv;
+      if (!FOLDW) h = __dmul_rn(__dmul_rn(wxB, a.wy[row]), gv);
+      h = __dmul_rn((mzx || zrow) ? 0.0 : 1.0, h);
+      *po = h;
+      if (a.pcg) acc += __dmul_rn(__dmul_rn(po[rd], h), half ? mxBh : mxB);
     };
     if (rr < r0) {  // halo row below the chunk: only what the next element row needs of it
       pend0 = g[N - 1], pend1 = g[N], prevN1 = g[N + 1];
       continue;
     }
-    const bool hb = ey > 0 || wrapy, ht = ey < a.ney - 1 || wrapy;
-    const int ep = (ey + a.ney - 1) % a.ney;  // element row of the previous tile row
+    const bool hb = rr > 0 || lo_any, ht = rr < a.ney - 1 || hi_any;
+    const int ey = rr, ep = rr - 1;  // element rows of this and of the previous tile row (both inside the slab here)
+    double* pp = a.out + ((size_t)ep * N + N - 2) * pitch + xB;
     if (rr >= r1) {  // halo row above the chunk: finishes the last two lines of the chunk
-      write(ep * N + N - 2, __dadd_rn(pend0, g[0]));
-      write(ep * N + N - 1, __dadd_rn(pend1, g[1]));
+      write(pp, ep * N + N - 2, __dadd_rn(pend0, g[0]), false, false);
+      write(pp + pitch, ep * N + N - 1, __dadd_rn(pend1, g[1]), false, true);
       continue;
     }
+    double* pc = a.out + ((size_t)ey * N) * pitch + xB;
     const double val1 = hb ? __dadd_rn(g[2], prevN1) : g[2];  // line 1: own tile + the tile below's extension row
     if (hb) {
       const double s = __dadd_rn(pend1, g[1]);                // y pair (after the x pairs)
       if (rr > r0) {
-        write(ep * N + N - 2, __dadd_rn(pend0, g[0]));        // line N-2 below: its tile + this tile's extension row
-        write(ep * N + N - 1, s);
+        write(pp, ep * N + N - 2, __dadd_rn(pend0, g[0]), false, false);   // + this tile's extension row
+        write(pp + pitch, ep * N + N - 1, s, false, true);
       }
-      write(ey * N, s);
+      write(pc, ey * N, s, false, true);
     } else {
-      write(ey * N, g[1]);
+      write(pc, ey * N, g[1], a.my0 != 0, false);
     }
 #pragma unroll
-    for (int j = 1; j <= N - 3; ++j) write(ey * N + j, j == 1 ? val1 : g[j + 1]);
+    for (int j = 1; j <= N - 3; ++j) {
+      pc += pitch;
+      write(pc, ey * N + j, j == 1 ? val1 : g[j + 1], false, false);
+    }
     pend0 = (N == 3) ? val1 : g[N - 1], pend1 = g[N], prevN1 = g[N + 1];
     if (!ht) {
-      write(ey * N + N - 2, pend0);
-      write(ey * N + N - 1, pend1);
+      write(pc + pitch, ey * N + N - 2, pend0, false, false);
+      write(pc + 2 * pitch, ey * N + N - 1, pend1, a.my1 != 0, false);
     }
   }
 
@@ -438,10 +532,12 @@ __global__ void __launch_bounds__(256, FdmCfg<N>::MINB) semb_fdm_kernel(const Fd
     const int bid = blockIdx.y * gridDim.x + blockIdx.x, nb = gridDim.x * gridDim.y;
     const double bs = semb_block_sum(acc, red, t, C::T);
     if (semb_last_block_uniform(bs, 0.0, a.partials, nullptr, a.counter, nb, bid, red, t, C::T, sh_tot)) {
+      // t = sum(r .* h .* mult); norm(r,Inf) was left in red[2] by the init / update kernel: advance the PCG state
+      SembScal* s = a.scal;
+      double tnew = sh_tot[0], rmax = s->red[2];
+      if (s->nranks > 1) semb_p2p_allgather(s, 1, tnew, rmax, &tnew, &rmax, t);  // combined in rank order over NVLink
       if (t == 0) {
-        // t = sum(r .* h .* mult); norm(r,Inf) was left in red[2] by the init / update kernel: advance the PCG state
-        SembScal* s = a.scal;
-        const double tnew = sh_tot[0], rmax = s->red[2];
+        if (ranks) *a.ep_dev += 1ull;   // (every CTA read the epoch long ago)
         if (a.pcg == 2) {
           s->t = tnew, s->t_prev = 0.0, s->iters = 0, s->warned = 0;
         } else {
@@ -460,8 +556,7 @@ __global__ void __launch_bounds__(256, FdmCfg<N>::MINB) semb_fdm_kernel(const Fd
 // the arrays every mesh holds: Jac = B/(wr_i*ws_j), G22 = B*(sx^2+sy^2), G11 = B*(rx^2+ry^2) (mesh.jl:117-123)
 __global__ void semb_fdm_lengths_kernel(const double* __restrict__ B, const double* __restrict__ G11,
                                         const double* __restrict__ G22, const double* __restrict__ wr,
-                                        const double* __restrict__ ws, long long pitch, int N, int Ex, int ney, double* hx,
-                                        double* hy) {
+                                        const double* __restrict__ ws, long long pitch, int N, int Ex, int ney, double* el) {
   __shared__ double red[32];
   const int e = blockIdx.x;
   if (e >= Ex * ney) return;
@@ -477,8 +572,11 @@ __global__ void semb_fdm_lengths_kernel(const double* __restrict__ B, const doub
   const double tx = semb_block_sum(sx, red, threadIdx.x, blockDim.x);
   const double ty = semb_block_sum(sy, red, threadIdx.x, blockDim.x);
   if (threadIdx.x == 0) {
-    hx[e] = tx / (double)(N * N);
-    hy[e] = ty / (double)(N * N);
+    const double hx = tx / (double)(N * N), hy = ty / (double)(N * N);
+    const size_t nel = (size_t)Ex * ney;
+    el[e] = 1.0 / (hx * hx);
+    el[nel + e] = 1.0 / (hy * hy);
+    el[2 * nel + e] = 1.0 / (hx * hy);
   }
 }
 
@@ -541,17 +639,89 @@ struct semb_fdm {
   semb_mesh* m = nullptr;
   double nu = 1.0, k = 0.0;
   int mx0 = 0, mx1 = 0, my0 = 0, my1 = 0;
-  double *d_hx = nullptr, *d_hy = nullptr, *d_tab = nullptr, *d_wx = nullptr, *d_wy = nullptr;
+  double *d_el = nullptr, *d_tab = nullptr, *d_wx = nullptr, *d_wy = nullptr;
+  // several ranks: ghost rows of r (IPC-exported, written by the neighbours), the neighbours' element scalings, epochs
+  uint4* d_ghost = nullptr;
+  void *peer_lo = nullptr, *peer_hi = nullptr;   // the neighbours' ghost rows as mapped into this process
+  double *d_el_lo = nullptr, *d_el_hi = nullptr;
+  unsigned long long* d_ep = nullptr;
+  unsigned long long ep_host = 0;
 };
 
 int semb_fdm_free_impl(semb_fdm* f) {
   if (!f) return SEMB_OK;
-  cudaFree(f->d_hx);
-  cudaFree(f->d_hy);
+  cudaFree(f->d_el);
   cudaFree(f->d_tab);
   cudaFree(f->d_wx);
   cudaFree(f->d_wy);
+  if (f->d_ghost) {
+    semb_comm_barrier(f->m->ctx);  // no neighbour may still be writing into (or mapping) the ghost rows
+    if (f->peer_lo) cudaIpcCloseMemHandle(f->peer_lo);
+    if (f->peer_hi && f->peer_hi != f->peer_lo) cudaIpcCloseMemHandle(f->peer_hi);
+    cudaFree(f->d_ghost);
+  }
+  cudaFree(f->d_el_lo);
+  cudaFree(f->d_el_hi);
+  cudaFree(f->d_ep);
   delete f;
+  return SEMB_OK;
+}
+
+// Several ranks: the halo tiles of a slab's first / last element row read N rows of r of the neighbour rank.  They arrive
+// in `d_ghost`, an allocation exported through CUDA IPC like the mesh's mailbox, as flag-in-data entries; the scalings of
+// the neighbours' adjoining element rows are exchanged once, here.  Collective over the communicator.
+static int fdm_setup_ranks(semb_fdm* f) {
+  semb_mesh* m = f->m;
+  semb_ctx* c = m->ctx;
+  const int N = m->nr, P = c->nranks, rk = c->rank;
+  SEMB_REQUIRE(m->p2p, "fdm: on several ranks the preconditioner needs the peer-memory transport (CUDA IPC between the GPUs)");
+  SEMB_REQUIRE(N >= 4, "fdm: on several ranks it needs nr >= 4");
+  double small = m->ney < 2 ? 1.0 : 0.0;
+  SEMB_TRY(semb_comm_allreduce_max(c, &small, 1));
+  SEMB_REQUIRE(small == 0.0, "fdm: on several ranks every slab needs at least 2 element rows");
+  const size_t gbytes = (size_t)4 * N * m->pitch * sizeof(uint4);
+  SEMB_CHECK_CUDA(cudaMalloc(&f->d_ghost, gbytes));
+  SEMB_CHECK_CUDA(cudaMemset(f->d_ghost, 0, gbytes));
+  SEMB_CHECK_CUDA(cudaMalloc(&f->d_ep, sizeof(unsigned long long)));
+  SEMB_CHECK_CUDA(cudaMemset(f->d_ep, 0, sizeof(unsigned long long)));
+  // IPC handles of every rank's ghost rows, all-gathered through the communicator; only the neighbours' are mapped
+  cudaIpcMemHandle_t mine;
+  SEMB_CHECK_CUDA(cudaIpcGetMemHandle(&mine, f->d_ghost));
+  char* d_h = nullptr;
+  SEMB_CHECK_CUDA(cudaMalloc(&d_h, (size_t)P * sizeof(cudaIpcMemHandle_t)));
+  SEMB_CHECK_CUDA(cudaMemcpy(d_h + (size_t)rk * sizeof(cudaIpcMemHandle_t), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+  SEMB_CHECK_NCCL(ncclAllGather(d_h + (size_t)rk * sizeof(cudaIpcMemHandle_t), d_h, sizeof(cudaIpcMemHandle_t), ncclChar, c->comm,
+                                c->stream));
+  std::vector<cudaIpcMemHandle_t> all(P);
+  SEMB_CHECK_CUDA(cudaMemcpyAsync(all.data(), d_h, (size_t)P * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost, c->stream));
+  SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_h);
+  if (m->halo_lo) SEMB_CHECK_CUDA(cudaIpcOpenMemHandle(&f->peer_lo, all[m->rank_lo], cudaIpcMemLazyEnablePeerAccess));
+  if (m->halo_hi) {
+    if (m->halo_lo && m->rank_hi == m->rank_lo) f->peer_hi = f->peer_lo;   // two ranks, periodic: one mapping
+    else SEMB_CHECK_CUDA(cudaIpcOpenMemHandle(&f->peer_hi, all[m->rank_hi], cudaIpcMemLazyEnablePeerAccess));
+  }
+  // element scalings of the adjoining rows: our first row goes down, our last row up (receives in the opposite
+  // order, so that two ranks that are each other's neighbour on both sides pair the messages correctly)
+  const size_t Ex = (size_t)m->Ex, nel = Ex * m->ney;
+  double* d_send = nullptr;
+  SEMB_CHECK_CUDA(cudaMalloc(&d_send, 6 * Ex * sizeof(double)));
+  SEMB_CHECK_CUDA(cudaMalloc(&f->d_el_lo, 3 * Ex * sizeof(double)));
+  SEMB_CHECK_CUDA(cudaMalloc(&f->d_el_hi, 3 * Ex * sizeof(double)));
+  for (int q = 0; q < 3; ++q) {
+    SEMB_CHECK_CUDA(cudaMemcpyAsync(d_send + q * Ex, f->d_el + q * nel, Ex * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    SEMB_CHECK_CUDA(cudaMemcpyAsync(d_send + (3 + q) * Ex, f->d_el + q * nel + (size_t)(m->ney - 1) * Ex, Ex * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, c->stream));
+  }
+  SEMB_CHECK_NCCL(ncclGroupStart());
+  if (m->halo_lo) SEMB_CHECK_NCCL(ncclSend(d_send, 3 * Ex, ncclDouble, m->rank_lo, c->comm, c->stream));
+  if (m->halo_hi) SEMB_CHECK_NCCL(ncclSend(d_send + 3 * Ex, 3 * Ex, ncclDouble, m->rank_hi, c->comm, c->stream));
+  if (m->halo_hi) SEMB_CHECK_NCCL(ncclRecv(f->d_el_hi, 3 * Ex, ncclDouble, m->rank_hi, c->comm, c->stream));
+  if (m->halo_lo) SEMB_CHECK_NCCL(ncclRecv(f->d_el_lo, 3 * Ex, ncclDouble, m->rank_lo, c->comm, c->stream));
+  SEMB_CHECK_NCCL(ncclGroupEnd());
+  SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(d_send);
+  SEMB_TRY(semb_comm_barrier(c));  // every rank's ghost rows exist and are mapped before anyone pushes
   return SEMB_OK;
 }
 
@@ -577,6 +747,17 @@ int semb_fdm_create_impl(semb_mesh* m, double nu, double k, int mx0, int mx1, in
     const int klo = dir == 0 ? (mx0 ? 1 : 2) : (gy0 ? 1 : 2), khi = dir == 0 ? (mx1 ? 1 : 2) : (gy1 ? 1 : 2);
     for (int cls = 0; cls < 4; ++cls) {
       SEMB_TRY(semb_fdm_tables(N, D.data(), w.data(), (cls & 1) ? klo : 0, (cls & 2) ? khi : 0, Sm.data(), lam.data()));
+      if (N >= 4) {
+        // counting weights W = 1/sqrt(number of subdomains holding the node) folded into the rows of S (both the
+        // nodes -> modes and the modes -> nodes products carry one W): the two nodes on either side of an interface
+        // lie in two subdomains along this direction (for N >= 4 that only depends on the class)
+        const bool lo = !(cls & 1), hi = !(cls & 2);
+        for (int i = 0; i < N2; ++i) {
+          const bool two = (lo && i <= 2) || (hi && i >= N - 1);
+          if (two)
+            for (int c = 0; c < N2; ++c) Sm[i + (size_t)c * N2] *= std::sqrt(0.5);
+        }
+      }
       fdm_slot_fill(N, Sm.data(), lam.data(), tab.data() + ((size_t)dir * 4 + cls) * TSZ);
     }
   }
@@ -600,21 +781,21 @@ int semb_fdm_create_impl(semb_mesh* m, double nu, double k, int mx0, int mx1, in
   SEMB_CHECK_CUDA(cudaMemcpy(f->d_wy, wy.data(), wy.size() * sizeof(double), cudaMemcpyHostToDevice));
   // element half-lengths
   const size_t ne = (size_t)m->Ex * m->ney;
-  SEMB_CHECK_CUDA(cudaMalloc(&f->d_hx, ne * sizeof(double)));
-  SEMB_CHECK_CUDA(cudaMalloc(&f->d_hy, ne * sizeof(double)));
+  SEMB_CHECK_CUDA(cudaMalloc(&f->d_el, 3 * ne * sizeof(double)));
   double *d_wr = nullptr, *d_ws = nullptr;
   SEMB_CHECK_CUDA(cudaMalloc(&d_wr, N * sizeof(double)));
   SEMB_CHECK_CUDA(cudaMalloc(&d_ws, N * sizeof(double)));
   SEMB_CHECK_CUDA(cudaMemcpy(d_wr, m->hwr.data(), N * sizeof(double), cudaMemcpyHostToDevice));
   SEMB_CHECK_CUDA(cudaMemcpy(d_ws, m->hws.data(), N * sizeof(double), cudaMemcpyHostToDevice));
   semb_fdm_lengths_kernel<<<(unsigned)ne, 64, 0, c->stream>>>(m->arr[SEMB_B], m->arr[SEMB_G11], m->arr[SEMB_G22], d_wr, d_ws,
-                                                              m->pitch, N, m->Ex, m->ney, f->d_hx, f->d_hy);
+                                                              m->pitch, N, m->Ex, m->ney, f->d_el);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaFree(d_wr);
   cudaFree(d_ws);
   SEMB_CHECK_CUDA(e);
   c->launches++;
+  if (c->nranks > 1) SEMB_TRY(fdm_setup_ranks(f));
   return SEMB_OK;
 }
 
@@ -626,8 +807,8 @@ int semb_fdm_apply_impl(semb_fdm* f, const double* r, double* out, int pcg) {
   a.r = r;
   a.out = out;
   a.tab = f->d_tab;
-  a.hx = f->d_hx;
-  a.hy = f->d_hy;
+  a.el = f->d_el;
+  a.nel = (long long)m->Ex * m->ney;
   a.wx = f->d_wx;
   a.wy = f->d_wy;
   a.mult_x = m->d_wx1d;
@@ -649,6 +830,16 @@ int semb_fdm_apply_impl(semb_fdm* f, const double* r, double* out, int pcg) {
   a.partials = m->d_partials;
   a.counter = m->d_counters + 6;
   a.pcg = pcg;
+  a.has_lo = f->d_ghost ? m->halo_lo : 0;
+  a.has_hi = f->d_ghost ? m->halo_hi : 0;
+  a.ghost = f->d_ghost;
+  a.peer_lo = (uint4*)f->peer_lo;
+  a.peer_hi = (uint4*)f->peer_hi;
+  a.el_lo = f->d_el_lo;
+  a.el_hi = f->d_el_hi;
+  a.ep_host = f->ep_host;
+  a.ep_dev = f->d_ep;
+  if (!pcg && f->d_ghost) f->ep_host++;   // (inside pcg the kernel's last CTA advances *ep_dev instead: graph replay)
   switch (m->nr) {
 #define SEMB_CASE(n) \
   case n:            \

@@ -72,6 +72,23 @@ def main():
         e = relerr(xg, loc(xo)) if np.max(np.abs(loc(xo))) > 0 else 0.0
         if e > 1e-9 or abs(ig["iters"] - io["iters"]) > max(3, int(0.02 * io["iters"])):
             fails.append(tag + " pcg err %g iters %d vs %d" % (e, ig["iters"], io["iters"]))
+        # FDM preconditioner on slabs: the halo tiles read the neighbour rank's rows of r through peer memory
+        if not os.environ.get("SEMB_NO_P2P") and nr >= 4 and Ey // world >= 2:
+            Po, Pg = so.fdm_schwarz(om, bc, 1.0, kk), sem.FdmPrecond(gm, bc, 1.0, kk)
+            r = so.mask(so.gatherScatter(so.splitmix_uniform(om.x.shape, seed=8) * om.mult, om), M)
+            ho = Po(r)
+            hg = Pg(loc(r))
+            e = float(np.max(np.abs(hg - loc(ho))) / np.max(np.abs(ho)))
+            if e > 1e-12:
+                fails.append(tag + " fdm apply %g" % e)
+            if not np.array_equal(Pg(loc(r)), hg):
+                fails.append(tag + " fdm apply not deterministic")
+            io2, ig2 = {}, {}
+            xo2 = so.pcg(b, lambda v: so.opLHS(v, 1.0, kk, M, om), opM=Po, mult=om.mult, tol=1e-10, info=io2)
+            xg2 = sem.pcg(loc(b), sem.OpLHS(gm, 1.0, kk, bc=bc), opM=Pg, mult=gm.mult, tol=1e-10, info=ig2)
+            e = relerr(xg2, loc(xo2)) if np.max(np.abs(loc(xo2))) > 0 else 0.0
+            if e > 1e-8 or abs(ig2["iters"] - io2["iters"]) > (0 if io2["iters"] <= 60 else 2):
+                fails.append(tag + " pcg+fdm err %g iters %d vs %d" % (e, ig2["iters"], io2["iters"]))
         gm.free()
     # Stokes split on slabs: element-local kernels + gatherScatter on both meshes + all-reduced PCG scalars
     for nr, Ex, Ey in [(7, 3, 8), (9, 4, 2 * world)]:

@@ -24,6 +24,10 @@ for nr, Ex, Ey, per in ((9, 30, 3, (False, False)), (8, 33, 2, (True, True)), (1
     sem.pcg(b, sem.OpLHS(m, 1.0, 0.3, bc="DDNN"), maxiter=20, info=info)
     sem.pcg(b, sem.OpLHS(m, 0.01, 300.0, bc="DDNN"), opM=sem.DiagPrecond(m, 300.0), maxiter=20, info=info)
     fa = m.field(u); m.dot_mult(fa, fa); m.norm_inf(fa)
+    if nr >= 3 and not (per[0] and Ex < 2) and not (per[1] and Ey < 2):   # FDM preconditioner: stand-alone and inside pcg
+        P = sem.FdmPrecond(m, "DDNN", 1.0, 0.3)
+        P(sem.mask(sem.gatherScatter(u * m.mult, m), M, m))
+        sem.pcg(b, sem.OpLHS(m, 1.0, 0.3, bc="DDNN"), opM=P, mult=m.mult, maxiter=10, info=info)
     sem.grad(u, m)
     m.free()
 # generic path, ABu, drivers
