@@ -220,6 +220,24 @@ def poisson_rhs(msh, bc):
     return rhs
 
 
+def time_fdm_pcg(sem, ctx, dist, msh, bc="DDDD", iters=40):
+    """(ms per FDM application, ms per FDM-preconditioned PCG iteration) on `msh`, device-resident, max over ranks."""
+    u, out, x = msh.field().fill_random(0x5EED), msh.field(), msh.field()
+    P = sem.FdmPrecond(msh, bc, 1.0, 0.0)
+    ms_fdm = time_steps(ctx, dist, lambda: P.apply_device(u, out), iters, 3) / iters
+    rhs = poisson_rhs(msh, bc)
+    msh.pcg_begin(rhs, x, nu=1.0, k=0.0, bc=bc, tol=0.0, maxiter=10 ** 9, precond=2)
+    msh.pcg_iterate(3)
+    barrier(dist, ctx)
+    ctx.timer_start()
+    msh.pcg_iterate(iters)
+    ms_pcg = max_over_ranks(dist, ctx.timer_stop()) / iters
+    barrier(dist, ctx)
+    for f in (u, out, x, rhs):
+        f.free()
+    return ms_fdm, ms_pcg
+
+
 def time_apply_and_pcg(ctx, dist, msh, steps, warmup, bc="DDDD", pcg_iters=100):
     """(ms per fused Poisson apply, ms per PCG iteration) on `msh`, device-resident, max over ranks."""
     u, out = msh.field().fill_random(0x5EED), msh.field()
@@ -300,13 +318,15 @@ def strong_block(sem, ctx, dist, world, rank, local, steps, peak):
         solo = sem.Context(local)
         m1 = sem.Mesh(nr, nr, E, E, (False, False), "wavy", ctx=solo)
         a1, p1 = time_apply_and_pcg(solo, None, m1, steps, 3)
+        f1, q1 = time_fdm_pcg(sem, solo, None, m1)
         m1.free()
         solo.close()
-        t = torch.tensor([a1, p1], dtype=torch.float64, device="cuda")
+        t = torch.tensor([a1, p1, f1, q1], dtype=torch.float64, device="cuda")
         dist.all_reduce(t)
-        a1, p1 = (t / world).tolist()
+        a1, p1, f1, q1 = (t / world).tolist()
         mN = sem.Mesh(nr, nr, E, E, (False, False), "wavy", ctx=ctx)   # Ey = E globally: split over the ranks
         aN, pN = time_apply_and_pcg(ctx, dist, mN, steps, 3)
+        fN, qN = time_fdm_pcg(sem, ctx, dist, mN)
         plan, tail = mN.plan(), mN.fused_tail()
         mN.peer_status()
         mN.free()
@@ -317,6 +337,8 @@ def strong_block(sem, ctx, dist, world, rank, local, steps, peak):
                     "pcg_ms_per_iter_1gpu": p1, "pcg_ms_per_iter": pN, "pcg_iters_per_s": 1e3 / pN,
                     "pcg_efficiency_vs_n1": p1 / (world * pN),
                     "apply_hbm_frac_per_gpu": ALG_BYTES_POISSON * ndof / world / (aN * 1e-3) / 1e9 / peak,
+                    "fdm_ms_1gpu": f1, "fdm_ms": fN, "fdm_efficiency_vs_n1": f1 / (world * fN),
+                    "fdm_pcg_ms_per_iter_1gpu": q1, "fdm_pcg_ms_per_iter": qN, "fdm_pcg_efficiency_vs_n1": q1 / (world * qN),
                     "strips_x_chunks": [plan["nstrips"], plan["nchunks"]], "fused_tail": tail}
     return out
 
@@ -336,6 +358,7 @@ def parity_block(sem, ctx, world, rank):
         gm = sem.Mesh.from_arrays(nr, nr, Ex, Ey, per, om.Dr, om.Ds, loc(om.G11), loc(om.G12), loc(om.G22), loc(om.B), ctx=ctx)
         u = so.splitmix_uniform(om.x.shape, seed=21)
         M = so.generateMask(list(bc), om).astype(np.float64)
+        tail_on = bool(gm.fused_tail())   # (the fused tail runs on peer memory: the transport the FDM exchange needs)
         if not np.array_equal(sem.gatherScatter(loc(u), gm), loc(so.gatherScatter(u, om))):
             fails.append("gatherScatter not bit-exact (nr=%d)" % nr)
         ref = so.opLHS(u, 1.0, 0.7, M, om)
@@ -351,6 +374,19 @@ def parity_block(sem, ctx, world, rank):
         ex = float(np.max(np.abs(xg - loc(xo))) / np.max(np.abs(xo)))
         if ex > 1e-10 or abs(ig["iters"] - io["iters"]) > max(3, int(0.02 * io["iters"])):
             fails.append("pcg err %.2e iters %d vs %d (nr=%d)" % (ex, ig["iters"], io["iters"], nr))
+        if tail_on and Ey // world >= 2:   # FDM preconditioner across the slabs (peer-memory transport only)
+            Po, Pg = so.fdm_schwarz(om, bc, 1.0, 0.7), sem.FdmPrecond(gm, bc, 1.0, 0.7)
+            r = so.mask(so.gatherScatter(so.splitmix_uniform(om.x.shape, seed=8) * om.mult, om), M)
+            ho = Po(r)
+            ef = float(np.max(np.abs(Pg(loc(r)) - loc(ho))) / np.max(np.abs(ho)))
+            worst = max(worst, ef)
+            if ef > 1e-12:
+                fails.append("fdm apply %.2e (nr=%d)" % (ef, nr))
+            io2, ig2 = {}, {}
+            so.pcg(b, opo, opM=Po, mult=om.mult, tol=1e-10, info=io2)
+            sem.pcg(loc(b), sem.OpLHS(gm, 1.0, 0.7, bc=bc), opM=Pg, mult=gm.mult, tol=1e-10, info=ig2)
+            if abs(ig2["iters"] - io2["iters"]) > (0 if io2["iters"] <= 60 else 2):
+                fails.append("pcg+fdm iters %d vs %d (nr=%d)" % (ig2["iters"], io2["iters"], nr))
         try:
             gm.peer_status()
         except Exception as ex2:
@@ -359,7 +395,7 @@ def parity_block(sem, ctx, world, rank):
         gm.free()
     v = ctx.allreduce_max([worst, float(len(fails))])
     return {"world": world, "ok": bool(v[1] == 0.0), "max_rel": float(v[0]), "fused_tail": tail,
-            "checks": "opLHS slab vs single-domain oracle < 1e-12, gatherScatter bit-exact, PCG count (+-2 %, min 3) and solution < 1e-10; "
+            "checks": "opLHS slab vs single-domain oracle < 1e-12, gatherScatter bit-exact, PCG count (+-2 %, min 3) and solution < 1e-10, FDM apply < 1e-12 and pcg+FDM count; "
                       "2 meshes (two strips; periodic x and y, three strips)", "fails_rank0": fails}
 
 

@@ -202,6 +202,15 @@ __device__ __forceinline__ void semb_fence_proxy_async() { asm volatile("fence.p
 #ifndef SEMB_LATE_B
 #define SEMB_LATE_B 1
 #endif
+// Where the contractions read their tables.  N <= 9: shared memory, broadcast LDS.128 (two entries per load).  N >= 10: the
+// kernel-parameter constant bank -- LDCU.128 into uniform registers, DFMA with a UR operand: the table loads leave the
+// shared-memory pipe, which at these sizes is the busiest unit (73 % of its cycles at N = 13, half of the wavefronts
+// being table loads: profiles/r01_strip13_r1l.txt).  Measured (profiles/r02_sweep_tables_constant_bank_r2x.txt):
+// N = 11: 70 -> 81 % of the HBM roof, N = 13: 63 -> 73 %, N = 9: 78 -> 79 % plain but 92 -> 85 % in the PCG variant.
+#ifndef SEMB_TABC_MIN_N
+#define SEMB_TABC_MIN_N 10
+#endif
+#define SEMB_TAB(q) (TABC ? (const double*)P.tab[q] : (const double*)(sT + (q) * TSZ))
 
 template <int N, bool PCGM, bool MASS, bool EO>
 __global__ void __launch_bounds__(StripCfg<N>::T, StripCfg<N>::MINB)
@@ -213,6 +222,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
   // 184 -> 56 bytes of spills, 0.618 -> 0.590 ms per preconditioned iteration at 512x512 order 8; the plain
   // apply measured 4 % slower in the late form, so it keeps the early one)
   constexpr bool LATE_B = SEMB_LATE_B && PCGM;
+  constexpr bool TABC = N >= SEMB_TABC_MIN_N;
   extern __shared__ __align__(128) double smem[];
   // [N][PW] transposition buffer, updated IN PLACE by the alternating mappings (each phase touches
   // every location from exactly one thread): u -> Dr u -> wr -> Dr^T wr
@@ -295,7 +305,9 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     if (MASS && LATE_B && first_arr == 1 && a.B && t < N)
       semb_bulk_prefetch_l2(a.B + (size_t)(r * N + t) * pitch + x0, row_bytes);
   };
-  for (int q = t; q < 4 * TSZ; q += C::T) sT[q] = (&P.tab[0][0])[q];
+  if (!TABC) {
+    for (int q = t; q < 4 * TSZ; q += C::T) sT[q] = (&P.tab[0][0])[q];
+  }
   if (t == 0) {
     semb_mbar_init(&bars[0], 1);
     semb_mbar_init(&bars[1], 1);
@@ -378,7 +390,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
     }
     if (PCGM && i + 1 < nrows) issue_p(row_of(i + 1));
     double us[N];  // us = Ds * u along y: us[j] = sum_k Ds(j,k) u[k]
-    semb_contract<N, EO>(sT + 0 * TSZ, u, us);
+    semb_contract<N, EO>(SEMB_TAB(0), u, us);
     __syncthreads();
     if (t < 32 && i + 1 < nrows) issue_rows(row_of(i + 1), 0, 1, SU, &bars[0]);  // u stage is free: prefetch the next row
     // ---- step 2 (A): ur = Dr * u along x -------------------------------------------------------------
@@ -386,7 +398,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
       double c[N], o[N];  // ur[m] = sum_i Dr(m,i) u[i]
 #pragma unroll
       for (int i = 0; i < N; ++i) c[i] = S1[colA + i];
-      semb_contract<N, EO>(sT + 1 * TSZ, c, o);
+      semb_contract<N, EO>(SEMB_TAB(1), c, o);
 #pragma unroll
       for (int m = 0; m < N; ++m) S1[colA + m] = o[m];
     }
@@ -402,7 +414,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
       ws[j] = fma(g12, ur, g22 * us[j]);            // lapl.jl:76
       if (inB) S1[j * PW + colB] = wr;
     }
-    semb_contract<N, EO>(sT + 2 * TSZ, ws, aus);  // (Ds^T ws)[m] = sum_j Ds(j,m) ws[j]
+    semb_contract<N, EO>(SEMB_TAB(2), ws, aus);  // (Ds^T ws)[m] = sum_j Ds(j,m) ws[j]
     double mt[N];  // k .* (B .* u), hlmz.jl:16 / mass.jl:17
     if (MASS && !LATE_B) {
 #pragma unroll
@@ -418,7 +430,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
       double c[N], o[N];  // (Dr^T wr)[m] = sum_i Dr(i,m) wr[i]
 #pragma unroll
       for (int i = 0; i < N; ++i) c[i] = S1[colA + i];
-      semb_contract<N, EO>(sT + 3 * TSZ, c, o);
+      semb_contract<N, EO>(SEMB_TAB(3), c, o);
 #pragma unroll
       for (int m = 0; m < N; ++m) S1[colA + m] = o[m];
     }
