@@ -385,7 +385,7 @@ def parity_block(sem, ctx, world, rank):
             io2, ig2 = {}, {}
             so.pcg(b, opo, opM=Po, mult=om.mult, tol=1e-10, info=io2)
             sem.pcg(loc(b), sem.OpLHS(gm, 1.0, 0.7, bc=bc), opM=Pg, mult=gm.mult, tol=1e-10, info=ig2)
-            if abs(ig2["iters"] - io2["iters"]) > (0 if io2["iters"] <= 60 else 2):
+            if abs(ig2["iters"] - io2["iters"]) > (0 if io2["iters"] <= 60 else max(3, int(0.02 * io2["iters"]))):
                 fails.append("pcg+fdm iters %d vs %d (nr=%d)" % (ig2["iters"], io2["iters"], nr))
         try:
             gm.peer_status()

@@ -29,6 +29,11 @@ def main():
              (9, 60, 3 * world + 1, (False, False), so.wavy, "DDDD")]   # three strips, several chunks per slab
     if world > 5:
         cases = [c for c in cases if c[2] >= world] + [(9, 8, 2 * world, (False, True), so.wavy, "DDNN")]
+    # one element row per rank (first row == last row of the slab), with and without the periodic wrap over the ranks
+    cases += [(9, 8, world, (False, False), so.wavy, "DDDD"), (7, 30, world, (False, True), so.wavy, "DDNN")]
+    only = os.environ.get("SEMB_DIST_CASES")   # e.g. "5,6": run a subset (debugging)
+    if only:
+        cases = [cases[int(i)] for i in only.split(",")]
     for nr, Ex, Ey, per, deform, bc in cases:
         if Ey < world:
             continue
@@ -39,6 +44,8 @@ def main():
         gm = sem.Mesh.from_arrays(nr, nr, Ex, Ey, per, om.Dr, om.Ds, loc(om.G11), loc(om.G12), loc(om.G22), loc(om.B),
                                   ctx=ctx)
         tag = "nr=%d %dx%d per=%s bc=%s" % (nr, Ex, Ey, per, bc)
+        if rank == 0 and os.environ.get("SEMB_DIST_VERBOSE"):
+            print("case", tag, flush=True)
         u = so.splitmix_uniform(om.x.shape, seed=21)
         M = so.generateMask(list(bc), om).astype(np.float64)
         if not np.array_equal(gm.mult, loc(om.mult)):
@@ -50,13 +57,18 @@ def main():
         e = relerr(sem.OpLHS(gm, 1.0, 0.7, bc=bc)(loc(u)), loc(so.opLHS(u, 1.0, 0.7, M, om)))
         if e > 1e-12:
             fails.append(tag + " opLHS %g" % e)
-        if gm.ney >= 2:   # every chunking of the slab gives the same bits (2-term interface sums)
+        if Ey // world >= 2:   # every chunking of the slab gives the same bits (2-term interface sums); an apply is
+            # collective (halo exchange), so the condition must not depend on the rank's own slab
             ref_bits = sem.OpLHS(gm, 1.0, 0.0, bc=bc)(loc(u))
             for nch in (1, gm.ney):
                 gm.set_chunks(nch)
                 if not np.array_equal(sem.OpLHS(gm, 1.0, 0.0, bc=bc)(loc(u)), ref_bits):
                     fails.append(tag + " opLHS bits change with %d chunks" % nch)
             gm.set_chunks(max(1, gm.ney // 2))
+        try:
+            gm.peer_status()   # a timed-out peer wait inside the apply kernels shows up here, not three calls later
+        except Exception as ex:
+            fails.append(tag + " " + str(ex)[:120])
         # device random fill uses the GLOBAL index: the slabs tile the single-domain stream
         if not np.array_equal(gm.field().fill_random(5).download(), loc(so.splitmix_uniform(om.x.shape, seed=5))):
             fails.append(tag + " fill_random")
@@ -87,7 +99,8 @@ def main():
             xo2 = so.pcg(b, lambda v: so.opLHS(v, 1.0, kk, M, om), opM=Po, mult=om.mult, tol=1e-10, info=io2)
             xg2 = sem.pcg(loc(b), sem.OpLHS(gm, 1.0, kk, bc=bc), opM=Pg, mult=gm.mult, tol=1e-10, info=ig2)
             e = relerr(xg2, loc(xo2)) if np.max(np.abs(loc(xo2))) > 0 else 0.0
-            if e > 1e-8 or abs(ig2["iters"] - io2["iters"]) > (0 if io2["iters"] <= 60 else 2):
+            # (same bar as the unpreconditioned solves: exact below the rounding horizon, the oracle's own 2 % spread above)
+            if e > 1e-8 or abs(ig2["iters"] - io2["iters"]) > (0 if io2["iters"] <= 60 else max(3, int(0.02 * io2["iters"]))):
                 fails.append(tag + " pcg+fdm err %g iters %d vs %d" % (e, ig2["iters"], io2["iters"]))
         gm.free()
     # Stokes split on slabs: element-local kernels + gatherScatter on both meshes + all-reduced PCG scalars
