@@ -530,7 +530,20 @@ static int mesh_build_plan(semb_mesh* m) {
   if (best > m->ney) best = m->ney;
   if ((long long)(best + 1) * m->nstrips > SEMB_NPARTIALS) best = SEMB_NPARTIALS / m->nstrips - 1;
   if (best < 1) best = 1;
+  // One rank, several waves of CTAs: the separate seam kernels are 2-3 % faster than the one-launch form (the tasks read
+  // the interface values back through L2 while the next wave streams; profiles/r02_ab_tail_r2h.txt: 771 vs 788 us per
+  // apply at 1112x1112 order 8, 2012 vs 2023 us per PCG iteration).  Everything that has launches or exchanges to
+  // save -- one wave (small meshes), several ranks -- keeps the one-launch form.  SEMB_FORCE_TAIL=1 keeps it always.
+  if (m->tail && P == 1 && (long long)m->nstrips * best >= 2LL * slots && !getenv("SEMB_FORCE_TAIL")) m->tail = false;
   SEMB_TRY(mesh_set_groups(m, best));
+  // pipelined host twin (semb_oplhs_host) on several ranks: every rank must take the same path (its halo exchange differs
+  // from the one-launch apply's), so the size criterion is agreed on once, here
+  m->host_pipe = (size_t)m->nxl * m->nyl >= ((size_t)1 << 22);
+  if (P > 1) {
+    double small = m->host_pipe ? 0.0 : 1.0;
+    SEMB_TRY(semb_comm_allreduce_max(c, &small, 1));
+    m->host_pipe = (small == 0.0);
+  }
   if (P > 1) SEMB_TRY(semb_comm_barrier(c));  // every mailbox is mapped and initialised before anyone pushes
   return SEMB_OK;
 }
@@ -2044,17 +2057,37 @@ static int oplhs_host_pipelined(semb_mesh* m, const double* u, double nu, double
         SEMB_TRY(semb_launch_seam_y(c, y, 0, 0, true, P2PArgs()));
       }
       SEMB_CHECK_CUDA(cudaEventRecord(ev_cmp[s], c->stream));
-      if (s > 0) {  // slab s-1 is final now
+      if (s > 0) {  // slab s-1 is final now (but for a line shared with a neighbour rank: that one goes last)
         int p0, p1;
         rows_of(s - 1, &p0, &p1);
         SEMB_CHECK_CUDA(cudaStreamWaitEvent(c->out_stream, ev_cmp[s], 0));
-        SEMB_TRY(copy_rows(false, p0, p1, c->out_stream));
+        SEMB_TRY(copy_rows(false, p0 + ((s == 1 && m->halo_lo) ? 1 : 0), p1, c->out_stream));
       }
     }
     int p0, p1;
     rows_of(nslab - 1, &p0, &p1);
     SEMB_CHECK_CUDA(cudaStreamWaitEvent(c->out_stream, ev_cmp[nslab - 1], 0));
-    SEMB_TRY(copy_rows(false, p0, p1, c->out_stream));
+    SEMB_TRY(copy_rows(false, p0 + ((nslab == 1 && m->halo_lo) ? 1 : 0), p1 - (m->halo_hi ? 1 : 0), c->out_stream));
+    if (m->halo_lo || m->halo_hi) {
+      // several ranks: the slab's first / last line is a y seam with the neighbour rank.  Both are x-complete now:
+      // exchange them (peer memory or NCCL), close the two seams, download the two lines
+      unsigned long long eph = 0;
+      SEMB_TRY(halo_exchange(m, fo->d, 0, &eph));
+      OpArgs y = a;
+      y.halo_lo = m->d_halo_lo;
+      y.halo_hi = m->d_halo_hi;
+      if (m->p2p) {
+        y.halo_lo = mail_halo(m, m->d_mailbox, (int)(eph & 1ull), 0);
+        y.halo_hi = mail_halo(m, m->d_mailbox, (int)(eph & 1ull), 1);
+      }
+      y.yseam = m->d_yseam;
+      y.nyseam = 0;
+      SEMB_TRY(semb_launch_seam_y(c, y, m->halo_lo, m->halo_hi, true, p2p_args(m, eph)));
+      SEMB_CHECK_CUDA(cudaEventRecord(ev_cmp[0], c->stream));
+      SEMB_CHECK_CUDA(cudaStreamWaitEvent(c->out_stream, ev_cmp[0], 0));
+      if (m->halo_lo) SEMB_TRY(copy_rows(false, 0, 1, c->out_stream));
+      if (m->halo_hi) SEMB_TRY(copy_rows(false, m->nyl - 1, m->nyl, c->out_stream));
+    }
     SEMB_CHECK_CUDA(cudaStreamSynchronize(c->out_stream));
     SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
     return SEMB_OK;
@@ -2078,8 +2111,9 @@ extern "C" int semb_oplhs_host(semb_mesh* m, const double* u, const double* nu_a
   SEMB_ENTER(m->ctx);
   TmpFields t(m);
   semb_field *fu, *fo, *fn, *fk, *fm;
-  const bool pipe = m->fast && m->ctx->nranks == 1 && !m->pery && !nu_arr && !k_arr && !M_arr && m->nchunks >= 4 &&
-                    (size_t)m->nxl * m->nyl >= ((size_t)1 << 22) && (k == 0.0 || m->arr[SEMB_B]) && !getenv("SEMB_NO_PIPELINE");
+  // (several ranks: only rank-independent criteria -- the two paths exchange the halo rows differently)
+  const bool pipe = m->fast && !m->pery && !nu_arr && !k_arr && !M_arr && (m->nchunks >= 4 || m->ctx->nranks > 1) &&
+                    m->host_pipe && (k == 0.0 || m->arr[SEMB_B]) && !getenv("SEMB_NO_PIPELINE");
   if (pipe) {
     SEMB_TRY(t.make(nullptr, &fu));
     SEMB_TRY(t.make(nullptr, &fo));

@@ -205,6 +205,7 @@ struct semb_mesh {
   semb_field* pcg_x = nullptr;
   semb_pcg_opts pcg_opts;
   bool pcg_active = false;
+  bool host_pipe = false;              // semb_oplhs_host may take the pipelined path (agreed on by all ranks)
   bool pcg_keep_h = false;             // preconditioned PCG on the fused path: h kept in w_h
   // operator hook of the device-resident PCG: when set, an iteration is p = h + beta*p, w_Ap = pcg_custom(w_p),
   // sum(p.*Ap.*mult) by the reduction kernel, update -- instead of the fused strip kernel (Stokes Schur operator)

@@ -103,6 +103,23 @@ def main():
             if e > 1e-8 or abs(ig2["iters"] - io2["iters"]) > (0 if io2["iters"] <= 60 else max(3, int(0.02 * io2["iters"]))):
                 fails.append(tag + " pcg+fdm err %g iters %d vs %d" % (e, ig2["iters"], io2["iters"]))
         gm.free()
+    # pipelined host twin on slabs (semb_oplhs_host: upload | compute | download by slabs, the two lines shared with the
+    # neighbour ranks exchanged and downloaded last): same bits as the device-resident one-launch apply
+    if not only:
+        gm = sem.Mesh(9, 9, 256, 204 * world, (False, False), "wavy", ctx=ctx)
+        uu = np.asfortranarray(np.random.default_rng(100 + rank).standard_normal(gm.shape))
+        for kk in (0.0, 0.4):
+            hh = sem.OpLHS(gm, 1.3, kk, bc="DNDD")(uu)
+            fu, fo = gm.field(uu), gm.field()
+            gm.oplhs_device(fu, fo, nu=1.3, k=kk, bc="DNDD")
+            if not np.array_equal(hh, fo.download()):
+                fails.append("pipelined host twin differs from the device apply (k=%g)" % kk)
+            fu.free(); fo.free()
+        try:
+            gm.peer_status()
+        except Exception as ex:
+            fails.append("host twin: " + str(ex)[:120])
+        gm.free()
     # Stokes split on slabs: element-local kernels + gatherScatter on both meshes + all-reduced PCG scalars
     for nr, Ex, Ey in [(7, 3, 8), (9, 4, 2 * world)]:
         if Ey < world:
