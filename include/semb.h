@@ -209,7 +209,9 @@ int semb_pcg_status(semb_mesh* m, long long* iters, double* resinf, int* done);
  * eigen(Ax,Bx), eigen(Ay,By) (examples/p2d_explicit.jl:109-141).  Built here in the form in which it works as the opM of
  * pcg (pcg.jl:37): the same tensor solve on every element extended by one node into its neighbours, combined
  * symmetrically with counting weights (the CPU checker restates it as fdm_schwarz; 5-8x fewer iterations).
- * One per mesh: semb_fdm_create registers it, semb_pcg_opts.precond = 2 uses it, semb_fdm_apply is h = opM(r). */
+ * One per mesh: semb_fdm_create registers it, semb_pcg_opts.precond = 2 uses it, semb_fdm_apply is h = opM(r).
+ * Several ranks (y-slabs): create / destroy / apply are collective; needs the peer-memory transport (CUDA IPC), nr >= 4
+ * and at least two element rows per rank; the result has the single-rank bits. */
 typedef struct semb_fdm semb_fdm;
 int semb_fdm_create(semb_mesh* m, const char bc[4], double nu, double k, semb_fdm** out);
 int semb_fdm_destroy(semb_mesh* m);

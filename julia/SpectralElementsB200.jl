@@ -396,6 +396,25 @@ struct DiagPrecond
     b0::Float64
 end
 
+"""FdmPrecond(msh,bc,ν,k): the fast-diagonalisation preconditioner as opM of pcg -- the reference's commented-out
+lapl_fdm(b,Bi,Sx,Sy,Sxi,Syi,Di) (lapl.jl:105-119, set-up examples/p2d_explicit.jl:109-141), applied on every element
+extended by one node into its neighbours and combined symmetrically (include/semb.h).  ν, k: the constant coefficients
+of the operator it approximates; bc: its ['D','N',...] flags.  One per mesh; collective on several ranks."""
+struct FdmPrecond
+    msh::Mesh
+    function FdmPrecond(msh::Mesh, bc, ν::Real = 1.0, k::Real = 0.0)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:semb_fdm_create, libsemb), Cint, (Ptr{Cvoid}, Cstring, Cdouble, Cdouble, Ref{Ptr{Cvoid}}),
+                    devmesh(msh), bcstr(bc), ν, k, h))
+        return new(msh)
+    end
+end
+function (P::FdmPrecond)(r::Array)      # h = opM(r) for a continuous r
+    out = similar(r, Float64)
+    check(ccall((:semb_fdm_apply_host, libsemb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), devmesh(P.msh), f64(r), out))
+    return out
+end
+
 # pcg(b,opA;opM,mult,ifv,tol,maxiter), pcg.jl:16-60 -- device-resident.
 # mult: the device loop weights its inner products with the mesh's own msh.mult, what every caller in the reference passes
 # (diffusion.jl:71, examples/p2d.jl:60).  DEVIATION from the bare default: pcg.jl:18 defaults mult to ones(size(b)); here
@@ -405,8 +424,8 @@ function pcg(b, opA::OpLHS; opM = nothing, mult = nothing, ifv = false, tol = 1e
         throw(ArgumentError("pcg: mult must be msh.mult (or nothing = msh.mult); the device loop has no other weighting"))
     x = zeros(Float64, size(b))
     (pν, sν, kν) = coef(opA.ν); (pk, sk, kk) = coef(opA.k)
-    prec = opM isa DiagPrecond
-    o = Ref(PcgOpts(sν, C_NULL, sk, C_NULL, C_NULL, C_NULL, prec ? 1 : 0, prec ? opM.b0 : 1.0, tol, maxiter, 0))
+    prec = opM isa DiagPrecond ? 1 : (opM isa FdmPrecond ? 2 : 0)
+    o = Ref(PcgOpts(sν, C_NULL, sk, C_NULL, C_NULL, C_NULL, prec, prec == 1 ? opM.b0 : 1.0, tol, maxiter, 0))
     it = Ref{Clonglong}(0); res = Ref{Cdouble}(0.0)
     rc = GC.@preserve kν kk check(ccall((:semb_pcg_host, libsemb), Cint,
         (Ptr{Cvoid}, Ref{PcgOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
@@ -436,6 +455,6 @@ function solve!(cdn::ConvectionDiffusion)
     return
 end
 
-export OpLHS, DiagPrecond, StokesB200, release!, comm_unique_id, comm_init
+export OpLHS, DiagPrecond, FdmPrecond, StokesB200, release!, comm_unique_id, comm_init
 
 end # module

@@ -74,11 +74,11 @@ struct FdmTab {
   static constexpr int OFF_LAM = 1, OFF_F = (1 + N2 + 1) & ~1, OFF_G = OFF_F + N2 * NP;
   static constexpr int SIZE = OFF_G + N2 * NP;
   // S: (N2 x N2) column-major (S[i + m*N2]), lam[N2]; returns the slot (host)
-  static void fill(const double* S, const double* lam, double* slot) {
+  static void fill(const double* S, const double* lam, double* slot, bool allow_eo) {
     for (int q = 0; q < SIZE; ++q) slot[q] = 0.0;
     // parity of every mode (padding modes: zero vectors, lambda = inf, count as even)
     int par[N2];
-    bool eo = true;
+    bool eo = allow_eo;
     for (int m = 0; m < N2; ++m) {
       double se = 0.0, so = 0.0, nn = 0.0;
       for (int i = 0; i < N2; ++i) {
@@ -245,10 +245,22 @@ __device__ __forceinline__ double fdm_rcp(double x) {
 // The counting weights W are folded into the rows of the eigenvector tables (N >= 4: the weight of a tile node only
 // depends on the class of the element; N = 3 multiplies explicitly).  Every sum has two terms (three for N = 3), in a
 // fixed order: the result does not depend on the launch geometry.
+// Kernel parameters: the arguments plus the INTERIOR class's even-odd tables (x, y).  Read from the parameter constant bank
+// they reach the DFMAs through LDCU.128 / uniform registers instead of broadcast LDS.128 (the strip kernel's trick for
+// N >= 10, semb_strip.cuh): the shared-memory pipe, 62 % busy at N = 9 with half of its wavefronts being table loads,
+// keeps the tile traffic only.  Boundary classes (no even-odd split) keep their tables in shared memory.
 template <int N>
-__global__ void __launch_bounds__(256, FdmCfg<N>::MINB) semb_fdm_kernel(const FdmArgs a) {
+struct FdmParams {
+  FdmArgs a;
+  int cok;  // the interior tables are even-odd (symmetric nodes): use them; otherwise every class goes through shared memory
+  alignas(16) double tc[2][FdmTab<N + 2>::SIZE];
+};
+
+template <int N>
+__global__ void __launch_bounds__(256, FdmCfg<N>::MINB) semb_fdm_kernel(const __grid_constant__ FdmParams<N> P) {
   using C = FdmCfg<N>;
   using TB = FdmTab<C::N2>;
+  const FdmArgs& a = P.a;
   constexpr int N2 = C::N2, BX = C::BX, S = C::S, PW = C::PW, TSZ = C::TSZ;
   constexpr bool FOLDW = N >= 4;
   extern __shared__ __align__(16) double sm[];
@@ -398,7 +410,7 @@ __global__ void __launch_bounds__(256, FdmCfg<N>::MINB) semb_fdm_kernel(const Fd
   };
   load_el(ra);
   __syncthreads();
-  const bool eox = Tx[0] != 0.0;
+  const bool cxA = P.cok && clsA == 0;   // interior element: even-odd tables from the constant bank
   int cy_loaded = -1;
   double pend0 = 0.0, pend1 = 0.0, prevN1 = 0.0;
   double acc = 0.0;
@@ -413,7 +425,7 @@ __global__ void __launch_bounds__(256, FdmCfg<N>::MINB) semb_fdm_kernel(const Fd
       cy_loaded = cy;
       __syncthreads();
     }
-    const bool eoy = sTy[0] != 0.0;
+    const bool cyc = P.cok && cy == 0;   // interior element row (block-uniform)
     // element scalings 1/hx^2, 1/hy^2, 1/(hx*hy): loaded one element row ahead (volatile asm: the loads stay here)
     const double ihx2 = el_n[0], ihy2 = el_n[1], sc = el_n[2];
     if (q + 1 < nq) load_el(rr + 1);
@@ -431,7 +443,7 @@ __global__ void __launch_bounds__(256, FdmCfg<N>::MINB) semb_fdm_kernel(const Fd
           col[jj] = (y >= 0 && y < a.nyl) ? __dmul_rn(__dmul_rn(wxB, a.wy[y]), col[jj]) : 0.0;
         }
       }
-      if (eoy) fdm_fwd<N2, true>(sTy, col, o);
+      if (cyc) fdm_fwd<N2, true>(P.tc[1], col, o);
       else fdm_fwd<N2, false>(sTy, col, o);
 #pragma unroll
       for (int c = 0; c < N2; ++c) S1[c * PW + colB] = o[c];
@@ -445,17 +457,24 @@ __global__ void __launch_bounds__(256, FdmCfg<N>::MINB) semb_fdm_kernel(const Fd
       double c[N2], o[N2];
 #pragma unroll
       for (int i = 0; i < N2; ++i) c[i] = S1[colA + i];
-      if (eox) fdm_fwd<N2, true>(Tx, c, o);
-      else fdm_fwd<N2, false>(Tx, c, o);
       // Di = 1/(nu*(lx+ly)+k) (p2d_explicit.jl:131-134), times the 1/(hx*hy) of the two S/sqrt(h) pairs
+      auto scale = [&](const double* T) {
 #pragma unroll
-      for (int m = 0; m < N2; ++m) {
-        double d = fdm_rcp(fma(a.nu, fma(Tx[TB::OFF_LAM + m], ihx2, ly), a.k));
-        if (!(fabs(d) <= 1e8)) d = 0.0;  // null mode of an all-free subdomain; padding modes (lambda = inf) give 0 too
-        o[m] *= d * sc;
+        for (int m = 0; m < N2; ++m) {
+          double d = fdm_rcp(fma(a.nu, fma(T[TB::OFF_LAM + m], ihx2, ly), a.k));
+          if (!(fabs(d) <= 1e8)) d = 0.0;  // null mode of an all-free subdomain; padding modes (lambda = inf) give 0 too
+          o[m] *= d * sc;
+        }
+      };
+      if (cxA) {
+        fdm_fwd<N2, true>(P.tc[0], c, o);
+        scale(P.tc[0]);
+        fdm_bwd<N2, true>(P.tc[0], o, c);
+      } else {
+        fdm_fwd<N2, false>(Tx, c, o);
+        scale(Tx);
+        fdm_bwd<N2, false>(Tx, o, c);
       }
-      if (eox) fdm_bwd<N2, true>(Tx, o, c);
-      else fdm_bwd<N2, false>(Tx, o, c);
 #pragma unroll
       for (int i = 0; i < N2; ++i) S1[colA + i] = c[i];
     }
@@ -466,7 +485,7 @@ __global__ void __launch_bounds__(256, FdmCfg<N>::MINB) semb_fdm_kernel(const Fd
       double c[N2];
 #pragma unroll
       for (int m = 0; m < N2; ++m) c[m] = S1[m * PW + colB];
-      if (eoy) fdm_bwd<N2, true>(sTy, c, g);
+      if (cyc) fdm_bwd<N2, true>(P.tc[1], c, g);
       else fdm_bwd<N2, false>(sTy, c, g);
       if (iB <= 1 || iB >= N) {
 #pragma unroll
@@ -583,9 +602,14 @@ __global__ void semb_fdm_lengths_kernel(const double* __restrict__ B, const doub
 // Launch geometry: strips of at most BX-2 output elements; the number of chunks minimises (waves of CTAs) x (element
 // rows a CTA marches through, its two halo rows included)
 template <int N>
-int launch_fdm(semb_ctx* ctx, const FdmArgs& a, int npartials) {
+int launch_fdm(semb_ctx* ctx, const FdmArgs& a, int npartials, const double* htab, int cok) {
   using C = FdmCfg<N>;
   auto kern = semb_fdm_kernel<N>;
+  FdmParams<N> P;
+  P.a = a;
+  P.cok = cok;
+  memcpy(P.tc[0], htab, sizeof(double) * C::TSZ);                          // x, interior class
+  memcpy(P.tc[1], htab + (size_t)4 * C::TSZ, sizeof(double) * C::TSZ);     // y, interior class
   static bool attr_done[64] = {false};
   static int occ[64] = {0};
   const int dev = ctx->device & 63;
@@ -604,7 +628,7 @@ int launch_fdm(semb_ctx* ctx, const FdmArgs& a, int npartials) {
     const long long cost = waves * ((a.ney + nch - 1) / nch + 2);
     if (best_cost < 0 || cost < best_cost) best_cost = cost, best = nch;
   }
-  kern<<<dim3(nstrips, best), 256, C::SMEM, ctx->stream>>>(a);
+  kern<<<dim3(nstrips, best), 256, C::SMEM, ctx->stream>>>(P);
   SEMB_CHECK_CUDA(cudaGetLastError());
   ctx->launches++;
   return SEMB_OK;
@@ -621,11 +645,11 @@ int fdm_slot_size(int N) {
   }
   return 0;
 }
-void fdm_slot_fill(int N, const double* S, const double* lam, double* slot) {
+void fdm_slot_fill(int N, const double* S, const double* lam, double* slot, bool allow_eo) {
   switch (N) {
-#define SEMB_CASE(n)                       \
-  case n:                                  \
-    FdmTab<n + 2>::fill(S, lam, slot);     \
+#define SEMB_CASE(n)                                 \
+  case n:                                            \
+    FdmTab<n + 2>::fill(S, lam, slot, allow_eo);     \
     break;
     SEMB_CASE(3) SEMB_CASE(4) SEMB_CASE(5) SEMB_CASE(6) SEMB_CASE(7) SEMB_CASE(8) SEMB_CASE(9) SEMB_CASE(10) SEMB_CASE(11)
     SEMB_CASE(12) SEMB_CASE(13) SEMB_CASE(14) SEMB_CASE(15) SEMB_CASE(16) SEMB_CASE(17)
@@ -640,6 +664,8 @@ struct semb_fdm {
   double nu = 1.0, k = 0.0;
   int mx0 = 0, mx1 = 0, my0 = 0, my1 = 0;
   double *d_el = nullptr, *d_tab = nullptr, *d_wx = nullptr, *d_wy = nullptr;
+  std::vector<double> h_tab;   // host copy of the tables (the interior class's travel as kernel parameters)
+  int cok = 0;                 // the interior tables are even-odd in both directions
   // several ranks: ghost rows of r (IPC-exported, written by the neighbours), the neighbours' element scalings, epochs
   uint4* d_ghost = nullptr;
   void *peer_lo = nullptr, *peer_hi = nullptr;   // the neighbours' ghost rows as mapped into this process
@@ -741,6 +767,7 @@ int semb_fdm_create_impl(semb_mesh* m, double nu, double k, int mx0, int mx1, in
   const int TSZ = fdm_slot_size(N);
   SEMB_REQUIRE(TSZ > 0, "fdm: no kernel for nr = %d (3..17)", N);
   std::vector<double> tab((size_t)2 * 4 * TSZ, 0.0), Sm((size_t)N2 * N2), lam(N2);
+  for (int pass = 0; pass < 2; ++pass) {
   for (int dir = 0; dir < 2; ++dir) {
     const std::vector<double>& D = dir == 0 ? m->hDr : m->hDs;
     const std::vector<double>& w = dir == 0 ? m->hwr : m->hws;
@@ -758,11 +785,19 @@ int semb_fdm_create_impl(semb_mesh* m, double nu, double k, int mx0, int mx1, in
             for (int c = 0; c < N2; ++c) Sm[i + (size_t)c * N2] *= std::sqrt(0.5);
         }
       }
-      fdm_slot_fill(N, Sm.data(), lam.data(), tab.data() + ((size_t)dir * 4 + cls) * TSZ);
+      // the even-odd layout only for the interior class (read from the constant bank); decided below for both directions
+      fdm_slot_fill(N, Sm.data(), lam.data(), tab.data() + ((size_t)dir * 4 + cls) * TSZ, cls == 0 && pass == 0);
     }
   }
+  const bool cok = tab[0] != 0.0 && tab[(size_t)4 * TSZ] != 0.0;
+  if (cok || pass == 1) {
+    f->cok = cok ? 1 : 0;
+    break;
+  }
+  }  // (second pass: an asymmetric D -- no even-odd split anywhere)
   SEMB_CHECK_CUDA(cudaMalloc(&f->d_tab, tab.size() * sizeof(double)));
   SEMB_CHECK_CUDA(cudaMemcpy(f->d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+  f->h_tab = tab;
   // counting weights W = 1/sqrt(cx*cy), separable: c = 1 + [neighbour below && i <= 1] + [neighbour above && i >= N-2]
   std::vector<double> wx((size_t)m->pitch, 0.0), wy((size_t)m->nyl, 0.0);
   for (int x = 0; x < m->nxl; ++x) {
@@ -843,7 +878,7 @@ int semb_fdm_apply_impl(semb_fdm* f, const double* r, double* out, int pcg) {
   switch (m->nr) {
 #define SEMB_CASE(n) \
   case n:            \
-    SEMB_TRY(launch_fdm<n>(c, a, m->npartials)); \
+    SEMB_TRY(launch_fdm<n>(c, a, m->npartials, f->h_tab.data(), f->cok)); \
     break;
     SEMB_CASE(3) SEMB_CASE(4) SEMB_CASE(5) SEMB_CASE(6) SEMB_CASE(7) SEMB_CASE(8) SEMB_CASE(9) SEMB_CASE(10) SEMB_CASE(11)
     SEMB_CASE(12) SEMB_CASE(13) SEMB_CASE(14) SEMB_CASE(15) SEMB_CASE(16) SEMB_CASE(17)

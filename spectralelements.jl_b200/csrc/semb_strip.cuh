@@ -222,7 +222,9 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
   // 184 -> 56 bytes of spills, 0.618 -> 0.590 ms per preconditioned iteration at 512x512 order 8; the plain
   // apply measured 4 % slower in the late form, so it keeps the early one)
   constexpr bool LATE_B = SEMB_LATE_B && PCGM;
-  constexpr bool TABC = N >= SEMB_TABC_MIN_N;
+  // (below 10 the A/B is mixed -- profiles/r02_sweep_tables_constant_bank_low_orders_r3d.txt: N = 6 gains in every
+  // variant (79 -> 84 % plain), N = 7 and 9 only in the plain apply (79 -> 85 %, 78 -> 79 %), N = 3-5 and 8 lose)
+  constexpr bool TABC = N >= SEMB_TABC_MIN_N || N == 6 || ((N == 7 || N == 9) && !PCGM && !MASS);
   extern __shared__ __align__(128) double smem[];
   // [N][PW] transposition buffer, updated IN PLACE by the alternating mappings (each phase touches
   // every location from exactly one thread): u -> Dr u -> wr -> Dr^T wr
