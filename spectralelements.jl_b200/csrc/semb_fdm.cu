@@ -213,7 +213,10 @@ struct FdmCfg {
   static constexpr int TSZ = FdmTab<N2>::SIZE;
   static constexpr int SMEM = (2 * N2 * PW + 4 * TSZ) * 8;   // two tile buffers, 3 x tables + the y table in use
   static constexpr int MAXB = (227 * 1024) / (SMEM + 1024);
-  static constexpr int MINB = MAXB >= 3 ? 3 : (MAXB >= 2 ? 2 : 1);
+  // CTAs per SM: three (80 registers) only while that does not spill; from N = 7 on two CTAs at 128 registers are faster
+  // (N = 9: 136 bytes of spills and 34 % long-scoreboard stalls at 80 registers, 1.19 -> 0.96 ms per application at 128)
+  static constexpr int WANTB = N <= 6 ? 3 : 2;
+  static constexpr int MINB = MAXB >= WANTB ? WANTB : (MAXB >= 2 ? 2 : 1);
 };
 
 __device__ __forceinline__ void fdm_cp_async8(uint32_t dst_smem, const double* src) {
