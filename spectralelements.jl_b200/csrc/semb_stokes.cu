@@ -149,33 +149,53 @@ struct GsFusedArgs {
   int nr, ns, Ex, ney, nxl, nyl, perx, pery, mode, mx0, mx1, my0, my1;
   int raw_lo, raw_hi;  // multi-rank: row 0 / nyl-1 still wait for the neighbour's row: no epilogue yet
 };
-__global__ void semb_gs_fused_kernel(const GsFusedArgs a) {
+// A thread owns a pair of columns (16-byte loads / stores) and walks down the rows of its CTA row; everything that only
+// depends on the column -- element index, x partners, Dirichlet columns -- is computed once per thread.  (The first
+// version, one node per thread with the index arithmetic per node, ran at 27 % of the HBM roof and was 47 % of the
+// Stokes Schur apply: profiles/r02_stokes_launches_r3j.txt.)
+__global__ void __launch_bounds__(256) semb_gs_fused_kernel(const GsFusedArgs a) {
+  const int x = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (x >= a.nxl) return;
+  const bool vb = x + 1 < a.nxl;  // (nxl may be odd: the pad column keeps its zero)
+  // x partners of the two nodes: -1 none, else the column (the pair's other node, or a neighbouring pair's)
+  auto partner = [&](int xx) {
+    const int e = xx / a.nr, i = xx - e * a.nr;
+    if (i == a.nr - 1) return e < a.Ex - 1 ? xx + 1 : (a.perx ? 0 : -1);
+    if (i == 0) return e > 0 ? xx - 1 : (a.perx ? a.nxl - 1 : -1);
+    return -1;
+  };
+  const int pa = partner(x), pb = vb ? partner(x + 1) : -1;
+  const bool za = (x == 0 && a.mx0) || (x == a.nxl - 1 && a.mx1), zb = vb && (x + 1 == a.nxl - 1 && a.mx1);
+  const size_t pitch = (size_t)a.pitch;
+  auto row_sum = [&](const double* __restrict__ r, double& ga, double& gb) {   // x pairs of one row
+    const double2 v = *reinterpret_cast<const double2*>(r + x);
+    ga = v.x, gb = v.y;
+    if (pa >= 0) ga = __dadd_rn(ga, pa == x + 1 ? v.y : r[pa]);
+    if (pb >= 0) gb = __dadd_rn(gb, pb == x ? v.x : r[pb]);
+  };
   for (int row = blockIdx.y; row < a.nyl; row += gridDim.y) {
     const int rl = row / a.ns, j = row - rl * a.ns;
     int yp = -1;
     if (j == a.ns - 1) yp = rl < a.ney - 1 ? row + 1 : (a.pery ? 0 : -1);
     else if (j == 0) yp = rl > 0 ? row - 1 : (a.pery ? a.nyl - 1 : -1);
-    const double* ur = a.u + (size_t)row * a.pitch;
-    const double* up = a.u + (size_t)(yp < 0 ? row : yp) * a.pitch;
-    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < a.nxl; x += gridDim.x * blockDim.x) {
-      const int e = x / a.nr, i = x - e * a.nr;
-      int xp = -1;
-      if (i == a.nr - 1) xp = e < a.Ex - 1 ? x + 1 : (a.perx ? 0 : -1);
-      else if (i == 0) xp = e > 0 ? x - 1 : (a.perx ? a.nxl - 1 : -1);
-      double g = ur[x];
-      if (xp >= 0) g = __dadd_rn(g, ur[xp]);
-      if (yp >= 0) {
-        double h = up[x];
-        if (xp >= 0) h = __dadd_rn(h, up[xp]);
-        g = __dadd_rn(g, h);
-      }
-      if (a.mode && !(row == 0 && a.raw_lo) && !(row == a.nyl - 1 && a.raw_hi)) {
-        const bool z = (x == 0 && a.mx0) || (x == a.nxl - 1 && a.mx1) || (row == 0 && a.my0) || (row == a.nyl - 1 && a.my1);
-        g = __dmul_rn(z ? 0.0 : 1.0, g);
-        if (a.mode == 1) g = __ddiv_rn(__dmul_rn(g, a.Bi[(size_t)row * a.pitch + x]), a.b0);
-      }
-      a.out[(size_t)row * a.pitch + x] = g;
+    double ga, gb;
+    row_sum(a.u + (size_t)row * pitch, ga, gb);
+    if (yp >= 0) {   // the y pair of the two x pairs: (a+b)+(c+d), gatherScatter.jl:13
+      double ha, hb;
+      row_sum(a.u + (size_t)yp * pitch, ha, hb);
+      ga = __dadd_rn(ga, ha), gb = __dadd_rn(gb, hb);
     }
+    if (a.mode && !(row == 0 && a.raw_lo) && !(row == a.nyl - 1 && a.raw_hi)) {
+      const bool zr = (row == 0 && a.my0) || (row == a.nyl - 1 && a.my1);
+      ga = __dmul_rn((za || zr) ? 0.0 : 1.0, ga);
+      gb = __dmul_rn((zb || zr) ? 0.0 : 1.0, gb);
+      if (a.mode == 1) {
+        const double2 bi = *reinterpret_cast<const double2*>(a.Bi + (size_t)row * pitch + x);
+        ga = __dmul_rn(ga, bi.x), gb = __dmul_rn(gb, bi.y);
+        if (a.b0 != 1.0) ga = __ddiv_rn(ga, a.b0), gb = __ddiv_rn(gb, a.b0);   // (x / 1.0 == x: same bits, no division)
+      }
+    }
+    *reinterpret_cast<double2*>(a.out + (size_t)row * pitch + x) = make_double2(ga, vb ? gb : 0.0);
   }
 }
 
@@ -292,9 +312,9 @@ int semb_launch_gs_fused(semb_ctx* ctx, semb_mesh* m, const double* u, double* o
   a.raw_lo = m->halo_lo;
   a.raw_hi = m->halo_hi;
   if (stage == 0) {
-    int gx = (m->nxl + 255) / 256;
-    if (gx > 1024) gx = 1024;
-    const int gy = m->nyl > 32768 ? 32768 : m->nyl;
+    const int gx = ((m->nxl + 1) / 2 + 255) / 256;
+    int gy = (ctx->sm_count * 8 + gx - 1) / gx;   // eight resident CTAs per SM, each walking down its share of the rows
+    if (gy > m->nyl) gy = m->nyl;
     semb_gs_fused_kernel<<<dim3(gx, gy), 256, 0, ctx->stream>>>(a);
   } else {
     if (mode == 0 || (!a.raw_lo && !a.raw_hi)) return SEMB_OK;

@@ -27,6 +27,29 @@ extern "C" int semb_gradT(semb_mesh* m, const semb_field* u, semb_field* ux, sem
   return semb_launch_gradT(m->ctx, m, u->d, nullptr, ux->d, uy->d);
 }
 
+// gatherScatter in one pass with a pointwise epilogue (semb_gs_fused_kernel; mode 0 none, 1 (M.*g).*Bi./b0, 2 M.*g); with
+// neighbour ranks the slab's boundary rows are completed by the halo exchange before their epilogue.  dst must not alias src.
+static int gs_one_pass(semb_mesh* m, const double* src, double* dst, int mode, double b0, const MaskFlags& f) {
+  SEMB_TRY(semb_launch_gs_fused(m->ctx, m, src, dst, mode, b0, f.mx0, f.mx1, f.my0, f.my1, 0));
+  if (m->halo_lo || m->halo_hi) {
+    unsigned long long eph = 0;
+    SEMB_TRY(halo_exchange(m, dst, 0, &eph));
+    OpArgs y;
+    fill_common(m, y);
+    y.halo_lo = m->d_halo_lo;
+    y.halo_hi = m->d_halo_hi;
+    if (m->p2p) {
+      y.halo_lo = mail_halo(m, m->d_mailbox, (int)(eph & 1ull), 0);
+      y.halo_hi = mail_halo(m, m->d_mailbox, (int)(eph & 1ull), 1);
+    }
+    y.out = dst;
+    y.nyseam = 0;  // only the received rows
+    SEMB_TRY(semb_launch_seam_y(m->ctx, y, m->halo_lo, m->halo_hi, false, p2p_args(m, eph)));
+    SEMB_TRY(semb_launch_gs_fused(m->ctx, m, src, dst, mode, b0, f.mx0, f.mx1, f.my0, f.my1, 1));
+  }
+  return SEMB_OK;
+}
+
 extern "C" int semb_approx_hlmz_inv(semb_mesh* m, const semb_field* u, double b0, const char bc[4], semb_field* out) {
   SEMB_REQUIRE(m, "null mesh");
   SEMB_ENTER(m->ctx);
@@ -46,23 +69,7 @@ extern "C" int semb_approx_hlmz_inv(semb_mesh* m, const semb_field* u, double b0
     const int modes[2] = {1, bc ? 2 : 0};
     const double* src[2] = {u->d, t->d};
     double* dst[2] = {t->d, out->d};
-    for (int k = 0; k < 2; ++k) {
-      SEMB_TRY(semb_launch_gs_fused(m->ctx, m, src[k], dst[k], modes[k], b0, f.mx0, f.mx1, f.my0, f.my1, 0));  // diver.jl:95-98 | :100-101
-      if (m->halo_lo || m->halo_hi) {
-        unsigned long long eph = 0;
-        SEMB_TRY(halo_exchange(m, dst[k], 0, &eph));
-        OpArgs y;
-        fill_common(m, y);
-        if (m->p2p) {
-          y.halo_lo = mail_halo(m, m->d_mailbox, (int)(eph & 1ull), 0);
-          y.halo_hi = mail_halo(m, m->d_mailbox, (int)(eph & 1ull), 1);
-        }
-        y.out = dst[k];
-        y.nyseam = 0;  // only the received rows
-        SEMB_TRY(semb_launch_seam_y(m->ctx, y, m->halo_lo, m->halo_hi, false, p2p_args(m, eph)));
-        SEMB_TRY(semb_launch_gs_fused(m->ctx, m, src[k], dst[k], modes[k], b0, f.mx0, f.mx1, f.my0, f.my1, 1));
-      }
-    }
+    for (int k = 0; k < 2; ++k) SEMB_TRY(gs_one_pass(m, src[k], dst[k], modes[k], b0, f));  // diver.jl:95-98 | :100-101
     return SEMB_OK;
   }
   SEMB_TRY(semb_gather_scatter(m, u, t));                                                            // diver.jl:95
@@ -215,7 +222,8 @@ extern "C" int semb_stokes_op(semb_stokes* s, const semb_field* q, semb_field* o
   SEMB_TRY(semb_approx_hlmz_inv(s->V, s->v1, s->b0, s->bcx, s->v3));          // HH^-1
   SEMB_TRY(semb_approx_hlmz_inv(s->V, s->v2, s->b0, s->bcy, s->v1));
   SEMB_TRY(stokes_diver(s, s->v3, s->v1, s->p_rhs, -1.0));                    // DD, and "return -Eq" (diver.jl:88)
-  return semb_gather_scatter(s->P, s->p_rhs, out);                           // stokes.jl:118
+  if (s->P->fast) return gs_one_pass(s->P, s->p_rhs->d, out->d, 0, 1.0, MaskFlags());  // stokes.jl:118, one pass
+  return semb_gather_scatter(s->P, s->p_rhs, out);
 }
 
 // makeStokesRHS!, stokes.jl:128-141, for the velocity (vx, vy) to be projected
