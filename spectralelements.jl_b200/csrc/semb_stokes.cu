@@ -167,22 +167,26 @@ __global__ void __launch_bounds__(256) semb_gs_fused_kernel(const GsFusedArgs a)
   const int pa = partner(x), pb = vb ? partner(x + 1) : -1;
   const bool za = (x == 0 && a.mx0) || (x == a.nxl - 1 && a.mx1), zb = vb && (x + 1 == a.nxl - 1 && a.mx1);
   const size_t pitch = (size_t)a.pitch;
+  const double* __restrict__ u = a.u;      // (out never aliases u or Bi: lets the loads of the next row pass this row's store)
+  const double* __restrict__ Bi = a.Bi;
+  double* __restrict__ out = a.out;
   auto row_sum = [&](const double* __restrict__ r, double& ga, double& gb) {   // x pairs of one row
     const double2 v = *reinterpret_cast<const double2*>(r + x);
     ga = v.x, gb = v.y;
     if (pa >= 0) ga = __dadd_rn(ga, pa == x + 1 ? v.y : r[pa]);
     if (pb >= 0) gb = __dadd_rn(gb, pb == x ? v.x : r[pb]);
   };
+#pragma unroll 2
   for (int row = blockIdx.y; row < a.nyl; row += gridDim.y) {
     const int rl = row / a.ns, j = row - rl * a.ns;
     int yp = -1;
     if (j == a.ns - 1) yp = rl < a.ney - 1 ? row + 1 : (a.pery ? 0 : -1);
     else if (j == 0) yp = rl > 0 ? row - 1 : (a.pery ? a.nyl - 1 : -1);
     double ga, gb;
-    row_sum(a.u + (size_t)row * pitch, ga, gb);
+    row_sum(u + (size_t)row * pitch, ga, gb);
     if (yp >= 0) {   // the y pair of the two x pairs: (a+b)+(c+d), gatherScatter.jl:13
       double ha, hb;
-      row_sum(a.u + (size_t)yp * pitch, ha, hb);
+      row_sum(u + (size_t)yp * pitch, ha, hb);
       ga = __dadd_rn(ga, ha), gb = __dadd_rn(gb, hb);
     }
     if (a.mode && !(row == 0 && a.raw_lo) && !(row == a.nyl - 1 && a.raw_hi)) {
@@ -190,12 +194,12 @@ __global__ void __launch_bounds__(256) semb_gs_fused_kernel(const GsFusedArgs a)
       ga = __dmul_rn((za || zr) ? 0.0 : 1.0, ga);
       gb = __dmul_rn((zb || zr) ? 0.0 : 1.0, gb);
       if (a.mode == 1) {
-        const double2 bi = *reinterpret_cast<const double2*>(a.Bi + (size_t)row * pitch + x);
+        const double2 bi = *reinterpret_cast<const double2*>(Bi + (size_t)row * pitch + x);
         ga = __dmul_rn(ga, bi.x), gb = __dmul_rn(gb, bi.y);
         if (a.b0 != 1.0) ga = __ddiv_rn(ga, a.b0), gb = __ddiv_rn(gb, a.b0);   // (x / 1.0 == x: same bits, no division)
       }
     }
-    *reinterpret_cast<double2*>(a.out + (size_t)row * pitch + x) = make_double2(ga, vb ? gb : 0.0);
+    *reinterpret_cast<double2*>(out + (size_t)row * pitch + x) = make_double2(ga, vb ? gb : 0.0);
   }
 }
 

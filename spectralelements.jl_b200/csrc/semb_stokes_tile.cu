@@ -21,6 +21,12 @@
 namespace {
 
 constexpr int STK_T = 128;
+#ifndef STK_MINB
+#define STK_MINB 3
+#endif
+
+// next batch's columns into L2 (one request per 32-byte sector): the column loads below then find their lines there
+__device__ __forceinline__ void stk_prefetch_l2(const double* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 struct StokesTileArgs {
   const double *in1, *in2;   // diverT: in1 = pr (mshP) ; diver: ux, uy (mshV)
@@ -46,7 +52,7 @@ struct StkCfg {
 
 // ---------------------------------------------------------------------------------------------------------------------
 template <int NV, int NP>
-__global__ void __launch_bounds__(STK_T) semb_diverT_tile_kernel(const StokesTileArgs a) {
+__global__ void __launch_bounds__(STK_T, STK_MINB) semb_diverT_tile_kernel(const StokesTileArgs a) {
   using C = StkCfg<NV, NP>;
   constexpr int EB = C::EB, S = C::S, SP = C::SP, PV = C::PV, PP = C::PP;
   constexpr int OFF_JR = 0, OFF_JS = C::TJ::SIZE, OFF_DRT = 2 * C::TJ::SIZE, OFF_DST = OFF_DRT + C::TDT::SIZE,
@@ -67,6 +73,21 @@ __global__ void __launch_bounds__(STK_T) semb_diverT_tile_kernel(const StokesTil
     const int r = b / nbx, e0 = (b - r * nbx) * EB, nbe = min(EB, a.Ex - e0);
     const bool actC = t < nbe * NV;
     const size_t gV = (size_t)r * NV * a.pitchV + (size_t)e0 * NV + t;
+    {
+      const int bn = b + gridDim.x;
+      if (bn < nbx * a.ney && (t & 3) == 0) {
+        const int rn = bn / nbx, en = (bn - rn * nbx) * EB;
+        if (t < min(EB, a.Ex - en) * NV) {
+          const size_t gn = (size_t)rn * NV * a.pitchV + (size_t)en * NV + t;
+#pragma unroll
+          for (int j = 0; j < NV; ++j) {
+            const size_t g = gn + (size_t)j * a.pitchV;
+            stk_prefetch_l2(a.B + g), stk_prefetch_l2(a.rx + g), stk_prefetch_l2(a.ry + g);
+            stk_prefetch_l2(a.sx + g), stk_prefetch_l2(a.sy + g);
+          }
+        }
+      }
+    }
     __syncthreads();  // tables in place; previous batch done with the tiles
     for (int q = t; q < NP * nbe * NP; q += STK_T) {  // pressure tile, coalesced rows
       const int n = q / (nbe * NP), xx = q - n * (nbe * NP), e = xx / NP, m = xx - e * NP;
@@ -147,7 +168,7 @@ __global__ void __launch_bounds__(STK_T) semb_diverT_tile_kernel(const StokesTil
 
 // ---------------------------------------------------------------------------------------------------------------------
 template <int NV, int NP>
-__global__ void __launch_bounds__(STK_T) semb_diver_tile_kernel(const StokesTileArgs a) {
+__global__ void __launch_bounds__(STK_T, STK_MINB) semb_diver_tile_kernel(const StokesTileArgs a) {
   using C = StkCfg<NV, NP>;
   constexpr int EB = C::EB, S = C::S, SP = C::SP, PV = C::PV, PP = C::PP;
   constexpr int OFF_DR = 0, OFF_DS = C::TD::SIZE, OFF_JRT = 2 * C::TD::SIZE, OFF_JST = OFF_JRT + C::TJT::SIZE,
@@ -167,6 +188,21 @@ __global__ void __launch_bounds__(STK_T) semb_diver_tile_kernel(const StokesTile
     const int r = b / nbx, e0 = (b - r * nbx) * EB, nbe = min(EB, a.Ex - e0);
     const bool actC = t < nbe * NV;
     const size_t gV = (size_t)r * NV * a.pitchV + (size_t)e0 * NV + t;
+    {
+      const int bn = b + gridDim.x;
+      if (bn < nbx * a.ney && (t & 3) == 0) {
+        const int rn = bn / nbx, en = (bn - rn * nbx) * EB;
+        if (t < min(EB, a.Ex - en) * NV) {
+          const size_t gn = (size_t)rn * NV * a.pitchV + (size_t)en * NV + t;
+#pragma unroll
+          for (int j = 0; j < NV; ++j) {
+            const size_t g = gn + (size_t)j * a.pitchV;
+            stk_prefetch_l2(a.in1 + g), stk_prefetch_l2(a.in2 + g), stk_prefetch_l2(a.B + g), stk_prefetch_l2(a.rx + g);
+            stk_prefetch_l2(a.ry + g), stk_prefetch_l2(a.sx + g), stk_prefetch_l2(a.sy + g);
+          }
+        }
+      }
+    }
     __syncthreads();
     // ---- C: columns of ux, uy -> registers and tiles; us = Ds * (ux, uy) ---------------------------------------------
     double us[2][NV], c1[NV], c2[NV];
@@ -240,7 +276,7 @@ __global__ void __launch_bounds__(STK_T) semb_diver_tile_kernel(const StokesTile
 template <int NV, int NP>
 int launch_stokes_tile(semb_ctx* ctx, const StokesTileArgs& a, bool transpose) {
   const int nbatch = ((a.Ex + StkCfg<NV, NP>::EB - 1) / StkCfg<NV, NP>::EB) * a.ney;
-  int grid = ctx->sm_count * 4;
+  int grid = ctx->sm_count * STK_MINB;   // persistent: the resident CTAs walk through the batches
   if (grid > nbatch) grid = nbatch;
   if (grid < 1) grid = 1;
   if (transpose)
