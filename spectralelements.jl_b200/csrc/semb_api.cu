@@ -535,6 +535,10 @@ static int mesh_build_plan(semb_mesh* m) {
   // apply at 1112x1112 order 8, 2012 vs 2023 us per PCG iteration).  Everything that has launches or exchanges to
   // save -- one wave (small meshes), several ranks -- keeps the one-launch form.  SEMB_FORCE_TAIL=1 keeps it always.
   if (m->tail && P == 1 && (long long)m->nstrips * best >= 2LL * slots && !getenv("SEMB_FORCE_TAIL")) m->tail = false;
+  // One rank, plain applies (no PCG reduction to save): the seam kernels also win on a single wave of CTAs (256x256
+  // order 8 Helmholtz, L2 flushed: 69.8 vs 73.7 us), the PCG iteration does not (156.5 vs 160.0 us) -- so on one rank
+  // the one-launch form serves the PCG-mode applies only
+  m->tail_plain = m->tail && (P > 1 || getenv("SEMB_FORCE_TAIL"));
   SEMB_TRY(mesh_set_groups(m, best));
   // pipelined host twin (semb_oplhs_host) on several ranks: every rank must take the same path (its halo exchange differs
   // from the one-launch apply's), so the size criterion is agreed on once, here
@@ -1112,7 +1116,7 @@ static int run_operator(semb_mesh* m, const double* u, double* out, const OpSpec
   a.mx1 = f.mx1;
   a.my0 = f.my0;
   a.my1 = f.my1;
-  if (m->fast && m->tail && sp.gs) {
+  if (m->fast && m->tail && sp.gs && (pcg || m->tail_plain)) {
     // ONE launch: the strip kernel's CTAs finish the interfaces, exchange the halo rows through peer memory and
     // (PCG) reduce + all-gather sum(p.*Ap.*mult) themselves (semb_tail.cuh)
     a.tail = 1;

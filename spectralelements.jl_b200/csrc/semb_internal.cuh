@@ -182,6 +182,7 @@ struct semb_mesh {
   unsigned long long ep_halo = 0;      // epoch of the stand-alone halo exchange (host-side; the others live in SembScal::ep_dev)
   // fused tail (semb_tail.cuh)
   bool tail = false;                   // interface completion fused into the strip kernel
+  bool tail_plain = false;             // ... also for applies outside PCG (several ranks; one rank: the seam kernels are faster)
   int ngroups = 0;                     // grid.y of the strip kernel (CTA rows); a CTA row marches through 1 or 2 chunks
   int* d_grp = nullptr;                // 2*ngroups chunk ids
   unsigned* d_tcnt = nullptr;

@@ -207,6 +207,13 @@ __device__ __forceinline__ void semb_fence_proxy_async() { asm volatile("fence.p
 // shared-memory pipe, which at these sizes is the busiest unit (73 % of its cycles at N = 13, half of the wavefronts
 // being table loads: profiles/r01_strip13_r1l.txt).  Measured (profiles/r02_sweep_tables_constant_bank_r2x.txt):
 // N = 11: 70 -> 81 % of the HBM roof, N = 13: 63 -> 73 %, N = 9: 78 -> 79 % plain but 92 -> 85 % in the PCG variant.
+// Helmholtz (plain apply with a mass term): the B rows of the NEXT element row go to L2 with the G rows (bulk prefetch), so
+// that the early column load at the top of the row is an L2 hit.  Measured per N (profiles/r02_sweep_b_prefetch_r3p.txt,
+// % of the 48-B roof): N = 6 76 -> 81, 8 76 -> 81, 9 72 -> 80, 10 76 -> 79; N = 7, 11, 12, 13 lose 1-3 points and keep the
+// plain form.  -DSEMB_B_PREFETCH_ALL=1 forces it everywhere (the A/B build).
+#ifndef SEMB_B_PREFETCH_ALL
+#define SEMB_B_PREFETCH_ALL 0
+#endif
 #ifndef SEMB_TABC_MIN_N
 #define SEMB_TABC_MIN_N 10
 #endif
@@ -222,6 +229,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
   // 184 -> 56 bytes of spills, 0.618 -> 0.590 ms per preconditioned iteration at 512x512 order 8; the plain
   // apply measured 4 % slower in the late form, so it keeps the early one)
   constexpr bool LATE_B = SEMB_LATE_B && PCGM;
+  constexpr bool BPF = SEMB_B_PREFETCH_ALL || N == 6 || (N >= 8 && N <= 10);
   // (below 10 the A/B is mixed -- profiles/r02_sweep_tables_constant_bank_low_orders_r3d.txt: N = 6 gains in every
   // variant (79 -> 84 % plain), N = 7 and 9 only in the plain apply (79 -> 85 %, 78 -> 79 %), N = 3-5 and 8 lose)
   constexpr bool TABC = N >= SEMB_TABC_MIN_N || N == 6 || ((N == 7 || N == 9) && !PCGM && !MASS);
@@ -304,7 +312,7 @@ semb_strip_kernel(const __grid_constant__ StripParams<N> P) {
 #endif
     }
     // general coefficients: B is read late (step 5) with plain loads; its rows travel to L2 alongside the G rows
-    if (MASS && LATE_B && first_arr == 1 && a.B && t < N)
+    if (MASS && (LATE_B || BPF) && first_arr == 1 && a.B && t < N)
       semb_bulk_prefetch_l2(a.B + (size_t)(r * N + t) * pitch + x0, row_bytes);
   };
   if (!TABC) {

@@ -104,10 +104,12 @@ def test_fused_oplhs(sem, ctx, nr, Ex, Ey, per, deform):
 @pytest.mark.parametrize("nr,Ex,Ey,per,deform", [CASES[0], CASES[3], CASES[7], CASES[8], CASES[9], CASES[10],
                                                  (2, 300, 4, (True, True), "box")])
 def test_fused_tail_equals_seam_kernels(sem, ctx, monkeypatch, nr, Ex, Ey, per, deform):
-    """One apply is ONE launch by default: the strip kernel's own CTAs finish the strip / chunk interfaces
-    (semb_tail.cuh).  The separate seam kernels remain (SEMB_NO_TAIL=1, the NCCL fallback and the pipelined host
+    """One apply is ONE launch (several ranks by default, PCG-mode applies always; here forced): the strip kernel's own
+    CTAs finish the strip / chunk interfaces (semb_tail.cuh).  The separate seam kernels remain (SEMB_NO_TAIL=1, the NCCL fallback and the pipelined host
     twin use them): both must give the same BITS for every chunking (2-term interface sums, gatherScatter.jl:13)."""
+    monkeypatch.setenv("SEMB_FORCE_TAIL", "1")   # (one rank: plain applies default to the seam kernels, PCG to the tail)
     om, gt = make_pair(sem, ctx, nr, Ex, Ey, per, deform)
+    monkeypatch.delenv("SEMB_FORCE_TAIL")
     monkeypatch.setenv("SEMB_NO_TAIL", "1")
     _, gs = make_pair(sem, ctx, nr, Ex, Ey, per, deform)
     monkeypatch.delenv("SEMB_NO_TAIL")

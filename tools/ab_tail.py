@@ -41,6 +41,7 @@ for nr, Ex, Ey, k in MESHES:
             os.environ["SEMB_NO_TAIL"] = "1"
         else:
             os.environ.pop("SEMB_NO_TAIL", None)
+            os.environ["SEMB_FORCE_TAIL"] = "1"
         m = sem.Mesh(nr, nr, Ex, Ey, (False, False), "wavy", ctx=ctx)
         u, out = m.field().fill_random(1), m.field()
         fn = lambda: m.oplhs_device(u, out, nu=1.0, k=k, bc="DDDD")
@@ -62,3 +63,4 @@ for nr, Ex, Ey, k in MESHES:
                                                             sust * 1e3, pcg * 1e3, m.plan()), flush=True)
         m.free()
 os.environ.pop("SEMB_NO_TAIL", None)
+os.environ.pop("SEMB_FORCE_TAIL", None)
