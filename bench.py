@@ -154,6 +154,30 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(local):
+    """One process per GPU: run this rank's host threads -- and hence first-touch its pinned staging buffers -- on the
+    NUMA node the GPU hangs off, as a multi-rank deployment would (with all ranks on node 0 the host-buffer twin is bound
+    by the inter-socket link: 8 ranks each moved their 1.6 GB per step at 1/8 of the one-rank rate).  Best effort."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def dist_setup(ngpus):
     """One process per GPU; torch.distributed (NCCL) is plumbing: rendezvous, barriers, max-over-ranks."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -166,6 +190,8 @@ def dist_setup(ngpus):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if not os.environ.get("SEMB_BENCH_NO_NUMA"):
+            os.environ["SEMB_BENCH_NUMA_NODE"] = str(bind_to_gpu_numa_node(local))
     return world, rank, local, dist
 
 
@@ -535,7 +561,8 @@ def run_semb(args):
         ems = max_over_ranks(dist, ems) / nst
         e2e = {"value": ndof_global / (ems * 1e-3) / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": nbytes * world,
                "d2h_bytes_per_step": nbytes * world, "ms_per_step": ems,
-               "api": "semb_oplhs_host (C ABI host-buffer twin of opLHS), pinned host buffers"}
+               "api": "semb_oplhs_host (C ABI host-buffer twin of opLHS), pinned host buffers",
+               "host_numa_node_rank0": os.environ.get("SEMB_BENCH_NUMA_NODE")}
         ctx.lib.semb_free_pinned(hp_in)
         ctx.lib.semb_free_pinned(hp_out)
 
