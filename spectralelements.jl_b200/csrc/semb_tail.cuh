@@ -198,7 +198,6 @@ __device__ __forceinline__ void semb_tail_run(const OpArgs& a, const SembTailTas
     for (int u = 0; u < U; ++u) {  // ---- every load of every item
       SembTailItem& I = it[u];
       if (!I.valid) continue;
-      const uint4* rem = (I.y0 == 0) ? rem_lo : rem_hi;  // (only read when rem1 / rem2)
       const size_t i0 = (size_t)I.y0 * pitch + I.x0, i1 = (size_t)I.y1 * pitch + I.x1;
       const size_t i2 = (size_t)I.y2 * pitch + I.x0, i3 = (size_t)I.y2 * pitch + I.x1;
       I.v[0] = __ldcg(&a.out[i0]);
