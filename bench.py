@@ -634,6 +634,21 @@ def run_semb(args):
                                           "diag-preconditioned PCG), %dx%d elements, order 8, %d DOF" % (E4, E4, nV),
                               "steps_per_s": 1.0 / dt4, "ms_per_step": dt4 * 1e3, "pcg_iters_last": cdn.pcg_iters[-1],
                               "gdof_steps_per_s": nV / dt4 / 1e9, "ms_per_dealiased_advect_incl_alloc": dta * 1e3}
+        # the same steps with the opt-in FDM preconditioner as opM (not the reference's iteration counts: reported beside)
+        try:
+            cdn.set_precond("fdm")
+            for _ in range(2):
+                sem.step_b(cdn)
+            ctx.sync()
+            t0 = time.perf_counter()
+            for _ in range(nst):
+                sem.step_b(cdn)
+            ctx.sync()
+            dt4f = (time.perf_counter() - t0) / nst
+            extra["cfg4_cd2d"]["fdm_preconditioner"] = {"ms_per_step": dt4f * 1e3, "pcg_iters_last": cdn.pcg_iters[-1],
+                                                        "speedup": dt4 / dt4f}
+        except sem.SembError as ex:
+            extra["cfg4_cd2d"]["fdm_preconditioner"] = {"error": str(ex)[:120]}
         cdn.free(); mV.free(); mD.free()
 
     # ---- BASELINE configs[4]: Stokes pressure-velocity split, order 10 velocity / order 8 pressure, 1/2/4/8 GPUs --------

@@ -242,6 +242,11 @@ int semb_diffusion_begin_step(semb_diffusion* d, double* time, long long* istep)
 int semb_diffusion_finish_step(semb_diffusion* d, double tol, long long* iters, double* resinf);
 /* time[k+1], bdfA[k], bdfB[k+1] (time.jl:70-82); any pointer may be NULL */
 int semb_diffusion_state(semb_diffusion* d, double* time, double* bdfA, double* bdfB, long long* istep);
+/* The opM of the step's solve (pcg.jl:37): kind 0 = the reference's (identity in diffusion.jl:71, opPrecond = u./B./b0 in
+ * convectionDiffusion.jl:87-91,118), kind 2 = the FDM preconditioner of nu*lapl + b0*mass (lapl.jl:105-119; registered on the
+ * mesh like semb_fdm_create, constant viscosity only -- otherwise the step keeps kind 0).  Opt-in: same solution to the
+ * solver tolerance, several times fewer iterations, but not the reference's iteration counts. */
+int semb_diffusion_set_precond(semb_diffusion* d, int kind);
 
 /* ---- explicit dealiased convection and the ConvectionDiffusion driver -------------------- */
 /* grad(u,msh), grad.jl:15-34: ux = rx.*ur + sx.*us, uy = ry.*ur + sy.*us (needs a mesh built from x,y) */

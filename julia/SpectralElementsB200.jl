@@ -310,6 +310,15 @@ function driver(eq, mshV::Mesh, mshD::Union{Mesh,Nothing} = nothing)
     end
 end
 
+"""set_precond!(eq, kind): the opM of the step's solve (pcg.jl:37) -- `:reference` is what the reference passes (identity in
+diffusion.jl:71, opPrecond in convectionDiffusion.jl:118), `:fdm` the FDM preconditioner of ν*lapl + b0*mass (lapl.jl:105-119;
+constant ν only): same solution to the solver tolerance in several times fewer iterations, but not the reference's
+iteration counts.  Opt-in."""
+set_precond!(dfn::Diffusion, kind::Symbol) =
+    check(ccall((:semb_diffusion_set_precond, libsemb), Cint, (Ptr{Cvoid}, Cint), driver(dfn, dfn.msh), kind == :fdm ? 2 : 0))
+set_precond!(cdn::ConvectionDiffusion, kind::Symbol) =
+    check(ccall((:semb_diffusion_set_precond, libsemb), Cint, (Ptr{Cvoid}, Cint), driver(cdn, cdn.mshV, cdn.mshD), kind == :fdm ? 2 : 0))
+
 # one step of either equation: updateHist! + time/BDF update on the device, the user closures on the host (only
 # what a closure other than the no-op fixU! may have changed is uploaded), makeRHS! + solve! on the device
 function devstep!(eq, d::Ptr{Cvoid}, msh::Mesh, setBC!, setForcing!, setVisc!; tol = 1e-8, sync_velocity = true)
@@ -455,6 +464,6 @@ function solve!(cdn::ConvectionDiffusion)
     return
 end
 
-export OpLHS, DiagPrecond, FdmPrecond, StokesB200, release!, comm_unique_id, comm_init
+export OpLHS, DiagPrecond, FdmPrecond, set_precond!, StokesB200, release!, comm_unique_id, comm_init
 
 end # module

@@ -878,6 +878,13 @@ class Diffusion:
         else:
             self.__dict__[name] = value
 
+    def set_precond(self, kind="reference"):
+        """opM of the step's solve (pcg.jl:37): "reference" = what the reference passes (identity in diffusion.jl:71,
+        opPrecond = u./B./b0 in convectionDiffusion.jl:118); "fdm" = the FDM preconditioner of nu*lapl + b0*mass
+        (lapl.jl:105-119; constant viscosity only): same solution to the solver tolerance in several times fewer
+        iterations, but not the reference's iteration counts -- opt-in."""
+        check(self.lib.semb_diffusion_set_precond(self.h, {"reference": 0, "fdm": 2}[kind]))
+
     def free(self):
         if self.__dict__.get("h"):
             self.lib.semb_diffusion_destroy(self.h)

@@ -101,6 +101,7 @@ _SIGS = {
     "semb_diffusion_begin_step": ([vp, c_double_p, c_ll_p], C.c_int),
     "semb_diffusion_finish_step": ([vp, C.c_double, c_ll_p, c_double_p], C.c_int),
     "semb_diffusion_state": ([vp, c_double_p, c_double_p, c_double_p, c_ll_p], C.c_int),
+    "semb_diffusion_set_precond": ([vp, C.c_int], C.c_int),
     "semb_grad": ([vp, vp, vp, vp], C.c_int),
     "semb_advect": ([vp, vp, vp, vp, vp, vp], C.c_int),
     "semb_convdiff_create": ([vp, vp, C.c_char_p, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(vp)], C.c_int),

@@ -1756,6 +1756,7 @@ struct semb_diffusion {
   semb_field *vx = nullptr, *vy = nullptr;
   std::vector<semb_field*> adv;
   AdvectWork* work = nullptr;
+  int precond_kind = 0;  // 0: the reference's opM (identity for Diffusion, u./B./b0 for ConvectionDiffusion), 2: FDM
 };
 
 extern "C" int semb_diffusion_create(semb_mesh* m, const char bc[4], double Ti, double Tf, double dt, int k,
@@ -1898,11 +1899,37 @@ extern "C" int semb_diffusion_finish_step(semb_diffusion* d, double tol, long lo
     o.precond = 1;
     o.prec_b0 = d->bdfB[0];
   }
+  if (d->precond_kind == 2) {
+    // opt-in: the FDM preconditioner (lapl.jl:105-119) of nu*lapl + bdfB[1]*mass instead of the reference's opM.  It needs
+    // a constant viscosity; the tables do not depend on (nu, k), so following the BDF start-up only resets two scalars
+    bool cst = false;
+    double v = 0.0;
+    SEMB_TRY(field_constant(m, d->nu, &cst, &v));
+    if (cst && v > 0.0 && d->bdfB[0] >= 0.0 && m->fast && m->nr >= 3 && (c->nranks == 1 || m->p2p)) {
+      if (!m->fdm || strncmp(m->fdm_bc, d->bc, 4) != 0) {
+        semb_fdm* h = nullptr;
+        SEMB_TRY(semb_fdm_create(m, d->bc, v, d->bdfB[0], &h));
+      } else {
+        SEMB_TRY(semb_fdm_set_coeffs_impl(m->fdm, v, d->bdfB[0]));
+      }
+      o.precond = 2;
+      o.prec_b0 = 1.0;
+    }
+  }
   int rc = semb_pcg(m, &o, d->rhs, d->x, iters, resinf);
   if (rc < 0) return rc;
   SEMB_TRY(semb_field_copy(d->u, d->x));
   SEMB_TRY(semb_field_axpby(1.0, d->ub, 1.0, d->u));  // u .+= ub
   return rc;
+}
+
+// kind 0: the reference's preconditioner (pcg.jl:37 opM = identity in diffusion.jl:71, opPrecond in convectionDiffusion.jl:118);
+// kind 2: the FDM preconditioner (lapl.jl:105-119, semb_fdm_create) -- fewer iterations, other iterates within the tolerance
+extern "C" int semb_diffusion_set_precond(semb_diffusion* d, int kind) {
+  SEMB_REQUIRE(d, "null diffusion");
+  SEMB_REQUIRE(kind == 0 || kind == 2, "semb_diffusion_set_precond: kind must be 0 (the reference's) or 2 (FDM)");
+  d->precond_kind = kind;
+  return SEMB_OK;
 }
 
 extern "C" int semb_diffusion_state(semb_diffusion* d, double* time, double* bdfA, double* bdfB, long long* istep) {
@@ -2217,6 +2244,7 @@ extern "C" int semb_fdm_create(semb_mesh* m, const char bc[4], double nu, double
     return rc;
   }
   m->fdm = h;
+  memcpy(m->fdm_bc, bc ? bc : "NNNN", 4);
   *out = h;
   return SEMB_OK;
 }

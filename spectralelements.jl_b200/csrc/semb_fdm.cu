@@ -837,6 +837,14 @@ int semb_fdm_create_impl(semb_mesh* m, double nu, double k, int mx0, int mx1, in
   return SEMB_OK;
 }
 
+// the tables do not depend on the coefficients of nu*lapl + k*mass: only Di = 1/(nu*(lx+ly)+k) does, inside the kernel
+int semb_fdm_set_coeffs_impl(semb_fdm* f, double nu, double k) {
+  SEMB_REQUIRE(f && nu > 0.0 && k >= 0.0, "fdm: needs nu > 0, k >= 0");
+  f->nu = nu;
+  f->k = k;
+  return SEMB_OK;
+}
+
 // h = opM(r); pcg: 0 stand-alone, 1 inside pcg (reduction + advance), 2 first call of a solve
 int semb_fdm_apply_impl(semb_fdm* f, const double* r, double* out, int pcg) {
   semb_mesh* m = f->m;

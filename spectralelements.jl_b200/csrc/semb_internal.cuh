@@ -212,6 +212,7 @@ struct semb_mesh {
   // sum(p.*Ap.*mult) by the reduction kernel, update -- instead of the fused strip kernel (Stokes Schur operator)
   std::function<int()> pcg_custom;
   struct semb_fdm* fdm = nullptr;      // FDM preconditioner registered on this mesh (semb_fdm_create), used by precond = 2
+  char fdm_bc[4] = {0, 0, 0, 0};       // the boundary flags it was built for
   std::vector<semb_field*> fields;     // live fields (for leak-free destroy)
   std::vector<semb_field*> host_tmp;   // cached device fields of the *_host twins
 };
@@ -307,6 +308,7 @@ int semb_fdm_create_impl(semb_mesh* m, double nu, double k, int mx0, int mx1, in
                          semb_fdm** out);
 int semb_fdm_free_impl(semb_fdm* f);
 int semb_fdm_apply_impl(semb_fdm* f, const double* r, double* out, int pcg);
+int semb_fdm_set_coeffs_impl(semb_fdm* f, double nu, double k);
 
 // launchers implemented in the .cu files
 int semb_launch_strip(semb_ctx* ctx, const OpArgs& a, const double* hDr, const double* hDs, int nstrips,
