@@ -31,7 +31,13 @@ def build(c):
     info = {}
     x = so.pcg(b, lambda v: so.opLHS(v, c["nu"], c["k"], M, m), mult=m.mult, tol=1e-8, info=info)
     x12 = so.pcg(b, lambda v: so.opLHS(v, c["nu"], c["k"], M, m), mult=m.mult, tol=1e-12)
-    return dict(G11=m.G11, G12=m.G12, G22=m.G22, B=m.B, mult=m.mult, Dr=m.Dr, x=m.x, y=m.y, M=M, u=u,
+    # FDM preconditioner: h = opM(r) for a continuous masked r, and the preconditioned iteration count
+    P = so.fdm_schwarz(m, c["bc"], c["nu"], c["k"])
+    fr = so.mask(so.gatherScatter(u * m.mult, m), M)
+    finfo = {}
+    so.pcg(b, lambda v: so.opLHS(v, c["nu"], c["k"], M, m), opM=P, mult=m.mult, tol=1e-8, info=finfo)
+    return dict(fdm_r=fr, fdm_h=P(fr), pcg_fdm_iters=np.array(finfo["iters"]),
+                G11=m.G11, G12=m.G12, G22=m.G22, B=m.B, mult=m.mult, Dr=m.Dr, x=m.x, y=m.y, M=M, u=u,
                 lapl=so.lapl(u, m), hlmz=so.hlmz(u, c["nu"], c["k"], m), gs=so.gatherScatter(u, m),
                 oplhs=so.opLHS(u, c["nu"], c["k"], M, m), rhs=b, pcg_x=x, pcg_x_tol12=x12,
                 pcg_iters=np.array(info["iters"]), pcg_hist=np.array(info["hist"][:13]))
