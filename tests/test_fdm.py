@@ -116,3 +116,23 @@ def test_gpu_pcg_with_fdm(sem, ctx, nr, E, deform, bc, k):
         assert np.max(np.abs(xg12 - xo12)) < 1e-10 * np.max(np.abs(xo12))
     finally:
         gm.free()
+
+
+@pytest.mark.parametrize("n", list(range(3, 18)))
+def test_interior_class_eigenvectors_are_even_or_odd(sem, n):
+    """What the device kernel's even-odd tables rely on (semb_fdm.cu, FdmTab): the extended 1-D operator of an element with
+    a neighbour on both sides is symmetric under i <-> n+1-i, so every eigenvector of libsemb's decomposition is even or
+    odd, with ceil((n+2)/2) even and floor((n+2)/2) odd ones; a boundary class is not (it takes the full products)."""
+    z, w = so.gausslobatto(n)
+    D = so.derivMat(z)
+    S, lam = sem.fdm_tables(D, w, "N", "N")
+    assert np.all(np.isfinite(lam))
+    ne = no = 0
+    for m in range(n + 2):
+        v = S[:, m]
+        even, odd = np.max(np.abs(v - v[::-1])), np.max(np.abs(v + v[::-1]))
+        assert min(even, odd) < 1e-10 * np.max(np.abs(v)), (n, m)
+        ne, no = ne + (even < odd), no + (odd < even)
+    assert ne == (n + 3) // 2 and no == (n + 2) // 2
+    Sb, _ = sem.fdm_tables(D, w, "D", "N")
+    assert any(min(np.max(np.abs(Sb[:, m] - Sb[::-1, m])), np.max(np.abs(Sb[:, m] + Sb[::-1, m]))) > 1e-6 for m in range(n))
