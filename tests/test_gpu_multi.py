@@ -11,9 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _ngpu():
+    """GPUs on this box, asked of a child process: importing torch HERE, after the session's libsemb context exists, is
+    what an in-process count would depend on (on a 2-GPU box the in-process form skipped these tests when they ran after
+    the other GPU tests)."""
     try:
-        import torch
-        return torch.cuda.device_count()
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=60).stdout
+        return sum(1 for line in out.splitlines() if line.startswith("GPU "))
     except Exception:
         return 0
 
