@@ -675,6 +675,7 @@ struct semb_fdm {
   double *d_el_lo = nullptr, *d_el_hi = nullptr;
   unsigned long long* d_ep = nullptr;
   unsigned long long ep_host = 0;
+  bool ranks_ready = false;   // the collective set-up completed (on every rank)
 };
 
 int semb_fdm_free_impl(semb_fdm* f) {
@@ -684,7 +685,9 @@ int semb_fdm_free_impl(semb_fdm* f) {
   cudaFree(f->d_wx);
   cudaFree(f->d_wy);
   if (f->d_ghost) {
-    semb_comm_barrier(f->m->ctx);  // no neighbour may still be writing into (or mapping) the ghost rows
+    // no neighbour may still be writing into (or mapping) the ghost rows (a set-up that failed did so on every rank, before
+    // anyone could push: no barrier then)
+    if (f->ranks_ready) semb_comm_barrier(f->m->ctx);
     if (f->peer_lo) cudaIpcCloseMemHandle(f->peer_lo);
     if (f->peer_hi && f->peer_hi != f->peer_lo) cudaIpcCloseMemHandle(f->peer_hi);
     cudaFree(f->d_ghost);
@@ -725,11 +728,17 @@ static int fdm_setup_ranks(semb_fdm* f) {
   SEMB_CHECK_CUDA(cudaMemcpyAsync(all.data(), d_h, (size_t)P * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost, c->stream));
   SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
   cudaFree(d_h);
-  if (m->halo_lo) SEMB_CHECK_CUDA(cudaIpcOpenMemHandle(&f->peer_lo, all[m->rank_lo], cudaIpcMemLazyEnablePeerAccess));
-  if (m->halo_hi) {
+  cudaError_t eo = cudaSuccess;
+  if (m->halo_lo) eo = cudaIpcOpenMemHandle(&f->peer_lo, all[m->rank_lo], cudaIpcMemLazyEnablePeerAccess);
+  if (eo == cudaSuccess && m->halo_hi) {
     if (m->halo_lo && m->rank_hi == m->rank_lo) f->peer_hi = f->peer_lo;   // two ranks, periodic: one mapping
-    else SEMB_CHECK_CUDA(cudaIpcOpenMemHandle(&f->peer_hi, all[m->rank_hi], cudaIpcMemLazyEnablePeerAccess));
+    else eo = cudaIpcOpenMemHandle(&f->peer_hi, all[m->rank_hi], cudaIpcMemLazyEnablePeerAccess);
   }
+  if (eo != cudaSuccess) cudaGetLastError();
+  // every rank must take the same path from here on (the exchanges below and the barrier in the destructor are collective)
+  double bad = eo == cudaSuccess ? 0.0 : 1.0;
+  SEMB_TRY(semb_comm_allreduce_max(c, &bad, 1));
+  SEMB_REQUIRE(bad == 0.0, "fdm: mapping a neighbour rank's ghost rows (CUDA IPC) failed on some rank: %s", cudaGetErrorString(eo));
   // element scalings of the adjoining rows: our first row goes down, our last row up (receives in the opposite
   // order, so that two ranks that are each other's neighbour on both sides pair the messages correctly)
   const size_t Ex = (size_t)m->Ex, nel = Ex * m->ney;
@@ -751,6 +760,7 @@ static int fdm_setup_ranks(semb_fdm* f) {
   SEMB_CHECK_CUDA(cudaStreamSynchronize(c->stream));
   cudaFree(d_send);
   SEMB_TRY(semb_comm_barrier(c));  // every rank's ghost rows exist and are mapped before anyone pushes
+  f->ranks_ready = true;
   return SEMB_OK;
 }
 
