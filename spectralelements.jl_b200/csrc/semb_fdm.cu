@@ -11,12 +11,13 @@
 // in), Di = 1/(nu*(lx + ly) + k).  Element half-lengths hx, hy come from the element-averaged metric; an element's
 // extension is taken with its own half-length, so S and lambda depend on the element only through S/sqrt(h), lambda/h^2
 // and three reference decompositions per direction (first / interior / last element) serve the whole mesh
-// (semb_fdm_tables, semb_host.cpp).  5-8x fewer PCG iterations than no preconditioner on the BASELINE meshes.
+// (semb_fdm_tables, semb_host.cpp).  6-8x fewer PCG iterations than no preconditioner on the BASELINE meshes.
 //
-// One kernel per application (semb_fdm_kernel<N>): gathers the (N+2)^2 tiles of W.*r, applies the four contractions out of
-// registers (the strip kernel's two thread<->line mappings), sums the tile entries that land on a node and on its
-// duplicates -- x overlaps, x pairs, y overlaps, y pairs, the association of gatherScatter.jl:13 -- applies W and the mask
-// and, inside pcg, accumulates sum(r .* h .* mult) (pcg.jl:45) deterministically.  16 bytes per node of HBM traffic.
+// One kernel per application (semb_fdm_kernel<N>): gathers the (N+2)^2 tiles of r, applies the four contractions out of
+// registers (the strip kernel's two thread<->line mappings; W is folded into the tables), sums the tile entries that land
+// on a node and on its duplicates -- x overlaps, x pairs, y overlaps, y pairs, the association of gatherScatter.jl:13 --
+// applies the mask and, inside pcg, accumulates sum(r .* h .* mult) (pcg.jl:45) deterministically.  16 bytes per node
+// of HBM traffic; on several ranks the neighbour slabs' boundary rows of r arrive through peer memory (below).
 #include "semb_reduce.cuh"
 #include "semb_vec.cuh"
 
@@ -25,10 +26,10 @@ namespace {
 struct FdmArgs {
   const double* r;      // residual (continuous)
   double* out;          // h = opM(r)
-  const double* tab;    // [dir 2][class 4][N2*N2 + N2]: S (column-major: S[ii + c*N2]) then lambda
+  const double* tab;    // [dir 2][class 4][FdmTab<N+2>::SIZE] contraction tables (layouts: FdmTab)
   const double* el;     // [3][nel]: 1/hx^2, 1/hy^2, 1/(hx*hy) of the elements (hx, hy: half-lengths)
   long long nel;
-  const double* wx;     // W = wx[x] * wy[y]
+  const double* wx;     // W = wx[x] * wy[y]: only read for N = 3 (N >= 4: folded into the tables)
   const double* wy;
   const double* mult_x; // mult(x,y) = mult_x[x] * mult_y[y]  (PCG reduction)
   const double* mult_y;
