@@ -756,9 +756,9 @@ def cpu_reference(nr, E, sample_rows, reps):
             "seconds_per_apply_sample": dt}
 
 
-def cpu_reference_c(nr, E, rows, reps=3):
-    """The same fused opLHS on an E x rows-element slab through oracle/_build/libsem_oracle_c.so (built by
-    __graft_entry__.build(); single thread unless the toolchain had OpenMP)."""
+def c_oracle_stepper(nr, E, rows):
+    """(step, ndof, free, threads): one fused opLHS apply on an E x rows-element slab through
+    oracle/_build/libsem_oracle_c.so (built by __graft_entry__.build(); OpenMP over the elements when the toolchain has it)."""
     lib_path = os.path.join(ROOT, "oracle", "_build", "libsem_oracle_c.so")
     if not os.path.exists(lib_path):
         raise FileNotFoundError("oracle/_build/libsem_oracle_c.so not built")
@@ -777,19 +777,26 @@ def cpu_reference_c(nr, E, rows, reps=3):
     except AttributeError:
         nthr = 1
     h = lib.so_mesh_create(nr, nr, E, rows, 0, 0, 2)   # 2 = wavy
+    n = nr * E * nr * rows
+    u = np.random.default_rng(0x5EED).uniform(-1.0, 1.0, n)
+    out, M = np.zeros(n), np.zeros(n)
+    P = lambda a: a.ctypes.data_as(dp)
+    lib.so_generate_mask(h, b"DDDD", P(M))
+    step = lambda: lib.so_oplhs(h, P(u), None, 1.0, None, 0.0, P(M), P(out))
+    return step, n, (lambda: lib.so_mesh_free(h)), nthr
+
+
+def cpu_reference_c(nr, E, rows, reps=3):
+    """The fused opLHS on an E x rows-element slab through the plain-C restatement, `reps` applies after one warm-up."""
+    step, n, free, nthr = c_oracle_stepper(nr, E, rows)
     try:
-        n = nr * E * nr * rows
-        u = np.random.default_rng(0x5EED).uniform(-1.0, 1.0, n)
-        out, M = np.zeros(n), np.zeros(n)
-        P = lambda a: a.ctypes.data_as(dp)
-        lib.so_generate_mask(h, b"DDDD", P(M))
-        lib.so_oplhs(h, P(u), None, 1.0, None, 0.0, P(M), P(out))
+        step()
         t0 = time.perf_counter()
         for _ in range(reps):
-            lib.so_oplhs(h, P(u), None, 1.0, None, 0.0, P(M), P(out))
+            step()
         dt = (time.perf_counter() - t0) / reps
     finally:
-        lib.so_mesh_free(h)
+        free()
     return {"value": n / dt / 1e9, "unit": "GDOF/s", "cores": nthr,
             "sample": "oracle/sem_oracle.c opLHS (plain C loops per element, OpenMP over elements: %d thread(s)) on a %dx%d-element "
                       "slab (%d DOF), %d applies, %.3f s each" % (nthr, E, rows, n, reps, dt)}
@@ -797,51 +804,61 @@ def cpu_reference_c(nr, E, rows, reps=3):
 
 def run_reference(args):
     """--impl reference: the reference's CPU path (restated, oracle/) on the host cores, rank 0 only.  Two restatements
-    exist -- NumPy/OpenBLAS (line-faithful to the Julia code, all host threads) and plain C loops per element (one
-    thread); the line reports the FASTER of the two, so that the GPU/CPU ratio is not flattered by the slower one."""
+    exist -- NumPy/OpenBLAS (line-faithful to the Julia code, all host threads) and plain C loops per element (OpenMP
+    over the elements); a probe picks the FASTER of the two, so that the GPU/CPU ratio is not flattered by the slower
+    one, and that one is then timed for exactly --steps K applies after --warmup W, each step one apply on a y-slab
+    sample of the headline mesh sized so that the whole run stays within about a minute."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     args.cpu_rows = min(args.cpu_rows, args.elements)
-    cpu = cpu_reference(args.nr, args.elements, args.cpu_rows, reps=1)
-    # K timed steps + W warm-up on the bounded sample
+    cpu = cpu_reference(args.nr, args.elements, args.cpu_rows, reps=1)   # probe: both restatements, a few applies each
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import sem_oracle as so
-    om = so.make_mesh(args.nr, args.nr, args.elements, args.cpu_rows, (False, False), so.wavy, dense_qqt=False)
-    M = so.generateMask(list("DDDD"), om).astype(np.float64)
-    u = so.splitmix_uniform(om.x.shape)
-    steps, warm = min(args.steps, 5), min(args.warmup, 1)
-    for _ in range(warm):
-        so.opLHS(u, 1.0, 0.0, M, om)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        so.opLHS(u, 1.0, 0.0, M, om)
-    dt = (time.perf_counter() - t0) / steps
-    val = u.size / dt / 1e9
-    sample_dofs, which = u.size, "numpy"
-    cpu["numpy_value"] = val
+    K, W = max(1, args.steps), max(0, args.warmup)
+    cpu["numpy_value"] = cpu["value"]
     c_port = cpu.get("c_port") or {}
-    if isinstance(c_port.get("value"), float) and c_port["value"] > val:   # the compiled restatement is faster: report it
-        rows_c = min(args.cpu_rows, 64)
-        sample_dofs = (args.nr * args.elements) * (args.nr * rows_c)
-        val, dt, which = c_port["value"], sample_dofs / c_port["value"] / 1e9, "c"
-        cpu["cores"] = c_port.get("cores", 1)
-        cpu["sample"] = c_port["sample"] + " (faster than the NumPy/OpenBLAS restatement: %.4f GDOF/s on %s threads)" % (
-            cpu["numpy_value"], cpu.get("cores"))
-    cpu["value"] = val
+    use_c = isinstance(c_port.get("value"), float) and c_port["value"] > cpu["value"]
+    budget_s = 60.0
+    per_row_dofs = args.nr * args.elements * args.nr
+    if use_c:
+        rows0 = min(args.cpu_rows, 64)
+        rows = int(max(4, min(rows0, budget_s * c_port["value"] * 1e9 / ((K + W) * per_row_dofs))))
+        step, ndof, free, nthr = c_oracle_stepper(args.nr, args.elements, rows)
+        which = "c"
+    else:
+        rows = int(max(4, min(args.cpu_rows, budget_s * cpu["value"] * 1e9 / ((K + W) * per_row_dofs))))
+        om = so.make_mesh(args.nr, args.nr, args.elements, rows, (False, False), so.wavy, dense_qqt=False)
+        M = so.generateMask(list("DDDD"), om).astype(np.float64)
+        u = so.splitmix_uniform(om.x.shape)
+        step, ndof, free, nthr, which = (lambda: so.opLHS(u, 1.0, 0.0, M, om)), u.size, (lambda: None), cpu.get("cores"), "numpy"
+    try:
+        for _ in range(W):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            step()
+        dt = (time.perf_counter() - t0) / K
+    finally:
+        free()
+    val = ndof / dt / 1e9
+    cpu["value"], cpu["cores"] = val, nthr
+    cpu["sample"] = ("%s restatement (oracle/sem_oracle.%s), %d threads: %d applies after %d warm-ups on a %dx%d-element y-slab of "
+                     "the headline mesh (%d DOF), %.3f s each; the other restatement probed at %.4f GDOF/s"
+                     % ("plain-C/OpenMP" if use_c else "NumPy/OpenBLAS", "c" if use_c else "py", nthr or 0, K, W, args.elements,
+                        rows, ndof, dt, cpu["numpy_value"] if use_c else (c_port.get("value") or float("nan"))))
+    workload = ("fused Laplacian+QQ^T+mask apply (opLHS, Poisson nu=1 k=0, bc DDDD), order %d (nr=%d), %dx%d elements per GPU, "
+                "wavy-deformed box, %d DOF per GPU" % (args.nr - 1, args.nr, args.elements, args.elements,
+                                                       (args.nr * args.elements) ** 2))
     line = {"impl": "reference", "metric": "laplacian_gs_mask_apply_throughput", "value": val, "unit": "GDOF/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "fused Laplacian+QQ^T+mask apply (opLHS, Poisson nu=1 k=0, bc DDDD), order %d "
-                                   "(nr=%d), %dx%d elements per GPU, wavy-deformed box, %d DOF per GPU"
-                                   % (args.nr - 1, args.nr, args.elements, args.elements,
-                                      (args.nr * args.elements) ** 2),
+            "config": {"workload": workload,
                        "sample": "each step = one apply on a y-slab of that mesh (%d DOF, %s restatement); throughput per DOF, "
-                                 "so comparable with the GPU arm although config and steps are a bounded sample"
-                                 % (sample_dofs, which)},
+                                 "so comparable with the GPU arm although each step is a bounded sample" % (ndof, which)},
             "cpu_baseline": cpu,
             "e2e": {"value": val, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "reference = CPU restatement of the Julia path (oracle/: NumPy/OpenBLAS and plain C; the faster is reported); "
+            "note": "reference = CPU restatement of the Julia path (oracle/: NumPy/OpenBLAS and plain C; the faster is timed); "
                     "Julia is not installed"}
     print(json.dumps(line))
 
