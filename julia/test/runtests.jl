@@ -82,4 +82,21 @@ end
         end
     end
 end
+
+# ---- FDM preconditioner (the reference has it only as commented-out sketches, lapl.jl:105-119: no CPU twin to compare
+# with -- what can be held is that it is a preconditioner: same solution, several times fewer iterations) ---------------
+@testset "FdmPrecond as opM of pcg" begin
+    for (name, msh, bc) in cases
+        M  = convert(Array{Float64}, generateMask(bc, msh))
+        op = OpLHS(msh, 1.0, 1.0, M)
+        b  = gatherScatter(mask(mass(ones(size(msh.x)), msh), M), msh)
+        P  = FdmPrecond(msh, bc, 1.0, 1.0)
+        x0 = pcg(b, op; mult = msh.mult, tol = 1e-12)
+        x1 = pcg(b, op; opM = P, mult = msh.mult, tol = 1e-12)
+        @test relerr(x1, x0) < 1e-9
+        r  = mask(gatherScatter(b .* msh.mult, msh), M)
+        h  = P(r)
+        @test sum(r .* h .* msh.mult) > 0                                  # positive definite in pcg's inner product
+    end
+end
 #
