@@ -136,3 +136,76 @@ def test_interior_class_eigenvectors_are_even_or_odd(sem, n):
     assert ne == (n + 3) // 2 and no == (n + 2) // 2
     Sb, _ = sem.fdm_tables(D, w, "D", "N")
     assert any(min(np.max(np.abs(Sb[:, m] - Sb[::-1, m])), np.max(np.abs(Sb[:, m] + Sb[::-1, m]))) > 1e-6 for m in range(n))
+
+
+@pytest.mark.parametrize("nr,Ex,Ey,per,deform,bc,nu,k", [(5, 3, 2, (False, False), so.wavy, "DNDD", 1.3, 0.5),
+                                                        (4, 2, 3, (True, False), so.fixU, "NNDN", 1.0, 0.2),
+                                                        (6, 2, 2, (False, True), so.wavy, "DDNN", 0.7, 0.0)])
+def test_fdm_schwarz_equals_a_dense_assembly_with_direct_subdomain_solves(nr, Ex, Ey, per, deform, bc, nu, k):
+    """Independent pin of the oracle's fdm_schwarz: the same preconditioner assembled WITHOUT eigen-decompositions -- every
+    extended subdomain operator nu*(By (x) Ax + Ay (x) Bx) + k*(By (x) Bx) built as a dense matrix from the 1-D stiffness /
+    mass pairs and solved directly -- must give the same h = opM(r) (the tensor solve of lapl_fdm, lapl.jl:112-119, is
+    exactly that inverse written in the generalized eigenbasis)."""
+    msh = so.make_mesh(nr, nr, Ex, Ey, per, deform)
+    n = nr
+    M = so.generateMask(list(bc), msh).astype(np.float64)
+    z1, w = so.gausslobatto(n)
+    D = so.derivMat(z1)
+    A0 = D.T @ np.diag(w) @ D
+    elavg = lambda a: a.reshape(n, Ex, n, Ey, order="F").mean(axis=(0, 2))
+    Jw = msh.B / np.asfortranarray(np.outer(np.kron(np.ones(Ex), w), np.kron(np.ones(Ey), w)))
+    hx, hy = elavg(Jw * np.sqrt(msh.G22 / msh.B)), elavg(Jw * np.sqrt(msh.G11 / msh.B))
+
+    def one_d(e, E, periodic, bclo, bchi, h):
+        """(A, B diagonal, active tile indices, global node of every tile index) of element e extended by one node"""
+        A, Bd = np.zeros((n + 2, n + 2)), np.zeros(n + 2)
+        A[1:n + 1, 1:n + 1] += A0 / h
+        Bd[1:n + 1] += h * w
+        glob = [None] + [e * n + i for i in range(n)] + [None]
+        act = np.ones(n + 2, dtype=bool)
+        if e > 0 or periodic:
+            A[0:2, 0:2] += A0[n - 2:, n - 2:] / h
+            Bd[0:2] += h * w[n - 2:]
+            glob[0] = ((e - 1) % E) * n + n - 2
+        else:
+            act[0] = False
+            act[1] = bclo != "D"
+        if e < E - 1 or periodic:
+            A[n:, n:] += A0[:2, :2] / h
+            Bd[n:] += h * w[:2]
+            glob[n + 1] = ((e + 1) % E) * n + 1
+        else:
+            act[n + 1] = False
+            act[n] = bchi != "D"
+        idx = np.nonzero(act)[0]
+        return A[np.ix_(idx, idx)], Bd[idx], idx, [glob[i] for i in idx]
+
+    r = so.mask(so.gatherScatter(so.splitmix_uniform(msh.x.shape, seed=8) * msh.mult, msh), M)
+    cnt = np.zeros(msh.x.shape)
+    parts = []
+    for ex in range(Ex):
+        for ey in range(Ey):
+            Ax, Bx, ix, gx = one_d(ex, Ex, per[0], bc[0], bc[1], hx[ex, ey])
+            Ay, By, iy, gy = one_d(ey, Ey, per[1], bc[2], bc[3], hy[ex, ey])
+            # every tile node with a global image counts (Dirichlet nodes too: the oracle's counting ignores the mask)
+            gxa = [g for g in ([((ex - 1) % Ex) * n + n - 2] if (ex > 0 or per[0]) else []) + [ex * n + i for i in range(n)]
+                   + ([((ex + 1) % Ex) * n + 1] if (ex < Ex - 1 or per[0]) else [])]
+            gya = [g for g in ([((ey - 1) % Ey) * n + n - 2] if (ey > 0 or per[1]) else []) + [ey * n + j for j in range(n)]
+                   + ([((ey + 1) % Ey) * n + 1] if (ey < Ey - 1 or per[1]) else [])]
+            cnt[np.ix_(gxa, gya)] += 1.0
+            parts.append((Ax, Bx, gx, Ay, By, gy))
+    W = 1.0 / np.sqrt(np.maximum(so.gatherScatter(cnt, msh), 1.0))
+    rw = W * r
+    z = np.zeros(msh.x.shape)
+    for Ax, Bx, gx, Ay, By, gy in parts:
+        T = rw[np.ix_(gx, gy)]
+        # column-major vec: vec(Ax T By) = (By (x) Ax) vec(T)
+        Ae = nu * (np.kron(np.diag(By), Ax) + np.kron(Ay, np.diag(Bx))) + k * np.kron(np.diag(By), np.diag(Bx))
+        if k == 0.0 and np.linalg.matrix_rank(Ae) < Ae.shape[0]:
+            U = np.linalg.pinv(Ae) @ T.reshape(-1, order="F")       # all-free subdomain: the null mode is cut off
+        else:
+            U = np.linalg.solve(Ae, T.reshape(-1, order="F"))
+        z[np.ix_(gx, gy)] += U.reshape(T.shape, order="F")
+    h_dense = so.mask(W * so.gatherScatter(z, msh), M)
+    h_eig = so.fdm_schwarz(msh, bc, nu, k)(r)
+    assert np.max(np.abs(h_eig - h_dense)) < 1e-10 * np.max(np.abs(h_dense))
